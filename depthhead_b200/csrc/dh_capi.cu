@@ -1,0 +1,290 @@
+// dh_capi.cu — the extern "C" boundary declared in include/depthhead_cuda.h.
+// Every entry point catches everything (nothing unwinds across the ABI) and records a
+// thread-local message for dh_last_error().
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+
+#include "../../include/depthhead_cuda.h"
+#include "dh_ctx.hpp"
+#include "dh_forest.hpp"
+#include "dh_json.hpp"
+
+struct dh_forest {
+    std::unique_ptr<dh::HostForest> hf;
+};
+struct dh_ctx {
+    std::unique_ptr<dh::Context> cx;
+};
+
+namespace {
+
+thread_local std::string g_last_error = "";
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+template <typename F>
+int guarded(F&& body) {
+    try {
+        body();
+        return DH_OK;
+    } catch (const dh::JsonError& e) {
+        return fail(DH_E_JSON, std::string("json: ") + e.what());
+    } catch (const dh::ModelError& e) {
+        return fail(e.code, e.what());
+    } catch (const std::bad_alloc&) {
+        return fail(DH_E_ARG, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(DH_E_ARG, e.what());
+    } catch (...) {
+        return fail(DH_E_ARG, "unknown error");
+    }
+}
+
+#define REQUIRE(cond, msg) \
+    do {                   \
+        if (!(cond)) throw dh::ModelError(DH_E_ARG, msg); \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char* dh_last_error(void) { return g_last_error.c_str(); }
+int dh_abi_version(void) { return DH_ABI_VERSION; }
+
+int dh_forest_from_json(const char* json, size_t len, dh_forest** out) {
+    return guarded([&] {
+        REQUIRE(json && out, "dh_forest_from_json: NULL argument");
+        *out = nullptr;
+        dh::RawForest raw = dh::parse_hough_prediction_json(json, len);
+        std::unique_ptr<dh_forest> f(new dh_forest());
+        f->hf.reset(dh::flatten_forest(raw));
+        *out = f.release();
+    });
+}
+
+int dh_forest_from_arrays(const dh_forest_arrays* a, dh_forest** out) {
+    return guarded([&] {
+        REQUIRE(a && out, "dh_forest_from_arrays: NULL argument");
+        *out = nullptr;
+        REQUIRE(a->n_trees >= 1 && a->tree_node_off && a->tree_leaf_off && a->prob && a->vote_off,
+                "dh_forest_from_arrays: missing arrays");
+        dh::RawForest raw;
+        raw.stepwidth = a->stepwidth;
+        raw.subimage_width = a->subimage_width;
+        raw.subimage_height = a->subimage_height;
+        raw.meanshift_iterations = a->meanshift_iterations;
+        raw.gaussian_sigma = a->gaussian_sigma;
+        raw.n_trees = a->n_trees;
+        const int T = a->n_trees;
+        raw.tree_node_off.assign(a->tree_node_off, a->tree_node_off + T + 1);
+        raw.tree_leaf_off.assign(a->tree_leaf_off, a->tree_leaf_off + T + 1);
+        const int64_t NN = raw.tree_node_off[T], NL = raw.tree_leaf_off[T];
+        REQUIRE(NN >= 0 && NL >= 1, "dh_forest_from_arrays: bad offsets");
+        if (NN) {
+            REQUIRE(a->rects && a->threshold && a->child, "dh_forest_from_arrays: missing node arrays");
+            raw.rects.assign(a->rects, a->rects + NN * 8);
+            raw.threshold.assign(a->threshold, a->threshold + NN);
+            raw.child.assign(a->child, a->child + NN * 2);
+        }
+        raw.prob.assign(a->prob, a->prob + NL);
+        raw.vote_off.assign(a->vote_off, a->vote_off + NL + 1);
+        const int64_t NV = raw.vote_off[NL];
+        REQUIRE(NV >= 0, "dh_forest_from_arrays: bad vote offsets");
+        if (NV) {
+            REQUIRE(a->offsets && a->rotations, "dh_forest_from_arrays: missing vote arrays");
+            raw.offsets.assign(a->offsets, a->offsets + NV * 3);
+            raw.rotations.assign(a->rotations, a->rotations + NV * 3);
+        }
+        std::unique_ptr<dh_forest> f(new dh_forest());
+        f->hf.reset(dh::flatten_forest(raw));
+        *out = f.release();
+    });
+}
+
+void dh_forest_free(dh_forest* f) { delete f; }
+
+uint32_t dh_forest_get_stepwidth(const dh_forest* f) { return f ? f->hf->stepwidth.load() : 0; }
+int dh_forest_set_stepwidth(dh_forest* f, uint32_t v) {
+    return guarded([&] {
+        REQUIRE(f, "NULL forest");
+        if (v == 0) throw dh::ModelError(DH_E_SHAPE, "stepwidth 0: the reference's sliding window never advances (prediction.rs:684)");
+        f->hf->stepwidth.store(v);
+    });
+}
+uint32_t dh_forest_get_meanshift_iterations(const dh_forest* f) { return f ? f->hf->meanshift_iterations.load() : 0; }
+int dh_forest_set_meanshift_iterations(dh_forest* f, uint32_t v) {
+    return guarded([&] {
+        REQUIRE(f, "NULL forest");
+        REQUIRE(v <= 65535, "meanshift_iterations > 65535 is not supported");
+        f->hf->meanshift_iterations.store(v);
+    });
+}
+float dh_forest_get_sigma(const dh_forest* f) { return f ? f->hf->gaussian_sigma : 0.0f; }
+int dh_forest_set_sigma(dh_forest* f, float v) {
+    return guarded([&] {
+        REQUIRE(f, "NULL forest");
+        // update_sigma (prediction.rs:320-326): ignored if unchanged or <= 0 (NaN compares false
+        // on both tests in the reference and would be stored; it is rejected here)
+        REQUIRE(v == v, "sigma is NaN");
+        if (v == f->hf->gaussian_sigma || v <= 0.0f) return;
+        f->hf->gaussian_sigma = v;
+        f->hf->sigma_version.fetch_add(1);
+    });
+}
+uint32_t dh_forest_get_subimage_width(const dh_forest* f) { return f ? f->hf->subimage_width : 0; }
+uint32_t dh_forest_get_subimage_height(const dh_forest* f) { return f ? f->hf->subimage_height : 0; }
+int32_t dh_forest_n_trees(const dh_forest* f) { return f ? f->hf->n_trees : 0; }
+int64_t dh_forest_n_nodes(const dh_forest* f) { return f ? (int64_t)f->hf->n_nodes() : 0; }
+int64_t dh_forest_n_leaves(const dh_forest* f) { return f ? (int64_t)f->hf->n_leaves() : 0; }
+int64_t dh_forest_n_votes(const dh_forest* f) { return f ? (int64_t)f->hf->n_votes() : 0; }
+
+int dh_ctx_create(int device, dh_ctx** out) {
+    return guarded([&] {
+        REQUIRE(out, "dh_ctx_create: NULL out");
+        *out = nullptr;
+        std::unique_ptr<dh_ctx> c(new dh_ctx());
+        c->cx.reset(new dh::Context(device));
+        *out = c.release();
+    });
+}
+void dh_ctx_free(dh_ctx* c) {
+    try {
+        delete c;
+    } catch (...) {
+    }
+}
+int dh_ctx_set_stream(dh_ctx* c, void* s) {
+    return guarded([&] {
+        REQUIRE(c, "NULL ctx");
+        c->cx->set_stream(s);
+    });
+}
+int dh_ctx_set_chunk_frames(dh_ctx* c, uint32_t frames) {
+    return guarded([&] {
+        REQUIRE(c, "NULL ctx");
+        c->cx->set_chunk_frames(frames);
+    });
+}
+int dh_ctx_synchronize(dh_ctx* c) {
+    return guarded([&] {
+        REQUIRE(c, "NULL ctx");
+        c->cx->synchronize();
+    });
+}
+
+int dh_predict(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+               const float* midp_guess, const double* rot_guess, dh_result* out) {
+    return guarded([&] {
+        REQUIRE(c && f && depth && K && out, "dh_predict: NULL argument");
+        c->cx->predict(*f->hf, depth, w, h, K, midp_guess, rot_guess, out);
+    });
+}
+int dh_predict_batch(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h,
+                     const float K[9], int depth_loc, dh_result* out) {
+    return guarded([&] {
+        REQUIRE(c && f && K && (n == 0 || (depth && out)), "dh_predict_batch: NULL argument");
+        REQUIRE(depth_loc == DH_DEPTH_HOST || depth_loc == DH_DEPTH_DEVICE, "dh_predict_batch: bad depth_loc");
+        c->cx->predict_batch(*f->hf, depth, n, w, h, K, depth_loc, out);
+    });
+}
+int dh_predict_mask(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask) {
+    return guarded([&] {
+        REQUIRE(c && f && depth && mask, "dh_predict_mask: NULL argument");
+        c->cx->predict_mask(*f->hf, depth, w, h, mask);
+    });
+}
+int dh_hough_image_raw(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h,
+                       const float K[9], uint16_t* votes) {
+    return guarded([&] {
+        REQUIRE(c && f && depth && K && votes, "dh_hough_image_raw: NULL argument");
+        c->cx->hough_image_raw(*f->hf, depth, w, h, K, votes);
+    });
+}
+
+int dh_ctx_enable_stage_timing(dh_ctx* c, int on) {
+    return guarded([&] {
+        REQUIRE(c, "NULL ctx");
+        c->cx->enable_timing(on != 0);
+    });
+}
+int dh_ctx_stage_ms(dh_ctx* c, float ms[DH_N_STAGES]) {
+    return guarded([&] {
+        REQUIRE(c && ms, "NULL argument");
+        std::memcpy(ms, c->cx->stage_ms(), sizeof(float) * DH_N_STAGES);
+    });
+}
+int dh_ctx_counters(dh_ctx* c, uint64_t counters[DH_N_COUNTERS]) {
+    return guarded([&] {
+        REQUIRE(c && counters, "NULL argument");
+        std::memcpy(counters, c->cx->counters(), sizeof(uint64_t) * DH_N_COUNTERS);
+    });
+}
+
+int dh_ctx_enable_debug(dh_ctx* c, int on) {
+    return guarded([&] {
+        REQUIRE(c, "NULL ctx");
+        c->cx->enable_debug(on != 0);
+    });
+}
+int dh_debug_dims(dh_ctx* c, uint32_t* npx, uint32_t* npy, uint32_t* n_trees) {
+    return guarded([&] {
+        REQUIRE(c, "NULL ctx");
+        c->cx->debug_dims(npx, npy, n_trees);
+    });
+}
+int dh_debug_leaf_indices(dh_ctx* c, int32_t* leaf) {
+    return guarded([&] {
+        REQUIRE(c && leaf, "NULL argument");
+        c->cx->debug_leaf(leaf);
+    });
+}
+int dh_debug_patches(dh_ctx* c, float* p3, uint8_t* gate) {
+    return guarded([&] {
+        REQUIRE(c, "NULL ctx");
+        c->cx->debug_patches(p3, gate);
+    });
+}
+int dh_debug_seeds(dh_ctx* c, uint32_t* guess_pos, uint32_t* guess_rot, int32_t seed_mid[3], int32_t seed_rot[3]) {
+    return guarded([&] {
+        REQUIRE(c, "NULL ctx");
+        c->cx->debug_seeds(guess_pos, guess_rot, seed_mid, seed_rot);
+    });
+}
+int dh_debug_votes(dh_ctx* c, int which, int32_t* keys, uint32_t* vals, uint64_t* n, int32_t* reach) {
+    return guarded([&] {
+        REQUIRE(c, "NULL ctx");
+        REQUIRE((keys == nullptr) == (vals == nullptr), "keys and vals must both be NULL or both be set");
+        c->cx->debug_votes(which, keys, vals, n, reach);
+    });
+}
+int dh_debug_meanshift(dh_ctx* c, int which, int32_t* pos, uint32_t* n_iter) {
+    return guarded([&] {
+        REQUIRE(c && n_iter, "NULL argument");
+        c->cx->debug_meanshift(which, pos, n_iter);
+    });
+}
+int dh_debug_meanshift_flags(dh_ctx* c, uint32_t flags[2]) {
+    return guarded([&] {
+        REQUIRE(c && flags, "NULL argument");
+        uint32_t n = 0;
+        c->cx->debug_meanshift(0, nullptr, &n);
+        n = 0;
+        c->cx->debug_meanshift(1, nullptr, &n);
+        flags[0] = c->cx->last_ms_flags(0);
+        flags[1] = c->cx->last_ms_flags(1);
+    });
+}
+int dh_debug_leaf_static(dh_ctx* c, const dh_forest* f, uint32_t* valtoadd, uint8_t* rot_ok, uint8_t* off_ok) {
+    return guarded([&] {
+        REQUIRE(c && f, "NULL argument");
+        c->cx->debug_leaf_static(*f->hf, valtoadd, rot_ok, off_ok);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,713 @@
+// dh_ctx.cu — per-GPU context: device copy of the model, scratch, TMA descriptor, and the chunked
+// prediction pipeline that stands in for HoughPrediction::predict_parameter_generic
+// (prediction.rs:421-493).  Host orchestration only; the arithmetic is in dh_kernels.cu.
+#include "dh_ctx.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace dh {
+
+#define DH_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            throw ModelError(DH_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+    } while (0)
+
+namespace {
+
+template <typename T>
+void dev_alloc(T*& p, size_t n) {
+    p = nullptr;
+    if (n == 0) n = 1;
+    DH_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T)));
+}
+template <typename T>
+void dev_free(T*& p) {
+    if (p) cudaFree((void*)p);
+    p = nullptr;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) throw ModelError(DH_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    long x = std::strtol(v, nullptr, 10);
+    return x > 0 ? (uint32_t)x : dflt;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+Context::Context(int device) : device_(device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw ModelError(DH_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                        " (libdepthhead_cuda has no CPU fallback)");
+    if (device < 0 || device >= count) throw ModelError(DH_E_ARG, "device index out of range");
+    DH_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DH_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        throw ModelError(DH_E_CUDA, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                        "; this library contains sm_100a code only");
+    n_sms_ = prop.multiProcessorCount;
+    smem_optin_ = (uint32_t)prop.sharedMemPerBlockOptin;
+    DH_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    DH_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    stream_ = own_stream_;
+    for (int i = 0; i < 2; ++i) {
+        DH_CUDA(cudaEventCreateWithFlags(&ev_copied_[i], cudaEventDisableTiming));
+        DH_CUDA(cudaEventCreateWithFlags(&ev_consumed_[i], cudaEventDisableTiming));
+    }
+    dev_alloc(d_counters_, DH_N_COUNTERS);
+    dev_alloc(d_pool_, 1);
+    DH_CUDA(cudaHostAlloc((void**)&h_fs_, sizeof(FrameState), cudaHostAllocDefault));
+    DH_CUDA(cudaHostAlloc((void**)&h_counters_, sizeof(unsigned long long) * DH_N_COUNTERS, cudaHostAllocDefault));
+    chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 256);
+    debug_sync_ = env_u32("DH_DEBUG_SYNC", 0) != 0;
+    std::memset(stage_ms_, 0, sizeof(stage_ms_));
+    std::memset(counters_, 0, sizeof(counters_));
+}
+
+Context::~Context() {
+    cudaSetDevice(device_);
+    cudaDeviceSynchronize();
+    free_scratch();
+    free_forest();
+    dev_free(d_hash_keys_);
+    dev_free(d_hash_vals_);
+    dev_free(d_counters_);
+    dev_free(d_pool_);
+    dev_free(d_aux32_);
+    dev_free(d_aux16_);
+    dev_free(d_aux8_);
+    if (h_fs_) cudaFreeHost(h_fs_);
+    if (h_counters_) cudaFreeHost(h_counters_);
+    if (h_results_) cudaFreeHost(h_results_);
+    if (h_pool_) cudaFreeHost(h_pool_);
+    for (auto ev : timing_events_) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        if (ev_copied_[i]) cudaEventDestroy(ev_copied_[i]);
+        if (ev_consumed_[i]) cudaEventDestroy(ev_consumed_[i]);
+    }
+    if (own_stream_) cudaStreamDestroy(own_stream_);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
+}
+
+void Context::set_stream(void* s) { stream_ = s ? reinterpret_cast<cudaStream_t>(s) : own_stream_; }
+void Context::set_chunk_frames(uint32_t f) { chunk_frames_ = f ? std::min<uint32_t>(f, 32768u) : env_u32("DH_CHUNK_FRAMES", 256); }
+void Context::synchronize() {
+    DH_CUDA(cudaSetDevice(device_));
+    DH_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ------------------------------------------------------------------------------------------------ model upload
+void Context::free_forest() {
+    dev_free(df_nodes_);
+    dev_free(df_roots_);
+    dev_free(df_leaf_prob_);
+    dev_free(df_leaf_info_);
+    dev_free(df_offsets_);
+    dev_free(df_rot_bins_);
+    dev_free(df_kernel_);
+    df_serial_ = 0;
+}
+
+void Context::ensure_forest(const HostForest& hf) {
+    if (df_serial_ != hf.serial) {
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        free_forest();
+        const size_t NN = hf.n_nodes(), NL = hf.n_leaves(), NV = hf.n_votes();
+        dev_alloc(df_nodes_, NN);
+        dev_alloc(df_roots_, (size_t)hf.n_trees);
+        dev_alloc(df_leaf_prob_, NL);
+        dev_alloc(df_leaf_info_, NL);
+        dev_alloc(df_offsets_, NV * 3);
+        dev_alloc(df_rot_bins_, NV);
+        dev_alloc(df_kernel_, (size_t)kKernelCells);
+        if (NN) DH_CUDA(cudaMemcpyAsync(df_nodes_, hf.nodes.data(), NN * sizeof(NodeRec), cudaMemcpyHostToDevice, stream_));
+        DH_CUDA(cudaMemcpyAsync(df_roots_, hf.roots.data(), hf.roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        DH_CUDA(cudaMemcpyAsync(df_leaf_prob_, hf.leaf_prob.data(), NL * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        if (NV) {
+            DH_CUDA(cudaMemcpyAsync(df_offsets_, hf.offsets.data(), NV * 3 * sizeof(float), cudaMemcpyHostToDevice, stream_));
+            DH_CUDA(cudaMemcpyAsync(df_rot_bins_, hf.rot_bins.data(), NV * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+        }
+        // K5: per-leaf covariance-trace gates + valtoadd, computed on the device once per model
+        uint32_t *d_vs = nullptr, *d_nv = nullptr;
+        double* d_rot = nullptr;
+        dev_alloc(d_vs, NL);
+        dev_alloc(d_nv, NL);
+        dev_alloc(d_rot, NV * 3);
+        DH_CUDA(cudaMemcpyAsync(d_vs, hf.leaf_vote_start.data(), NL * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+        DH_CUDA(cudaMemcpyAsync(d_nv, hf.leaf_n_votes.data(), NL * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+        if (NV) DH_CUDA(cudaMemcpyAsync(d_rot, hf.rotations.data(), NV * 3 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        launch_leaf_gates(df_leaf_prob_, d_vs, d_nv, df_offsets_, d_rot, df_leaf_info_, (uint32_t)NL, stream_);
+        DH_CUDA(cudaGetLastError());
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        dev_free(d_vs);
+        dev_free(d_nv);
+        dev_free(d_rot);
+        df_serial_ = hf.serial;
+        df_sigma_version_ = 0;
+        df_n_leaves_ = NL;
+        const double avg = NL ? (double)NV / (double)NL : 0.0;
+        lanes_per_hit_ = avg >= 48.0 ? 32u : (avg >= 12.0 ? 8u : 1u);
+    }
+    const uint64_t sv = hf.sigma_version.load();
+    if (df_sigma_version_ != sv) {
+        // get_or_build_kernel (prediction.rs:310-317): rebuilt lazily after update_sigma
+        std::vector<float> k((size_t)kKernelCells);
+        build_meanshift_kernel(hf.gaussian_sigma, k.data());
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        DH_CUDA(cudaMemcpy(df_kernel_, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
+        df_sigma_version_ = sv;
+    }
+    fdev_.nodes = df_nodes_;
+    fdev_.roots = df_roots_;
+    fdev_.leaf_prob = df_leaf_prob_;
+    fdev_.leaf_info = df_leaf_info_;
+    fdev_.offsets = df_offsets_;
+    fdev_.rot_bins = df_rot_bins_;
+    fdev_.ms_kernel = df_kernel_;
+    fdev_.n_trees = hf.n_trees;
+}
+
+// ------------------------------------------------------------------------------------------------ scratch
+void Context::free_scratch() {
+    for (int i = 0; i < 2; ++i) dev_free(d_depth_[i]);
+    dev_free(d_sat_);
+    dev_free(d_leaf_);
+    dev_free(d_p3_);
+    dev_free(d_gate_);
+    dev_free(d_hits_);
+    dev_free(d_grids_);
+    dev_free(d_fs_);
+    dev_free(d_results_);
+    dev_free(d_ms_trace_);
+    sk_ = ScratchKey();
+}
+
+TilePlan Context::plan_tiles(const Geometry& g) const {
+    // Choose the patch tile that minimises total shared-memory fill traffic per frame, subject to
+    // the tile (plus bookkeeping) fitting `limit` bytes so that several CTAs share an SM.
+    const uint32_t limits[3] = {75000u, 113000u, smem_optin_ > 2048u ? smem_optin_ - 1024u : smem_optin_};
+    for (uint32_t limit : limits) {
+        TilePlan best{};
+        double best_cost = 1e300;
+        for (uint32_t tpy = 1; tpy <= std::min<uint32_t>(g.npy, 64u); ++tpy)
+            for (uint32_t tpx = 1; tpx <= std::min<uint32_t>(g.npx, 64u); ++tpx) {
+                // the TMA origin is rounded down to 4 elements (16 B); unless every tile origin is
+                // already aligned, the window needs up to 3 extra columns
+                const uint32_t slack = ((tpx * g.stride) & 3u) ? 3u : 0u;
+                const uint32_t tw = ((tpx - 1) * g.stride + g.sw + 1 + slack + 3) & ~3u;
+                const uint32_t th = (tpy - 1) * g.stride + g.sh + 1;
+                if (tw > 256 || th > 256) continue;  // TMA box limit per dimension
+                const uint32_t bytes = traverse_smem_bytes(tw, th, tpx * tpy);
+                if (bytes > limit) continue;
+                const uint32_t tiles_x = (g.npx + tpx - 1) / tpx, tiles_y = (g.npy + tpy - 1) / tpy;
+                // per-tile fixed cost ~ 8 KB equivalent (launch, barrier, compaction)
+                const double cost = (double)tiles_x * tiles_y * ((double)tw * th * 4.0 + 8192.0);
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best = TilePlan{tpx, tpy, tiles_x, tiles_y, tw, th, bytes, 512u};
+                }
+            }
+        if (best.tpx) return best;
+    }
+    throw ModelError(DH_E_SHAPE, "sub-image too large: its summed-area window does not fit in shared memory");
+}
+
+void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9]) {
+    const uint32_t sw = hf.subimage_width, sh = hf.subimage_height, stride = hf.stepwidth.load();
+    if (stride == 0) throw ModelError(DH_E_SHAPE, "stepwidth 0: the reference's sliding window never advances");
+    if (w < sw || h < sh)
+        throw ModelError(DH_E_SHAPE, "image smaller than the sub-image (the reference underflows u32 at prediction.rs:546-548)");
+    if (w > 32768 || h > 32768) throw ModelError(DH_E_SHAPE, "image larger than 32768 pixels per side is not supported");
+    if (w < (uint32_t)kGuessGridParts || h < (uint32_t)kGuessGridParts)
+        throw ModelError(DH_E_SHAPE, "image smaller than 20 pixels per side: the reference's 20x20 seed grid has empty cells");
+    const uint32_t cap = std::max<uint32_t>(1u, std::min<uint32_t>(chunk_frames_, std::max<uint32_t>(n_frames_hint, 1u)));
+    ScratchKey k{w, h, sw, sh, stride, (uint32_t)hf.n_trees, cap, debug_ ? hf.meanshift_iterations.load() : 0u};
+    Geometry& g = geom_;
+    if (!k.same_shape(sk_) || k.frames > sk_.frames) {
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        free_scratch();
+        g = Geometry();
+        g.w = w; g.h = h; g.sw = sw; g.sh = sh;
+        g.left_w = sw / 2; g.left_h = sh / 2;  // prediction.rs:535-538
+        g.stride = stride;
+        // y = left_h; while y < h - right_h { .. y += s }  (prediction.rs:544-548,684-686)
+        const uint32_t right_w = sw - g.left_w, right_h = sh - g.left_h;
+        const uint32_t span_x = (w - right_w) - g.left_w, span_y = (h - right_h) - g.left_h;  // = w - sw, h - sh
+        g.npx = span_x == 0 ? 0 : (span_x + stride - 1) / stride;
+        g.npy = span_y == 0 ? 0 : (span_y + stride - 1) / stride;
+        g.P = g.npx * g.npy;
+        g.sat_pitch = (w + 1 + 3) & ~3u;
+        g.n_trees = (uint32_t)hf.n_trees;
+        if ((uint64_t)g.P * g.n_trees > 0x7fffffffull) throw ModelError(DH_E_SHAPE, "too many patch x tree pairs per frame");
+        const size_t F = cap, P = std::max<uint32_t>(g.P, 1u), T = g.n_trees;
+        dev_alloc(d_sat_, F * (size_t)(h + 1) * g.sat_pitch);
+        DH_CUDA(cudaMemsetAsync(d_sat_, 0, F * (size_t)(h + 1) * g.sat_pitch * sizeof(uint32_t), stream_));  // row 0 stays 0
+        dev_alloc(d_leaf_, F * P * T);
+        dev_alloc(d_p3_, F * P * 3);
+        dev_alloc(d_gate_, F * P);
+        dev_alloc(d_hits_, F * P * T);
+        dev_alloc(d_grids_, F * (size_t)(kPosGridCells + kRotGridCells));
+        dev_alloc(d_fs_, F);
+        dev_alloc(d_results_, F);
+        if (k.trace_iters) dev_alloc(d_ms_trace_, F * 2 * (size_t)k.trace_iters * 3);
+        if (g.P) {
+            tiles_ = plan_tiles(g);
+            // TMA descriptor over the SAT scratch: [F][h+1][pitch] u32, box = one tile
+            const cuuint64_t gdim[3] = {(cuuint64_t)(w + 1), (cuuint64_t)(h + 1), (cuuint64_t)F};
+            const cuuint64_t gstr[2] = {(cuuint64_t)g.sat_pitch * 4u, (cuuint64_t)g.sat_pitch * 4u * (h + 1)};
+            const cuuint32_t box[3] = {tiles_.tw, tiles_.th, 1u};
+            const cuuint32_t estr[3] = {1u, 1u, 1u};
+            CUresult r = get_encode_fn()(&sat_map_, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_sat_, gdim, gstr, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) throw ModelError(DH_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+        }
+        sk_ = k;
+        // hash pool: grows on demand (overflow -> retry), start at 2 slots per patch x tree
+        ensure_pool(std::max<unsigned long long>((unsigned long long)F * P * T * 2ull, 1ull << 16));
+    }
+    std::memcpy(g.K, K, sizeof(float) * 9);
+    mat3_inverse_f32(K, g.Kinv);
+}
+
+void Context::ensure_staging(int slots) {
+    const size_t n = (size_t)sk_.frames * sk_.w * sk_.h;
+    for (int i = 0; i < slots && i < 2; ++i)
+        if (!d_depth_[i]) dev_alloc(d_depth_[i], n);
+}
+
+void Context::ensure_pool(unsigned long long slots) {
+    if (slots <= pool_capacity_) return;
+    DH_CUDA(cudaStreamSynchronize(stream_));
+    dev_free(d_hash_keys_);
+    dev_free(d_hash_vals_);
+    dev_alloc(d_hash_keys_, (size_t)slots);
+    dev_alloc(d_hash_vals_, (size_t)slots);
+    pool_capacity_ = slots;
+}
+
+FrameBuffers Context::buffers(const uint16_t* depth) const {
+    FrameBuffers b{};
+    b.depth = depth;
+    b.sat = d_sat_;
+    b.leaf = d_leaf_;
+    b.p3 = d_p3_;
+    b.gate = d_gate_;
+    b.hits = d_hits_;
+    b.grids = d_grids_;
+    b.fs = d_fs_;
+    b.hash_keys = d_hash_keys_;
+    b.hash_vals = d_hash_vals_;
+    b.pool = d_pool_;
+    b.results = d_results_;
+    b.ms_trace = d_ms_trace_;
+    b.ms_trace_cap = sk_.trace_iters;
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------ timing helpers
+cudaEvent_t Context::next_event() {
+    if (ev_used_ == timing_events_.size()) {
+        cudaEvent_t e;
+        DH_CUDA(cudaEventCreate(&e));
+        timing_events_.push_back(e);
+    }
+    return timing_events_[ev_used_++];
+}
+void Context::stage_check(const char* name) {
+    if (!debug_sync_) return;
+    cudaError_t e = cudaStreamSynchronize(stream_);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) throw ModelError(DH_E_CUDA, std::string("stage `") + name + "` failed: " + cudaGetErrorString(e));
+}
+void Context::mark(int stage_begin_of) {
+    if (!timing_) return;
+    cudaEvent_t e = next_event();
+    DH_CUDA(cudaEventRecord(e, stream_));
+    marks_.push_back({stage_begin_of, e});
+}
+
+// ------------------------------------------------------------------------------------------------ one pass
+// Front end shared by every entry point: SAT + traversal (+ zeroed per-frame state).
+void Context::run_front(const FrameBuffers& b, uint32_t n, const FrameState* guess_state) {
+    const Geometry& g = geom_;
+    DH_CUDA(cudaMemsetAsync(d_fs_, 0, sizeof(FrameState) * n, stream_));
+    DH_CUDA(cudaMemsetAsync(d_grids_, 0, sizeof(uint32_t) * (size_t)(kPosGridCells + kRotGridCells) * n, stream_));
+    if (guess_state) {
+        *h_fs_ = *guess_state;
+        DH_CUDA(cudaMemcpyAsync(d_fs_, h_fs_, sizeof(FrameState), cudaMemcpyHostToDevice, stream_));
+    }
+    mark(DH_STAGE_SAT);
+    launch_sat(b, g, n, stream_);
+    launches_ += 2;
+    stage_check("sat");
+    mark(DH_STAGE_TRAVERSE);
+    if (g.P) {
+        launch_traverse(sat_map_, b, g, tiles_, fdev_, n, stream_);
+        launches_ += 1;
+        stage_check("traverse");
+    }
+}
+
+void Context::run_back(const FrameBuffers& b, uint32_t n, uint32_t iterations) {
+    const Geometry& g = geom_;
+    const uint32_t reach = 12u * iterations + 16u;
+    last_reach_ = reach;
+    const uint32_t splits = std::max<uint32_t>(1u, std::min<uint32_t>(64u, ((uint32_t)n_sms_ * 4u + n - 1) / n));
+    mark(DH_STAGE_GATE);
+    if (g.P) {
+        launch_gate(b, g, fdev_, n, stream_);
+        launches_ += 1;
+        stage_check("gate");
+    }
+    mark(DH_STAGE_COARSE);
+    launch_coarse(b, g, fdev_, n, splits, lanes_per_hit_, stream_);
+    stage_check("coarse");
+    mark(DH_STAGE_INSERT);
+    launch_plan_and_clear(b, n, pool_capacity_, stream_);
+    stage_check("plan/clear");
+    launch_insert(b, g, fdev_, n, splits, lanes_per_hit_, reach, stream_);
+    stage_check("insert");
+    mark(DH_STAGE_MEANSHIFT);
+    launch_meanshift(b, fdev_, n, iterations, reach, stream_);
+    stage_check("meanshift");
+    launches_ += 5;
+    mark(DH_STAGE_D2H);
+    launch_counters(b, g, n, d_counters_, stream_);
+    launches_ += 1;
+    DH_CUDA(cudaGetLastError());
+}
+
+void Context::begin_call() {
+    DH_CUDA(cudaSetDevice(device_));
+    launches_ = 0;
+    retries_ = 0;
+    ev_used_ = 0;
+    marks_.clear();
+    std::memset(stage_ms_, 0, sizeof(stage_ms_));
+    DH_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(unsigned long long) * DH_N_COUNTERS, stream_));
+}
+
+void Context::end_call() {
+    DH_CUDA(cudaMemcpyAsync(h_counters_, d_counters_, sizeof(unsigned long long) * DH_N_COUNTERS, cudaMemcpyDeviceToHost, stream_));
+    DH_CUDA(cudaStreamSynchronize(stream_));
+    for (int k = 0; k < DH_N_COUNTERS; ++k) counters_[k] = h_counters_[k];
+    counters_[9] = launches_;
+    counters_[11] = retries_;
+    if (timing_) {
+        // marks_ are (stage that begins here, event); a stage lasts until the next mark
+        for (size_t i = 0; i + 1 < marks_.size(); ++i) {
+            if (marks_[i].first < 0) continue;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, marks_[i].second, marks_[i + 1].second) == cudaSuccess) stage_ms_[marks_[i].first] += ms;
+        }
+        for (auto& c : copy_marks_) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c.first, c.second) == cudaSuccess) stage_ms_[DH_STAGE_H2D] += ms;
+        }
+    }
+    copy_marks_.clear();
+}
+
+// ------------------------------------------------------------------------------------------------ public entry points
+void Context::predict(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+                      const float* midp_guess, const double* rot_guess, dh_result* out) {
+    begin_call();
+    ensure_forest(hf);
+    ensure_scratch(hf, w, h, 1, K);
+    ensure_staging(1);
+    const uint32_t iterations = hf.meanshift_iterations.load();
+    DH_CUDA(cudaMemcpyAsync(d_depth_[0], depth, (size_t)w * h * sizeof(uint16_t), cudaMemcpyHostToDevice, stream_));
+    FrameState gs;
+    std::memset(&gs, 0, sizeof(gs));
+    if (midp_guess) {
+        gs.has_guess |= 1u;
+        for (int k = 0; k < 3; ++k) gs.midp_guess[k] = midp_guess[k];
+    }
+    if (rot_guess) {
+        gs.has_guess |= 2u;
+        for (int k = 0; k < 3; ++k) gs.rot_guess[k] = rot_guess[k];
+    }
+    for (int attempt = 0;; ++attempt) {
+        FrameBuffers b = buffers(d_depth_[0]);
+        run_front(b, 1, &gs);
+        run_back(b, 1, iterations);
+        PoolState ps;
+        DH_CUDA(cudaMemcpyAsync(&ps, d_pool_, sizeof(ps), cudaMemcpyDeviceToHost, stream_));
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        if (!ps.overflow) break;
+        if (attempt >= 3) throw ModelError(DH_E_CUDA, "vote accumulator pool overflow persisted after growing");
+        ++retries_;
+        ensure_pool(ps.total_slots + ps.total_slots / 4);
+    }
+    DH_CUDA(cudaMemcpyAsync(out, d_results_, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
+    mark(-1);
+    end_call();
+    have_debug_ = debug_;
+    debug_iterations_ = iterations;
+}
+
+void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h,
+                            const float K[9], int depth_loc, dh_result* out) {
+    begin_call();
+    have_debug_ = false;
+    if (n == 0) {
+        end_call();
+        return;
+    }
+    ensure_forest(hf);
+    ensure_scratch(hf, w, h, n, K);
+    const uint32_t iterations = hf.meanshift_iterations.load();
+    const uint32_t F = sk_.frames;
+    const uint32_t n_chunks = (n + F - 1) / F;
+    const size_t frame_px = (size_t)w * h;
+    // pinned staging for results and per-chunk pool state
+    if (h_results_cap_ < n) {
+        if (h_results_) cudaFreeHost(h_results_);
+        h_results_ = nullptr;
+        DH_CUDA(cudaHostAlloc((void**)&h_results_, sizeof(dh_result) * n, cudaHostAllocDefault));
+        h_results_cap_ = n;
+    }
+    if (h_pool_cap_ < n_chunks) {
+        if (h_pool_) cudaFreeHost(h_pool_);
+        h_pool_ = nullptr;
+        DH_CUDA(cudaHostAlloc((void**)&h_pool_, sizeof(PoolState) * n_chunks, cudaHostAllocDefault));
+        h_pool_cap_ = n_chunks;
+    }
+    auto enqueue_chunk = [&](uint32_t c, const uint16_t* d_depth) {
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+        FrameBuffers b = buffers(d_depth);
+        run_front(b, nc, nullptr);
+        run_back(b, nc, iterations);
+        DH_CUDA(cudaMemcpyAsync(h_pool_ + c, d_pool_, sizeof(PoolState), cudaMemcpyDeviceToHost, stream_));
+        DH_CUDA(cudaMemcpyAsync(h_results_ + f0, d_results_, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, stream_));
+    };
+    if (depth_loc != DH_DEPTH_DEVICE) ensure_staging(2);
+    if (depth_loc == DH_DEPTH_DEVICE) {
+        for (uint32_t c = 0; c < n_chunks; ++c) enqueue_chunk(c, depth + (size_t)c * F * frame_px);
+    } else {
+        // double-buffered staging: the copy of chunk c+1 overlaps the kernels of chunk c
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const int slot = (int)(c & 1u);
+            const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+            if (c >= 2) DH_CUDA(cudaStreamWaitEvent(copy_stream_, ev_consumed_[slot], 0));
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (timing_) {
+                t0 = next_event();
+                t1 = next_event();
+                DH_CUDA(cudaEventRecord(t0, copy_stream_));
+            }
+            DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
+                                    cudaMemcpyHostToDevice, copy_stream_));
+            if (timing_) {
+                DH_CUDA(cudaEventRecord(t1, copy_stream_));
+                copy_marks_.push_back({t0, t1});
+            }
+            DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
+            DH_CUDA(cudaStreamWaitEvent(stream_, ev_copied_[slot], 0));
+            enqueue_chunk(c, d_depth_[slot]);
+            DH_CUDA(cudaEventRecord(ev_consumed_[slot], stream_));
+        }
+    }
+    mark(-1);
+    DH_CUDA(cudaStreamSynchronize(stream_));
+    // accumulator pool too small for some chunk: grow once to the largest demand and redo those
+    unsigned long long need = 0;
+    for (uint32_t c = 0; c < n_chunks; ++c)
+        if (h_pool_[c].overflow) need = std::max(need, h_pool_[c].total_slots);
+    if (need) {
+        ensure_pool(need + need / 4);
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            if (!h_pool_[c].overflow) continue;
+            ++retries_;
+            const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+            const uint16_t* d = depth + (size_t)f0 * frame_px;
+            if (depth_loc != DH_DEPTH_DEVICE) {
+                DH_CUDA(cudaMemcpyAsync(d_depth_[0], d, (size_t)nc * frame_px * sizeof(uint16_t), cudaMemcpyHostToDevice, stream_));
+                d = d_depth_[0];
+            }
+            const bool t = timing_;
+            timing_ = false;  // retried chunks are not part of the stage breakdown
+            enqueue_chunk(c, d);
+            timing_ = t;
+            DH_CUDA(cudaStreamSynchronize(stream_));
+            if (h_pool_[c].overflow) throw ModelError(DH_E_CUDA, "vote accumulator pool overflow persisted after growing");
+        }
+    }
+    end_call();
+    std::memcpy(out, h_results_, sizeof(dh_result) * n);
+}
+
+void Context::predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask) {
+    begin_call();
+    have_debug_ = false;
+    ensure_forest(hf);
+    const float K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    ensure_scratch(hf, w, h, 1, K);
+    ensure_staging(1);
+    DH_CUDA(cudaMemcpyAsync(d_depth_[0], depth, (size_t)w * h * sizeof(uint16_t), cudaMemcpyHostToDevice, stream_));
+    FrameBuffers b = buffers(d_depth_[0]);
+    run_front(b, 1, nullptr);
+    if (aux8_cap_ < (size_t)w * h) {
+        dev_free(d_aux8_);
+        dev_alloc(d_aux8_, (size_t)w * h);
+        aux8_cap_ = (size_t)w * h;
+    }
+    DH_CUDA(cudaMemsetAsync(d_aux8_, 0, (size_t)w * h, stream_));
+    if (geom_.P) {
+        launch_mask(b, geom_, fdev_, d_aux8_, stream_);
+        launches_ += 1;
+    }
+    DH_CUDA(cudaGetLastError());
+    DH_CUDA(cudaMemcpyAsync(mask, d_aux8_, (size_t)w * h, cudaMemcpyDeviceToHost, stream_));
+    mark(-1);
+    end_call();
+}
+
+void Context::hough_image_raw(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+                              uint16_t* votes) {
+    begin_call();
+    have_debug_ = false;
+    ensure_forest(hf);
+    ensure_scratch(hf, w, h, 1, K);
+    ensure_staging(1);
+    DH_CUDA(cudaMemcpyAsync(d_depth_[0], depth, (size_t)w * h * sizeof(uint16_t), cudaMemcpyHostToDevice, stream_));
+    FrameBuffers b = buffers(d_depth_[0]);
+    run_front(b, 1, nullptr);
+    const size_t px = (size_t)w * h;
+    if (aux32_cap_ < px) {
+        dev_free(d_aux32_);
+        dev_free(d_aux16_);
+        dev_alloc(d_aux32_, px);
+        dev_alloc(d_aux16_, px);
+        aux32_cap_ = px;
+    }
+    DH_CUDA(cudaMemsetAsync(d_aux32_, 0, px * sizeof(uint32_t), stream_));
+    if (geom_.P) {
+        launch_hough_image(b, geom_, fdev_, d_aux32_, d_aux16_, stream_);
+        launches_ += 2;
+        DH_CUDA(cudaGetLastError());
+        DH_CUDA(cudaMemcpyAsync(votes, d_aux16_, px * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream_));
+    } else {
+        std::memset(votes, 0, px * sizeof(uint16_t));
+    }
+    mark(-1);
+    end_call();
+}
+
+// ------------------------------------------------------------------------------------------------ debug exports
+void Context::require_debug() const {
+    if (!have_debug_) throw ModelError(DH_E_STATE, "no debug state: call dh_ctx_enable_debug(ctx, 1) and then dh_predict");
+}
+void Context::debug_dims(uint32_t* npx, uint32_t* npy, uint32_t* n_trees) const {
+    require_debug();
+    if (npx) *npx = geom_.npx;
+    if (npy) *npy = geom_.npy;
+    if (n_trees) *n_trees = geom_.n_trees;
+}
+void Context::debug_leaf(int32_t* leaf) {
+    require_debug();
+    const size_t P = geom_.P, T = geom_.n_trees;
+    std::vector<int32_t> tmp(P * T);
+    DH_CUDA(cudaMemcpy(tmp.data(), d_leaf_, P * T * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < T; ++t)  // device layout [T][P] -> exported [P][T]
+        for (size_t p = 0; p < P; ++p) leaf[p * T + t] = tmp[t * P + p];
+}
+void Context::debug_patches(float* p3, uint8_t* gate) {
+    require_debug();
+    const size_t P = geom_.P;
+    if (gate) DH_CUDA(cudaMemcpy(gate, d_gate_, P, cudaMemcpyDeviceToHost));
+    if (p3) DH_CUDA(cudaMemcpy(p3, d_p3_, P * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+}
+void Context::debug_seeds(uint32_t* guess_pos, uint32_t* guess_rot, int32_t* seed_mid, int32_t* seed_rot) {
+    require_debug();
+    if (guess_pos) DH_CUDA(cudaMemcpy(guess_pos, d_grids_, kPosGridCells * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (guess_rot) DH_CUDA(cudaMemcpy(guess_rot, d_grids_ + kPosGridCells, kRotGridCells * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    FrameState fs;
+    DH_CUDA(cudaMemcpy(&fs, d_fs_, sizeof(fs), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; ++k) {
+        if (seed_mid) seed_mid[k] = fs.seed_mid[k];
+        if (seed_rot) seed_rot[k] = fs.seed_rot[k];
+    }
+}
+void Context::debug_votes(int which, int32_t* keys, uint32_t* vals, uint64_t* n, int32_t* reach) {
+    require_debug();
+    if (which < 0 || which > 1) throw ModelError(DH_E_ARG, "which must be 0 (centre) or 1 (rotation)");
+    unsigned long long* d_count = nullptr;
+    dev_alloc(d_count, 1);
+    DH_CUDA(cudaMemset(d_count, 0, sizeof(unsigned long long)));
+    int32_t* d_keys = nullptr;
+    uint32_t* d_vals = nullptr;
+    FrameState fs;
+    DH_CUDA(cudaMemcpy(&fs, d_fs_, sizeof(fs), cudaMemcpyDeviceToHost));
+    const size_t cap = fs.hash_cap[which];
+    if (keys) {
+        dev_alloc(d_keys, std::max<size_t>(cap, 1) * 3);
+        dev_alloc(d_vals, std::max<size_t>(cap, 1));
+    }
+    FrameBuffers b = buffers(d_depth_[0]);
+    launch_hash_dump(b, 0, which, d_keys, d_vals, d_count, stream_);
+    DH_CUDA(cudaStreamSynchronize(stream_));
+    unsigned long long cnt = 0;
+    DH_CUDA(cudaMemcpy(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (keys) {
+        DH_CUDA(cudaMemcpy(keys, d_keys, cnt * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        DH_CUDA(cudaMemcpy(vals, d_vals, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    dev_free(d_keys);
+    dev_free(d_vals);
+    dev_free(d_count);
+    if (n) *n = cnt;
+    if (reach) *reach = (int32_t)last_reach_;
+}
+void Context::debug_meanshift(int which, int32_t* pos, uint32_t* n_iter) {
+    require_debug();
+    if (which < 0 || which > 1) throw ModelError(DH_E_ARG, "which must be 0 (centre) or 1 (rotation)");
+    FrameState fs;
+    DH_CUDA(cudaMemcpy(&fs, d_fs_, sizeof(fs), cudaMemcpyDeviceToHost));
+    const uint32_t ran = std::min<uint32_t>(fs.ms_iters[which], sk_.trace_iters);
+    const uint32_t room = n_iter ? *n_iter : 0;
+    const uint32_t cnt = std::min(ran, room);
+    if (pos && cnt && d_ms_trace_)
+        DH_CUDA(cudaMemcpy(pos, d_ms_trace_ + (size_t)which * sk_.trace_iters * 3, (size_t)cnt * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (n_iter) *n_iter = ran;
+    last_ms_flags_[which] = fs.ms_flags[which];
+}
+void Context::debug_leaf_static(const HostForest& hf, uint32_t* valtoadd, uint8_t* rot_ok, uint8_t* off_ok) {
+    DH_CUDA(cudaSetDevice(device_));
+    ensure_forest(hf);
+    std::vector<LeafInfo> li(df_n_leaves_);
+    DH_CUDA(cudaMemcpy(li.data(), df_leaf_info_, li.size() * sizeof(LeafInfo), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < li.size(); ++i) {
+        if (valtoadd) valtoadd[i] = li[i].valtoadd;
+        if (rot_ok) rot_ok[i] = (li[i].flags & kLeafRotOk) ? 1 : 0;
+        if (off_ok) off_ok[i] = (li[i].flags & kLeafOffOk) ? 1 : 0;
+    }
+}
+
+}  // namespace dh

@@ -1,0 +1,141 @@
+// dh_ctx.hpp — per-GPU prediction context (see dh_ctx.cu).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+#include "dh_forest.hpp"
+#include "dh_kernels.cuh"
+
+namespace dh {
+
+struct ScratchKey {
+    uint32_t w = 0, h = 0, sw = 0, sh = 0, stride = 0, n_trees = 0, frames = 0, trace_iters = 0;
+    bool same_shape(const ScratchKey& o) const {
+        return w == o.w && h == o.h && sw == o.sw && sh == o.sh && stride == o.stride && n_trees == o.n_trees &&
+               trace_iters == o.trace_iters;
+    }
+};
+
+class Context {
+public:
+    explicit Context(int device);
+    ~Context();
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+
+    void set_stream(void* s);
+    void set_chunk_frames(uint32_t f);
+    void synchronize();
+    void enable_timing(bool on) { timing_ = on; }
+    void enable_debug(bool on) { debug_ = on; if (!on) have_debug_ = false; }
+    const float* stage_ms() const { return stage_ms_; }
+    const uint64_t* counters() const { return counters_; }
+
+    void predict(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+                 const float* midp_guess, const double* rot_guess, dh_result* out);
+    void predict_batch(const HostForest& hf, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h,
+                       const float K[9], int depth_loc, dh_result* out);
+    void predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask);
+    void hough_image_raw(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+                         uint16_t* votes);
+
+    void debug_dims(uint32_t* npx, uint32_t* npy, uint32_t* n_trees) const;
+    void debug_leaf(int32_t* leaf);
+    void debug_patches(float* p3, uint8_t* gate);
+    void debug_seeds(uint32_t* guess_pos, uint32_t* guess_rot, int32_t* seed_mid, int32_t* seed_rot);
+    void debug_votes(int which, int32_t* keys, uint32_t* vals, uint64_t* n, int32_t* reach);
+    void debug_meanshift(int which, int32_t* pos, uint32_t* n_iter);
+    void debug_leaf_static(const HostForest& hf, uint32_t* valtoadd, uint8_t* rot_ok, uint8_t* off_ok);
+    uint32_t last_ms_flags(int which) const { return last_ms_flags_[which & 1]; }
+    const TilePlan& tile_plan() const { return tiles_; }
+
+private:
+    void ensure_forest(const HostForest& hf);
+    void free_forest();
+    void ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9]);
+    void ensure_staging(int slots);
+    void free_scratch();
+    void ensure_pool(unsigned long long slots);
+    TilePlan plan_tiles(const Geometry& g) const;
+    FrameBuffers buffers(const uint16_t* depth) const;
+    void run_front(const FrameBuffers& b, uint32_t n, const FrameState* guess_state);
+    void run_back(const FrameBuffers& b, uint32_t n, uint32_t iterations);
+    void begin_call();
+    void end_call();
+    cudaEvent_t next_event();
+    void mark(int stage);
+    void stage_check(const char* name);
+    void require_debug() const;
+
+    int device_ = 0;
+    int n_sms_ = 148;
+    uint32_t smem_optin_ = 0;
+    cudaStream_t own_stream_ = nullptr, copy_stream_ = nullptr, stream_ = nullptr;
+    cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_consumed_[2] = {nullptr, nullptr};
+
+    // device copy of the model
+    uint64_t df_serial_ = 0, df_sigma_version_ = 0;
+    size_t df_n_leaves_ = 0;
+    NodeRec* df_nodes_ = nullptr;
+    int32_t* df_roots_ = nullptr;
+    double* df_leaf_prob_ = nullptr;
+    LeafInfo* df_leaf_info_ = nullptr;
+    float* df_offsets_ = nullptr;
+    uint32_t* df_rot_bins_ = nullptr;
+    float* df_kernel_ = nullptr;
+    ForestDev fdev_{};
+    uint32_t lanes_per_hit_ = 1;
+
+    // scratch for one chunk of frames
+    ScratchKey sk_;
+    Geometry geom_{};
+    TilePlan tiles_{};
+    CUtensorMap sat_map_{};
+    uint32_t chunk_frames_ = 256;
+    uint16_t* d_depth_[2] = {nullptr, nullptr};
+    uint32_t* d_sat_ = nullptr;
+    int32_t* d_leaf_ = nullptr;
+    float* d_p3_ = nullptr;
+    uint8_t* d_gate_ = nullptr;
+    Hit* d_hits_ = nullptr;
+    uint32_t* d_grids_ = nullptr;
+    FrameState* d_fs_ = nullptr;
+    dh_result* d_results_ = nullptr;
+    int32_t* d_ms_trace_ = nullptr;
+    unsigned long long* d_hash_keys_ = nullptr;
+    uint32_t* d_hash_vals_ = nullptr;
+    unsigned long long pool_capacity_ = 0;
+    PoolState* d_pool_ = nullptr;
+    unsigned long long* d_counters_ = nullptr;
+    uint32_t* d_aux32_ = nullptr;
+    uint16_t* d_aux16_ = nullptr;
+    uint8_t* d_aux8_ = nullptr;
+    size_t aux32_cap_ = 0, aux8_cap_ = 0;
+
+    // pinned host staging
+    FrameState* h_fs_ = nullptr;
+    unsigned long long* h_counters_ = nullptr;
+    dh_result* h_results_ = nullptr;
+    size_t h_results_cap_ = 0;
+    PoolState* h_pool_ = nullptr;
+    size_t h_pool_cap_ = 0;
+
+    // measurement
+    bool timing_ = false, debug_ = false, have_debug_ = false, debug_sync_ = false;
+    uint32_t debug_iterations_ = 0, last_reach_ = 0;
+    uint32_t last_ms_flags_[2] = {0, 0};
+    std::vector<cudaEvent_t> timing_events_;
+    size_t ev_used_ = 0;
+    std::vector<std::pair<int, cudaEvent_t>> marks_;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> copy_marks_;
+    float stage_ms_[DH_N_STAGES];
+    uint64_t counters_[DH_N_COUNTERS];
+    uint64_t launches_ = 0, retries_ = 0;
+};
+
+}  // namespace dh

@@ -1,0 +1,47 @@
+// dh_types.hpp — plain structs shared by the host model (dh_forest.cpp) and the CUDA kernels.
+#pragma once
+
+#include <cstdint>
+
+namespace dh {
+
+// prediction.rs:270-286 compile-time constants of the reference's prediction path
+constexpr int kGuessGridParts = 20;        // GUESS_GRID_PARTS
+constexpr int kRotGridParts = 120;         // ROT_GRID_PARTS
+constexpr double kMaxVarianceRot = 400.0;  // MAX_VARIANCE_ROT (f64)
+constexpr float kMaxVarianceOffset = 5200.0f;  // MAX_VARIANCE_OFFSET (f32)
+constexpr int kKernelSize = 20;            // build_kernel(20, sigma), prediction.rs:314
+constexpr int kKernelCells = kKernelSize * kKernelSize * kKernelSize;  // 8000
+constexpr int kPosGridCells = kGuessGridParts * kGuessGridParts;       // 400
+constexpr int kRotGridCells = kGuessGridParts * kGuessGridParts * kGuessGridParts;  // 8000
+
+// One internal node, 32 bytes = exactly one L2 sector.  houghforest.rs:63-68 NodeParam
+// (two patch-relative half-open rectangles + f64 threshold) plus the two child links.
+// child[bit], bit = (avg1 - avg2 > threshold)  (houghforest.rs:185-193).
+// child >= 0: global node index;  child < 0: ~(global leaf id).
+struct alignas(32) NodeRec {
+    uint8_t r[8];      // r1.x0, r1.y0, r1.x1, r1.y1, r2.x0, r2.y0, r2.x1, r2.y1  (bottomright exclusive)
+    double threshold;
+    int32_t child[2];
+    uint32_t pad[2];
+};
+static_assert(sizeof(NodeRec) == 32, "NodeRec must be one 32-byte sector");
+
+// Per-leaf static quantities (prediction.rs:594-600,643 — constant per leaf, recomputed per hit by
+// the reference).  Filled on the device by leaf_gate_kernel.
+struct alignas(16) LeafInfo {
+    uint32_t vote_start;  // first vote in the vote tables
+    uint32_t n_votes;     // offsets.len() == rotations.len()
+    uint32_t valtoadd;    // ((1000.0*prob) as usize / n) as u32
+    uint32_t flags;       // bit0 rot_ok (trace(cov rot) <= 400), bit1 off_ok (trace(cov off) <= 5200)
+};
+static_assert(sizeof(LeafInfo) == 16, "LeafInfo must be 16 bytes");
+constexpr uint32_t kLeafRotOk = 1u, kLeafOffOk = 2u;
+
+// One voting patch*tree pair: which patch (for p3) and which leaf.
+struct Hit {
+    uint32_t patch;
+    uint32_t leaf;
+};
+
+}  // namespace dh

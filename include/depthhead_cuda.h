@@ -1,0 +1,176 @@
+/* depthhead_cuda.h — C ABI of libdepthhead_cuda.so: the B200 (sm_100a) replacement for
+ * depthhead's Hough-forest prediction path.
+ *
+ * These are the entry points a thin Rust crate (`depthhead-cuda`) binds with
+ * an `extern "C"` block to stand in for `HoughPrediction::predict_parameter_parallel` and its
+ * siblings.  Plain pointers and sizes only; nothing here unwinds across the boundary; there is
+ * NO CPU fallback — without a usable CUDA device every compute call returns DH_E_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the depthhead repository):
+ *   src/hough/prediction.rs:239-256   struct HoughPrediction (serde JSON)      -> dh_forest_*
+ *   src/hough/prediction.rs:320-331   update_sigma / sigma                     -> dh_forest_{set,get}_sigma
+ *   src/hough/prediction.rs:242,255   pub stepwidth, pub meanshift_iterations  -> dh_forest_{get,set}_*
+ *   src/types.rs:405-446              IntrinsicMatrix                          -> `const float K[9]`
+ *   src/hough/prediction.rs:376-409   predict_parameter{,_parallel}            -> dh_predict, dh_predict_batch
+ *   src/hough/prediction.rs:259-267   struct PredictionResult                  -> dh_result
+ *   src/hough/prediction.rs:850-905   predict_mask                             -> dh_predict_mask
+ *   src/hough/prediction.rs:760-841   build_hough_image (votes, before blur)   -> dh_hough_image_raw
+ */
+#ifndef DEPTHHEAD_CUDA_H
+#define DEPTHHEAD_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DH_ABI_VERSION 1
+
+/* error codes (0 = ok) */
+#define DH_OK 0
+#define DH_E_JSON (-1)   /* malformed document / forest the reference itself would panic on */
+#define DH_E_SHAPE (-2)  /* image smaller than the sub-image, zero stride, unsupported sizes */
+#define DH_E_CUDA (-3)   /* no device, wrong architecture, CUDA runtime failure */
+#define DH_E_ARG (-4)    /* NULL / out-of-range argument */
+#define DH_E_STATE (-5)  /* debug query without a preceding debug-enabled predict */
+
+typedef struct dh_forest dh_forest; /* immutable model: shareable across threads and GPUs */
+typedef struct dh_ctx dh_ctx;       /* one per GPU per host thread: stream, scratch, device copy */
+
+/* prediction.rs:259-267 PredictionResult.  mid_point: whole millimetres; rotation: radians
+ * (multiples of 3 degrees, pi = 3.14159 as in the reference); bounding_box: always 0,0,0,0
+ * (topleft x,y, bottomright x,y) because the reference never predicts it. */
+typedef struct dh_result {
+    float mid_point[3];
+    uint32_t _pad;
+    double rotation[3];
+    uint32_t bounding_box[4];
+} dh_result;
+
+/* Thread-local description of the last failure in this thread (never NULL). */
+const char* dh_last_error(void);
+int dh_abi_version(void);
+
+/* ------------------------------------------------------------------ model (HoughPrediction) */
+/* serde_json::from_str::<HoughPrediction>(json)  (Readme.md:82-86, prediction.rs:239-256).
+ * Parses the document, flattens the forest into structure-of-arrays node/leaf/vote tables and
+ * validates everything the reference would panic on at prediction time.  Host-only. */
+int dh_forest_from_json(const char* json, size_t len, dh_forest** out);
+
+/* Same model from already-flat arrays (the binary SoA form; skips JSON for very large forests).
+ * tree_node_off/tree_leaf_off: n_trees+1 prefix offsets; rects: int32[n_nodes][8] =
+ * r1.topleft x,y, r1.bottomright x,y, r2...; child: int32[n_nodes][2], >=0 = node index local to
+ * the tree (root = 0), <0 = ~(leaf index local to the tree); vote_off: n_leaves+1. */
+typedef struct dh_forest_arrays {
+    uint32_t stepwidth, subimage_width, subimage_height, meanshift_iterations;
+    float gaussian_sigma;
+    int32_t n_trees;
+    const int64_t* tree_node_off;
+    const int64_t* tree_leaf_off;
+    const int32_t* rects;
+    const double* threshold;
+    const int32_t* child;
+    const double* prob;
+    const int64_t* vote_off;
+    const float* offsets;     /* [n_votes][3] mm  */
+    const double* rotations;  /* [n_votes][3] deg */
+} dh_forest_arrays;
+int dh_forest_from_arrays(const dh_forest_arrays* a, dh_forest** out);
+void dh_forest_free(dh_forest* f);
+
+uint32_t dh_forest_get_stepwidth(const dh_forest* f);
+int dh_forest_set_stepwidth(dh_forest* f, uint32_t v);              /* pub field, prediction.rs:242 */
+uint32_t dh_forest_get_meanshift_iterations(const dh_forest* f);
+int dh_forest_set_meanshift_iterations(dh_forest* f, uint32_t v);   /* pub field, prediction.rs:255 */
+float dh_forest_get_sigma(const dh_forest* f);                      /* sigma(), prediction.rs:329 */
+int dh_forest_set_sigma(dh_forest* f, float v);                     /* update_sigma, prediction.rs:320-326:
+                                                                       ignored if v<=0 or unchanged */
+uint32_t dh_forest_get_subimage_width(const dh_forest* f);
+uint32_t dh_forest_get_subimage_height(const dh_forest* f);
+int32_t dh_forest_n_trees(const dh_forest* f);
+int64_t dh_forest_n_nodes(const dh_forest* f);
+int64_t dh_forest_n_leaves(const dh_forest* f);
+int64_t dh_forest_n_votes(const dh_forest* f);
+/* Leaf numbering used by the debug exports: global leaf id = tree_leaf_off[t] + index in file order. */
+
+/* ------------------------------------------------------------------ context */
+int dh_ctx_create(int device, dh_ctx** out);
+void dh_ctx_free(dh_ctx* c);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*; NULL = the context's own stream). */
+int dh_ctx_set_stream(dh_ctx* c, void* cuda_stream);
+/* Frames processed per pipeline pass (scratch is sized for this many); 0 = default. */
+int dh_ctx_set_chunk_frames(dh_ctx* c, uint32_t frames);
+int dh_ctx_synchronize(dh_ctx* c);
+
+/* ------------------------------------------------------------------ prediction */
+#define DH_DEPTH_HOST 0   /* depth points to host memory (pinned preferred) */
+#define DH_DEPTH_DEVICE 1 /* depth points to device memory on the context's GPU */
+
+/* predict_parameter_parallel (prediction.rs:397-409).  depth: w*h u16 millimetres, row-major,
+ * 0 = invalid (types.rs:10).  K: row-major 3x3 intrinsic matrix.  midp_guess (mm) and rot_guess
+ * (radians) may be NULL = None.  Synchronous: *out is valid on return. */
+int dh_predict(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+               const float* midp_guess, const double* rot_guess, dh_result* out);
+
+/* n independent frames [n][h][w] with seeds = None, results to out[n] (host).  depth_loc says
+ * where `depth` lives.  Synchronous. */
+int dh_predict_batch(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h,
+                     const float K[9], int depth_loc, dh_result* out);
+
+/* predict_mask (prediction.rs:850-905): mask[h][w] u8 to host memory. */
+int dh_predict_mask(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask);
+/* build_hough_image before its gaussian blur (prediction.rs:760-841): votes[h][w] u16 to host. */
+int dh_hough_image_raw(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h,
+                       const float K[9], uint16_t* votes);
+
+/* ------------------------------------------------------------------ measurement */
+/* Per-stage device time (CUDA events on the context's stream) of the LAST dh_predict_batch call,
+ * summed over its chunks, in milliseconds.  Order of stages: see DH_STAGE_*. */
+#define DH_STAGE_H2D 0
+#define DH_STAGE_SAT 1
+#define DH_STAGE_TRAVERSE 2
+#define DH_STAGE_GATE 3
+#define DH_STAGE_COARSE 4
+#define DH_STAGE_INSERT 5
+#define DH_STAGE_MEANSHIFT 6
+#define DH_STAGE_D2H 7
+#define DH_N_STAGES 8
+int dh_ctx_enable_stage_timing(dh_ctx* c, int on);
+int dh_ctx_stage_ms(dh_ctx* c, float ms[DH_N_STAGES]);
+/* Work counters of the last dh_predict/dh_predict_batch call:
+ * [0] frames, [1] patches (all), [2] valid (non-background) patches, [3] patch*tree evals,
+ * [4] node visits, [5] gate-passing patches, [6] hits (patch*tree that vote), [7] centre votes cast,
+ * [8] rotation votes cast, [9] kernel launches, [10] mean-shift iterations run (both accumulators),
+ * [11] hash-pool retries. */
+#define DH_N_COUNTERS 12
+int dh_ctx_counters(dh_ctx* c, uint64_t counters[DH_N_COUNTERS]);
+
+/* ------------------------------------------------------------------ debug exports (parity tests) */
+/* Keep the intermediates of the last dh_predict call (single frame) on the device. */
+int dh_ctx_enable_debug(dh_ctx* c, int on);
+/* patches per row / column of the sliding window of the last call */
+int dh_debug_dims(dh_ctx* c, uint32_t* npx, uint32_t* npy, uint32_t* n_trees);
+/* leaf[P][T] global leaf id, -1 = background patch; visited may be NULL */
+int dh_debug_leaf_indices(dh_ctx* c, int32_t* leaf /*[P*T]*/);
+/* p3[P][3] back-projected patch centres; gate[P] = 1 iff mean prob > 0.7 */
+int dh_debug_patches(dh_ctx* c, float* p3, uint8_t* gate);
+/* coarse seed grids (400 + 8000 u32) and the seeds handed to mean-shift */
+int dh_debug_seeds(dh_ctx* c, uint32_t* guess_pos, uint32_t* guess_rot, int32_t seed_mid[3], int32_t seed_rot[3]);
+/* Accumulator contents as unsorted (key, value) lists.  which: 0 = centre, 1 = rotation.
+ * Only cells within the mean-shift reach of the seed are stored; *reach returns
+ * that radius.  Call with keys == NULL to get the count. */
+int dh_debug_votes(dh_ctx* c, int which, int32_t* keys /*[n][3]*/, uint32_t* vals, uint64_t* n, int32_t* reach);
+/* mean-shift trajectory: positions after each executed iteration; *n_iter in/out */
+int dh_debug_meanshift(dh_ctx* c, int which, int32_t* pos /*[n_iter][3]*/, uint32_t* n_iter);
+/* flags of the last mean-shift runs: bit0 = zero-sum break (meanshift.rs:385-388), bit1 = a probe
+ * fell outside the stored reach (must never happen) */
+int dh_debug_meanshift_flags(dh_ctx* c, uint32_t flags[2]);
+/* per-leaf static quantities computed by the leaf-gate kernel: valtoadd, rot_ok, off_ok */
+int dh_debug_leaf_static(dh_ctx* c, const dh_forest* f, uint32_t* valtoadd, uint8_t* rot_ok, uint8_t* off_ok);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEPTHHEAD_CUDA_H */

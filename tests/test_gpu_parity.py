@@ -1,0 +1,268 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): leaf index per patch x tree bit-exact; votes exact (integer bins
+and u32 sums — tighter than the 1e-5 relative the north star allows); seeds identical; final head
+centre / rotation identical (the bar is 1 mm / 0.1 degree, i.e. the same 3-degree bin).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from depthhead_b200 import Context, HoughPrediction, IntrinsicMatrix, capi, synth
+
+pytestmark = pytest.mark.gpu
+
+K = IntrinsicMatrix.default_kinect_intrinsic()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _filter_acc(keys, vals, seed, reach):
+    if len(vals) == 0:
+        return keys.reshape(0, 3), vals
+    m = (vals > 0) & np.all(np.abs(keys.astype(np.int64) - np.asarray(seed, np.int64)) <= reach, axis=1)
+    return keys[m], vals[m]
+
+
+def _compare_frame(ctx, hp, of, depth, midp_guess=None, rot_guess=None, check_patches=True):
+    ctx.enable_debug(True)
+    res = hp.predict_parameter_parallel(depth, K, midp_guess, rot_guess, ctx=ctx)
+    tr = of.predict(depth, synth.KINECT_K, midp_guess, rot_guess, mode=oracle.MODE_SAT, keep=True)
+    npx, npy, T = ctx.debug_dims()
+    assert (npx, npy, T) == (tr.npx, tr.npy, of.n_trees)
+    # --- leaf index per patch x tree: bit-exact
+    leaf = ctx.debug_leaf_indices()
+    assert np.array_equal(leaf, tr.leaf), "leaf ids differ at %d of %d" % (np.sum(leaf != tr.leaf), leaf.size)
+    if check_patches:
+        p3, gate = ctx.debug_patches()
+        assert np.array_equal(gate, tr.gate)
+        g = gate.astype(bool)
+        assert np.array_equal(p3[g].view(np.uint32), tr.p3[g].view(np.uint32)), "p3 not bit-exact"
+    # --- coarse grids + seeds
+    gp, gr, sm, sr = ctx.debug_seeds()
+    assert np.array_equal(gp, tr.guess_pos)
+    assert np.array_equal(gr, tr.guess_rot)
+    assert np.array_equal(sm, tr.seed_mid)
+    assert np.array_equal(sr, tr.seed_rot)
+    # --- accumulators (cells within the stored reach of the seed)
+    for which, (ok, ov, seed) in enumerate(((tr.mid_keys, tr.mid_vals, tr.seed_mid), (tr.rot_keys, tr.rot_vals, tr.seed_rot))):
+        gk, gv, reach = ctx.debug_votes(which)
+        assert reach >= 10 * of.meanshift_iterations + 10
+        ek, ev = _filter_acc(ok, ov, seed, reach)
+        gk, gv = _filter_acc(gk, gv, seed, reach)
+        assert np.array_equal(gk, ek), "accumulator %d keys differ (%d vs %d cells)" % (which, len(gk), len(ek))
+        assert np.array_equal(gv, ev), "accumulator %d sums differ" % which
+    # --- mean-shift trajectories: GPU stops at a fixed point, the reference repeats it
+    for which, otrace in enumerate((tr.ms_mid, tr.ms_rot)):
+        gtrace = ctx.debug_meanshift(which)
+        n = len(gtrace)
+        assert n <= len(otrace) or len(otrace) == 0
+        assert np.array_equal(gtrace, otrace[:n])
+        if n and n < len(otrace):
+            assert np.all(otrace[n:] == otrace[n - 1]), "early exit was not a fixed point"
+    f0, f1 = ctx.debug_meanshift_flags()
+    assert (f0 & 2) == 0 and (f1 & 2) == 0, "mean-shift probed outside the stored reach"
+    assert bool(f0 & 1) == tr.ms_mid_zero and bool(f1 & 1) == tr.ms_rot_zero
+    # --- result
+    assert np.array_equal(res.mid_point, tr.mid_point)
+    assert np.array_equal(res.rotation.view(np.uint64), tr.rotation.view(np.uint64))
+    assert res.bounding_box == (0, 0, 0, 0)
+    ctx.enable_debug(False)
+    return res, tr
+
+
+def test_small_forest_every_stage(ctx, small_case):
+    arr, js, frames = small_case
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    for d in frames:
+        _compare_frame(ctx, hp, of, d)
+
+
+@pytest.mark.parametrize("stride,depth,trees", [(5, 10, 10), (7, 8, 5), (16, 12, 3)])
+def test_mid_forest(ctx, stride, depth, trees):
+    arr = synth.make_forest(seed=21 + stride, n_trees=trees, max_depth=depth, shuffle_nodes=True)
+    js = synth.forest_to_json(arr, stepwidth=stride)
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    for d in synth.make_frames(2, seed=100 + stride):
+        _compare_frame(ctx, hp, of, d)
+
+
+def test_sparse_trees_and_ragged_rects(ctx):
+    arr = synth.make_forest(seed=5, n_trees=6, max_depth=12, stop_prob=0.25, ragged_rects=True, shuffle_nodes=True)
+    js = synth.forest_to_json(arr, stepwidth=6)
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    for d in synth.make_frames(2, seed=77):
+        _compare_frame(ctx, hp, of, d)
+
+
+def test_caller_seeds(ctx, small_case):
+    arr, js, frames = small_case
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    d = frames[0]
+    auto, tr = _compare_frame(ctx, hp, of, d)
+    # seed near the head: find a dense region from the oracle's own accumulator
+    k = tr.mid_keys[np.argmax(tr.mid_vals)] if len(tr.mid_vals) else np.array([0, 0, 900])
+    _compare_frame(ctx, hp, of, d, midp_guess=[float(k[0]) + 3.7, float(k[1]) - 2.2, float(k[2]) + 5.5],
+                   rot_guess=[0.2, -0.35, 0.05])
+    _compare_frame(ctx, hp, of, d, midp_guess=[12.5, -40.25, 950.0], rot_guess=None)
+    _compare_frame(ctx, hp, of, d, midp_guess=None, rot_guess=[-1.0, 1.0, 0.5])
+
+
+def test_sigma_iterations_stepwidth_setters(ctx, small_case):
+    arr, js, frames = small_case
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    hp.update_sigma(3.0)
+    of.update_sigma(3.0)
+    hp.meanshift_iterations = 7
+    of.meanshift_iterations = 7
+    hp.stepwidth = 13
+    of.stepwidth = 13
+    _compare_frame(ctx, hp, of, frames[1])
+    hp.update_sigma(-2.0)  # ignored (prediction.rs:321)
+    assert hp.sigma() == 3.0
+    hp.meanshift_iterations = 0
+    of.meanshift_iterations = 0
+    _compare_frame(ctx, hp, of, frames[1])
+
+
+def test_edge_frames(ctx, small_case):
+    arr, js, frames = small_case
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    h, w = 480, 640
+    empty = np.zeros((h, w), np.uint16)                       # everything is background
+    full = np.full((h, w), 65535, np.uint16)                  # maximum depth everywhere (u32 SAT wraps)
+    one = empty.copy()
+    one[240, 320] = 1234                                      # a single valid pixel
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 65536, (h, w)).astype(np.uint16)  # random u16
+    for d in (empty, full, one, noise):
+        _compare_frame(ctx, hp, of, d)
+
+
+def test_ragged_image_sizes(ctx, small_case):
+    arr, js, frames = small_case
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    rng = np.random.default_rng(9)
+    for (h, w) in ((80, 80), (81, 97), (123, 211), (480, 637)):
+        d = np.where(rng.random((h, w)) < 0.6, rng.integers(400, 1500, (h, w)), 0).astype(np.uint16)
+        _compare_frame(ctx, hp, of, d)
+
+
+def test_leaf_static_gates(ctx):
+    arr = synth.make_forest(seed=8, n_trees=3, max_depth=8)
+    js = synth.forest_to_json(arr, stepwidth=10)
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    v, r, o = hp.debug_leaf_static(ctx)
+    n_rot = n_off = 0
+    for leaf in range(hp.n_leaves):
+        ev, tr_rot, tr_off = of.leaf_static(leaf)
+        nv = int(arr["vote_off"][leaf + 1] - arr["vote_off"][leaf])
+        if nv == 0:
+            assert v[leaf] == 0 and r[leaf] == 0 and o[leaf] == 0
+            continue
+        assert v[leaf] == ev
+        assert bool(r[leaf]) == bool(tr_rot <= 400.0)
+        assert bool(o[leaf]) == bool(tr_off <= np.float32(5200.0))
+        n_rot += int(r[leaf])
+        n_off += int(o[leaf])
+    assert 0 < n_rot < hp.n_leaves and 0 < n_off < hp.n_leaves  # both outcomes exercised
+
+
+def test_batch_matches_single_and_oracle(ctx):
+    arr = synth.make_forest(seed=2, n_trees=10, max_depth=9)
+    js = synth.forest_to_json(arr, stepwidth=5)
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    frames = synth.make_frames(11, seed=31)
+    ctx.set_chunk_frames(4)  # 3 chunks, the last one ragged
+    out = hp.predict_batch(frames, K, ctx=ctx)
+    cnt = ctx.counters()
+    assert cnt["frames"] == 11 and cnt["launches"] > 0
+    ctx.set_chunk_frames(0)
+    for i, d in enumerate(frames):
+        tr = of.predict(d, synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+        assert np.array_equal(out["mid_point"][i], tr.mid_point)
+        assert np.array_equal(out["rotation"][i], tr.rotation)
+        single = hp.predict_parameter_parallel(d, K, ctx=ctx)
+        assert np.array_equal(single.mid_point, out["mid_point"][i])
+        assert np.array_equal(single.rotation, out["rotation"][i])
+
+
+def test_device_resident_batch(ctx):
+    import torch
+    arr = synth.make_forest(seed=4, n_trees=5, max_depth=8)
+    hp = HoughPrediction.from_arrays(arr, stepwidth=5)
+    frames = synth.make_frames(6, seed=41)
+    host = hp.predict_batch(frames, K, ctx=ctx)
+    dev = torch.from_numpy(frames.view(np.int16)).cuda()
+    torch.cuda.synchronize()
+    out = hp.predict_batch(None, K, ctx=ctx, device_ptr=dev.data_ptr(), n=6, w=640, h=480)
+    assert np.array_equal(out["mid_point"], host["mid_point"])
+    assert np.array_equal(out["rotation"], host["rotation"])
+
+
+def test_json_and_arrays_loaders_agree(ctx, small_case):
+    arr, js, frames = small_case
+    a = HoughPrediction.from_json(js)
+    b = HoughPrediction.from_arrays(arr, stepwidth=10)
+    ra = a.predict_batch(frames, K, ctx=ctx)
+    rb = b.predict_batch(frames, K, ctx=ctx)
+    assert np.array_equal(ra["mid_point"], rb["mid_point"]) and np.array_equal(ra["rotation"], rb["rotation"])
+
+
+def test_predict_mask_and_hough_image(ctx, small_case):
+    arr, js, frames = small_case
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    for d in frames[:2]:
+        assert np.array_equal(hp.predict_mask(d, ctx=ctx), of.predict_mask(d))
+        assert np.array_equal(hp.hough_image_raw(d, K, ctx=ctx), of.hough_image_raw(d, synth.KINECT_K))
+    hp.stepwidth = 7
+    of.stepwidth = 7
+    assert np.array_equal(hp.predict_mask(frames[2], ctx=ctx), of.predict_mask(frames[2]))
+
+
+def test_shape_errors(ctx, small_case):
+    arr, js, frames = small_case
+    hp = HoughPrediction.from_json(js)
+    small = np.zeros((60, 60), np.uint16)
+    with pytest.raises(capi.DhError) as e:
+        hp.predict_parameter_parallel(small, K, ctx=ctx)
+    assert e.value.code == capi.DH_E_SHAPE
+
+
+def test_full_size_properties(ctx):
+    """BASELINE configs[1] shape (10 trees, depth 15, stride 5) — size-independent properties:
+    batch == per-frame, chunking-independent, permutation-equivariant, deterministic."""
+    arr = synth.make_forest(seed=1, n_trees=10, max_depth=15)
+    hp = HoughPrediction.from_arrays(arr, stepwidth=5)
+    frames = synth.make_frames(24, seed=7)
+    a = hp.predict_batch(frames, K, ctx=ctx)
+    ctx.set_chunk_frames(5)
+    b = hp.predict_batch(frames, K, ctx=ctx)
+    ctx.set_chunk_frames(0)
+    assert np.array_equal(a["mid_point"], b["mid_point"]) and np.array_equal(a["rotation"], b["rotation"])
+    perm = np.random.default_rng(0).permutation(len(frames))
+    c = hp.predict_batch(frames[perm], K, ctx=ctx)
+    assert np.array_equal(c["mid_point"], a["mid_point"][perm]) and np.array_equal(c["rotation"], a["rotation"][perm])
+    cnt = ctx.counters()
+    assert cnt["evals"] == cnt["valid_patches"] * 10
+    assert cnt["node_visits"] == cnt["evals"] * 15  # full depth-15 trees: every walk visits 15 nodes
+    # spot-check three frames end to end against the oracle
+    of = oracle.OracleForest(arr, 5, 80, 80, 8.0, 20)
+    for i in (0, 11, 23):
+        tr = of.predict(frames[i], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+        assert np.array_equal(a["mid_point"][i], tr.mid_point) and np.array_equal(a["rotation"][i], tr.rotation)
