@@ -23,6 +23,9 @@
 //   * u32 vote sums wrap (release build);  * f32/f64 arithmetic is never contracted into FMA.
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <sched.h>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -30,6 +33,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <memory>
 #include <string>
 #include <tuple>
 #include <unordered_map>
@@ -380,6 +384,87 @@ constexpr size_t ROT_GRID_PARTS = 120;
 constexpr double MAX_VARIANCE_ROT = 400.0;
 constexpr float MAX_VARIANCE_OFFSET = 5200.0f;
 
+// ---------------------------------------------------------------- fork-join pool
+// Stand-in for the rayon pool behind stamm's forest_predictions_parallel (prediction.rs:407): one
+// fork-join over the trees PER PATCH.  Persistent workers spin on an epoch counter (rayon's
+// workers also spin before sleeping), grab tree indices from an atomic counter, and the caller
+// joins by waiting for the done counter.  Two job slots alternate so that a straggler still
+// looking at the previous job only ever sees an exhausted counter.
+class TreePool {
+public:
+    typedef void (*Fn)(void* ctx, int index);
+    explicit TreePool(int workers) {
+        stop_.store(false);
+        epoch_.store(0);
+        for (int i = 0; i < 2; ++i) {
+            slots_[i].next.store(1 << 30);
+            slots_[i].done.store(0);
+        }
+        for (int i = 0; i < workers; ++i) threads_.emplace_back([this] { worker(); });
+    }
+    ~TreePool() {
+        stop_.store(true);
+        for (auto& t : threads_) t.join();
+    }
+    int workers() const { return (int)threads_.size(); }
+    void run(int n, Fn fn, void* ctx) {
+        const uint64_t e = epoch_.load(std::memory_order_relaxed) + 1;
+        Job& j = slots_[e & 1];
+        j.fn = fn;
+        j.ctx = ctx;
+        j.n = n;
+        j.done.store(0, std::memory_order_relaxed);
+        j.next.store(0, std::memory_order_release);
+        epoch_.store(e, std::memory_order_release);
+        drain(j);
+        while (j.done.load(std::memory_order_acquire) < n) cpu_relax();
+    }
+
+private:
+    struct Job {
+        Fn fn = nullptr;
+        void* ctx = nullptr;
+        int n = 0;
+        alignas(64) std::atomic<int> next;
+        alignas(64) std::atomic<int> done;
+    };
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    static void drain(Job& j) {
+        for (;;) {
+            const int i = j.next.fetch_add(1, std::memory_order_acq_rel);
+            if (i >= j.n) break;
+            j.fn(j.ctx, i);
+            j.done.fetch_add(1, std::memory_order_release);
+        }
+    }
+    void worker() {
+        uint64_t seen = 0;
+        unsigned spins = 0;
+        while (!stop_.load(std::memory_order_relaxed)) {
+            const uint64_t e = epoch_.load(std::memory_order_acquire);
+            if (e == seen) {
+                cpu_relax();
+                if (++spins > 20000) {
+                    sched_yield();
+                    spins = 0;
+                }
+                continue;
+            }
+            seen = e;
+            spins = 0;
+            drain(slots_[e & 1]);
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::atomic<bool> stop_;
+    alignas(64) std::atomic<uint64_t> epoch_;
+    Job slots_[2];
+};
+
 enum Mode { MODE_NAIVE = 0, MODE_SAT = 1 };
 
 struct Trace {
@@ -443,6 +528,8 @@ void build_hough_cube(const Forest& forest, const Params& prm, const Image& img,
     }
     std::vector<int64_t> leafs(T);
     std::vector<int> visited(T);
+    std::unique_ptr<TreePool> pool;  // caller + (tree_threads-1) workers
+    if (tree_threads > 1) pool.reset(new TreePool(tree_threads - 1));
 
     size_t pidx = 0;
     uint32_t y = left_h;  // :544-548
@@ -470,13 +557,10 @@ void build_hough_cube(const Forest& forest, const Params& prm, const Image& img,
                         leafs[t] = tree_predict(forest, t, [&](const Rect& r) { return average_value_in_rect(img, sub, r); }, &v);
                     visited[t] = v;
                 };
-#ifdef _OPENMP
-                if (tree_threads > 1) {
-#pragma omp parallel for num_threads(tree_threads) schedule(static)
-                    for (int t = 0; t < T; ++t) run_tree(t);
-                } else
-#endif
-                {
+                if (pool) {
+                    struct Ctx { decltype(run_tree)* f; } c{&run_tree};
+                    pool->run(T, [](void* p, int t) { (*static_cast<Ctx*>(p)->f)(t); }, &c);
+                } else {
                     for (int t = 0; t < T; ++t) run_tree(t);
                 }
             }
