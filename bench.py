@@ -65,12 +65,19 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.mark = 0
+        self.bad = None
+
+    def begin_region(self):
+        """Only samples taken after this call count (the sampler itself starts earlier because
+        nvidia-smi takes a few hundred ms to produce its first line)."""
+        self.mark = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -91,9 +98,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.mark:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
+                self.bad = ln
                 continue
             try:
                 sm.append(float(f[1]))
@@ -103,8 +111,11 @@ class ClockSampler:
             for name, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if not sm and self.bad:
+            out["nvidia_smi_says"] = self.bad[:200]
+        return out
 
 
 def make_workload(rank: int, n_frames: int):
@@ -280,17 +291,26 @@ def main():
         return ms, wall * 1000.0, stage, counters, out
 
     # ---- warm-up (also sizes scratch and the accumulator pool)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     for _ in range(min(args.warmup, 2)):
         step_host()
-
-    sampler = ClockSampler(local)
-    sampler.start()
+    # keep the GPU under the same load until nvidia-smi is producing samples (untimed)
+    t_wait = time.perf_counter()
+    while len(sampler.lines) < 2 and time.perf_counter() - t_wait < 3.0:
+        step_device()
+    sampler.begin_region()
     ctx.enable_stage_timing(True)
     ms_dev, wall_dev, stage, counters, out_dev = timed(step_device, args.steps, with_stages=True)
     ctx.enable_stage_timing(False)
     ms_e2e, wall_e2e, _, _, out_host = timed(step_host, args.steps)
+    # the timed regions last ~0.2 s: extend the sampled window with identical untimed steps so the
+    # clock record has enough samples under the same load
+    t_wait = time.perf_counter()
+    while len(sampler.lines) - sampler.mark < 8 and time.perf_counter() - t_wait < 2.0:
+        step_device()
     clocks = sampler.stop()
     assert np.array_equal(out_dev["mid_point"], out_host["mid_point"]) and np.array_equal(out_dev["rotation"], out_host["rotation"])
 
@@ -336,7 +356,7 @@ def main():
         "gpu_launches": int(counters["launches"]),
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
         "wall_ms_per_step": wall_dev / args.steps,
-        "work_per_step": {k: counters[k] // args.steps for k in ("frames", "valid_patches", "evals", "node_visits", "gate_patches", "hits", "centre_votes", "rot_votes", "meanshift_iters", "pool_retries")},
+        "work_per_step": {k: counters[k] // args.steps for k in ("frames", "valid_patches", "evals", "node_visits", "gate_patches", "hits", "centre_votes", "rot_votes", "meanshift_iters", "cube_rebuilds")},
         "roofline": roofline, "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -121,17 +121,20 @@ class Context:
         return gp, gr, sm, sr
 
     def debug_votes(self, which: int):
-        """(keys[n,3] i32, vals[n] u32, reach) sorted by key; cells within `reach` of the seed."""
+        """(keys[n,3] i32, vals[n] u32, box_origin[3], box_dim) sorted by key: the non-zero cells of the
+        dense accumulator cube around the last mean-shift position."""
         L = capi.load()
-        n, reach = C.c_uint64(), C.c_int32()
-        capi.check(L.dh_debug_votes(self._h, int(which), None, None, C.byref(n), C.byref(reach)))
+        n, dim = C.c_uint64(), C.c_int32()
+        org = np.zeros(3, np.int32)
+        capi.check(L.dh_debug_votes(self._h, int(which), None, None, C.byref(n), capi.ptr(org), C.byref(dim)))
         keys = np.zeros((n.value, 3), np.int32)
         vals = np.zeros(n.value, np.uint32)
         if n.value:
-            capi.check(L.dh_debug_votes(self._h, int(which), capi.ptr(keys), capi.ptr(vals), C.byref(n), C.byref(reach)))
+            capi.check(L.dh_debug_votes(self._h, int(which), capi.ptr(keys), capi.ptr(vals), C.byref(n), capi.ptr(org),
+                                        C.byref(dim)))
             order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
             keys, vals = keys[order], vals[order]
-        return keys, vals, reach.value
+        return keys, vals, org, dim.value
 
     def debug_meanshift(self, which: int, max_iter: int = 65535):
         L = capi.load()

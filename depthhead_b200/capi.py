@@ -15,10 +15,10 @@ from . import _build
 
 DH_OK, DH_E_JSON, DH_E_SHAPE, DH_E_CUDA, DH_E_ARG, DH_E_STATE = 0, -1, -2, -3, -4, -5
 DH_DEPTH_HOST, DH_DEPTH_DEVICE = 0, 1
-DH_N_STAGES, DH_N_COUNTERS = 8, 12
-STAGES = ("h2d", "sat", "traverse", "gate", "coarse", "insert", "meanshift", "d2h")
+DH_N_STAGES, DH_N_COUNTERS = 6, 12
+STAGES = ("h2d", "sat", "traverse", "gate", "vote_meanshift", "d2h")
 COUNTERS = ("frames", "patches", "valid_patches", "evals", "node_visits", "gate_patches", "hits",
-            "centre_votes", "rot_votes", "launches", "meanshift_iters", "pool_retries")
+            "centre_votes", "rot_votes", "launches", "meanshift_iters", "cube_rebuilds")
 
 
 class DhError(RuntimeError):
@@ -82,7 +82,7 @@ SIGNATURES = {
     "dh_debug_leaf_indices": (C.c_int, [_vp, _vp]),
     "dh_debug_patches": (C.c_int, [_vp, _vp, _vp]),
     "dh_debug_seeds": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
-    "dh_debug_votes": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(_u64), C.POINTER(_i32)]),
+    "dh_debug_votes": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(_u64), _vp, C.POINTER(_i32)]),
     "dh_debug_meanshift": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(_u32)]),
     "dh_debug_meanshift_flags": (C.c_int, [_vp, _vp]),
     "dh_debug_leaf_static": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),

@@ -256,11 +256,12 @@ int dh_debug_seeds(dh_ctx* c, uint32_t* guess_pos, uint32_t* guess_rot, int32_t 
         c->cx->debug_seeds(guess_pos, guess_rot, seed_mid, seed_rot);
     });
 }
-int dh_debug_votes(dh_ctx* c, int which, int32_t* keys, uint32_t* vals, uint64_t* n, int32_t* reach) {
+int dh_debug_votes(dh_ctx* c, int which, int32_t* keys, uint32_t* vals, uint64_t* n, int32_t box_origin[3],
+                   int32_t* box_dim) {
     return guarded([&] {
         REQUIRE(c, "NULL ctx");
         REQUIRE((keys == nullptr) == (vals == nullptr), "keys and vals must both be NULL or both be set");
-        c->cx->debug_votes(which, keys, vals, n, reach);
+        c->cx->debug_votes(which, keys, vals, n, box_origin, box_dim);
     });
 }
 int dh_debug_meanshift(dh_ctx* c, int which, int32_t* pos, uint32_t* n_iter) {

@@ -80,7 +80,7 @@ Context::Context(int device) : device_(device) {
         DH_CUDA(cudaEventCreateWithFlags(&ev_consumed_[i], cudaEventDisableTiming));
     }
     dev_alloc(d_counters_, DH_N_COUNTERS);
-    dev_alloc(d_pool_, 1);
+    dev_alloc(d_work_counter_, 1);
     DH_CUDA(cudaHostAlloc((void**)&h_fs_, sizeof(FrameState), cudaHostAllocDefault));
     DH_CUDA(cudaHostAlloc((void**)&h_counters_, sizeof(unsigned long long) * DH_N_COUNTERS, cudaHostAllocDefault));
     chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 256);
@@ -94,17 +94,15 @@ Context::~Context() {
     cudaDeviceSynchronize();
     free_scratch();
     free_forest();
-    dev_free(d_hash_keys_);
-    dev_free(d_hash_vals_);
+    dev_free(d_boxes_);
+    dev_free(d_work_counter_);
     dev_free(d_counters_);
-    dev_free(d_pool_);
     dev_free(d_aux32_);
     dev_free(d_aux16_);
     dev_free(d_aux8_);
     if (h_fs_) cudaFreeHost(h_fs_);
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_results_) cudaFreeHost(h_results_);
-    if (h_pool_) cudaFreeHost(h_pool_);
     for (auto ev : timing_events_) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
         if (ev_copied_[i]) cudaEventDestroy(ev_copied_[i]);
@@ -199,7 +197,8 @@ void Context::free_scratch() {
     dev_free(d_leaf_);
     dev_free(d_p3_);
     dev_free(d_gate_);
-    dev_free(d_hits_);
+    dev_free(d_chits_);
+    dev_free(d_rhits_);
     dev_free(d_grids_);
     dev_free(d_fs_);
     dev_free(d_results_);
@@ -245,7 +244,16 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
     if (w > 32768 || h > 32768) throw ModelError(DH_E_SHAPE, "image larger than 32768 pixels per side is not supported");
     if (w < (uint32_t)kGuessGridParts || h < (uint32_t)kGuessGridParts)
         throw ModelError(DH_E_SHAPE, "image smaller than 20 pixels per side: the reference's 20x20 seed grid has empty cells");
-    const uint32_t cap = std::max<uint32_t>(1u, std::min<uint32_t>(chunk_frames_, std::max<uint32_t>(n_frames_hint, 1u)));
+    // frames per pass: the requested chunk, but never more than ~12 GB of per-frame scratch
+    uint32_t cap = std::max<uint32_t>(1u, std::min<uint32_t>(chunk_frames_, std::max<uint32_t>(n_frames_hint, 1u)));
+    {
+        const uint64_t npx = (w - sw + stride - 1) / stride, npy = (h - sh + stride - 1) / stride;
+        const uint64_t PT = std::max<uint64_t>(npx * npy, 1) * (uint64_t)hf.n_trees;
+        const uint64_t per_frame = (uint64_t)(h + 1) * ((w + 4) & ~3ull) * 4 + PT * (4 + sizeof(CentreHit) + sizeof(RotHit)) +
+                                   npx * npy * 13 + (uint64_t)w * h * 4 + 40000;
+        const uint64_t budget = 12ull << 30;
+        cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(cap, budget / per_frame));
+    }
     ScratchKey k{w, h, sw, sh, stride, (uint32_t)hf.n_trees, cap, debug_ ? hf.meanshift_iterations.load() : 0u};
     Geometry& g = geom_;
     if (!k.same_shape(sk_) || k.frames > sk_.frames) {
@@ -270,7 +278,8 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
         dev_alloc(d_leaf_, F * P * T);
         dev_alloc(d_p3_, F * P * 3);
         dev_alloc(d_gate_, F * P);
-        dev_alloc(d_hits_, F * P * T);
+        dev_alloc(d_chits_, F * P * T);
+        dev_alloc(d_rhits_, F * P * T);
         dev_alloc(d_grids_, F * (size_t)(kPosGridCells + kRotGridCells));
         dev_alloc(d_fs_, F);
         dev_alloc(d_results_, F);
@@ -288,8 +297,14 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
             if (r != CUDA_SUCCESS) throw ModelError(DH_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
         }
         sk_ = k;
-        // hash pool: grows on demand (overflow -> retry), start at 2 slots per patch x tree
-        ensure_pool(std::max<unsigned long long>((unsigned long long)F * P * T * 2ull, 1ull << 16));
+    }
+    // accumulator cubes: one per persistent CTA of vote_meanshift_kernel (3 CTAs per SM)
+    const uint32_t want_ctas = (uint32_t)n_sms_ * 3u;
+    if (vm_ctas_ < want_ctas) {
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        dev_free(d_boxes_);
+        dev_alloc(d_boxes_, (size_t)want_ctas * vote_box_cells());
+        vm_ctas_ = want_ctas;
     }
     std::memcpy(g.K, K, sizeof(float) * 9);
     mat3_inverse_f32(K, g.Kinv);
@@ -301,16 +316,6 @@ void Context::ensure_staging(int slots) {
         if (!d_depth_[i]) dev_alloc(d_depth_[i], n);
 }
 
-void Context::ensure_pool(unsigned long long slots) {
-    if (slots <= pool_capacity_) return;
-    DH_CUDA(cudaStreamSynchronize(stream_));
-    dev_free(d_hash_keys_);
-    dev_free(d_hash_vals_);
-    dev_alloc(d_hash_keys_, (size_t)slots);
-    dev_alloc(d_hash_vals_, (size_t)slots);
-    pool_capacity_ = slots;
-}
-
 FrameBuffers Context::buffers(const uint16_t* depth) const {
     FrameBuffers b{};
     b.depth = depth;
@@ -318,15 +323,16 @@ FrameBuffers Context::buffers(const uint16_t* depth) const {
     b.leaf = d_leaf_;
     b.p3 = d_p3_;
     b.gate = d_gate_;
-    b.hits = d_hits_;
+    b.chits = d_chits_;
+    b.rhits = d_rhits_;
     b.grids = d_grids_;
     b.fs = d_fs_;
-    b.hash_keys = d_hash_keys_;
-    b.hash_vals = d_hash_vals_;
-    b.pool = d_pool_;
+    b.boxes = d_boxes_;
+    b.work_counter = d_work_counter_;
     b.results = d_results_;
     b.ms_trace = d_ms_trace_;
     b.ms_trace_cap = sk_.trace_iters;
+    b.debug = debug_ ? 1u : 0u;
     return b;
 }
 
@@ -376,27 +382,19 @@ void Context::run_front(const FrameBuffers& b, uint32_t n, const FrameState* gue
 
 void Context::run_back(const FrameBuffers& b, uint32_t n, uint32_t iterations) {
     const Geometry& g = geom_;
-    const uint32_t reach = 12u * iterations + 16u;
-    last_reach_ = reach;
-    const uint32_t splits = std::max<uint32_t>(1u, std::min<uint32_t>(64u, ((uint32_t)n_sms_ * 4u + n - 1) / n));
     mark(DH_STAGE_GATE);
     if (g.P) {
         launch_gate(b, g, fdev_, n, stream_);
         launches_ += 1;
         stage_check("gate");
     }
-    mark(DH_STAGE_COARSE);
-    launch_coarse(b, g, fdev_, n, splits, lanes_per_hit_, stream_);
-    stage_check("coarse");
-    mark(DH_STAGE_INSERT);
-    launch_plan_and_clear(b, n, pool_capacity_, stream_);
-    stage_check("plan/clear");
-    launch_insert(b, g, fdev_, n, splits, lanes_per_hit_, reach, stream_);
-    stage_check("insert");
-    mark(DH_STAGE_MEANSHIFT);
-    launch_meanshift(b, fdev_, n, iterations, reach, stream_);
-    stage_check("meanshift");
-    launches_ += 5;
+    mark(DH_STAGE_VOTE_MEANSHIFT);
+    // debug mode (single frame): one CTA per work item so both accumulator cubes survive the launch
+    const bool static_items = debug_ && n == 1;
+    const uint32_t ctas = std::min<uint32_t>(vm_ctas_, 2u * n);
+    launch_vote_meanshift(b, g, fdev_, n, iterations, ctas, lanes_per_hit_, static_items, stream_);
+    launches_ += 1;
+    stage_check("vote_meanshift");
     mark(DH_STAGE_D2H);
     launch_counters(b, g, n, d_counters_, stream_);
     launches_ += 1;
@@ -406,7 +404,6 @@ void Context::run_back(const FrameBuffers& b, uint32_t n, uint32_t iterations) {
 void Context::begin_call() {
     DH_CUDA(cudaSetDevice(device_));
     launches_ = 0;
-    retries_ = 0;
     ev_used_ = 0;
     marks_.clear();
     std::memset(stage_ms_, 0, sizeof(stage_ms_));
@@ -418,7 +415,6 @@ void Context::end_call() {
     DH_CUDA(cudaStreamSynchronize(stream_));
     for (int k = 0; k < DH_N_COUNTERS; ++k) counters_[k] = h_counters_[k];
     counters_[9] = launches_;
-    counters_[11] = retries_;
     if (timing_) {
         // marks_ are (stage that begins here, event); a stage lasts until the next mark
         for (size_t i = 0; i + 1 < marks_.size(); ++i) {
@@ -453,17 +449,10 @@ void Context::predict(const HostForest& hf, const uint16_t* depth, uint32_t w, u
         gs.has_guess |= 2u;
         for (int k = 0; k < 3; ++k) gs.rot_guess[k] = rot_guess[k];
     }
-    for (int attempt = 0;; ++attempt) {
+    {
         FrameBuffers b = buffers(d_depth_[0]);
         run_front(b, 1, &gs);
         run_back(b, 1, iterations);
-        PoolState ps;
-        DH_CUDA(cudaMemcpyAsync(&ps, d_pool_, sizeof(ps), cudaMemcpyDeviceToHost, stream_));
-        DH_CUDA(cudaStreamSynchronize(stream_));
-        if (!ps.overflow) break;
-        if (attempt >= 3) throw ModelError(DH_E_CUDA, "vote accumulator pool overflow persisted after growing");
-        ++retries_;
-        ensure_pool(ps.total_slots + ps.total_slots / 4);
     }
     DH_CUDA(cudaMemcpyAsync(out, d_results_, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
     mark(-1);
@@ -493,18 +482,11 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
         DH_CUDA(cudaHostAlloc((void**)&h_results_, sizeof(dh_result) * n, cudaHostAllocDefault));
         h_results_cap_ = n;
     }
-    if (h_pool_cap_ < n_chunks) {
-        if (h_pool_) cudaFreeHost(h_pool_);
-        h_pool_ = nullptr;
-        DH_CUDA(cudaHostAlloc((void**)&h_pool_, sizeof(PoolState) * n_chunks, cudaHostAllocDefault));
-        h_pool_cap_ = n_chunks;
-    }
     auto enqueue_chunk = [&](uint32_t c, const uint16_t* d_depth) {
         const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
         FrameBuffers b = buffers(d_depth);
         run_front(b, nc, nullptr);
         run_back(b, nc, iterations);
-        DH_CUDA(cudaMemcpyAsync(h_pool_ + c, d_pool_, sizeof(PoolState), cudaMemcpyDeviceToHost, stream_));
         DH_CUDA(cudaMemcpyAsync(h_results_ + f0, d_results_, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, stream_));
     };
     if (depth_loc != DH_DEPTH_DEVICE) ensure_staging(2);
@@ -536,29 +518,6 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
     }
     mark(-1);
     DH_CUDA(cudaStreamSynchronize(stream_));
-    // accumulator pool too small for some chunk: grow once to the largest demand and redo those
-    unsigned long long need = 0;
-    for (uint32_t c = 0; c < n_chunks; ++c)
-        if (h_pool_[c].overflow) need = std::max(need, h_pool_[c].total_slots);
-    if (need) {
-        ensure_pool(need + need / 4);
-        for (uint32_t c = 0; c < n_chunks; ++c) {
-            if (!h_pool_[c].overflow) continue;
-            ++retries_;
-            const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
-            const uint16_t* d = depth + (size_t)f0 * frame_px;
-            if (depth_loc != DH_DEPTH_DEVICE) {
-                DH_CUDA(cudaMemcpyAsync(d_depth_[0], d, (size_t)nc * frame_px * sizeof(uint16_t), cudaMemcpyHostToDevice, stream_));
-                d = d_depth_[0];
-            }
-            const bool t = timing_;
-            timing_ = false;  // retried chunks are not part of the stage breakdown
-            enqueue_chunk(c, d);
-            timing_ = t;
-            DH_CUDA(cudaStreamSynchronize(stream_));
-            if (h_pool_[c].overflow) throw ModelError(DH_E_CUDA, "vote accumulator pool overflow persisted after growing");
-        }
-    }
     end_call();
     std::memcpy(out, h_results_, sizeof(dh_result) * n);
 }
@@ -655,7 +614,7 @@ void Context::debug_seeds(uint32_t* guess_pos, uint32_t* guess_rot, int32_t* see
         if (seed_rot) seed_rot[k] = fs.seed_rot[k];
     }
 }
-void Context::debug_votes(int which, int32_t* keys, uint32_t* vals, uint64_t* n, int32_t* reach) {
+void Context::debug_votes(int which, int32_t* keys, uint32_t* vals, uint64_t* n, int32_t* box_origin, int32_t* box_dim) {
     require_debug();
     if (which < 0 || which > 1) throw ModelError(DH_E_ARG, "which must be 0 (centre) or 1 (rotation)");
     unsigned long long* d_count = nullptr;
@@ -665,17 +624,17 @@ void Context::debug_votes(int which, int32_t* keys, uint32_t* vals, uint64_t* n,
     uint32_t* d_vals = nullptr;
     FrameState fs;
     DH_CUDA(cudaMemcpy(&fs, d_fs_, sizeof(fs), cudaMemcpyDeviceToHost));
-    const size_t cap = fs.hash_cap[which];
+    const size_t cells = vote_box_cells();
     if (keys) {
-        dev_alloc(d_keys, std::max<size_t>(cap, 1) * 3);
-        dev_alloc(d_vals, std::max<size_t>(cap, 1));
+        dev_alloc(d_keys, cells * 3);
+        dev_alloc(d_vals, cells);
     }
     FrameBuffers b = buffers(d_depth_[0]);
-    launch_hash_dump(b, 0, which, d_keys, d_vals, d_count, stream_);
+    launch_box_dump(b, 0, which, d_keys, d_vals, d_count, stream_);
     DH_CUDA(cudaStreamSynchronize(stream_));
     unsigned long long cnt = 0;
     DH_CUDA(cudaMemcpy(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost));
-    if (keys) {
+    if (keys && cnt) {
         DH_CUDA(cudaMemcpy(keys, d_keys, cnt * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
         DH_CUDA(cudaMemcpy(vals, d_vals, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
@@ -683,7 +642,9 @@ void Context::debug_votes(int which, int32_t* keys, uint32_t* vals, uint64_t* n,
     dev_free(d_vals);
     dev_free(d_count);
     if (n) *n = cnt;
-    if (reach) *reach = (int32_t)last_reach_;
+    if (box_origin)
+        for (int k = 0; k < 3; ++k) box_origin[k] = fs.box_org[which][k];
+    if (box_dim) *box_dim = fs.box_valid[which] ? (int32_t)vote_box_dim() : 0;
 }
 void Context::debug_meanshift(int which, int32_t* pos, uint32_t* n_iter) {
     require_debug();

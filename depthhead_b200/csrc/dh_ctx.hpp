@@ -48,7 +48,7 @@ public:
     void debug_leaf(int32_t* leaf);
     void debug_patches(float* p3, uint8_t* gate);
     void debug_seeds(uint32_t* guess_pos, uint32_t* guess_rot, int32_t* seed_mid, int32_t* seed_rot);
-    void debug_votes(int which, int32_t* keys, uint32_t* vals, uint64_t* n, int32_t* reach);
+    void debug_votes(int which, int32_t* keys, uint32_t* vals, uint64_t* n, int32_t* box_origin, int32_t* box_dim);
     void debug_meanshift(int which, int32_t* pos, uint32_t* n_iter);
     void debug_leaf_static(const HostForest& hf, uint32_t* valtoadd, uint8_t* rot_ok, uint8_t* off_ok);
     uint32_t last_ms_flags(int which) const { return last_ms_flags_[which & 1]; }
@@ -60,7 +60,6 @@ private:
     void ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9]);
     void ensure_staging(int slots);
     void free_scratch();
-    void ensure_pool(unsigned long long slots);
     TilePlan plan_tiles(const Geometry& g) const;
     FrameBuffers buffers(const uint16_t* depth) const;
     void run_front(const FrameBuffers& b, uint32_t n, const FrameState* guess_state);
@@ -102,15 +101,15 @@ private:
     int32_t* d_leaf_ = nullptr;
     float* d_p3_ = nullptr;
     uint8_t* d_gate_ = nullptr;
-    Hit* d_hits_ = nullptr;
+    CentreHit* d_chits_ = nullptr;
+    RotHit* d_rhits_ = nullptr;
     uint32_t* d_grids_ = nullptr;
     FrameState* d_fs_ = nullptr;
     dh_result* d_results_ = nullptr;
     int32_t* d_ms_trace_ = nullptr;
-    unsigned long long* d_hash_keys_ = nullptr;
-    uint32_t* d_hash_vals_ = nullptr;
-    unsigned long long pool_capacity_ = 0;
-    PoolState* d_pool_ = nullptr;
+    uint32_t* d_boxes_ = nullptr;         // accumulator cubes, one per persistent CTA
+    uint32_t vm_ctas_ = 0;
+    uint32_t* d_work_counter_ = nullptr;
     unsigned long long* d_counters_ = nullptr;
     uint32_t* d_aux32_ = nullptr;
     uint16_t* d_aux16_ = nullptr;
@@ -122,12 +121,10 @@ private:
     unsigned long long* h_counters_ = nullptr;
     dh_result* h_results_ = nullptr;
     size_t h_results_cap_ = 0;
-    PoolState* h_pool_ = nullptr;
-    size_t h_pool_cap_ = 0;
 
     // measurement
     bool timing_ = false, debug_ = false, have_debug_ = false, debug_sync_ = false;
-    uint32_t debug_iterations_ = 0, last_reach_ = 0;
+    uint32_t debug_iterations_ = 0;
     uint32_t last_ms_flags_[2] = {0, 0};
     std::vector<cudaEvent_t> timing_events_;
     size_t ev_used_ = 0;
@@ -135,7 +132,7 @@ private:
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> copy_marks_;
     float stage_ms_[DH_N_STAGES];
     uint64_t counters_[DH_N_COUNTERS];
-    uint64_t launches_ = 0, retries_ = 0;
+    uint64_t launches_ = 0;
 };
 
 }  // namespace dh

@@ -298,6 +298,12 @@ HostForest* flatten_forest(const RawForest& raw) {
                 rec.r[k * 4 + 3] = (uint8_t)y1;
             }
             rec.threshold = raw.threshold[(size_t)(n0 + old)];
+            {
+                const uint32_t c1 = (uint32_t)(rec.r[2] - rec.r[0]) * (uint32_t)(rec.r[3] - rec.r[1]);
+                const uint32_t c2 = (uint32_t)(rec.r[6] - rec.r[4]) * (uint32_t)(rec.r[7] - rec.r[5]);
+                const double dd = (double)((uint64_t)(c1 ? c1 : 1u) * (uint64_t)(c2 ? c2 : 1u));  // exact (< 2^32)
+                rec.thr_scaled = rec.threshold * dd;
+            }
             for (int b = 0; b < 2; ++b) {
                 const int32_t c = raw.child[(size_t)(n0 + old) * 2 + b];
                 rec.child[b] = c >= 0 ? newidx[c] : ~(int32_t)(l0 + (int64_t)(~c));

@@ -4,12 +4,12 @@
 //   K1  sat_rows / sat_cols      u16 depth -> u32 summed-area table (wrap-around exact, see below)
 //   K2  traverse_kernel          TMA-staged SAT tile in shared memory; one thread per patch x tree
 //                                walks root->leaf (houghforest.rs:185-193, types.rs:317-339)
-//   K3a gate_kernel              ordered f64 prob sum, 0.7 gate, back-projection, hit list
+//   K3  gate_kernel              ordered f64 prob sum, 0.7 gate, back-projection, hit lists
 //                                (prediction.rs:551-554,582-595)
-//   K3b coarse_vote_kernel       coarse seed grids + arg-max seeds (prediction.rs:601-747)
-//   K4a plan/clear/insert        per-frame open-addressing hash accumulators = SparseArray3D<u32>
-//                                (meanshift.rs:14-68), restricted to the mean-shift reach of the seed
-//   K4b meanshift_kernel         meanshift.rs:328-407 in reference accumulation order
+//   K4  vote_meanshift_kernel    persistent, one work item per (frame, accumulator): coarse seed
+//                                grid + arg-max seed (prediction.rs:601-752), dense local cube of
+//                                the SparseArray3D<u32> accumulator (meanshift.rs:14-68), mean-shift
+//                                in reference accumulation order (meanshift.rs:328-407)
 //   K5  leaf_gate_kernel         estimate_mean_cov traces + valtoadd per leaf, once per model
 //                                (meancov_estimation.rs:359-378, prediction.rs:594-600,643)
 //
@@ -29,9 +29,6 @@
 namespace dh {
 
 namespace dev {
-
-constexpr unsigned long long kEmptyKey = ~0ull;
-constexpr long long kKeyBias = 1ll << 20;
 
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,48 +65,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdull;
-    k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ull;
-    k ^= k >> 33;
-    return k;
-}
-
-// Key of an accumulator cell relative to the mean-shift seed; false if outside the stored reach.
-__device__ __forceinline__ bool make_key(int x, int y, int z, const int32_t* seed, long long reach,
-                                         unsigned long long* key) {
-    const long long dx = (long long)x - seed[0], dy = (long long)y - seed[1], dz = (long long)z - seed[2];
-    if (dx < -reach || dx > reach || dy < -reach || dy > reach || dz < -reach || dz > reach) return false;
-    *key = (unsigned long long)(dx + kKeyBias) | ((unsigned long long)(dy + kKeyBias) << 21) |
-           ((unsigned long long)(dz + kKeyBias) << 42);
-    return true;
-}
-
-__device__ __forceinline__ void hash_add(unsigned long long* keys, uint32_t* vals, uint32_t cap,
-                                         unsigned long long key, uint32_t w) {
-    uint32_t slot = (uint32_t)mix64(key) & (cap - 1);
-    while (true) {
-        const unsigned long long prev = atomicCAS(&keys[slot], kEmptyKey, key);
-        if (prev == kEmptyKey || prev == key) {
-            atomicAdd(&vals[slot], w);
-            return;
-        }
-        slot = (slot + 1) & (cap - 1);
-    }
-}
-__device__ __forceinline__ uint32_t hash_get(const unsigned long long* keys, const uint32_t* vals, uint32_t cap,
-                                             unsigned long long key) {
-    uint32_t slot = (uint32_t)mix64(key) & (cap - 1);
-    while (true) {
-        const unsigned long long k = keys[slot];
-        if (k == key) return vals[slot];
-        if (k == kEmptyKey) return 0u;
-        slot = (slot + 1) & (cap - 1);
-    }
 }
 
 // IntrinsicMatrix::img_to_space_coord (types.rs:432-445) with Mat3*Vec3 of
@@ -305,19 +260,32 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
         const uint32_t* o = tile + ly * g.stride * tp.tw + lx * g.stride + dx;
         int32_t node = __ldg(roots + t);
         while (node >= 0) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(nodes + node));
-            const int2 ch = __ldg(reinterpret_cast<const int2*>(nodes + node) + 2);
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(nodes + node));      // rects, threshold
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(nodes + node) + 1);  // children, threshold*c1*c2
             // SubImage::average_value_in_rect (types.rs:317-339) via four SAT taps per rectangle
             const uint32_t ax0 = a.x & 0xffu, ay0 = (a.x >> 8) & 0xffu, ax1 = (a.x >> 16) & 0xffu, ay1 = a.x >> 24;
             const uint32_t bx0 = a.y & 0xffu, by0 = (a.y >> 8) & 0xffu, bx1 = (a.y >> 16) & 0xffu, by1 = a.y >> 24;
             const uint32_t s1 = o[ay1 * tp.tw + ax1] - o[ay0 * tp.tw + ax1] - o[ay1 * tp.tw + ax0] + o[ay0 * tp.tw + ax0];
             const uint32_t s2 = o[by1 * tp.tw + bx1] - o[by0 * tp.tw + bx1] - o[by1 * tp.tw + bx0] + o[by0 * tp.tw + bx0];
             const uint32_t c1 = (ax1 - ax0) * (ay1 - ay0), c2 = (bx1 - bx0) * (by1 - by0);
-            const double avg1 = c1 ? __ddiv_rn(__uint2double_rn(s1), __uint2double_rn(c1)) : 0.0;
-            const double avg2 = c2 ? __ddiv_rn(__uint2double_rn(s2), __uint2double_rn(c2)) : 0.0;
-            const double thr = __hiloint2double((int)a.w, (int)a.z);
-            // HoughTreeFunctions::binarize (houghforest.rs:185-193)
-            node = (__dsub_rn(avg1, avg2) > thr) ? ch.y : ch.x;
+            // HoughTreeFunctions::binarize (houghforest.rs:185-193): avg1 - avg2 > threshold with
+            // avg = sum as f64 / count as f64.  Filtered exact predicate: the real number
+            // avg1 - avg2 is N/D with N = s1*c2 - s2*c1, D = c1*c2 (exact in i64); the reference's
+            // three roundings move it by < 3e-11, i.e. < 0.13 in units of 1/D, so whenever
+            // |N - threshold*D| > 2 the sign of N - threshold*D IS the reference's answer.
+            // Only near-ties (and NaN thresholds) take the IEEE-division path below.
+            const uint32_t d1 = c1 ? c1 : 1u, d2 = c2 ? c2 : 1u;  // empty rect: sum 0, avg 0.0 (types.rs:335-337)
+            const long long N = (long long)((unsigned long long)s1 * d2) - (long long)((unsigned long long)s2 * d1);
+            const double diff = __dsub_rn(__ll2double_rn(N), __hiloint2double((int)b.w, (int)b.z));
+            bool bit;
+            if (fabs(diff) > 2.0) {
+                bit = diff > 0.0;
+            } else {
+                const double avg1 = c1 ? __ddiv_rn(__uint2double_rn(s1), __uint2double_rn(c1)) : 0.0;
+                const double avg2 = c2 ? __ddiv_rn(__uint2double_rn(s2), __uint2double_rn(c2)) : 0.0;
+                bit = __dsub_rn(avg1, avg2) > __hiloint2double((int)a.w, (int)a.z);
+            }
+            node = bit ? (int)b.y : (int)b.x;
             ++visits;
         }
         const uint32_t gp = (py0 + ly) * g.npx + (px0 + lx);
@@ -336,7 +304,11 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
     }
 }
 
-// ================================================================ K3a: patch gate + hit list
+// ================================================================ K3: patch gate + hit lists
+// One thread per patch: ordered f64 probability sum and the 0.7 gate (prediction.rs:582-584), the
+// back-projected centre (prediction.rs:551-554), and one record per voting patch x tree pair in
+// two compact per-frame lists (centre votes / rotation votes).  Everything that is constant per
+// leaf (valtoadd, spread gates) was precomputed by leaf_gate_kernel.
 __global__ void __launch_bounds__(256) gate_kernel(FrameBuffers b, Geometry g, const double* __restrict__ leaf_prob,
                                                    const LeafInfo* __restrict__ leaf_info) {
     const uint32_t frame = blockIdx.y;
@@ -347,7 +319,7 @@ __global__ void __launch_bounds__(256) gate_kernel(FrameBuffers b, Geometry g, c
     const uint32_t lane = threadIdx.x & 31u;
 
     bool gate = false;
-    uint32_t cnt = 0;
+    uint32_t cnt_c = 0, cnt_r = 0;
     unsigned long long nmid = 0, nrot = 0;
     float p3[3] = {0.f, 0.f, 0.f};
     if (p < g.P) {
@@ -369,49 +341,70 @@ __global__ void __launch_bounds__(256) gate_kernel(FrameBuffers b, Geometry g, c
                 const int32_t L = leaf_f[(size_t)t * g.P + p];
                 if (!(__ldg(leaf_prob + L) > 0.0)) continue;  // prediction.rs:590
                 const LeafInfo li = leaf_info[L];
-                if (li.valtoadd == 0u || (li.flags & (kLeafRotOk | kLeafOffOk)) == 0u) continue;
-                ++cnt;
-                if (li.flags & kLeafOffOk) nmid += li.n_votes;
-                if (li.flags & kLeafRotOk) nrot += li.n_votes;
+                if (li.valtoadd == 0u) continue;  // zero-weight votes never change a sum
+                if (li.flags & kLeafOffOk) { ++cnt_c; nmid += li.n_votes; }
+                if (li.flags & kLeafRotOk) { ++cnt_r; nrot += li.n_votes; }
             }
         }
         if (b.gate) b.gate[(size_t)frame * g.P + p] = gate ? 1 : 0;
     }
-    // warp-aggregated append to the frame's hit list
-    uint32_t incl = cnt;
+    // warp-aggregated append to the frame's two hit lists
+    uint32_t incl_c = cnt_c, incl_r = cnt_r;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (uint32_t)d) incl += n;
+        const uint32_t nc = __shfl_up_sync(0xffffffffu, incl_c, d), nr = __shfl_up_sync(0xffffffffu, incl_r, d);
+        if (lane >= (uint32_t)d) { incl_c += nc; incl_r += nr; }
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t tot_c = __shfl_sync(0xffffffffu, incl_c, 31), tot_r = __shfl_sync(0xffffffffu, incl_r, 31);
     const uint32_t ngate = __popc(__ballot_sync(0xffffffffu, gate));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         nmid += __shfl_xor_sync(0xffffffffu, nmid, d);
         nrot += __shfl_xor_sync(0xffffffffu, nrot, d);
     }
-    uint32_t basei = 0;
+    uint32_t base_c = 0, base_r = 0;
     if (lane == 0) {
-        if (total) basei = atomicAdd(&fs->n_hits, total);
+        if (tot_c) base_c = atomicAdd(&fs->n_chits, tot_c);
+        if (tot_r) base_r = atomicAdd(&fs->n_rhits, tot_r);
         if (ngate) atomicAdd(&fs->n_gate, ngate);
         if (nmid) atomicAdd(&fs->n_mid_votes, nmid);
         if (nrot) atomicAdd(&fs->n_rot_votes, nrot);
     }
-    basei = __shfl_sync(0xffffffffu, basei, 0);
-    if (cnt) {
-        Hit* out = b.hits + (size_t)frame * g.P * T + basei + (incl - cnt);
+    base_c = __shfl_sync(0xffffffffu, base_c, 0);
+    base_r = __shfl_sync(0xffffffffu, base_r, 0);
+    if (cnt_c | cnt_r) {
+        CentreHit* oc = b.chits + (size_t)frame * g.P * T + base_c + (incl_c - cnt_c);
+        RotHit* orr = b.rhits + (size_t)frame * g.P * T + base_r + (incl_r - cnt_r);
         for (int t = 0; t < T; ++t) {
             const int32_t L = leaf_f[(size_t)t * g.P + p];
             if (!(__ldg(leaf_prob + L) > 0.0)) continue;
             const LeafInfo li = leaf_info[L];
-            if (li.valtoadd == 0u || (li.flags & (kLeafRotOk | kLeafOffOk)) == 0u) continue;
-            *out++ = Hit{p, (uint32_t)L};
+            if (li.valtoadd == 0u) continue;
+            if (li.flags & kLeafOffOk) *oc++ = CentreHit{{p3[0], p3[1], p3[2]}, li.vote_start, li.n_votes, li.valtoadd};
+            if (li.flags & kLeafRotOk) *orr++ = RotHit{li.vote_start, li.n_votes, li.valtoadd, 0u};
         }
     }
 }
 
-// ================================================================ K3b: coarse grids + seeds
+// ================================================================ K4: votes + seeds + mean-shift
+// ONE persistent kernel does everything after the gate.  A work item is one accumulator of one
+// frame (centre or rotation — they are independent in the reference too, prediction.rs:469-472);
+// CTAs pull items from an atomic counter.  Per item:
+//   1. coarse pass   expand the frame's hits into the 20x20 (centre) or 20^3 (rotation) seed grid
+//                    in shared memory, arg-max -> seed            (prediction.rs:601-752, 437-460)
+//   2. box build     SparseArray3D<u32> (meanshift.rs:14-68) restricted to a dense kBox^3 cube of
+//                    cells around the current position, in an L2-resident per-CTA workspace:
+//                    plain u32 atomicAdd per in-box vote, no hashing, votes outside never touch memory
+//   3. mean-shift    meanshift.rs:328-407 in reference accumulation order on that cube.
+// A round moves the position by at most 10 cells, the cube leaves 14 cells of margin around the
+// 20^3 window; if the window would leave the cube, the cube is rebuilt around the current position
+// (counted in FrameState::rebuilds).  Results are therefore exactly those of the unbounded map.
+constexpr int kBox = 48;                      // cells per axis of the dense cube
+constexpr int kBoxCells = kBox * kBox * kBox; // 110 592 cells = 432 KB
+constexpr int kVmThreads = 512;
+constexpr int kVmWarps = kVmThreads / 32;
+constexpr int kMsHistory = 64;
+
 struct Best {
     uint32_t val, idx;
 };
@@ -440,324 +433,331 @@ __device__ Best block_argmax(const uint32_t* cells, int n, Best* s_red) {
     return r;
 }
 
-template <int G>
-__global__ void __launch_bounds__(256) coarse_vote_kernel(FrameBuffers b, Geometry g, ForestDev f) {
-    __shared__ uint32_t s_pos[kPosGridCells];
-    __shared__ uint32_t s_rot[kRotGridCells];
-    __shared__ Best s_red[8];
-    __shared__ unsigned long long s_sum[8];
-    __shared__ uint32_t s_cnt[8];
-    __shared__ uint32_t s_last;
-    const uint32_t frame = blockIdx.y;
-    FrameState* fs = b.fs + frame;
-    for (int i = threadIdx.x; i < kPosGridCells; i += blockDim.x) s_pos[i] = 0;
-    for (int i = threadIdx.x; i < kRotGridCells; i += blockDim.x) s_rot[i] = 0;
-    __syncthreads();
-
-    const uint32_t n_hits = fs->n_hits;
-    const Hit* hits = b.hits + (size_t)frame * g.P * g.n_trees;
-    const float* p3f = b.p3 + (size_t)frame * g.P * 3;
-    const uint32_t groups_per_block = blockDim.x / G;
+// Visits every centre vote of the frame: fn(nx, ny, nz, weight) with np = p3 - offset
+// (prediction.rs:647); votes with np.z < 0 are skipped (prediction.rs:650).  G lanes share a hit.
+template <int G, typename F>
+__device__ __forceinline__ void for_each_centre_vote(const CentreHit* __restrict__ hits, uint32_t n_hits,
+                                                     const float* __restrict__ offsets, F&& fn) {
     const uint32_t sub = threadIdx.x % G;
-    for (uint32_t hi = blockIdx.x * groups_per_block + threadIdx.x / G; hi < n_hits; hi += gridDim.x * groups_per_block) {
-        const Hit hit = hits[hi];
-        const LeafInfo li = f.leaf_info[hit.leaf];
-        const float px = p3f[hit.patch * 3 + 0], py = p3f[hit.patch * 3 + 1], pz = p3f[hit.patch * 3 + 2];
-        for (uint32_t k = sub; k < li.n_votes; k += G) {
-            const uint32_t v = li.vote_start + k;
-            if (li.flags & kLeafRotOk) {  // prediction.rs:629-636
-                const uint32_t bins = __ldg(f.rot_bins + v);
-                const uint32_t r1 = bins & 0xffu, r2 = (bins >> 8) & 0xffu, r3 = (bins >> 16) & 0xffu;
-                const uint32_t q1 = r1 * kGuessGridParts / kRotGridParts, q2 = r2 * kGuessGridParts / kRotGridParts,
-                               q3 = r3 * kGuessGridParts / kRotGridParts;
-                atomicAdd(&s_rot[q3 * 400 + q2 * 20 + q1], li.valtoadd);
-            }
-            if (li.flags & kLeafOffOk) {  // prediction.rs:644-677
-                float np[3];
-                np[0] = __fsub_rn(px, __ldg(f.offsets + (size_t)v * 3 + 0));
-                np[1] = __fsub_rn(py, __ldg(f.offsets + (size_t)v * 3 + 1));
-                np[2] = __fsub_rn(pz, __ldg(f.offsets + (size_t)v * 3 + 2));
-                if (np[2] < 0.0f) continue;
-                float p2[2];
-                space_to_img(g.K, np, p2);
-                // max!/min! macros (prediction.rs:19-25): plain comparisons, NaN -> 0.0
-                const float mx = (p2[0] > 0.0f) ? p2[0] : 0.0f;
-                const float x2d = (mx < (float)(g.w - 1)) ? mx : (float)(g.w - 1);
-                const float my = (p2[1] > 0.0f) ? p2[1] : 0.0f;
-                const float y2d = (my < (float)(g.h - 1)) ? my : (float)(g.h - 1);
-                const uint32_t cx = __float2uint_rz(x2d) * kGuessGridParts / g.w;
-                const uint32_t cy = __float2uint_rz(y2d) * kGuessGridParts / g.h;
-                atomicAdd(&s_pos[cy * kGuessGridParts + cx], li.valtoadd);
-            }
+    for (uint32_t hi = threadIdx.x / G; hi < n_hits; hi += kVmThreads / G) {
+        const CentreHit h = hits[hi];
+        for (uint32_t k = sub; k < h.n_votes; k += G) {
+            const float* o = offsets + (size_t)(h.vote_start + k) * 3;
+            const float nx = __fsub_rn(h.p3[0], __ldg(o + 0)), ny = __fsub_rn(h.p3[1], __ldg(o + 1)),
+                        nz = __fsub_rn(h.p3[2], __ldg(o + 2));
+            if (nz < 0.0f) continue;
+            fn(nx, ny, nz, h.valtoadd);
         }
     }
-    __syncthreads();
-    uint32_t* gpos = b.grids + (size_t)frame * (kPosGridCells + kRotGridCells);
-    uint32_t* grot = gpos + kPosGridCells;
-    for (int i = threadIdx.x; i < kPosGridCells; i += blockDim.x)
-        if (s_pos[i]) atomicAdd(&gpos[i], s_pos[i]);
-    for (int i = threadIdx.x; i < kRotGridCells; i += blockDim.x)
-        if (s_rot[i]) atomicAdd(&grot[i], s_rot[i]);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&fs->ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-
-    // ---- last block of the frame: arg-max seeds (prediction.rs:694-752, 437-460)
-    for (int i = threadIdx.x; i < kPosGridCells; i += blockDim.x) s_pos[i] = __ldcg(gpos + i);
-    for (int i = threadIdx.x; i < kRotGridCells; i += blockDim.x) s_rot[i] = __ldcg(grot + i);
-    __syncthreads();
-    const Best bp = block_argmax(s_pos, kPosGridCells, s_red);
-    const Best br = block_argmax(s_rot, kRotGridCells, s_red);
-    const uint32_t gpw = g.w / kGuessGridParts, gph = g.h / kGuessGridParts;  // :706-707
-    const uint32_t cgx = bp.idx % kGuessGridParts, cgy = bp.idx / kGuessGridParts;
-    unsigned long long zs = 0;
-    uint32_t zc = 0;
-    const uint16_t* img = b.depth + (size_t)frame * g.h * g.w;
-    for (uint32_t i = threadIdx.x; i < gpw * gph; i += blockDim.x) {
-        const uint32_t xx = gpw * cgx + i % gpw, yy = gph * cgy + i / gpw;
-        const uint32_t v = img[(size_t)yy * g.w + xx];
-        if (v > 0) {
-            zs += v;
-            zc += 1;
-        }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        zs += __shfl_xor_sync(0xffffffffu, zs, d);
-        zc += __shfl_xor_sync(0xffffffffu, zc, d);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        s_sum[threadIdx.x >> 5] = zs;
-        s_cnt[threadIdx.x >> 5] = zc;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        zs = 0;
-        zc = 0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
-            zs += s_sum[i];
-            zc += s_cnt[i];
-        }
-        const float meanz = zc > 0 ? (float)__ddiv_rn((double)zs, (double)zc) : 0.0f;  // :721-725
-        const float mxf = __fmul_rn(__fadd_rn((float)cgx, 0.5f), (float)gpw);
-        const float myf = __fmul_rn(__fadd_rn((float)cgy, 0.5f), (float)gph);
-        float m3[3];
-        img_to_space(g.Kinv, mxf, myf, meanz, m3);
-        int32_t sm[3] = {__float2int_rz(m3[0]), __float2int_rz(m3[1]), __float2int_rz(m3[2])};  // :750
-        if (fs->has_guess & 1u)  // :437-441
-            for (int k = 0; k < 3; ++k) sm[k] = __float2int_rz(fs->midp_guess[k]);
-        const uint32_t rc[3] = {br.idx % 20u, (br.idx % 400u) / 20u, br.idx / 400u};
-        for (int k = 0; k < 3; ++k) {
-            // :745-747 then :458-460
-            double deg = __ddiv_rn(__dadd_rn(__dmul_rn((double)rc[k], 360.0), 180.0), (double)kGuessGridParts);
-            if (fs->has_guess & 2u)  // :448-450
-                deg = __dadd_rn(__ddiv_rn(__dmul_rn(fs->rot_guess[k], 180.0), 3.14159), 180.0);
-            fs->seed_rot[k] = __double2int_rz(__ddiv_rn(__dmul_rn(deg, (double)kRotGridParts), 360.0));
-            fs->seed_mid[k] = sm[k];
+}
+// Visits every rotation vote of the frame: fn(r1, r2, r3, weight), bins precomputed per vote.
+template <int G, typename F>
+__device__ __forceinline__ void for_each_rot_vote(const RotHit* __restrict__ hits, uint32_t n_hits,
+                                                  const uint32_t* __restrict__ rot_bins, F&& fn) {
+    const uint32_t sub = threadIdx.x % G;
+    for (uint32_t hi = threadIdx.x / G; hi < n_hits; hi += kVmThreads / G) {
+        const RotHit h = hits[hi];
+        for (uint32_t k = sub; k < h.n_votes; k += G) {
+            const uint32_t bins = __ldg(rot_bins + h.vote_start + k);
+            fn((int)(bins & 0xffu), (int)((bins >> 8) & 0xffu), (int)((bins >> 16) & 0xffu), h.valtoadd);
         }
     }
 }
 
-// ================================================================ K4a: hash accumulators
-__device__ __forceinline__ unsigned long long pow2ceil(unsigned long long v) {
-    unsigned long long c = 64;
-    while (c < v) c <<= 1;
-    return c;
-}
-__global__ void plan_hash_kernel(FrameState* fs, PoolState* pool, uint32_t n_frames, unsigned long long capacity) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    unsigned long long off = 0;
-    for (uint32_t i = 0; i < n_frames; ++i) {
-        const unsigned long long nm = fs[i].n_mid_votes, nr = fs[i].n_rot_votes;
-        unsigned long long cm = nm ? pow2ceil(2 * nm) : 0;
-        unsigned long long cr = nr ? pow2ceil(2 * nr) : 0;
-        if (cr > (1ull << 22)) cr = 1ull << 22;  // at most 120^3 distinct rotation cells
-        if (cm > (1ull << 31)) cm = 1ull << 31;
-        fs[i].hash_off[0] = off;
-        fs[i].hash_cap[0] = (uint32_t)cm;
-        off += cm;
-        fs[i].hash_off[1] = off;
-        fs[i].hash_cap[1] = (uint32_t)cr;
-        off += cr;
-    }
-    pool->total_slots = off;
-    pool->capacity = capacity;
-    if (off > capacity) {
-        pool->overflow = 1;
-        for (uint32_t i = 0; i < n_frames; ++i) fs[i].hash_cap[0] = fs[i].hash_cap[1] = 0;
-    } else {
-        pool->overflow = 0;
-    }
-}
-__global__ void __launch_bounds__(256) hash_clear_kernel(unsigned long long* keys, uint32_t* vals, const PoolState* pool) {
-    const unsigned long long n = pool->overflow ? 0ull : pool->total_slots;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        keys[i] = kEmptyKey;
-        vals[i] = 0u;
-    }
+__device__ __forceinline__ bool in_box(int x, int y, int z, const int32_t* org, uint32_t* idx) {
+    const long long rx = (long long)x - org[0], ry = (long long)y - org[1], rz = (long long)z - org[2];
+    if (rx < 0 || rx >= kBox || ry < 0 || ry >= kBox || rz < 0 || rz >= kBox) return false;
+    *idx = ((uint32_t)rz * kBox + (uint32_t)ry) * kBox + (uint32_t)rx;
+    return true;
 }
 
 template <int G>
-__global__ void __launch_bounds__(256) insert_kernel(FrameBuffers b, Geometry g, ForestDev f, uint32_t reach) {
-    const uint32_t frame = blockIdx.y;
-    const FrameState* fs = b.fs + frame;
-    const uint32_t cap_mid = fs->hash_cap[0], cap_rot = fs->hash_cap[1];
-    unsigned long long* kmid = b.hash_keys + fs->hash_off[0];
-    uint32_t* vmid = b.hash_vals + fs->hash_off[0];
-    unsigned long long* krot = b.hash_keys + fs->hash_off[1];
-    uint32_t* vrot = b.hash_vals + fs->hash_off[1];
-    int32_t seed_mid[3] = {fs->seed_mid[0], fs->seed_mid[1], fs->seed_mid[2]};
-    int32_t seed_rot[3] = {fs->seed_rot[0], fs->seed_rot[1], fs->seed_rot[2]};
-    const uint32_t n_hits = fs->n_hits;
-    const Hit* hits = b.hits + (size_t)frame * g.P * g.n_trees;
-    const float* p3f = b.p3 + (size_t)frame * g.P * 3;
-    const uint32_t groups_per_block = blockDim.x / G;
-    const uint32_t sub = threadIdx.x % G;
-    for (uint32_t hi = blockIdx.x * groups_per_block + threadIdx.x / G; hi < n_hits; hi += gridDim.x * groups_per_block) {
-        const Hit hit = hits[hi];
-        const LeafInfo li = f.leaf_info[hit.leaf];
-        const float px = p3f[hit.patch * 3 + 0], py = p3f[hit.patch * 3 + 1], pz = p3f[hit.patch * 3 + 2];
-        for (uint32_t k = sub; k < li.n_votes; k += G) {
-            const uint32_t v = li.vote_start + k;
-            unsigned long long key;
-            if ((li.flags & kLeafRotOk) && cap_rot) {  // rot[(r1,r2,r3)] += valtoadd, prediction.rs:635
-                const uint32_t bins = __ldg(f.rot_bins + v);
-                if (make_key((int)(bins & 0xffu), (int)((bins >> 8) & 0xffu), (int)((bins >> 16) & 0xffu), seed_rot,
-                             reach, &key))
-                    hash_add(krot, vrot, cap_rot, key, li.valtoadd);
-            }
-            if ((li.flags & kLeafOffOk) && cap_mid) {  // mid[(x,y,z)] += valtoadd, prediction.rs:647-667
-                const float nx = __fsub_rn(px, __ldg(f.offsets + (size_t)v * 3 + 0));
-                const float ny = __fsub_rn(py, __ldg(f.offsets + (size_t)v * 3 + 1));
-                const float nz = __fsub_rn(pz, __ldg(f.offsets + (size_t)v * 3 + 2));
-                if (nz < 0.0f) continue;
-                // z3d / ZSCALEFACTOR(=1) is exact
-                if (make_key(__float2int_rz(nx), __float2int_rz(ny), __float2int_rz(nz), seed_mid, reach, &key))
-                    hash_add(kmid, vmid, cap_mid, key, li.valtoadd);
-            }
-        }
-    }
-}
-
-// ================================================================ K4b: mean-shift
-// MeanShift::meanshift (meanshift.rs:328-407) for SparseArray3D<u32>: window offsets -10..+9 per
-// axis, x outermost / z innermost, f32 numerators and denominator accumulated SEQUENTIALLY in that
-// order (only non-zero cells contribute; adding them in order is all that matters), position
-// truncated every iteration, exactly `iterations` rounds unless the denominator is exactly 0.
-// A round that leaves the position unchanged makes every later round identical, so the loop
-// stops there (result-neutral).
-constexpr int kMsThreads = 256;
-__global__ void __launch_bounds__(kMsThreads) meanshift_kernel(FrameBuffers b, const float* __restrict__ kern,
-                                                               uint32_t iterations, uint32_t reach) {
-    __shared__ uint32_t s_f[kKernelCells];         // cell factor, overwritten by its f32 weight
-    __shared__ uint32_t s_mask[kKernelCells / 32]; // non-zero cells, bit j of word c = ord c*32+j
-    __shared__ int32_t s_pos[3];
-    __shared__ uint32_t s_flags, s_done;
-    const uint32_t frame = blockIdx.y, which = blockIdx.x;
-    FrameState* fs = b.fs + frame;
-    const uint32_t cap = fs->hash_cap[which];
-    const unsigned long long* keys = b.hash_keys + fs->hash_off[which];
-    const uint32_t* vals = b.hash_vals + fs->hash_off[which];
-    const int32_t* seedp = which == 0 ? fs->seed_mid : fs->seed_rot;
-    const int32_t seed[3] = {seedp[0], seedp[1], seedp[2]};
+__global__ void __launch_bounds__(kVmThreads, 3) vote_meanshift_kernel(FrameBuffers b, Geometry g, ForestDev f,
+                                                                        uint32_t n_frames, uint32_t iterations,
+                                                                        uint32_t static_items) {
+    __shared__ uint32_t s_buf[kRotGridCells];         // seed grid, later the window weights (f32 bits)
+    __shared__ uint32_t s_mask[kKernelCells / 32];    // non-zero window cells, bit j of word c = ord c*32+j
+    __shared__ int32_t s_hist[kMsHistory + 1][3];     // positions P_0 (seed), P_1, ... for cycle detection
+    __shared__ Best s_red[kVmWarps];
+    __shared__ unsigned long long s_sum[kVmWarps];
+    __shared__ uint32_t s_cnt[kVmWarps];
+    __shared__ int32_t s_pos[3], s_org[3];
+    __shared__ uint32_t s_flags, s_done, s_item;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    constexpr int kChunks = kKernelCells / 32;  // 250
-    if (tid == 0) {
-        s_pos[0] = seed[0]; s_pos[1] = seed[1]; s_pos[2] = seed[2];
-        s_flags = 0; s_done = 0;
-    }
-    __syncthreads();
-    uint32_t it = 0;
-    for (; it < iterations; ++it) {
-        const int32_t pos[3] = {s_pos[0], s_pos[1], s_pos[2]};
-        // 1. gather the 20^3 window; ord enumerates the cells in the reference loop order
-        //    (x outermost, z innermost).  Each warp owns whole 32-cell chunks so that the ballot
-        //    below yields the chunk's non-zero mask; non-zero cells are replaced by their weight
-        //    kernel[(x+10, y+10, z+10)] * (factor as f32)  (meanshift.rs:370-377; dense kernel
-        //    index z*400 + y*20 + x, meanshift.rs:78-88).
-        for (uint32_t c = warp; c < (uint32_t)kChunks; c += kMsThreads / 32) {
-            const uint32_t ord = c * 32 + lane;
-            const uint32_t xo = ord / 400u, yo = (ord / 20u) % 20u, zo = ord % 20u;
-            const int ax = (int)((uint32_t)pos[0] + (uint32_t)((int)xo - 10)),
-                      ay = (int)((uint32_t)pos[1] + (uint32_t)((int)yo - 10)),
-                      az = (int)((uint32_t)pos[2] + (uint32_t)((int)zo - 10));
-            uint32_t fct = 0;
-            unsigned long long key;
-            if (make_key(ax, ay, az, seed, reach, &key)) {
-                if (cap) fct = hash_get(keys, vals, cap, key);
-            } else {
-                atomicOr(&s_flags, 2u);  // probe outside the stored reach (never expected)
+    uint32_t* box = b.boxes + (size_t)blockIdx.x * kBoxCells;
+    constexpr uint32_t kChunks = kKernelCells / 32;  // 250
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = static_items ? blockIdx.x : atomicAdd(b.work_counter, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= 2u * n_frames) break;
+        const uint32_t frame = item >> 1, which = item & 1u;
+        FrameState* fs = b.fs + frame;
+        const size_t hit_base = (size_t)frame * g.P * g.n_trees;
+        const CentreHit* chits = b.chits + hit_base;
+        const RotHit* rhits = b.rhits + hit_base;
+        const uint32_t n_hits = which == 0 ? fs->n_chits : fs->n_rhits;
+        const bool guessed = (fs->has_guess >> which) & 1u;
+
+        // ------------------------------------------------------------ 1. seed
+        if (which == 0) {
+            int32_t sm[3] = {0, 0, 0};
+            if (!guessed || b.debug) {
+                // 20x20 grid, one private copy per warp to keep the shared atomics uncontended
+                for (int i = tid; i < kVmWarps * kPosGridCells; i += kVmThreads) s_buf[i] = 0;
+                __syncthreads();
+                uint32_t* mine = s_buf + warp * kPosGridCells;
+                for_each_centre_vote<G>(chits, n_hits, f.offsets, [&](float nx, float ny, float nz, uint32_t wgt) {
+                    const float np[3] = {nx, ny, nz};
+                    float p2[2];
+                    space_to_img(g.K, np, p2);  // prediction.rs:661
+                    // max!/min! macros (prediction.rs:19-25): plain comparisons, NaN -> 0.0
+                    const float mx = (p2[0] > 0.0f) ? p2[0] : 0.0f;
+                    const float x2d = (mx < (float)(g.w - 1)) ? mx : (float)(g.w - 1);
+                    const float my = (p2[1] > 0.0f) ? p2[1] : 0.0f;
+                    const float y2d = (my < (float)(g.h - 1)) ? my : (float)(g.h - 1);
+                    const uint32_t cx = __float2uint_rz(x2d) * kGuessGridParts / g.w;  // :671-674
+                    const uint32_t cy = __float2uint_rz(y2d) * kGuessGridParts / g.h;
+                    atomicAdd(&mine[cy * kGuessGridParts + cx], wgt);
+                });
+                __syncthreads();
+                for (int i = tid; i < kPosGridCells; i += kVmThreads) {
+                    uint32_t v = 0;
+                    for (int w2 = 0; w2 < kVmWarps; ++w2) v += s_buf[w2 * kPosGridCells + i];
+                    s_buf[kVmWarps * kPosGridCells + i] = v;  // 16*400 + 400 <= 8000
+                }
+                __syncthreads();
+                uint32_t* gridp = s_buf + kVmWarps * kPosGridCells;
+                uint32_t* gout = b.grids + (size_t)frame * (kPosGridCells + kRotGridCells);
+                for (int i = tid; i < kPosGridCells; i += kVmThreads) gout[i] = gridp[i];
+                const Best bp = block_argmax(gridp, kPosGridCells, s_red);
+                // z = mean of the non-zero depth in the winning grid part (prediction.rs:706-725)
+                const uint32_t gpw = g.w / kGuessGridParts, gph = g.h / kGuessGridParts;
+                const uint32_t cgx = bp.idx % kGuessGridParts, cgy = bp.idx / kGuessGridParts;
+                unsigned long long zs = 0;
+                uint32_t zc = 0;
+                const uint16_t* img = b.depth + (size_t)frame * g.h * g.w;
+                for (uint32_t i = tid; i < gpw * gph; i += kVmThreads) {
+                    const uint32_t v = img[(size_t)(gph * cgy + i / gpw) * g.w + gpw * cgx + i % gpw];
+                    if (v > 0) {
+                        zs += v;
+                        zc += 1;
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    zs += __shfl_xor_sync(0xffffffffu, zs, d);
+                    zc += __shfl_xor_sync(0xffffffffu, zc, d);
+                }
+                if (lane == 0) {
+                    s_sum[warp] = zs;
+                    s_cnt[warp] = zc;
+                }
+                __syncthreads();
+                zs = 0;
+                zc = 0;
+                for (int i = 0; i < kVmWarps; ++i) {
+                    zs += s_sum[i];
+                    zc += s_cnt[i];
+                }
+                const float meanz = zc > 0 ? (float)__ddiv_rn((double)zs, (double)zc) : 0.0f;
+                const float mxf = __fmul_rn(__fadd_rn((float)cgx, 0.5f), (float)gpw);  // :727-729
+                const float myf = __fmul_rn(__fadd_rn((float)cgy, 0.5f), (float)gph);
+                float m3[3];
+                img_to_space(g.Kinv, mxf, myf, meanz, m3);
+                for (int k = 0; k < 3; ++k) sm[k] = __float2int_rz(m3[k]);  // :750
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, fct != 0u);
-            if (lane == 0) s_mask[c] = m;
-            if (fct) s_f[ord] = __float_as_uint(__fmul_rn(__ldg(kern + zo * 400u + yo * 20u + xo), (float)fct));
+            if (guessed)  // prediction.rs:437-441
+                for (int k = 0; k < 3; ++k) sm[k] = __float2int_rz(fs->midp_guess[k]);
+            if (tid == 0)
+                for (int k = 0; k < 3; ++k) s_pos[k] = fs->seed_mid[k] = sm[k];
+        } else {
+            int32_t sr[3];
+            uint32_t rc[3] = {0u, 0u, 0u};
+            if (!guessed || b.debug) {
+                for (int i = tid; i < kRotGridCells; i += kVmThreads) s_buf[i] = 0;
+                __syncthreads();
+                for_each_rot_vote<G>(rhits, n_hits, f.rot_bins, [&](int r1, int r2, int r3, uint32_t wgt) {
+                    // rough = r * 20 / 120 (prediction.rs:630-636), dense index z*400 + y*20 + x
+                    const uint32_t q1 = (uint32_t)r1 * kGuessGridParts / kRotGridParts,
+                                   q2 = (uint32_t)r2 * kGuessGridParts / kRotGridParts,
+                                   q3 = (uint32_t)r3 * kGuessGridParts / kRotGridParts;
+                    atomicAdd(&s_buf[q3 * 400 + q2 * 20 + q1], wgt);
+                });
+                __syncthreads();
+                uint32_t* gout = b.grids + (size_t)frame * (kPosGridCells + kRotGridCells) + kPosGridCells;
+                for (int i = tid; i < kRotGridCells; i += kVmThreads) gout[i] = s_buf[i];
+                const Best br = block_argmax(s_buf, kRotGridCells, s_red);  // :733-742
+                rc[0] = br.idx % 20u;
+                rc[1] = (br.idx % 400u) / 20u;
+                rc[2] = br.idx / 400u;
+            }
+            for (int k = 0; k < 3; ++k) {
+                // :745-747, or the caller's guess :448-450; then :458-460
+                double deg = __ddiv_rn(__dadd_rn(__dmul_rn((double)rc[k], 360.0), 180.0), (double)kGuessGridParts);
+                if (guessed) deg = __dadd_rn(__ddiv_rn(__dmul_rn(fs->rot_guess[k], 180.0), 3.14159), 180.0);
+                sr[k] = __double2int_rz(__ddiv_rn(__dmul_rn(deg, (double)kRotGridParts), 360.0));
+            }
+            if (tid == 0)
+                for (int k = 0; k < 3; ++k) s_pos[k] = fs->seed_rot[k] = sr[k];
+        }
+        if (tid == 0) {
+            s_flags = 0;
+            s_done = 0;
+            s_org[0] = s_org[1] = s_org[2] = 0;
         }
         __syncthreads();
-        // 2. sequential f32 accumulation: lanes 0..2 own the numerator components, lane 3 the
-        //    denominator; each adds the non-zero cells in reference order.
-        if (warp == 0) {
-            float acc = 0.0f;
-            if (lane < 4) {
-                for (uint32_t c = 0; c < (uint32_t)kChunks; ++c) {
-                    uint32_t m = s_mask[c];
-                    while (m) {
-                        const uint32_t ord = c * 32 + (uint32_t)(__ffs((int)m) - 1);
-                        m &= m - 1;
-                        const float wgt = __uint_as_float(s_f[ord]);
-                        float comp = 1.0f;
-                        if (lane == 0) comp = (float)(int)((uint32_t)pos[0] + (uint32_t)((int)(ord / 400u) - 10));
-                        else if (lane == 1) comp = (float)(int)((uint32_t)pos[1] + (uint32_t)((int)((ord / 20u) % 20u) - 10));
-                        else if (lane == 2) comp = (float)(int)((uint32_t)pos[2] + (uint32_t)((int)(ord % 20u) - 10));
-                        acc = __fadd_rn(acc, __fmul_rn(comp, wgt));  // num += abs_pos * w ; den += w
+        if (tid == 0) {
+            s_hist[0][0] = s_pos[0]; s_hist[0][1] = s_pos[1]; s_hist[0][2] = s_pos[2];
+        }
+
+        // ------------------------------------------------------------ 2 + 3. box build, mean-shift rounds
+        bool have_box = false;
+        uint32_t rebuilds = 0;
+        uint32_t it = 0;
+        for (; it < iterations; ++it) {
+            __syncthreads();
+            const int32_t pos[3] = {s_pos[0], s_pos[1], s_pos[2]};
+            int32_t org[3] = {s_org[0], s_org[1], s_org[2]};
+            bool inside = have_box;
+            for (int k = 0; k < 3; ++k) {
+                const long long lo = (long long)pos[k] - 10 - org[k], hi = (long long)pos[k] + 9 - org[k];
+                if (lo < 0 || hi >= kBox) inside = false;
+            }
+            if (!inside) {
+                // (re)build the cube around the current position
+                if (have_box) ++rebuilds;
+                __syncthreads();
+                for (int k = 0; k < 3; ++k) org[k] = (int32_t)((uint32_t)pos[k] - (uint32_t)(kBox / 2));
+                if (tid == 0)
+                    for (int k = 0; k < 3; ++k) s_org[k] = org[k];
+                uint4* bz = reinterpret_cast<uint4*>(box);
+                for (int i = tid; i < kBoxCells / 4; i += kVmThreads) __stcg(bz + i, make_uint4(0u, 0u, 0u, 0u));
+                __threadfence();
+                __syncthreads();
+                if (which == 0) {
+                    for_each_centre_vote<G>(chits, n_hits, f.offsets, [&](float nx, float ny, float nz, uint32_t wgt) {
+                        uint32_t idx;  // mid[(x as i32, y as i32, z as i32)] += valtoadd  (prediction.rs:667)
+                        if (in_box(__float2int_rz(nx), __float2int_rz(ny), __float2int_rz(nz), org, &idx))
+                            atomicAdd(box + idx, wgt);
+                    });
+                } else {
+                    for_each_rot_vote<G>(rhits, n_hits, f.rot_bins, [&](int r1, int r2, int r3, uint32_t wgt) {
+                        uint32_t idx;  // rot[(r1, r2, r3)] += valtoadd  (prediction.rs:635)
+                        if (in_box(r1, r2, r3, org, &idx)) atomicAdd(box + idx, wgt);
+                    });
+                }
+                __threadfence();
+                __syncthreads();
+                have_box = true;
+            }
+            // gather the 20^3 window.  ord enumerates the cells in the reference loop order (x
+            // outermost, z innermost, offsets -10..+9: meanshift.rs:340-346); each warp owns whole
+            // 32-cell chunks so one ballot yields the chunk's non-zero mask.  Non-zero cells are
+            // replaced by their weight kernel[(x+10, y+10, z+10)] * (factor as f32)
+            // (meanshift.rs:370-377; dense kernel index z*400 + y*20 + x, meanshift.rs:78-88).
+            const uint32_t bx = (uint32_t)((long long)pos[0] - 10 - org[0]), by = (uint32_t)((long long)pos[1] - 10 - org[1]),
+                           bzz = (uint32_t)((long long)pos[2] - 10 - org[2]);
+            for (uint32_t c = warp; c < kChunks; c += kVmWarps) {
+                const uint32_t ord = c * 32 + lane;
+                const uint32_t xo = ord / 400u, yo = (ord / 20u) % 20u, zo = ord % 20u;
+                const uint32_t fct = __ldcg(box + ((bzz + zo) * kBox + (by + yo)) * kBox + (bx + xo));
+                const uint32_t m = __ballot_sync(0xffffffffu, fct != 0u);
+                if (lane == 0) s_mask[c] = m;
+                if (fct) s_buf[ord] = __float_as_uint(__fmul_rn(__ldg(f.ms_kernel + zo * 400u + yo * 20u + xo), (float)fct));
+            }
+            __syncthreads();
+            // sequential f32 accumulation in reference order: lanes 0..2 own the numerator
+            // components, lane 3 the denominator (meanshift.rs:337-380).
+            if (warp == 0) {
+                float acc = 0.0f;
+                if (lane < 4) {
+                    for (uint32_t c = 0; c < kChunks; ++c) {
+                        uint32_t m = s_mask[c];
+                        while (m) {
+                            const uint32_t ord = c * 32 + (uint32_t)(__ffs((int)m) - 1);
+                            m &= m - 1;
+                            const float wgt = __uint_as_float(s_buf[ord]);
+                            float comp = 1.0f;
+                            if (lane == 0) comp = (float)(int)((uint32_t)pos[0] + (uint32_t)((int)(ord / 400u) - 10));
+                            else if (lane == 1) comp = (float)(int)((uint32_t)pos[1] + (uint32_t)((int)((ord / 20u) % 20u) - 10));
+                            else if (lane == 2) comp = (float)(int)((uint32_t)pos[2] + (uint32_t)((int)(ord % 20u) - 10));
+                            acc = __fadd_rn(acc, __fmul_rn(comp, wgt));  // num += abs_pos * w ; den += w
+                        }
+                    }
+                }
+                const float den = __shfl_sync(0xffffffffu, acc, 3);
+                if (den == 0.0f) {  // "Breaking meanshift - zero sum" (meanshift.rs:385-388)
+                    if (lane == 0) {
+                        s_flags |= 1u;
+                        s_done = 1;
+                    }
+                } else {
+                    const int np = __float2int_rz(__fdiv_rn(acc, den));  // meanshift.rs:391-394
+                    const int nx = __shfl_sync(0xffffffffu, np, 0), ny = __shfl_sync(0xffffffffu, np, 1),
+                              nz = __shfl_sync(0xffffffffu, np, 2);
+                    // Cycle detection (result-neutral): the update is a deterministic function of
+                    // the position, so once P_{k+1} equals an earlier P_j the sequence is periodic
+                    // with period k+1-j and P_iterations is read off the history (a fixed point is
+                    // the period-1 case).
+                    const uint32_t k1 = it + 1;
+                    int found = -1;
+                    if (k1 <= (uint32_t)kMsHistory) {
+                        for (uint32_t j = lane; j < k1; j += 32)
+                            if (s_hist[j][0] == nx && s_hist[j][1] == ny && s_hist[j][2] == nz) found = (int)j;
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) found = max(found, __shfl_xor_sync(0xffffffffu, found, d));
+                    }
+                    if (lane == 0) {
+                        if (b.ms_trace && it < b.ms_trace_cap) {
+                            int32_t* tr = b.ms_trace + (((size_t)frame * 2 + which) * b.ms_trace_cap + it) * 3;
+                            tr[0] = nx; tr[1] = ny; tr[2] = nz;
+                        }
+                        if (found >= 0) {
+                            const uint32_t j = (uint32_t)found, period = k1 - j;
+                            const uint32_t fin = j + (iterations - j) % period;  // index of P_iterations (< k1)
+                            s_pos[0] = s_hist[fin][0]; s_pos[1] = s_hist[fin][1]; s_pos[2] = s_hist[fin][2];
+                            s_done = 2;
+                        } else {
+                            s_pos[0] = nx; s_pos[1] = ny; s_pos[2] = nz;
+                            if (k1 <= (uint32_t)kMsHistory) {
+                                s_hist[k1][0] = nx; s_hist[k1][1] = ny; s_hist[k1][2] = nz;
+                            }
+                        }
                     }
                 }
             }
-            const float den = __shfl_sync(0xffffffffu, acc, 3);
-            if (den == 0.0f) {  // "Breaking meanshift - zero sum" (meanshift.rs:385-388)
-                if (lane == 0) {
-                    atomicOr(&s_flags, 1u);
-                    s_done = 1;
-                }
-            } else {
-                const int np = __float2int_rz(__fdiv_rn(acc, den));  // meanshift.rs:391-394
-                const int nx = __shfl_sync(0xffffffffu, np, 0), ny = __shfl_sync(0xffffffffu, np, 1),
-                          nz = __shfl_sync(0xffffffffu, np, 2);
-                if (lane == 0) {
-                    if (b.ms_trace && it < b.ms_trace_cap) {
-                        int32_t* tr = b.ms_trace + (((size_t)frame * 2 + which) * b.ms_trace_cap + it) * 3;
-                        tr[0] = nx; tr[1] = ny; tr[2] = nz;
-                    }
-                    if (nx == pos[0] && ny == pos[1] && nz == pos[2]) s_done = 2;  // fixed point
-                    s_pos[0] = nx; s_pos[1] = ny; s_pos[2] = nz;
-                }
+            __syncthreads();
+            if (s_done) {
+                if (s_done == 2) ++it;  // this round was executed
+                break;
             }
         }
         __syncthreads();
-        if (s_done) {
-            if (s_done == 2) ++it;  // this round was executed
-            break;
+        if (tid == 0) {
+            fs->ms_iters[which] = it;
+            fs->ms_flags[which] = s_flags;
+            fs->rebuilds[which] = rebuilds;
+            fs->box_slot[which] = blockIdx.x;
+            for (int k = 0; k < 3; ++k) fs->box_org[which][k] = s_org[k];
+            fs->box_valid[which] = have_box ? 1u : 0u;
+            dh_result* r = b.results + frame;
+            if (which == 0) {  // prediction.rs:486-488
+                r->mid_point[0] = (float)s_pos[0];
+                r->mid_point[1] = (float)s_pos[1];
+                r->mid_point[2] = (float)s_pos[2];
+                r->_pad = 0;
+                r->bounding_box[0] = r->bounding_box[1] = r->bounding_box[2] = r->bounding_box[3] = 0;  // :491
+            } else {           // prediction.rs:477-482
+                for (int k = 0; k < 3; ++k)
+                    r->rotation[k] = __dmul_rn(__ddiv_rn(__dsub_rn((double)s_pos[k], (double)kRotGridParts / 2.0),
+                                                         (double)(kRotGridParts / 2)),
+                                               3.14159);
+            }
         }
-    }
-    if (tid == 0) {
-        fs->ms_iters[which] = it;
-        fs->ms_flags[which] = s_flags;
-        dh_result* r = b.results + frame;
-        if (which == 0) {  // prediction.rs:486-488
-            r->mid_point[0] = (float)s_pos[0];
-            r->mid_point[1] = (float)s_pos[1];
-            r->mid_point[2] = (float)s_pos[2];
-            r->_pad = 0;
-            r->bounding_box[0] = r->bounding_box[1] = r->bounding_box[2] = r->bounding_box[3] = 0;  // :491
-        } else {           // prediction.rs:477-482
-            for (int k = 0; k < 3; ++k)
-                r->rotation[k] = __dmul_rn(__ddiv_rn(__dsub_rn((double)s_pos[k], (double)kRotGridParts / 2.0),
-                                                     (double)(kRotGridParts / 2)),
-                                           3.14159);
-        }
+        if (static_items) break;
     }
 }
 
@@ -888,32 +888,29 @@ __global__ void narrow_u16_kernel(const uint32_t* __restrict__ in, uint16_t* __r
     if (i < n) out[i] = (uint16_t)(in[i] & 0xffffu);
 }
 
-// ================================================================ debug: dump one hash table
-__global__ void hash_dump_kernel(FrameBuffers b, uint32_t frame, int which, int32_t* keys_out, uint32_t* vals_out,
-                                 unsigned long long* count) {
+// ================================================================ debug: dump one accumulator cube
+__global__ void box_dump_kernel(FrameBuffers b, uint32_t frame, int which, int32_t* keys_out, uint32_t* vals_out,
+                                unsigned long long* count) {
     const FrameState* fs = b.fs + frame;
-    const uint32_t cap = fs->hash_cap[which];
-    const unsigned long long* keys = b.hash_keys + fs->hash_off[which];
-    const uint32_t* vals = b.hash_vals + fs->hash_off[which];
-    const int32_t* seed = which == 0 ? fs->seed_mid : fs->seed_rot;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const unsigned long long k = keys[i];
-        if (k == kEmptyKey) continue;
+    if (!fs->box_valid[which]) return;
+    const uint32_t* box = b.boxes + (size_t)fs->box_slot[which] * kBoxCells;
+    const int32_t* org = fs->box_org[which];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)kBoxCells; i += gridDim.x * blockDim.x) {
+        const uint32_t v = box[i];
+        if (!v) continue;
         const unsigned long long o = atomicAdd(count, 1ull);
         if (keys_out) {
-            keys_out[o * 3 + 0] = (int32_t)((long long)(k & 0x1fffffull) - kKeyBias + seed[0]);
-            keys_out[o * 3 + 1] = (int32_t)((long long)((k >> 21) & 0x1fffffull) - kKeyBias + seed[1]);
-            keys_out[o * 3 + 2] = (int32_t)((long long)((k >> 42) & 0x1fffffull) - kKeyBias + seed[2]);
-            vals_out[o] = vals[i];
+            keys_out[o * 3 + 0] = org[0] + (int32_t)(i % kBox);
+            keys_out[o * 3 + 1] = org[1] + (int32_t)((i / kBox) % kBox);
+            keys_out[o * 3 + 2] = org[2] + (int32_t)(i / (kBox * kBox));
+            vals_out[o] = v;
         }
     }
 }
 
 // ================================================================ work counters of a pass
 __global__ void __launch_bounds__(256) counters_kernel(const FrameState* __restrict__ fs, uint32_t n_frames,
-                                                       unsigned long long* __restrict__ out, uint32_t P, uint32_t T,
-                                                       const PoolState* __restrict__ pool) {
-    if (pool->overflow) return;  // this pass will be redone with a larger pool: do not count it twice
+                                                       unsigned long long* __restrict__ out, uint32_t P, uint32_t T) {
     unsigned long long v[DH_N_COUNTERS];
     for (int k = 0; k < DH_N_COUNTERS; ++k) v[k] = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_frames; i += gridDim.x * blockDim.x) {
@@ -924,10 +921,11 @@ __global__ void __launch_bounds__(256) counters_kernel(const FrameState* __restr
         v[3] += (unsigned long long)f.n_valid * T;
         v[4] += f.node_visits;
         v[5] += f.n_gate;
-        v[6] += f.n_hits;
+        v[6] += f.n_chits + f.n_rhits;
         v[7] += f.n_mid_votes;
         v[8] += f.n_rot_votes;
         v[10] += f.ms_iters[0] + f.ms_iters[1];
+        v[11] += f.rebuilds[0] + f.rebuilds[1];
     }
     for (int k = 0; k < DH_N_COUNTERS; ++k) {
         unsigned long long x = v[k];
@@ -982,31 +980,18 @@ void launch_gate(const FrameBuffers& b, const Geometry& g, const ForestDev& f, u
     gate_kernel<<<gr, 256, 0, s>>>(b, g, f.leaf_prob, f.leaf_info);
 }
 
-void launch_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t splits,
-                   uint32_t lanes_per_hit, cudaStream_t s) {
-    dim3 gr(splits, n_frames);
-    if (lanes_per_hit >= 32) coarse_vote_kernel<32><<<gr, 256, 0, s>>>(b, g, f);
-    else if (lanes_per_hit >= 8) coarse_vote_kernel<8><<<gr, 256, 0, s>>>(b, g, f);
-    else coarse_vote_kernel<1><<<gr, 256, 0, s>>>(b, g, f);
-}
+uint32_t vote_box_cells() { return (uint32_t)kBoxCells; }
+uint32_t vote_box_dim() { return (uint32_t)kBox; }
 
-void launch_plan_and_clear(const FrameBuffers& b, uint32_t n_frames, unsigned long long capacity, cudaStream_t s) {
-    plan_hash_kernel<<<1, 32, 0, s>>>(b.fs, b.pool, n_frames, capacity);
-    hash_clear_kernel<<<148 * 8, 256, 0, s>>>(b.hash_keys, b.hash_vals, b.pool);
-}
-
-void launch_insert(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t splits,
-                   uint32_t lanes_per_hit, uint32_t reach, cudaStream_t s) {
-    dim3 gr(splits, n_frames);
-    if (lanes_per_hit >= 32) insert_kernel<32><<<gr, 256, 0, s>>>(b, g, f, reach);
-    else if (lanes_per_hit >= 8) insert_kernel<8><<<gr, 256, 0, s>>>(b, g, f, reach);
-    else insert_kernel<1><<<gr, 256, 0, s>>>(b, g, f, reach);
-}
-
-void launch_meanshift(const FrameBuffers& b, const ForestDev& f, uint32_t n_frames, uint32_t iterations,
-                      uint32_t reach, cudaStream_t s) {
-    dim3 gr(2, n_frames);
-    meanshift_kernel<<<gr, kMsThreads, 0, s>>>(b, f.ms_kernel, iterations, reach);
+void launch_vote_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
+                           uint32_t iterations, uint32_t n_ctas, uint32_t lanes_per_hit, bool static_items,
+                           cudaStream_t s) {
+    if (!static_items) cudaMemsetAsync(b.work_counter, 0, sizeof(uint32_t), s);
+    const uint32_t grid = static_items ? 2u * n_frames : n_ctas;
+    const uint32_t st = static_items ? 1u : 0u;
+    if (lanes_per_hit >= 32) vote_meanshift_kernel<32><<<grid, kVmThreads, 0, s>>>(b, g, f, n_frames, iterations, st);
+    else if (lanes_per_hit >= 8) vote_meanshift_kernel<8><<<grid, kVmThreads, 0, s>>>(b, g, f, n_frames, iterations, st);
+    else vote_meanshift_kernel<1><<<grid, kVmThreads, 0, s>>>(b, g, f, n_frames, iterations, st);
 }
 
 void launch_leaf_gates(const double* leaf_prob, const uint32_t* vote_start, const uint32_t* n_votes,
@@ -1031,12 +1016,12 @@ void launch_hough_image(const FrameBuffers& b, const Geometry& g, const ForestDe
 void launch_counters(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, unsigned long long* out,
                      cudaStream_t s) {
     const uint32_t blocks = (n_frames + 255) / 256;
-    counters_kernel<<<blocks, 256, 0, s>>>(b.fs, n_frames, out, g.P, g.n_trees, b.pool);
+    counters_kernel<<<blocks, 256, 0, s>>>(b.fs, n_frames, out, g.P, g.n_trees);
 }
 
-void launch_hash_dump(const FrameBuffers& b, uint32_t frame, int which, int32_t* keys, uint32_t* vals,
-                      unsigned long long* count, cudaStream_t s) {
-    hash_dump_kernel<<<256, 256, 0, s>>>(b, frame, which, keys, vals, count);
+void launch_box_dump(const FrameBuffers& b, uint32_t frame, int which, int32_t* keys, uint32_t* vals,
+                     unsigned long long* count, cudaStream_t s) {
+    box_dump_kernel<<<128, 256, 0, s>>>(b, frame, which, keys, vals, count);
 }
 
 }  // namespace dh

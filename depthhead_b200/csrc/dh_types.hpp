@@ -23,7 +23,9 @@ struct alignas(32) NodeRec {
     uint8_t r[8];      // r1.x0, r1.y0, r1.x1, r1.y1, r2.x0, r2.y0, r2.x1, r2.y1  (bottomright exclusive)
     double threshold;
     int32_t child[2];
-    uint32_t pad[2];
+    // threshold * c1 * c2 (pixel counts of the two rectangles, empty -> 1), rounded once: lets the
+    // kernel decide the node test by exact integer cross-multiplication away from ties.
+    double thr_scaled;
 };
 static_assert(sizeof(NodeRec) == 32, "NodeRec must be one 32-byte sector");
 
@@ -38,10 +40,21 @@ struct alignas(16) LeafInfo {
 static_assert(sizeof(LeafInfo) == 16, "LeafInfo must be 16 bytes");
 constexpr uint32_t kLeafRotOk = 1u, kLeafOffOk = 2u;
 
-// One voting patch*tree pair: which patch (for p3) and which leaf.
-struct Hit {
-    uint32_t patch;
-    uint32_t leaf;
+// One voting patch x tree pair, split by accumulator.  The gate kernel copies the per-leaf
+// constants in, so the vote passes read hit -> votes with no further indirection.
+struct CentreHit {
+    float p3[3];          // back-projected patch centre (prediction.rs:554)
+    uint32_t vote_start;  // first offset vote of the leaf
+    uint32_t n_votes;
+    uint32_t valtoadd;
 };
+static_assert(sizeof(CentreHit) == 24, "CentreHit must be 24 bytes");
+struct alignas(16) RotHit {
+    uint32_t vote_start;  // first rotation vote of the leaf
+    uint32_t n_votes;
+    uint32_t valtoadd;
+    uint32_t pad;
+};
+static_assert(sizeof(RotHit) == 16, "RotHit must be 16 bytes");
 
 }  // namespace dh

@@ -88,7 +88,7 @@ def _q(x, step):
 
 def make_forest(seed: int = 0, n_trees: int = 10, max_depth: int = 15, sub_w: int = 80, sub_h: int = 80,
                 rect_scale: float = 0.3, stop_prob: float = 0.0, votes_lo: int = 2, votes_hi: int = 8,
-                shuffle_nodes: bool = False, ragged_rects: bool = False) -> dict:
+                shuffle_nodes: bool = False, ragged_rects: bool = False, tie_thresholds: bool = False) -> dict:
     """Random-init forest as flat arrays (the same layout oracle.forest_arrays_from_doc returns).
 
     stop_prob == 0: full binary trees (2^D - 1 nodes, 2^D leaves per tree).
@@ -144,6 +144,14 @@ def make_forest(seed: int = 0, n_trees: int = 10, max_depth: int = 15, sub_w: in
         rects = np.stack([ox[:, 0], oy[:, 0], ox[:, 0] + ww[:, 0], oy[:, 0] + hh[:, 0],
                           ox[:, 1], oy[:, 1], ox[:, 1] + ww[:, 1], oy[:, 1] + hh[:, 1]], axis=1).astype(np.int64)
         thr = _q(rng.uniform(-256, 256, n_nodes), 1 / 16).clip(-256, 255.9375)
+        if tie_thresholds:
+            # thresholds sitting exactly on / next to values avg1 - avg2 can take (multiples of
+            # 1/576 for 24x24 rectangles, 0 for identical rectangles): exercises exact ties
+            pool = np.array([0.0, -0.0, 1e-12, -1e-12, 1 / 576, -1 / 576, 25 / 576, 1 / 64, -1 / 64, 0.5, -0.5,
+                             np.nextafter(1 / 576, 1), np.nextafter(1 / 576, 0), 3.0, -3.0, 1 / 3])
+            thr = pool[rng.integers(0, len(pool), n_nodes)]
+            same = rng.random(n_nodes) < 0.3
+            rects[same, 4:8] = rects[same, 0:4]  # r2 == r1 -> avg1 - avg2 == 0 exactly
         if shuffle_nodes and n_nodes > 2:
             perm = np.concatenate([[0], 1 + rng.permutation(n_nodes - 1)])  # new file position -> old index
             inv = np.empty(n_nodes, np.int64)

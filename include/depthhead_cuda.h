@@ -132,18 +132,16 @@ int dh_hough_image_raw(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uin
 #define DH_STAGE_SAT 1
 #define DH_STAGE_TRAVERSE 2
 #define DH_STAGE_GATE 3
-#define DH_STAGE_COARSE 4
-#define DH_STAGE_INSERT 5
-#define DH_STAGE_MEANSHIFT 6
-#define DH_STAGE_D2H 7
-#define DH_N_STAGES 8
+#define DH_STAGE_VOTE_MEANSHIFT 4
+#define DH_STAGE_D2H 5
+#define DH_N_STAGES 6
 int dh_ctx_enable_stage_timing(dh_ctx* c, int on);
 int dh_ctx_stage_ms(dh_ctx* c, float ms[DH_N_STAGES]);
 /* Work counters of the last dh_predict/dh_predict_batch call:
  * [0] frames, [1] patches (all), [2] valid (non-background) patches, [3] patch*tree evals,
- * [4] node visits, [5] gate-passing patches, [6] hits (patch*tree that vote), [7] centre votes cast,
- * [8] rotation votes cast, [9] kernel launches, [10] mean-shift iterations run (both accumulators),
- * [11] hash-pool retries. */
+ * [4] node visits, [5] gate-passing patches, [6] hits (voting patch*tree pairs, both lists), [7] centre
+ * votes cast, [8] rotation votes cast, [9] kernel launches, [10] mean-shift rounds run (both
+ * accumulators), [11] accumulator-cube rebuilds. */
 #define DH_N_COUNTERS 12
 int dh_ctx_counters(dh_ctx* c, uint64_t counters[DH_N_COUNTERS]);
 
@@ -159,13 +157,14 @@ int dh_debug_patches(dh_ctx* c, float* p3, uint8_t* gate);
 /* coarse seed grids (400 + 8000 u32) and the seeds handed to mean-shift */
 int dh_debug_seeds(dh_ctx* c, uint32_t* guess_pos, uint32_t* guess_rot, int32_t seed_mid[3], int32_t seed_rot[3]);
 /* Accumulator contents as unsorted (key, value) lists.  which: 0 = centre, 1 = rotation.
- * Only cells within the mean-shift reach of the seed are stored; *reach returns
- * that radius.  Call with keys == NULL to get the count. */
-int dh_debug_votes(dh_ctx* c, int which, int32_t* keys /*[n][3]*/, uint32_t* vals, uint64_t* n, int32_t* reach);
+ * The device keeps the cells of a dense cube of box_dim^3 cells starting at box_origin (the cube
+ * around the last mean-shift position); only its non-zero cells are returned.
+ * Call with keys == NULL to get the count (at most box_dim^3). */
+int dh_debug_votes(dh_ctx* c, int which, int32_t* keys /*[n][3]*/, uint32_t* vals, uint64_t* n,
+                   int32_t box_origin[3], int32_t* box_dim);
 /* mean-shift trajectory: positions after each executed iteration; *n_iter in/out */
 int dh_debug_meanshift(dh_ctx* c, int which, int32_t* pos /*[n_iter][3]*/, uint32_t* n_iter);
-/* flags of the last mean-shift runs: bit0 = zero-sum break (meanshift.rs:385-388), bit1 = a probe
- * fell outside the stored reach (must never happen) */
+/* flags of the last mean-shift runs: bit0 = zero-sum break (meanshift.rs:385-388) */
 int dh_debug_meanshift_flags(dh_ctx* c, uint32_t flags[2]);
 /* per-leaf static quantities computed by the leaf-gate kernel: valtoadd, rot_ok, off_ok */
 int dh_debug_leaf_static(dh_ctx* c, const dh_forest* f, uint32_t* valtoadd, uint8_t* rot_ok, uint8_t* off_ok);

@@ -22,10 +22,12 @@ def ctx():
     c.close()
 
 
-def _filter_acc(keys, vals, seed, reach):
-    if len(vals) == 0:
-        return keys.reshape(0, 3), vals
-    m = (vals > 0) & np.all(np.abs(keys.astype(np.int64) - np.asarray(seed, np.int64)) <= reach, axis=1)
+def _filter_acc(keys, vals, origin, dim):
+    """non-zero cells inside the cube [origin, origin + dim)^3"""
+    if len(vals) == 0 or dim == 0:
+        return keys.reshape(-1, 3)[:0], vals[:0]
+    rel = keys.astype(np.int64) - np.asarray(origin, np.int64)
+    m = (vals > 0) & np.all((rel >= 0) & (rel < dim), axis=1)
     return keys[m], vals[m]
 
 
@@ -49,24 +51,33 @@ def _compare_frame(ctx, hp, of, depth, midp_guess=None, rot_guess=None, check_pa
     assert np.array_equal(gr, tr.guess_rot)
     assert np.array_equal(sm, tr.seed_mid)
     assert np.array_equal(sr, tr.seed_rot)
-    # --- accumulators (cells within the stored reach of the seed)
-    for which, (ok, ov, seed) in enumerate(((tr.mid_keys, tr.mid_vals, tr.seed_mid), (tr.rot_keys, tr.rot_vals, tr.seed_rot))):
-        gk, gv, reach = ctx.debug_votes(which)
-        assert reach >= 10 * of.meanshift_iterations + 10
-        ek, ev = _filter_acc(ok, ov, seed, reach)
-        gk, gv = _filter_acc(gk, gv, seed, reach)
+    # --- accumulators: every cell of the dense cube around the final position must equal the
+    #     reference's SparseArray3D (and the cube must contain the final 20^3 window)
+    final = (tr.mid_point.astype(np.int64), np.round(tr.rotation / 3.14159 * 60 + 60).astype(np.int64))
+    for which, (ok, ov) in enumerate(((tr.mid_keys, tr.mid_vals), (tr.rot_keys, tr.rot_vals))):
+        gk, gv, org, dim = ctx.debug_votes(which)
+        if of.meanshift_iterations == 0:
+            assert dim == 0
+            continue
+        assert dim >= 20 + 2 * 10
+        ek, ev = _filter_acc(ok, ov, org, dim)
         assert np.array_equal(gk, ek), "accumulator %d keys differ (%d vs %d cells)" % (which, len(gk), len(ek))
         assert np.array_equal(gv, ev), "accumulator %d sums differ" % which
-    # --- mean-shift trajectories: GPU stops at a fixed point, the reference repeats it
-    for which, otrace in enumerate((tr.ms_mid, tr.ms_rot)):
+    # --- mean-shift trajectories: the GPU stops as soon as a position repeats (fixed point or
+    #     cycle) and reads the final position off the history; the reference keeps iterating.
+    for which, (otrace, seed) in enumerate(((tr.ms_mid, tr.seed_mid), (tr.ms_rot, tr.seed_rot))):
         gtrace = ctx.debug_meanshift(which)
         n = len(gtrace)
-        assert n <= len(otrace) or len(otrace) == 0
+        assert n <= len(otrace)
         assert np.array_equal(gtrace, otrace[:n])
-        if n and n < len(otrace):
-            assert np.all(otrace[n:] == otrace[n - 1]), "early exit was not a fixed point"
+        if n and n < len(otrace) and not (tr.ms_mid_zero, tr.ms_rot_zero)[which]:
+            seq = [tuple(seed)] + [tuple(p) for p in gtrace]
+            j = seq.index(seq[-1])
+            assert j < len(seq) - 1, "early exit without a repeated position"
+            period = (len(seq) - 1) - j
+            for m in range(n + 1, len(otrace) + 1):
+                assert tuple(otrace[m - 1]) == seq[j + (m - j) % period], "periodic extension mismatch"
     f0, f1 = ctx.debug_meanshift_flags()
-    assert (f0 & 2) == 0 and (f1 & 2) == 0, "mean-shift probed outside the stored reach"
     assert bool(f0 & 1) == tr.ms_mid_zero and bool(f1 & 1) == tr.ms_rot_zero
     # --- result
     assert np.array_equal(res.mid_point, tr.mid_point)
@@ -100,6 +111,22 @@ def test_sparse_trees_and_ragged_rects(ctx):
     hp = HoughPrediction.from_json(js)
     of = oracle.OracleForest.from_json(js)
     for d in synth.make_frames(2, seed=77):
+        _compare_frame(ctx, hp, of, d)
+
+
+def test_exact_ties_in_the_node_test(ctx):
+    """Thresholds exactly on (and one ulp around) values avg1 - avg2 can take, identical
+    rectangles, flat and staircase frames: the filtered integer predicate must fall back to the
+    IEEE-division path and still agree with the reference arithmetic bit for bit."""
+    arr = synth.make_forest(seed=17, n_trees=8, max_depth=10, tie_thresholds=True)
+    js = synth.forest_to_json(arr, stepwidth=5)
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    h, w = 480, 640
+    flat = np.full((h, w), 1000, np.uint16)
+    stairs = (1000 + (np.arange(w)[None, :] // 24) + 0 * np.arange(h)[:, None]).astype(np.uint16)
+    ramp = (500 + np.arange(w)[None, :] + np.arange(h)[:, None]).astype(np.uint16)
+    for d in (flat, stairs, ramp, synth.make_frames(1, seed=5)[0]):
         _compare_frame(ctx, hp, of, d)
 
 
