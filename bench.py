@@ -320,7 +320,8 @@ def main():
 
     # ---- roofline of the dominant kernel (traversal), from this rank's live stage timers
     peak, peak_src = measured_peak_gbs()
-    launches = max(1, (n + (args.chunk or 256) - 1) // (args.chunk or 256)) * args.steps
+    dev_chunk = args.chunk or 1024  # library default for device-resident input
+    launches = max(1, (n + dev_chunk - 1) // dev_chunk) * args.steps
     trav_ms = stage.get("traverse", 0.0)
     alg_bytes = counters["node_visits"] * BYTES_PER_NODE_VISIT + counters["evals"] * BYTES_PER_LEAF_HEADER
     achieved = alg_bytes / (trav_ms / 1000.0) / 1e9 if trav_ms > 0 else None

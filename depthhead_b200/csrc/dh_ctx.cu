@@ -83,7 +83,7 @@ Context::Context(int device) : device_(device) {
     dev_alloc(d_work_counter_, 1);
     DH_CUDA(cudaHostAlloc((void**)&h_fs_, sizeof(FrameState), cudaHostAllocDefault));
     DH_CUDA(cudaHostAlloc((void**)&h_counters_, sizeof(unsigned long long) * DH_N_COUNTERS, cudaHostAllocDefault));
-    chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 256);
+    chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 0);  // 0 = adaptive (128 for host input, 1024 for device input)
     debug_sync_ = env_u32("DH_DEBUG_SYNC", 0) != 0;
     std::memset(stage_ms_, 0, sizeof(stage_ms_));
     std::memset(counters_, 0, sizeof(counters_));
@@ -113,7 +113,7 @@ Context::~Context() {
 }
 
 void Context::set_stream(void* s) { stream_ = s ? reinterpret_cast<cudaStream_t>(s) : own_stream_; }
-void Context::set_chunk_frames(uint32_t f) { chunk_frames_ = f ? std::min<uint32_t>(f, 32768u) : env_u32("DH_CHUNK_FRAMES", 256); }
+void Context::set_chunk_frames(uint32_t f) { chunk_frames_ = f ? std::min<uint32_t>(f, 32768u) : env_u32("DH_CHUNK_FRAMES", 0); }
 void Context::synchronize() {
     DH_CUDA(cudaSetDevice(device_));
     DH_CUDA(cudaStreamSynchronize(stream_));
@@ -126,6 +126,7 @@ void Context::free_forest() {
     dev_free(df_leaf_prob_);
     dev_free(df_leaf_info_);
     dev_free(df_offsets_);
+    dev_free(df_offsets3_);
     dev_free(df_rot_bins_);
     dev_free(df_kernel_);
     df_serial_ = 0;
@@ -140,14 +141,18 @@ void Context::ensure_forest(const HostForest& hf) {
         dev_alloc(df_roots_, (size_t)hf.n_trees);
         dev_alloc(df_leaf_prob_, NL);
         dev_alloc(df_leaf_info_, NL);
-        dev_alloc(df_offsets_, NV * 3);
+        dev_alloc(df_offsets_, NV);       // float4 per vote
+        dev_alloc(df_offsets3_, NV * 3);  // packed copy, only for the leaf-gate kernel below
         dev_alloc(df_rot_bins_, NV);
         dev_alloc(df_kernel_, (size_t)kKernelCells);
         if (NN) DH_CUDA(cudaMemcpyAsync(df_nodes_, hf.nodes.data(), NN * sizeof(NodeRec), cudaMemcpyHostToDevice, stream_));
         DH_CUDA(cudaMemcpyAsync(df_roots_, hf.roots.data(), hf.roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
         DH_CUDA(cudaMemcpyAsync(df_leaf_prob_, hf.leaf_prob.data(), NL * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        std::vector<float4> off4(NV);
+        for (size_t v = 0; v < NV; ++v) off4[v] = make_float4(hf.offsets[v * 3], hf.offsets[v * 3 + 1], hf.offsets[v * 3 + 2], 0.0f);
         if (NV) {
-            DH_CUDA(cudaMemcpyAsync(df_offsets_, hf.offsets.data(), NV * 3 * sizeof(float), cudaMemcpyHostToDevice, stream_));
+            DH_CUDA(cudaMemcpyAsync(df_offsets_, off4.data(), NV * sizeof(float4), cudaMemcpyHostToDevice, stream_));
+            DH_CUDA(cudaMemcpyAsync(df_offsets3_, hf.offsets.data(), NV * 3 * sizeof(float), cudaMemcpyHostToDevice, stream_));
             DH_CUDA(cudaMemcpyAsync(df_rot_bins_, hf.rot_bins.data(), NV * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
         }
         // K5: per-leaf covariance-trace gates + valtoadd, computed on the device once per model
@@ -159,12 +164,13 @@ void Context::ensure_forest(const HostForest& hf) {
         DH_CUDA(cudaMemcpyAsync(d_vs, hf.leaf_vote_start.data(), NL * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
         DH_CUDA(cudaMemcpyAsync(d_nv, hf.leaf_n_votes.data(), NL * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
         if (NV) DH_CUDA(cudaMemcpyAsync(d_rot, hf.rotations.data(), NV * 3 * sizeof(double), cudaMemcpyHostToDevice, stream_));
-        launch_leaf_gates(df_leaf_prob_, d_vs, d_nv, df_offsets_, d_rot, df_leaf_info_, (uint32_t)NL, stream_);
+        launch_leaf_gates(df_leaf_prob_, d_vs, d_nv, df_offsets3_, d_rot, df_leaf_info_, (uint32_t)NL, stream_);
         DH_CUDA(cudaGetLastError());
         DH_CUDA(cudaStreamSynchronize(stream_));
         dev_free(d_vs);
         dev_free(d_nv);
         dev_free(d_rot);
+        dev_free(df_offsets3_);
         df_serial_ = hf.serial;
         df_sigma_version_ = 0;
         df_n_leaves_ = NL;
@@ -193,6 +199,7 @@ void Context::ensure_forest(const HostForest& hf) {
 // ------------------------------------------------------------------------------------------------ scratch
 void Context::free_scratch() {
     for (int i = 0; i < 2; ++i) dev_free(d_depth_[i]);
+    staging_elems_ = 0;
     dev_free(d_sat_);
     dev_free(d_leaf_);
     dev_free(d_p3_);
@@ -236,6 +243,14 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
     throw ModelError(DH_E_SHAPE, "sub-image too large: its summed-area window does not fit in shared memory");
 }
 
+uint32_t Context::pick_chunk(uint32_t n_frames, int depth_loc) const {
+    // Host input: small chunks so the H2D copy of chunk c+1 hides behind the kernels of chunk c
+    // and the first kernels start early.  Device input: large chunks, so the persistent
+    // vote/mean-shift kernel has many work items per CTA and the launch tails are amortised.
+    uint32_t c = chunk_frames_ ? chunk_frames_ : (depth_loc == DH_DEPTH_DEVICE ? 1024u : 128u);
+    return std::max<uint32_t>(1u, std::min<uint32_t>(c, std::max<uint32_t>(n_frames, 1u)));
+}
+
 void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9]) {
     const uint32_t sw = hf.subimage_width, sh = hf.subimage_height, stride = hf.stepwidth.load();
     if (stride == 0) throw ModelError(DH_E_SHAPE, "stepwidth 0: the reference's sliding window never advances");
@@ -245,7 +260,7 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
     if (w < (uint32_t)kGuessGridParts || h < (uint32_t)kGuessGridParts)
         throw ModelError(DH_E_SHAPE, "image smaller than 20 pixels per side: the reference's 20x20 seed grid has empty cells");
     // frames per pass: the requested chunk, but never more than ~12 GB of per-frame scratch
-    uint32_t cap = std::max<uint32_t>(1u, std::min<uint32_t>(chunk_frames_, std::max<uint32_t>(n_frames_hint, 1u)));
+    uint32_t cap = std::max<uint32_t>(1u, n_frames_hint);
     {
         const uint64_t npx = (w - sw + stride - 1) / stride, npy = (h - sh + stride - 1) / stride;
         const uint64_t PT = std::max<uint64_t>(npx * npy, 1) * (uint64_t)hf.n_trees;
@@ -255,6 +270,7 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
         cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(cap, budget / per_frame));
     }
     ScratchKey k{w, h, sw, sh, stride, (uint32_t)hf.n_trees, cap, debug_ ? hf.meanshift_iterations.load() : 0u};
+    call_chunk_ = cap;  // frames per pass of this call (the scratch may be larger)
     Geometry& g = geom_;
     if (!k.same_shape(sk_) || k.frames > sk_.frames) {
         DH_CUDA(cudaStreamSynchronize(stream_));
@@ -298,8 +314,8 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
         }
         sk_ = k;
     }
-    // accumulator cubes: one per persistent CTA of vote_meanshift_kernel (3 CTAs per SM)
-    const uint32_t want_ctas = (uint32_t)n_sms_ * 3u;
+    // accumulator cubes: one per persistent CTA of vote_meanshift_kernel
+    const uint32_t want_ctas = (uint32_t)n_sms_ * vote_ctas_per_sm();
     if (vm_ctas_ < want_ctas) {
         DH_CUDA(cudaStreamSynchronize(stream_));
         dev_free(d_boxes_);
@@ -311,9 +327,15 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
 }
 
 void Context::ensure_staging(int slots) {
-    const size_t n = (size_t)sk_.frames * sk_.w * sk_.h;
+    const size_t n = (size_t)call_chunk_ * sk_.w * sk_.h;
+    if (n > staging_elems_) {
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        DH_CUDA(cudaStreamSynchronize(copy_stream_));
+        for (int i = 0; i < 2; ++i) dev_free(d_depth_[i]);
+        staging_elems_ = n;
+    }
     for (int i = 0; i < slots && i < 2; ++i)
-        if (!d_depth_[i]) dev_alloc(d_depth_[i], n);
+        if (!d_depth_[i]) dev_alloc(d_depth_[i], staging_elems_);
 }
 
 FrameBuffers Context::buffers(const uint16_t* depth) const {
@@ -470,9 +492,9 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
         return;
     }
     ensure_forest(hf);
-    ensure_scratch(hf, w, h, n, K);
+    ensure_scratch(hf, w, h, pick_chunk(n, depth_loc), K);
     const uint32_t iterations = hf.meanshift_iterations.load();
-    const uint32_t F = sk_.frames;
+    const uint32_t F = call_chunk_;
     const uint32_t n_chunks = (n + F - 1) / F;
     const size_t frame_px = (size_t)w * h;
     // pinned staging for results and per-chunk pool state

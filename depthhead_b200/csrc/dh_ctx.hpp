@@ -59,6 +59,7 @@ private:
     void free_forest();
     void ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9]);
     void ensure_staging(int slots);
+    uint32_t pick_chunk(uint32_t n_frames, int depth_loc) const;
     void free_scratch();
     TilePlan plan_tiles(const Geometry& g) const;
     FrameBuffers buffers(const uint16_t* depth) const;
@@ -84,7 +85,8 @@ private:
     int32_t* df_roots_ = nullptr;
     double* df_leaf_prob_ = nullptr;
     LeafInfo* df_leaf_info_ = nullptr;
-    float* df_offsets_ = nullptr;
+    float4* df_offsets_ = nullptr;
+    float* df_offsets3_ = nullptr;
     uint32_t* df_rot_bins_ = nullptr;
     float* df_kernel_ = nullptr;
     ForestDev fdev_{};
@@ -95,8 +97,10 @@ private:
     Geometry geom_{};
     TilePlan tiles_{};
     CUtensorMap sat_map_{};
-    uint32_t chunk_frames_ = 256;
+    uint32_t chunk_frames_ = 0;   // 0 = adaptive
+    uint32_t call_chunk_ = 1;
     uint16_t* d_depth_[2] = {nullptr, nullptr};
+    size_t staging_elems_ = 0;
     uint32_t* d_sat_ = nullptr;
     int32_t* d_leaf_ = nullptr;
     float* d_p3_ = nullptr;

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256) gate_kernel(FrameBuffers b, Geometry g, c
             if (!(__ldg(leaf_prob + L) > 0.0)) continue;
             const LeafInfo li = leaf_info[L];
             if (li.valtoadd == 0u) continue;
-            if (li.flags & kLeafOffOk) *oc++ = CentreHit{{p3[0], p3[1], p3[2]}, li.vote_start, li.n_votes, li.valtoadd};
+            if (li.flags & kLeafOffOk) *oc++ = CentreHit{{p3[0], p3[1], p3[2]}, li.vote_start, li.n_votes, li.valtoadd, {0u, 0u}};
             if (li.flags & kLeafRotOk) *orr++ = RotHit{li.vote_start, li.n_votes, li.valtoadd, 0u};
         }
     }
@@ -402,8 +402,11 @@ __global__ void __launch_bounds__(256) gate_kernel(FrameBuffers b, Geometry g, c
 constexpr int kBox = 48;                      // cells per axis of the dense cube
 constexpr int kBoxCells = kBox * kBox * kBox; // 110 592 cells = 432 KB
 constexpr int kVmThreads = 512;
+constexpr int kVmCtasPerSm = 2;               // 64 registers per thread: room for 4 vote records in flight
 constexpr int kVmWarps = kVmThreads / 32;
 constexpr int kMsHistory = 64;
+constexpr int kMsSegment = 2048;              // non-zero window cells summed per pass
+constexpr int kVmSmemBytes = kRotGridCells * 4 + 4 * kMsSegment * 4;
 
 struct Best {
     uint32_t val, idx;
@@ -434,19 +437,39 @@ __device__ Best block_argmax(const uint32_t* cells, int n, Best* s_red) {
 }
 
 // Visits every centre vote of the frame: fn(nx, ny, nz, weight) with np = p3 - offset
-// (prediction.rs:647); votes with np.z < 0 are skipped (prediction.rs:650).  G lanes share a hit.
+// (prediction.rs:647); votes with np.z < 0 are skipped (prediction.rs:650).  G lanes share a hit;
+// with G == 1 a thread loads up to four vote records before using them (memory-level parallelism:
+// these passes are bound by L2 latency, not bandwidth).
 template <int G, typename F>
 __device__ __forceinline__ void for_each_centre_vote(const CentreHit* __restrict__ hits, uint32_t n_hits,
-                                                     const float* __restrict__ offsets, F&& fn) {
+                                                     const float4* __restrict__ offsets, F&& fn) {
     const uint32_t sub = threadIdx.x % G;
     for (uint32_t hi = threadIdx.x / G; hi < n_hits; hi += kVmThreads / G) {
-        const CentreHit h = hits[hi];
-        for (uint32_t k = sub; k < h.n_votes; k += G) {
-            const float* o = offsets + (size_t)(h.vote_start + k) * 3;
-            const float nx = __fsub_rn(h.p3[0], __ldg(o + 0)), ny = __fsub_rn(h.p3[1], __ldg(o + 1)),
-                        nz = __fsub_rn(h.p3[2], __ldg(o + 2));
-            if (nz < 0.0f) continue;
-            fn(nx, ny, nz, h.valtoadd);
+        const uint4 ha = __ldg(reinterpret_cast<const uint4*>(hits + hi));
+        const uint2 hb = __ldg(reinterpret_cast<const uint2*>(hits + hi) + 2);
+        const float px = __uint_as_float(ha.x), py = __uint_as_float(ha.y), pz = __uint_as_float(ha.z);
+        const uint32_t v0 = ha.w, n = hb.x, wgt = hb.y;
+        if (G == 1) {
+            for (uint32_t k0 = 0; k0 < n; k0 += 4) {
+                float4 o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u < n) o[u] = __ldg(offsets + v0 + k0 + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u >= n) break;
+                    const float nx = __fsub_rn(px, o[u].x), ny = __fsub_rn(py, o[u].y), nz = __fsub_rn(pz, o[u].z);
+                    if (nz < 0.0f) continue;
+                    fn(nx, ny, nz, wgt);
+                }
+            }
+        } else {
+            for (uint32_t k = sub; k < n; k += G) {
+                const float4 o = __ldg(offsets + v0 + k);
+                const float nx = __fsub_rn(px, o.x), ny = __fsub_rn(py, o.y), nz = __fsub_rn(pz, o.z);
+                if (nz < 0.0f) continue;
+                fn(nx, ny, nz, wgt);
+            }
         }
     }
 }
@@ -456,10 +479,24 @@ __device__ __forceinline__ void for_each_rot_vote(const RotHit* __restrict__ hit
                                                   const uint32_t* __restrict__ rot_bins, F&& fn) {
     const uint32_t sub = threadIdx.x % G;
     for (uint32_t hi = threadIdx.x / G; hi < n_hits; hi += kVmThreads / G) {
-        const RotHit h = hits[hi];
-        for (uint32_t k = sub; k < h.n_votes; k += G) {
-            const uint32_t bins = __ldg(rot_bins + h.vote_start + k);
-            fn((int)(bins & 0xffu), (int)((bins >> 8) & 0xffu), (int)((bins >> 16) & 0xffu), h.valtoadd);
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(hits + hi));  // vote_start, n_votes, valtoadd
+        if (G == 1) {
+            for (uint32_t k0 = 0; k0 < h.y; k0 += 4) {
+                uint32_t bins[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u < h.y) bins[u] = __ldg(rot_bins + h.x + k0 + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u >= h.y) break;
+                    fn((int)(bins[u] & 0xffu), (int)((bins[u] >> 8) & 0xffu), (int)((bins[u] >> 16) & 0xffu), h.z);
+                }
+            }
+        } else {
+            for (uint32_t k = sub; k < h.y; k += G) {
+                const uint32_t bins = __ldg(rot_bins + h.x + k);
+                fn((int)(bins & 0xffu), (int)((bins >> 8) & 0xffu), (int)((bins >> 16) & 0xffu), h.z);
+            }
         }
     }
 }
@@ -472,11 +509,16 @@ __device__ __forceinline__ bool in_box(int x, int y, int z, const int32_t* org, 
 }
 
 template <int G>
-__global__ void __launch_bounds__(kVmThreads, 3) vote_meanshift_kernel(FrameBuffers b, Geometry g, ForestDev f,
+__global__ void __launch_bounds__(kVmThreads, kVmCtasPerSm) vote_meanshift_kernel(FrameBuffers b, Geometry g, ForestDev f,
                                                                         uint32_t n_frames, uint32_t iterations,
                                                                         uint32_t static_items) {
-    __shared__ uint32_t s_buf[kRotGridCells];         // seed grid, later the window weights (f32 bits)
+    // dynamic shared memory (kVmSmemBytes): 64 KB of the 66 KB do not fit the 48 KB static limit
+    extern __shared__ __align__(16) uint8_t vm_smem[];
+    uint32_t* s_buf = reinterpret_cast<uint32_t*>(vm_smem);  // [8000] seed grid, later the window weights (f32 bits)
+    float(*s_terms)[kMsSegment] = reinterpret_cast<float(*)[kMsSegment]>(vm_smem + kRotGridCells * 4);  // [4][kMsSegment]
+                                                      // per-cell summands (num x,y,z, den) in reference order
     __shared__ uint32_t s_mask[kKernelCells / 32];    // non-zero window cells, bit j of word c = ord c*32+j
+    __shared__ uint32_t s_off[kKernelCells / 32 + 1]; // rank of the first non-zero cell of every chunk
     __shared__ int32_t s_hist[kMsHistory + 1][3];     // positions P_0 (seed), P_1, ... for cycle detection
     __shared__ Best s_red[kVmWarps];
     __shared__ unsigned long long s_sum[kVmWarps];
@@ -669,25 +711,66 @@ __global__ void __launch_bounds__(kVmThreads, 3) vote_meanshift_kernel(FrameBuff
                 if (fct) s_buf[ord] = __float_as_uint(__fmul_rn(__ldg(f.ms_kernel + zo * 400u + yo * 20u + xo), (float)fct));
             }
             __syncthreads();
-            // sequential f32 accumulation in reference order: lanes 0..2 own the numerator
-            // components, lane 3 the denominator (meanshift.rs:337-380).
+            // Sequential f32 accumulation in reference order (meanshift.rs:337-380).  Only the chain
+            // of additions is inherently serial, so: (a) rank every non-zero cell in reference order
+            // (prefix sum over the chunk masks), (b) all threads compute the summands
+            // abs_pos * (influence * factor) and influence * factor into shared memory at that
+            // rank, (c) lanes 0..3 (num x, y, z, den) add them up one after the other.
             if (warp == 0) {
-                float acc = 0.0f;
-                if (lane < 4) {
-                    for (uint32_t c = 0; c < kChunks; ++c) {
-                        uint32_t m = s_mask[c];
-                        while (m) {
-                            const uint32_t ord = c * 32 + (uint32_t)(__ffs((int)m) - 1);
-                            m &= m - 1;
+                uint32_t run = 0;
+                for (uint32_t c0 = 0; c0 < kChunks; c0 += 32) {
+                    const uint32_t c = c0 + lane;
+                    const uint32_t n = c < kChunks ? (uint32_t)__popc(s_mask[c]) : 0u;
+                    uint32_t incl = n;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= (uint32_t)d) incl += o;
+                    }
+                    if (c < kChunks) s_off[c] = run + incl - n;
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) s_off[kChunks] = run;
+            }
+            __syncthreads();
+            const uint32_t nnz = s_off[kChunks];
+            float acc = 0.0f;
+            for (uint32_t seg = 0; seg < nnz; seg += kMsSegment) {
+                for (uint32_t c = warp; c < kChunks; c += kVmWarps) {
+                    if (s_off[c + 1] <= seg || s_off[c] >= seg + kMsSegment) continue;  // warp-uniform
+                    const uint32_t m = s_mask[c];
+                    if ((m >> lane) & 1u) {
+                        const uint32_t r = s_off[c] + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                        if (r >= seg && r < seg + kMsSegment) {
+                            const uint32_t ord = c * 32 + lane;
                             const float wgt = __uint_as_float(s_buf[ord]);
-                            float comp = 1.0f;
-                            if (lane == 0) comp = (float)(int)((uint32_t)pos[0] + (uint32_t)((int)(ord / 400u) - 10));
-                            else if (lane == 1) comp = (float)(int)((uint32_t)pos[1] + (uint32_t)((int)((ord / 20u) % 20u) - 10));
-                            else if (lane == 2) comp = (float)(int)((uint32_t)pos[2] + (uint32_t)((int)(ord % 20u) - 10));
-                            acc = __fadd_rn(acc, __fmul_rn(comp, wgt));  // num += abs_pos * w ; den += w
+                            const float fx = (float)(int)((uint32_t)pos[0] + (uint32_t)((int)(ord / 400u) - 10));
+                            const float fy = (float)(int)((uint32_t)pos[1] + (uint32_t)((int)((ord / 20u) % 20u) - 10));
+                            const float fz = (float)(int)((uint32_t)pos[2] + (uint32_t)((int)(ord % 20u) - 10));
+                            s_terms[0][r - seg] = __fmul_rn(fx, wgt);  // abs_pos * (influence * factor)
+                            s_terms[1][r - seg] = __fmul_rn(fy, wgt);
+                            s_terms[2][r - seg] = __fmul_rn(fz, wgt);
+                            s_terms[3][r - seg] = wgt;                 // influence * factor
                         }
                     }
                 }
+                __syncthreads();
+                if (warp == 0 && lane < 4) {
+                    const uint32_t cnt = min((uint32_t)kMsSegment, nnz - seg);
+                    const float* t = s_terms[lane];
+                    uint32_t i = 0;
+                    for (; i + 8 <= cnt; i += 8) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = t[i + u];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, v[u]);
+                    }
+                    for (; i < cnt; ++i) acc = __fadd_rn(acc, t[i]);
+                }
+                __syncthreads();
+            }
+            if (warp == 0) {
                 const float den = __shfl_sync(0xffffffffu, acc, 3);
                 if (den == 0.0f) {  // "Breaking meanshift - zero sum" (meanshift.rs:385-388)
                     if (lane == 0) {
@@ -876,7 +959,10 @@ __global__ void __launch_bounds__(256) hough_image_kernel(FrameBuffers b, Geomet
     img_to_space(g.Kinv, (float)x, (float)y, (float)b.depth[(size_t)y * g.w + x], p3);
     for (uint32_t k = 0; k < n; ++k) {
         float np[3], p2[2];
-        for (int c = 0; c < 3; ++c) np[c] = __fsub_rn(p3[c], f.offsets[(size_t)(v0 + k) * 3 + c]);
+        const float4 o = f.offsets[v0 + k];
+        np[0] = __fsub_rn(p3[0], o.x);
+        np[1] = __fsub_rn(p3[1], o.y);
+        np[2] = __fsub_rn(p3[2], o.z);
         space_to_img(g.K, np, p2);
         const int nx = __float2int_rz(p2[0]), ny = __float2int_rz(p2[1]);  // :816
         if (nx < 0 || (uint32_t)nx >= g.w || ny < 0 || (uint32_t)ny >= g.h) continue;
@@ -981,17 +1067,25 @@ void launch_gate(const FrameBuffers& b, const Geometry& g, const ForestDev& f, u
 }
 
 uint32_t vote_box_cells() { return (uint32_t)kBoxCells; }
+uint32_t vote_ctas_per_sm() { return (uint32_t)kVmCtasPerSm; }
 uint32_t vote_box_dim() { return (uint32_t)kBox; }
 
 void launch_vote_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
                            uint32_t iterations, uint32_t n_ctas, uint32_t lanes_per_hit, bool static_items,
                            cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(vote_meanshift_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVmSmemBytes);
+        cudaFuncSetAttribute(vote_meanshift_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVmSmemBytes);
+        cudaFuncSetAttribute(vote_meanshift_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVmSmemBytes);
+        configured = true;
+    }
     if (!static_items) cudaMemsetAsync(b.work_counter, 0, sizeof(uint32_t), s);
     const uint32_t grid = static_items ? 2u * n_frames : n_ctas;
     const uint32_t st = static_items ? 1u : 0u;
-    if (lanes_per_hit >= 32) vote_meanshift_kernel<32><<<grid, kVmThreads, 0, s>>>(b, g, f, n_frames, iterations, st);
-    else if (lanes_per_hit >= 8) vote_meanshift_kernel<8><<<grid, kVmThreads, 0, s>>>(b, g, f, n_frames, iterations, st);
-    else vote_meanshift_kernel<1><<<grid, kVmThreads, 0, s>>>(b, g, f, n_frames, iterations, st);
+    if (lanes_per_hit >= 32) vote_meanshift_kernel<32><<<grid, kVmThreads, kVmSmemBytes, s>>>(b, g, f, n_frames, iterations, st);
+    else if (lanes_per_hit >= 8) vote_meanshift_kernel<8><<<grid, kVmThreads, kVmSmemBytes, s>>>(b, g, f, n_frames, iterations, st);
+    else vote_meanshift_kernel<1><<<grid, kVmThreads, kVmSmemBytes, s>>>(b, g, f, n_frames, iterations, st);
 }
 
 void launch_leaf_gates(const double* leaf_prob, const uint32_t* vote_start, const uint32_t* n_votes,

@@ -57,7 +57,7 @@ struct ForestDev {
     const int32_t* roots;
     const double* leaf_prob;
     const LeafInfo* leaf_info;
-    const float* offsets;      // 3 per vote
+    const float4* offsets;     // per vote: x, y, z (mm), w unused — one 16-byte load
     const uint32_t* rot_bins;  // per vote
     const float* ms_kernel;    // 8000
     int32_t n_trees;
@@ -89,6 +89,7 @@ void launch_vote_meanshift(const FrameBuffers& b, const Geometry& g, const Fores
                            uint32_t iterations, uint32_t n_ctas, uint32_t lanes_per_hit, bool static_items,
                            cudaStream_t s);
 uint32_t vote_box_cells();
+uint32_t vote_ctas_per_sm();
 uint32_t vote_box_dim();
 void launch_leaf_gates(const double* leaf_prob, const uint32_t* vote_start, const uint32_t* n_votes,
                        const float* offsets, const double* rotations, LeafInfo* out, uint32_t n_leaves,

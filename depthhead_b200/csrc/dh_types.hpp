@@ -42,13 +42,14 @@ constexpr uint32_t kLeafRotOk = 1u, kLeafOffOk = 2u;
 
 // One voting patch x tree pair, split by accumulator.  The gate kernel copies the per-leaf
 // constants in, so the vote passes read hit -> votes with no further indirection.
-struct CentreHit {
+struct alignas(16) CentreHit {
     float p3[3];          // back-projected patch centre (prediction.rs:554)
     uint32_t vote_start;  // first offset vote of the leaf
     uint32_t n_votes;
     uint32_t valtoadd;
+    uint32_t pad[2];
 };
-static_assert(sizeof(CentreHit) == 24, "CentreHit must be 24 bytes");
+static_assert(sizeof(CentreHit) == 32, "CentreHit must be 32 bytes (two 16-byte loads)");
 struct alignas(16) RotHit {
     uint32_t vote_start;  // first rotation vote of the leaf
     uint32_t n_votes;
