@@ -122,6 +122,8 @@ void Context::synchronize() {
 // ------------------------------------------------------------------------------------------------ model upload
 void Context::free_forest() {
     dev_free(df_nodes_);
+    dev_free(df_hot_);
+    hot_tw_ = 0;
     dev_free(df_roots_);
     dev_free(df_leaf_prob_);
     dev_free(df_leaf_info_);
@@ -138,6 +140,8 @@ void Context::ensure_forest(const HostForest& hf) {
         free_forest();
         const size_t NN = hf.n_nodes(), NL = hf.n_leaves(), NV = hf.n_votes();
         dev_alloc(df_nodes_, NN);
+        dev_alloc(df_hot_, NN);
+        df_n_nodes_ = NN;
         dev_alloc(df_roots_, (size_t)hf.n_trees);
         dev_alloc(df_leaf_prob_, NL);
         dev_alloc(df_leaf_info_, NL);
@@ -187,6 +191,7 @@ void Context::ensure_forest(const HostForest& hf) {
         df_sigma_version_ = sv;
     }
     fdev_.nodes = df_nodes_;
+    fdev_.hot = df_hot_;
     fdev_.roots = df_roots_;
     fdev_.leaf_prob = df_leaf_prob_;
     fdev_.leaf_info = df_leaf_info_;
@@ -389,6 +394,10 @@ void Context::run_front(const FrameBuffers& b, uint32_t n, const FrameState* gue
     if (guess_state) {
         *h_fs_ = *guess_state;
         DH_CUDA(cudaMemcpyAsync(d_fs_, h_fs_, sizeof(FrameState), cudaMemcpyHostToDevice, stream_));
+    }
+    if (g.P && hot_tw_ != tiles_.tw) {  // node table for this tile plan (once per forest x plan)
+        launch_plan_nodes(df_nodes_, df_hot_, df_n_nodes_, tiles_.tw, stream_);
+        hot_tw_ = tiles_.tw;
     }
     mark(DH_STAGE_SAT);
     launch_sat(b, g, n, stream_);

@@ -33,35 +33,8 @@ namespace dev {
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// TMA: 3-D tiled bulk tensor load global -> shared, completion signalled on an mbarrier.
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-        : "memory");
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -178,61 +151,146 @@ __global__ void __launch_bounds__(128) sat_cols_kernel(uint32_t* __restrict__ sa
 }
 
 // ================================================================ K2: forest traversal
+// Node table prepared for one tile plan: see HotNode (dh_types.hpp).
+__global__ void __launch_bounds__(256) plan_nodes_kernel(const NodeRec* __restrict__ nodes, HotNode* __restrict__ hot,
+                                                         size_t n, uint32_t tw) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const NodeRec r = nodes[i];
+    HotNode h;
+    uint32_t c[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t x0 = r.r[k * 4 + 0], y0 = r.r[k * 4 + 1], x1 = r.r[k * 4 + 2], y1 = r.r[k * 4 + 3];
+        const uint32_t packed = (y0 * tw + x0) | ((x1 - x0) << 16) | ((y1 - y0) << 24);  // y0*tw + x0 <= 254*256+254
+        if (k == 0) h.r1 = packed; else h.r2 = packed;
+        c[k] = (x1 - x0) * (y1 - y0);
+        if (c[k] == 0u) c[k] = 1u;  // empty rect: sum 0, avg 0.0 (types.rs:335-337)
+    }
+    h.counts = c[0] | (c[1] << 16);
+    h.spare = 0u;
+    h.child[0] = r.child[0];
+    h.child[1] = r.child[1];
+    h.thr_scaled = r.thr_scaled;
+    hot[i] = h;
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+
+// HoughTreeFunctions::binarize (houghforest.rs:185-193) exactly as written: avg = sum as f64 /
+// count as f64 (types.rs:335-338), avg1 - avg2 > threshold.  Only reached at near-ties.
+__device__ __noinline__ bool binarize_ieee(const NodeRec* __restrict__ nodes, int32_t node, uint32_t s1, uint32_t s2) {
+    const NodeRec r = nodes[node];
+    const uint32_t c1 = (uint32_t)(r.r[2] - r.r[0]) * (uint32_t)(r.r[3] - r.r[1]);
+    const uint32_t c2 = (uint32_t)(r.r[6] - r.r[4]) * (uint32_t)(r.r[7] - r.r[5]);
+    const double avg1 = c1 ? __ddiv_rn(__uint2double_rn(s1), __uint2double_rn(c1)) : 0.0;
+    const double avg2 = c2 ? __ddiv_rn(__uint2double_rn(s2), __uint2double_rn(c2)) : 0.0;
+    return __dsub_rn(avg1, avg2) > r.threshold;
+}
+
 // One CTA per (tile of patches, frame).  The tile's SAT window (tw x th u32) is brought into
 // shared memory by ONE TMA bulk-tensor load; all 8 taps of every node test are then shared-memory
-// gathers.  Non-background patches of the tile are compacted (ballot) so that every lane of the
-// traversal loop owns a live patch x tree pair; lanes of a warp are neighbouring patches of the
-// same tree, so the upper levels read the same node record (broadcast) and nearby taps.
+// loads (32-bit shared addresses, ld.shared).  Tiles whose whole window is background (window sum
+// 0, four taps of the global SAT) skip the load.  Non-background patches of the tile are
+// compacted (ballot) so that every lane of the traversal loop owns a live patch x tree pair; lanes
+// of a warp are neighbouring patches of the same tree, so the upper levels read the same node
+// record (broadcast) and nearby taps.
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constant__ CUtensorMap sat_map,
+                                                            const HotNode* __restrict__ hot,
                                                             const NodeRec* __restrict__ nodes,
                                                             const int32_t* __restrict__ roots, int32_t* __restrict__ leaf,
+                                                            const uint32_t* __restrict__ sat,
                                                             FrameState* __restrict__ fs, Geometry g, TilePlan tp) {
     extern __shared__ uint8_t smem_raw[];
-    // 128-byte aligned tile (TMA destination), then the barrier, then the compacted patch list
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    uint32_t* tile = reinterpret_cast<uint32_t*>(base);
+    // 128-byte aligned tile (TMA destination), then the barrier, then the compacted patch list;
+    // everything is addressed through 32-bit shared-window addresses
+    const uint32_t tile_a = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t tile_bytes = tp.tw * tp.th * 4u;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(base + ((tile_bytes + 15u) & ~15u));
-    uint16_t* live = reinterpret_cast<uint16_t*>(bar + 2);
-    __shared__ uint32_t s_nlive;
+    const uint32_t bar_a = tile_a + ((tile_bytes + 15u) & ~15u);
+    const uint32_t live_a = bar_a + 16u;
+    __shared__ uint32_t s_nlive, s_empty;
 
     const uint32_t frame = blockIdx.y;
     const uint32_t tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
     const uint32_t px0 = tile_x * tp.tpx, py0 = tile_y * tp.tpy;  // first patch of the tile
     const uint32_t tid = threadIdx.x;
-
-    if (tid == 0) {
-        prefetch_tensormap(&sat_map);
-        mbar_init(bar, 1);
-        fence_mbar_init();
-        s_nlive = 0;
-    }
-    __syncthreads();
-    // TMA needs the innermost coordinate 16-byte aligned: start the tile at a multiple of 4
-    // elements and shift the patch origins by the slack dx (the planner widened tw for it).
-    const uint32_t x0 = px0 * g.stride, ax0 = x0 & ~3u, dx = x0 - ax0;
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar, tile_bytes);
-        tma_load_3d(tile, &sat_map, (int)ax0, (int)(py0 * g.stride), (int)frame, bar);
-    }
-    mbar_wait(bar, 0);
-
-    // ---- background test (prediction.rs:567-571: mean over the whole patch > 0  <=>  sum != 0)
     const uint32_t npt = tp.tpx * tp.tpy;
     const int T = (int)g.n_trees;
     int32_t* leaf_f = leaf + (size_t)frame * T * g.P;
+
+    // TMA needs the innermost coordinate 16-byte aligned: start the tile at a multiple of 4
+    // elements and shift the patch origins by the slack dx (the planner widened tw for it).
+    const uint32_t x0 = px0 * g.stride, y0 = py0 * g.stride, ax0 = x0 & ~3u, dx = x0 - ax0;
+    if (tid == 0) {
+        prefetch_tensormap(&sat_map);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1u) : "memory");
+        fence_mbar_init();
+        s_nlive = 0;
+        // window of the tile's patches: [x0, x1) x [y0, y1).  Its pixel sum is < 2^32 (<= 256*256
+        // pixels), so the modular four-tap difference is zero iff every patch is background.
+        const uint32_t lastx = min(px0 + tp.tpx, g.npx) - 1u, lasty = min(py0 + tp.tpy, g.npy) - 1u;
+        const uint32_t x1 = lastx * g.stride + g.sw, y1 = lasty * g.stride + g.sh;
+        const uint32_t* S = sat + (size_t)frame * (g.h + 1) * g.sat_pitch;
+        const uint32_t sum = __ldg(S + (size_t)y1 * g.sat_pitch + x1) - __ldg(S + (size_t)y0 * g.sat_pitch + x1) -
+                             __ldg(S + (size_t)y1 * g.sat_pitch + x0) + __ldg(S + (size_t)y0 * g.sat_pitch + x0);
+        s_empty = sum == 0u;
+        if (sum != 0u) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(tile_bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(tile_a),
+                "l"(&sat_map), "r"((int)ax0), "r"((int)y0), "r"((int)frame), "r"(bar_a)
+                : "memory");
+        }
+    }
+    __syncthreads();
+    if (s_empty) {  // prediction.rs:567-571 fails for every patch of the tile
+        for (uint32_t i = tid; i < npt * (uint32_t)T; i += kThreads) {
+            const uint32_t lp = i % npt, t = i / npt;
+            const uint32_t gx = px0 + lp % tp.tpx, gy = py0 + lp / tp.tpx;
+            if (gx < g.npx && gy < g.npy) leaf_f[(size_t)t * g.P + gy * g.npx + gx] = -1;
+        }
+        return;
+    }
+    {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+            "@P1 bra DONE;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}\n" ::"r"(bar_a),
+            "r"(0u)
+            : "memory");
+    }
+
+    // ---- background test (prediction.rs:567-571: mean over the whole patch > 0  <=>  sum != 0)
+    const uint32_t tw4 = tp.tw * 4u;
+    const uint32_t org_a = tile_a + dx * 4u;  // patch (0,0) of the tile
     uint32_t my_valid = 0;
     for (uint32_t lp = tid; lp < ((npt + 31u) & ~31u); lp += kThreads) {
         bool ok = false;
-        uint32_t gp = 0;
         if (lp < npt) {
             const uint32_t lx = lp % tp.tpx, ly = lp / tp.tpx;
             const uint32_t gx = px0 + lx, gy = py0 + ly;
             if (gx < g.npx && gy < g.npy) {
-                gp = gy * g.npx + gx;
-                const uint32_t* o = tile + ly * g.stride * tp.tw + lx * g.stride + dx;
-                const uint32_t sum = o[g.sh * tp.tw + g.sw] - o[g.sw] - o[g.sh * tp.tw] + o[0];
+                const uint32_t gp = gy * g.npx + gx;
+                const uint32_t o = org_a + ly * g.stride * tw4 + lx * g.stride * 4u;
+                const uint32_t sum = lds_u32(o + g.sh * tw4 + g.sw * 4u) - lds_u32(o + g.sw * 4u) - lds_u32(o + g.sh * tw4) + lds_u32(o);
                 ok = sum != 0u;
                 if (!ok)
                     for (int t = 0; t < T; ++t) leaf_f[(size_t)t * g.P + gp] = -1;
@@ -243,7 +301,7 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
         if ((tid & 31u) == 0 && m) basei = atomicAdd(&s_nlive, (uint32_t)__popc(m));
         basei = __shfl_sync(0xffffffffu, basei, 0);
         if (ok) {
-            live[basei + __popc(m & ((1u << (tid & 31u)) - 1u))] = (uint16_t)lp;
+            sts_u16(live_a + 2u * (basei + __popc(m & ((1u << (tid & 31u)) - 1u))), lp);
             ++my_valid;
         }
     }
@@ -251,41 +309,36 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
     const uint32_t nlive = s_nlive;
 
     // ---- root -> leaf walks: item = (tree, live patch); lanes = neighbouring live patches
-    unsigned long long visits = 0;
+    uint32_t visits = 0;
     const uint32_t items = nlive * (uint32_t)T;
+    const uint4* hot4 = reinterpret_cast<const uint4*>(hot);
     for (uint32_t it = tid; it < items; it += kThreads) {
         const uint32_t t = it / nlive;
-        const uint32_t lp = live[it - t * nlive];
+        const uint32_t lp = lds_u16(live_a + 2u * (it - t * nlive));
         const uint32_t lx = lp % tp.tpx, ly = lp / tp.tpx;
-        const uint32_t* o = tile + ly * g.stride * tp.tw + lx * g.stride + dx;
+        const uint32_t o = org_a + ly * g.stride * tw4 + lx * g.stride * 4u;
         int32_t node = __ldg(roots + t);
         while (node >= 0) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(nodes + node));      // rects, threshold
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(nodes + node) + 1);  // children, threshold*c1*c2
+            const uint4 A = __ldg(hot4 + 2 * (size_t)node);      // rect taps, pixel counts
+            const uint4 B = __ldg(hot4 + 2 * (size_t)node + 1);  // children, threshold * c1 * c2
             // SubImage::average_value_in_rect (types.rs:317-339) via four SAT taps per rectangle
-            const uint32_t ax0 = a.x & 0xffu, ay0 = (a.x >> 8) & 0xffu, ax1 = (a.x >> 16) & 0xffu, ay1 = a.x >> 24;
-            const uint32_t bx0 = a.y & 0xffu, by0 = (a.y >> 8) & 0xffu, bx1 = (a.y >> 16) & 0xffu, by1 = a.y >> 24;
-            const uint32_t s1 = o[ay1 * tp.tw + ax1] - o[ay0 * tp.tw + ax1] - o[ay1 * tp.tw + ax0] + o[ay0 * tp.tw + ax0];
-            const uint32_t s2 = o[by1 * tp.tw + bx1] - o[by0 * tp.tw + bx1] - o[by1 * tp.tw + bx0] + o[by0 * tp.tw + bx0];
-            const uint32_t c1 = (ax1 - ax0) * (ay1 - ay0), c2 = (bx1 - bx0) * (by1 - by0);
+            const uint32_t a00 = o + ((A.x & 0xffffu) << 2), aw = __byte_perm(A.x, 0u, 0x4442) << 2, ah = (A.x >> 24) * tw4;
+            const uint32_t b00 = o + ((A.y & 0xffffu) << 2), bw = __byte_perm(A.y, 0u, 0x4442) << 2, bh = (A.y >> 24) * tw4;
+            const uint32_t s1 = lds_u32(a00 + ah + aw) - lds_u32(a00 + aw) - lds_u32(a00 + ah) + lds_u32(a00);
+            const uint32_t s2 = lds_u32(b00 + bh + bw) - lds_u32(b00 + bw) - lds_u32(b00 + bh) + lds_u32(b00);
             // HoughTreeFunctions::binarize (houghforest.rs:185-193): avg1 - avg2 > threshold with
             // avg = sum as f64 / count as f64.  Filtered exact predicate: the real number
             // avg1 - avg2 is N/D with N = s1*c2 - s2*c1, D = c1*c2 (exact in i64); the reference's
-            // three roundings move it by < 3e-11, i.e. < 0.13 in units of 1/D, so whenever
-            // |N - threshold*D| > 2 the sign of N - threshold*D IS the reference's answer.
-            // Only near-ties (and NaN thresholds) take the IEEE-division path below.
-            const uint32_t d1 = c1 ? c1 : 1u, d2 = c2 ? c2 : 1u;  // empty rect: sum 0, avg 0.0 (types.rs:335-337)
+            // three roundings move it by < 3e-11, i.e. < 0.13 in units of 1/D, and thr*D carries
+            // one more rounding (< 0.13 whenever it can matter), so whenever |N - thr*D| > 2 the
+            // sign of N - thr*D IS the reference's answer.  Only near-ties (and NaN thresholds)
+            // take the IEEE-division path.
+            const uint32_t d1 = A.z & 0xffffu, d2 = A.z >> 16;
             const long long N = (long long)((unsigned long long)s1 * d2) - (long long)((unsigned long long)s2 * d1);
-            const double diff = __dsub_rn(__ll2double_rn(N), __hiloint2double((int)b.w, (int)b.z));
-            bool bit;
-            if (fabs(diff) > 2.0) {
-                bit = diff > 0.0;
-            } else {
-                const double avg1 = c1 ? __ddiv_rn(__uint2double_rn(s1), __uint2double_rn(c1)) : 0.0;
-                const double avg2 = c2 ? __ddiv_rn(__uint2double_rn(s2), __uint2double_rn(c2)) : 0.0;
-                bit = __dsub_rn(avg1, avg2) > __hiloint2double((int)a.w, (int)a.z);
-            }
-            node = bit ? (int)b.y : (int)b.x;
+            const double diff = __dsub_rn(__ll2double_rn(N), __hiloint2double((int)B.w, (int)B.z));
+            int32_t next = diff > 0.0 ? (int)B.y : (int)B.x;
+            if (!(fabs(diff) > 2.0)) next = binarize_ieee(nodes, node, s1, s2) ? (int)B.y : (int)B.x;
+            node = next;
             ++visits;
         }
         const uint32_t gp = (py0 + ly) * g.npx + (px0 + lx);
@@ -299,7 +352,7 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
         my_valid += __shfl_xor_sync(0xffffffffu, my_valid, d);
     }
     if ((tid & 31u) == 0) {
-        if (visits) atomicAdd(&fs[frame].node_visits, visits);
+        if (visits) atomicAdd(&fs[frame].node_visits, (unsigned long long)visits);
         if (my_valid) atomicAdd(&fs[frame].n_valid, my_valid);
     }
 }
@@ -1058,7 +1111,13 @@ void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Ge
         configured_smem = (int)tp.smem_bytes;
     }
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
-    traverse_kernel<kTraverseThreads><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, f.nodes, f.roots, b.leaf, b.fs, g, tp);
+    traverse_kernel<kTraverseThreads><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, f.hot, f.nodes, f.roots, b.leaf, b.sat,
+                                                                                  b.fs, g, tp);
+}
+
+void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, size_t n_nodes, uint32_t tile_width, cudaStream_t s) {
+    if (n_nodes == 0) return;
+    plan_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(nodes, hot, n_nodes, tile_width);
 }
 
 void launch_gate(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s) {

@@ -54,6 +54,7 @@ struct TilePlan {
 
 struct ForestDev {
     const NodeRec* nodes;
+    const HotNode* hot;        // nodes prepared for the current tile plan (plan_nodes_kernel)
     const int32_t* roots;
     const double* leaf_prob;
     const LeafInfo* leaf_info;
@@ -84,6 +85,7 @@ struct FrameBuffers {
 void launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s);
 void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s);
+void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, size_t n_nodes, uint32_t tile_width, cudaStream_t s);
 void launch_gate(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 void launch_vote_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
                            uint32_t iterations, uint32_t n_ctas, uint32_t lanes_per_hit, bool static_items,

@@ -29,6 +29,22 @@ struct alignas(32) NodeRec {
 };
 static_assert(sizeof(NodeRec) == 32, "NodeRec must be one 32-byte sector");
 
+// The same node prepared for one tile plan (the traversal kernel's hot table, built on the device
+// by plan_nodes_kernel whenever the forest or the shared-memory tile width changes).  Everything
+// the walk needs is precomputed: per rectangle the word offset of its top-left SAT tap inside the
+// shared-memory tile (y0 * tile_width + x0, relative to the patch origin) with width and height,
+// the two pixel counts (empty -> 1), the child links and threshold * c1 * c2.  NodeRec stays the
+// canonical record and is only read again at near-ties (IEEE-division path).
+struct alignas(32) HotNode {
+    uint32_t r1;       // off00 | width << 16 | height << 24
+    uint32_t r2;
+    uint32_t counts;   // c1 | c2 << 16, each max(pixel count, 1) <= 65025
+    uint32_t spare;
+    int32_t child[2];
+    double thr_scaled;
+};
+static_assert(sizeof(HotNode) == 32, "HotNode must be one 32-byte sector");
+
 // Per-leaf static quantities (prediction.rs:594-600,643 — constant per leaf, recomputed per hit by
 // the reference).  Filled on the device by leaf_gate_kernel.
 struct alignas(16) LeafInfo {
