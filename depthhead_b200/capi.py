@@ -15,8 +15,8 @@ from . import _build
 
 DH_OK, DH_E_JSON, DH_E_SHAPE, DH_E_CUDA, DH_E_ARG, DH_E_STATE = 0, -1, -2, -3, -4, -5
 DH_DEPTH_HOST, DH_DEPTH_DEVICE = 0, 1
-DH_N_STAGES, DH_N_COUNTERS = 6, 12
-STAGES = ("h2d", "sat", "traverse", "gate", "vote_meanshift", "d2h")
+DH_N_STAGES, DH_N_COUNTERS = 7, 12
+STAGES = ("h2d", "sat", "traverse", "gate", "vote", "meanshift", "d2h")
 COUNTERS = ("frames", "patches", "valid_patches", "evals", "node_visits", "gate_patches", "hits",
             "centre_votes", "rot_votes", "launches", "meanshift_iters", "cube_rebuilds")
 

@@ -80,7 +80,6 @@ Context::Context(int device) : device_(device) {
         DH_CUDA(cudaEventCreateWithFlags(&ev_consumed_[i], cudaEventDisableTiming));
     }
     dev_alloc(d_counters_, DH_N_COUNTERS);
-    dev_alloc(d_work_counter_, 1);
     DH_CUDA(cudaHostAlloc((void**)&h_fs_, sizeof(FrameState), cudaHostAllocDefault));
     DH_CUDA(cudaHostAlloc((void**)&h_counters_, sizeof(unsigned long long) * DH_N_COUNTERS, cudaHostAllocDefault));
     chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 0);  // 0 = adaptive (128 for host input, 1024 for device input)
@@ -94,8 +93,6 @@ Context::~Context() {
     cudaDeviceSynchronize();
     free_scratch();
     free_forest();
-    dev_free(d_boxes_);
-    dev_free(d_work_counter_);
     dev_free(d_counters_);
     dev_free(d_aux32_);
     dev_free(d_aux16_);
@@ -130,6 +127,8 @@ void Context::free_forest() {
     dev_free(df_offsets_);
     dev_free(df_offsets3_);
     dev_free(df_rot_bins_);
+    dev_free(df_rot_coarse_);
+    dev_free(df_leaf_box_);
     dev_free(df_kernel_);
     df_serial_ = 0;
 }
@@ -148,6 +147,8 @@ void Context::ensure_forest(const HostForest& hf) {
         dev_alloc(df_offsets_, NV);       // float4 per vote
         dev_alloc(df_offsets3_, NV * 3);  // packed copy, only for the leaf-gate kernel below
         dev_alloc(df_rot_bins_, NV);
+        dev_alloc(df_rot_coarse_, NV);
+        dev_alloc(df_leaf_box_, NL);
         dev_alloc(df_kernel_, (size_t)kKernelCells);
         if (NN) DH_CUDA(cudaMemcpyAsync(df_nodes_, hf.nodes.data(), NN * sizeof(NodeRec), cudaMemcpyHostToDevice, stream_));
         DH_CUDA(cudaMemcpyAsync(df_roots_, hf.roots.data(), hf.roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
@@ -168,7 +169,8 @@ void Context::ensure_forest(const HostForest& hf) {
         DH_CUDA(cudaMemcpyAsync(d_vs, hf.leaf_vote_start.data(), NL * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
         DH_CUDA(cudaMemcpyAsync(d_nv, hf.leaf_n_votes.data(), NL * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
         if (NV) DH_CUDA(cudaMemcpyAsync(d_rot, hf.rotations.data(), NV * 3 * sizeof(double), cudaMemcpyHostToDevice, stream_));
-        launch_leaf_gates(df_leaf_prob_, d_vs, d_nv, df_offsets3_, d_rot, df_leaf_info_, (uint32_t)NL, stream_);
+        launch_leaf_gates(df_leaf_prob_, d_vs, d_nv, df_offsets3_, d_rot, df_rot_bins_, df_leaf_info_, df_leaf_box_, df_rot_coarse_,
+                          (uint32_t)NL, stream_);
         DH_CUDA(cudaGetLastError());
         DH_CUDA(cudaStreamSynchronize(stream_));
         dev_free(d_vs);
@@ -197,6 +199,8 @@ void Context::ensure_forest(const HostForest& hf) {
     fdev_.leaf_info = df_leaf_info_;
     fdev_.offsets = df_offsets_;
     fdev_.rot_bins = df_rot_bins_;
+    fdev_.rot_coarse = df_rot_coarse_;
+    fdev_.leaf_box = df_leaf_box_;
     fdev_.ms_kernel = df_kernel_;
     fdev_.n_trees = hf.n_trees;
 }
@@ -209,8 +213,8 @@ void Context::free_scratch() {
     dev_free(d_leaf_);
     dev_free(d_p3_);
     dev_free(d_gate_);
-    dev_free(d_chits_);
-    dev_free(d_rhits_);
+    dev_free(d_gated_);
+    dev_free(d_cubes_);
     dev_free(d_grids_);
     dev_free(d_fs_);
     dev_free(d_results_);
@@ -269,8 +273,8 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
     {
         const uint64_t npx = (w - sw + stride - 1) / stride, npy = (h - sh + stride - 1) / stride;
         const uint64_t PT = std::max<uint64_t>(npx * npy, 1) * (uint64_t)hf.n_trees;
-        const uint64_t per_frame = (uint64_t)(h + 1) * ((w + 4) & ~3ull) * 4 + PT * (4 + sizeof(CentreHit) + sizeof(RotHit)) +
-                                   npx * npy * 13 + (uint64_t)w * h * 4 + 40000;
+        const uint64_t per_frame = (uint64_t)(h + 1) * ((w + 4) & ~3ull) * 4 + PT * 4 + npx * npy * 29 +
+                                   (uint64_t)w * h * 4 + 2ull * vote_box_cells() * 4 + 40000;
         const uint64_t budget = 12ull << 30;
         cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(cap, budget / per_frame));
     }
@@ -292,6 +296,13 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
         g.P = g.npx * g.npy;
         g.sat_pitch = (w + 1 + 3) & ~3u;
         g.n_trees = (uint32_t)hf.n_trees;
+        // exact division by multiply-high: floor(n / d) == umulhi(n, floor(2^32 / d) + 1) whenever n * d < 2^32
+        auto magic = [](uint32_t d) -> uint32_t {
+            const uint64_t nmax = (uint64_t)kGuessGridParts * (d - 1);
+            return (d >= 2 && nmax * d < (1ull << 32)) ? (uint32_t)((1ull << 32) / d) + 1u : 0u;
+        };
+        g.magic_w = magic(w);
+        g.magic_h = magic(h);
         if ((uint64_t)g.P * g.n_trees > 0x7fffffffull) throw ModelError(DH_E_SHAPE, "too many patch x tree pairs per frame");
         const size_t F = cap, P = std::max<uint32_t>(g.P, 1u), T = g.n_trees;
         dev_alloc(d_sat_, F * (size_t)(h + 1) * g.sat_pitch);
@@ -299,8 +310,8 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
         dev_alloc(d_leaf_, F * P * T);
         dev_alloc(d_p3_, F * P * 3);
         dev_alloc(d_gate_, F * P);
-        dev_alloc(d_chits_, F * P * T);
-        dev_alloc(d_rhits_, F * P * T);
+        dev_alloc(d_gated_, F * P);
+        dev_alloc(d_cubes_, F * 2 * (size_t)vote_box_cells());
         dev_alloc(d_grids_, F * (size_t)(kPosGridCells + kRotGridCells));
         dev_alloc(d_fs_, F);
         dev_alloc(d_results_, F);
@@ -318,14 +329,6 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
             if (r != CUDA_SUCCESS) throw ModelError(DH_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
         }
         sk_ = k;
-    }
-    // accumulator cubes: one per persistent CTA of vote_meanshift_kernel
-    const uint32_t want_ctas = (uint32_t)n_sms_ * vote_ctas_per_sm();
-    if (vm_ctas_ < want_ctas) {
-        DH_CUDA(cudaStreamSynchronize(stream_));
-        dev_free(d_boxes_);
-        dev_alloc(d_boxes_, (size_t)want_ctas * vote_box_cells());
-        vm_ctas_ = want_ctas;
     }
     std::memcpy(g.K, K, sizeof(float) * 9);
     mat3_inverse_f32(K, g.Kinv);
@@ -350,12 +353,10 @@ FrameBuffers Context::buffers(const uint16_t* depth) const {
     b.leaf = d_leaf_;
     b.p3 = d_p3_;
     b.gate = d_gate_;
-    b.chits = d_chits_;
-    b.rhits = d_rhits_;
+    b.gated = d_gated_;
     b.grids = d_grids_;
     b.fs = d_fs_;
-    b.boxes = d_boxes_;
-    b.work_counter = d_work_counter_;
+    b.cubes = d_cubes_;
     b.results = d_results_;
     b.ms_trace = d_ms_trace_;
     b.ms_trace_cap = sk_.trace_iters;
@@ -414,18 +415,16 @@ void Context::run_front(const FrameBuffers& b, uint32_t n, const FrameState* gue
 void Context::run_back(const FrameBuffers& b, uint32_t n, uint32_t iterations) {
     const Geometry& g = geom_;
     mark(DH_STAGE_GATE);
-    if (g.P) {
-        launch_gate(b, g, fdev_, n, stream_);
-        launches_ += 1;
-        stage_check("gate");
-    }
-    mark(DH_STAGE_VOTE_MEANSHIFT);
-    // debug mode (single frame): one CTA per work item so both accumulator cubes survive the launch
-    const bool static_items = debug_ && n == 1;
-    const uint32_t ctas = std::min<uint32_t>(vm_ctas_, 2u * n);
-    launch_vote_meanshift(b, g, fdev_, n, iterations, ctas, lanes_per_hit_, static_items, stream_);
-    launches_ += 1;
-    stage_check("vote_meanshift");
+    launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, lanes_per_hit_, stream_);
+    stage_check("gate + coarse grids");
+    mark(DH_STAGE_VOTE);
+    // the accumulator cubes of this pass start empty
+    if (iterations) DH_CUDA(cudaMemsetAsync(d_cubes_, 0, sizeof(uint32_t) * 2 * (size_t)vote_box_cells() * n, stream_));
+    launches_ += (uint64_t)launch_seed_and_cubes(b, g, fdev_, n, iterations, lanes_per_hit_, stream_);
+    stage_check("seeds + accumulator cubes");
+    mark(DH_STAGE_MEANSHIFT);
+    launches_ += (uint64_t)launch_meanshift(b, g, fdev_, n, iterations, stream_);
+    stage_check("mean-shift");
     mark(DH_STAGE_D2H);
     launch_counters(b, g, n, d_counters_, stream_);
     launches_ += 1;

@@ -91,6 +91,8 @@ private:
     float4* df_offsets_ = nullptr;
     float* df_offsets3_ = nullptr;
     uint32_t* df_rot_bins_ = nullptr;
+    uint16_t* df_rot_coarse_ = nullptr;
+    LeafBox* df_leaf_box_ = nullptr;
     float* df_kernel_ = nullptr;
     ForestDev fdev_{};
     uint32_t lanes_per_hit_ = 1;
@@ -108,15 +110,12 @@ private:
     int32_t* d_leaf_ = nullptr;
     float* d_p3_ = nullptr;
     uint8_t* d_gate_ = nullptr;
-    CentreHit* d_chits_ = nullptr;
-    RotHit* d_rhits_ = nullptr;
+    float4* d_gated_ = nullptr;           // gate-passing patches [F][P]
+    uint32_t* d_cubes_ = nullptr;         // accumulator cubes [F][2][kBox^3]
     uint32_t* d_grids_ = nullptr;
     FrameState* d_fs_ = nullptr;
     dh_result* d_results_ = nullptr;
     int32_t* d_ms_trace_ = nullptr;
-    uint32_t* d_boxes_ = nullptr;         // accumulator cubes, one per persistent CTA
-    uint32_t vm_ctas_ = 0;
-    uint32_t* d_work_counter_ = nullptr;
     unsigned long long* d_counters_ = nullptr;
     uint32_t* d_aux32_ = nullptr;
     uint16_t* d_aux16_ = nullptr;

@@ -4,12 +4,14 @@
 //   K1  sat_rows / sat_cols      u16 depth -> u32 summed-area table (wrap-around exact, see below)
 //   K2  traverse_kernel          TMA-staged SAT tile in shared memory; one thread per patch x tree
 //                                walks root->leaf (houghforest.rs:185-193, types.rs:317-339)
-//   K3  gate_kernel              ordered f64 prob sum, 0.7 gate, back-projection, hit lists
-//                                (prediction.rs:551-554,582-595)
-//   K4  vote_meanshift_kernel    persistent, one work item per (frame, accumulator): coarse seed
-//                                grid + arg-max seed (prediction.rs:601-752), dense local cube of
-//                                the SparseArray3D<u32> accumulator (meanshift.rs:14-68), mean-shift
-//                                in reference accumulation order (meanshift.rs:328-407)
+//   K3  gate_coarse_kernel       ordered f64 prob sum, 0.7 gate, back-projection, hit list and the two
+//                                coarse seed grids (prediction.rs:551-554,582-595,630-636,661-675)
+//   K4a seed_kernel              arg-max seeds (prediction.rs:694-752, 437-460)
+//   K4b box_build_kernel         dense local cubes of the SparseArray3D<u32> accumulators
+//                                (meanshift.rs:14-68, prediction.rs:635,667), one thread per hit
+//   K4c meanshift_warp_kernel    mean-shift in reference accumulation order (meanshift.rs:328-407),
+//                                one warp per accumulator; rebuild_meanshift_kernel is its fallback
+//                                for positions that drift out of the cube
 //   K5  leaf_gate_kernel         estimate_mean_cov traces + valtoadd per leaf, once per model
 //                                (meancov_estimation.rs:359-378, prediction.rs:594-600,643)
 //
@@ -24,6 +26,7 @@
 // naive loop bit for bit (types.rs:338).
 #include "dh_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 
 namespace dh {
@@ -357,30 +360,72 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
     }
 }
 
-// ================================================================ K3: patch gate + hit lists
-// One thread per patch: ordered f64 probability sum and the 0.7 gate (prediction.rs:582-584), the
-// back-projected centre (prediction.rs:551-554), and one record per voting patch x tree pair in
-// two compact per-frame lists (centre votes / rotation votes).  Everything that is constant per
-// leaf (valtoadd, spread gates) was precomputed by leaf_gate_kernel.
-__global__ void __launch_bounds__(256) gate_kernel(FrameBuffers b, Geometry g, const double* __restrict__ leaf_prob,
-                                                   const LeafInfo* __restrict__ leaf_info) {
-    const uint32_t frame = blockIdx.y;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int T = (int)g.n_trees;
+// ================================================================ K3: patch gate + coarse seed grids
+// Phase A, one thread per patch: ordered f64 probability sum and the 0.7 gate
+// (prediction.rs:582-584) and the back-projected centre (prediction.rs:551-554); gate-passing
+// patches are compacted into shared memory and appended to the frame's gated-patch list (one
+// reservation per CTA).  Phase B, one thread (or G lanes) per gated patch x tree pair: the leaf's
+// votes go into the two coarse seed grids (prediction.rs:630-636, 661-675) held in shared memory;
+// non-zero cells are then added to the frame's grids in global memory.  Everything that is
+// constant per leaf (valtoadd, spread gates) was precomputed by leaf_gate_kernel.
+constexpr int kGateThreads = 256;
+constexpr int kTouchedCap = 4096;
+
+// 2-D projection of one centre vote onto the 20x20 seed grid (prediction.rs:661-675)
+__device__ __forceinline__ uint32_t coarse_pos_cell(const Geometry& g, float nx, float ny, float nz) {
+    const float np[3] = {nx, ny, nz};
+    float p2[2];
+    space_to_img(g.K, np, p2);  // prediction.rs:661
+    // max!/min! macros (prediction.rs:19-25): plain comparisons, NaN -> 0.0
+    const float mx = (p2[0] > 0.0f) ? p2[0] : 0.0f;
+    const float x2d = (mx < (float)(g.w - 1)) ? mx : (float)(g.w - 1);
+    const float my = (p2[1] > 0.0f) ? p2[1] : 0.0f;
+    const float y2d = (my < (float)(g.h - 1)) ? my : (float)(g.h - 1);
+    // (x2d as usize) * 20 / w  (:671-674); the quotient by multiply-high when the host found an
+    // exact magic number (numerator * divisor < 2^32), else by division
+    const uint32_t nxi = __float2uint_rz(x2d) * kGuessGridParts, nyi = __float2uint_rz(y2d) * kGuessGridParts;
+    const uint32_t cx = g.magic_w ? __umulhi(nxi, g.magic_w) : nxi / g.w;
+    const uint32_t cy = g.magic_h ? __umulhi(nyi, g.magic_h) : nyi / g.h;
+    return cy * kGuessGridParts + cx;
+}
+template <int G>
+__global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers b, Geometry g, ForestDev f) {
+    __shared__ uint32_t s_grid[kPosGridCells + kRotGridCells];  // [0,400) centre, [400,8400) rotation
+    __shared__ float4 s_gated[kGateThreads];                     // p3 + patch index of the CTA's gated patches
+    __shared__ uint16_t s_touched[kTouchedCap];                  // rotation cells this CTA made non-zero
+    __shared__ uint32_t s_ngate, s_base, s_ntouched;
+    const uint32_t frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t p = blockIdx.x * kGateThreads + tid;
+    const uint32_t T = g.n_trees;
     const int32_t* leaf_f = b.leaf + (size_t)frame * T * g.P;
     FrameState* fs = b.fs + frame;
-    const uint32_t lane = threadIdx.x & 31u;
+    if (tid == 0) {
+        s_ngate = 0;
+        s_ntouched = 0;
+    }
+    __syncthreads();
 
+    // ---- phase A
     bool gate = false;
-    uint32_t cnt_c = 0, cnt_r = 0;
-    unsigned long long nmid = 0, nrot = 0;
     float p3[3] = {0.f, 0.f, 0.f};
     if (p < g.P) {
-        const bool valid = leaf_f[p] >= 0;
-        if (valid) {
-            // prob = sum(leaf.prob) / len: f64 fold from 0.0 in tree order (prediction.rs:582)
+        if (leaf_f[p] >= 0) {
+            // prob = sum(leaf.prob) / len: f64 fold from 0.0 in tree order (prediction.rs:582);
+            // four independent gathers in flight, the additions stay in tree order
             double s = 0.0;
-            for (int t = 0; t < T; ++t) s = __dadd_rn(s, __ldg(leaf_prob + leaf_f[(size_t)t * g.P + p]));
+            for (uint32_t t0 = 0; t0 < T; t0 += 4) {
+                int32_t L[4];
+                double pr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (t0 + u < T) L[u] = leaf_f[(size_t)(t0 + u) * g.P + p];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (t0 + u < T) pr[u] = __ldg(f.leaf_prob + L[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (t0 + u < T) s = __dadd_rn(s, pr[u]);
+            }
             gate = __ddiv_rn(s, (double)T) > 0.7;  // prediction.rs:584
         }
         if (gate) {
@@ -388,78 +433,128 @@ __global__ void __launch_bounds__(256) gate_kernel(FrameBuffers b, Geometry g, c
             const uint32_t x = g.left_w + gx * g.stride, y = g.left_h + gy * g.stride;
             const uint16_t z = b.depth[((size_t)frame * g.h + y) * g.w + x];  // prediction.rs:551
             img_to_space(g.Kinv, (float)x, (float)y, (float)z, p3);           // prediction.rs:554
-            float* o = b.p3 + ((size_t)frame * g.P + p) * 3;
-            o[0] = p3[0]; o[1] = p3[1]; o[2] = p3[2];
-            for (int t = 0; t < T; ++t) {
-                const int32_t L = leaf_f[(size_t)t * g.P + p];
-                if (!(__ldg(leaf_prob + L) > 0.0)) continue;  // prediction.rs:590
-                const LeafInfo li = leaf_info[L];
-                if (li.valtoadd == 0u) continue;  // zero-weight votes never change a sum
-                if (li.flags & kLeafOffOk) { ++cnt_c; nmid += li.n_votes; }
-                if (li.flags & kLeafRotOk) { ++cnt_r; nrot += li.n_votes; }
+            if (b.p3) {
+                float* o = b.p3 + ((size_t)frame * g.P + p) * 3;
+                o[0] = p3[0]; o[1] = p3[1]; o[2] = p3[2];
             }
         }
         if (b.gate) b.gate[(size_t)frame * g.P + p] = gate ? 1 : 0;
     }
-    // warp-aggregated append to the frame's two hit lists
-    uint32_t incl_c = cnt_c, incl_r = cnt_r;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t nc = __shfl_up_sync(0xffffffffu, incl_c, d), nr = __shfl_up_sync(0xffffffffu, incl_r, d);
-        if (lane >= (uint32_t)d) { incl_c += nc; incl_r += nr; }
+    {
+        const uint32_t m = __ballot_sync(0xffffffffu, gate);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_ngate, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (gate) s_gated[base + __popc(m & ((1u << lane) - 1u))] = make_float4(p3[0], p3[1], p3[2], __uint_as_float(p));
     }
-    const uint32_t tot_c = __shfl_sync(0xffffffffu, incl_c, 31), tot_r = __shfl_sync(0xffffffffu, incl_r, 31);
-    const uint32_t ngate = __popc(__ballot_sync(0xffffffffu, gate));
+    __syncthreads();
+    const uint32_t ngate = s_ngate;
+    if (ngate == 0u) return;
+    if (tid == 0) s_base = atomicAdd(&fs->n_gate, ngate);
+    for (int i = tid; i < kPosGridCells + kRotGridCells; i += kGateThreads) s_grid[i] = 0;
+    __syncthreads();
+    if (tid < ngate) b.gated[(size_t)frame * g.P + s_base + tid] = s_gated[tid];
+
+    // ---- phase B: pair = (tree, gated patch), neighbouring lanes = neighbouring gated patches.
+    // Consecutive centre votes of a thread mostly fall into the same 2-D cell, so equal cells are
+    // merged in a register before the shared atomic.
+    uint32_t cur = 0xffffffffu, acc = 0;
+    uint32_t cnt_c = 0, cnt_r = 0;
+    unsigned long long nmid = 0, nrot = 0;
+    const uint32_t sub = tid % G;
+    const uint32_t npairs = ngate * T;
+    for (uint32_t i = tid / G; i < npairs; i += kGateThreads / G) {
+        const uint32_t t = i / ngate;
+        const float4 h = s_gated[i - t * ngate];
+        const int32_t L = leaf_f[(size_t)t * g.P + __float_as_uint(h.w)];
+        const LeafInfo li = f.leaf_info[L];
+        if (!(li.flags & kLeafVotes)) continue;  // prob > 0 (prediction.rs:590), weight != 0, a spread gate open
+        if (li.flags & kLeafOffOk) {
+            if (sub == 0) { ++cnt_c; nmid += li.n_votes; }
+            for (uint32_t k0 = sub; k0 < li.n_votes; k0 += 4 * G) {
+                float4 o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u * G < li.n_votes) o[u] = __ldg(f.offsets + li.vote_start + k0 + u * G);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u * G >= li.n_votes) break;
+                    // np = p3 - offset (prediction.rs:647); np.z < 0 is skipped (:650)
+                    const float nx = __fsub_rn(h.x, o[u].x), ny = __fsub_rn(h.y, o[u].y), nz = __fsub_rn(h.z, o[u].z);
+                    if (nz < 0.0f) continue;
+                    const uint32_t cell = coarse_pos_cell(g, nx, ny, nz);
+                    if (cell == cur) {
+                        acc += li.valtoadd;
+                    } else {
+                        if (acc) atomicAdd(&s_grid[cur], acc);
+                        cur = cell;
+                        acc = li.valtoadd;
+                    }
+                }
+            }
+        }
+        if (li.flags & kLeafRotOk) {
+            if (sub == 0) { ++cnt_r; nrot += li.n_votes; }
+            for (uint32_t k0 = sub; k0 < li.n_votes; k0 += 4 * G) {
+                uint32_t cell[4];  // rough = r * 20 / 120 per axis (prediction.rs:630-636), static per vote
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u * G < li.n_votes) cell[u] = __ldg(f.rot_coarse + li.vote_start + k0 + u * G);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u * G >= li.n_votes) break;
+                    if (atomicAdd(&s_grid[kPosGridCells + cell[u]], li.valtoadd) == 0u) {
+                        const uint32_t slot = atomicAdd(&s_ntouched, 1u);
+                        if (slot < (uint32_t)kTouchedCap) s_touched[slot] = (uint16_t)cell[u];
+                    }
+                }
+            }
+        }
+    }
+    if (acc) atomicAdd(&s_grid[cur], acc);
+    // per-frame counters, one atomic per warp
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         nmid += __shfl_xor_sync(0xffffffffu, nmid, d);
         nrot += __shfl_xor_sync(0xffffffffu, nrot, d);
+        cnt_c += __shfl_xor_sync(0xffffffffu, cnt_c, d);
+        cnt_r += __shfl_xor_sync(0xffffffffu, cnt_r, d);
     }
-    uint32_t base_c = 0, base_r = 0;
     if (lane == 0) {
-        if (tot_c) base_c = atomicAdd(&fs->n_chits, tot_c);
-        if (tot_r) base_r = atomicAdd(&fs->n_rhits, tot_r);
-        if (ngate) atomicAdd(&fs->n_gate, ngate);
+        if (cnt_c) atomicAdd(&fs->n_chits, cnt_c);
+        if (cnt_r) atomicAdd(&fs->n_rhits, cnt_r);
         if (nmid) atomicAdd(&fs->n_mid_votes, nmid);
         if (nrot) atomicAdd(&fs->n_rot_votes, nrot);
     }
-    base_c = __shfl_sync(0xffffffffu, base_c, 0);
-    base_r = __shfl_sync(0xffffffffu, base_r, 0);
-    if (cnt_c | cnt_r) {
-        CentreHit* oc = b.chits + (size_t)frame * g.P * T + base_c + (incl_c - cnt_c);
-        RotHit* orr = b.rhits + (size_t)frame * g.P * T + base_r + (incl_r - cnt_r);
-        for (int t = 0; t < T; ++t) {
-            const int32_t L = leaf_f[(size_t)t * g.P + p];
-            if (!(__ldg(leaf_prob + L) > 0.0)) continue;
-            const LeafInfo li = leaf_info[L];
-            if (li.valtoadd == 0u) continue;
-            if (li.flags & kLeafOffOk) *oc++ = CentreHit{{p3[0], p3[1], p3[2]}, li.vote_start, li.n_votes, li.valtoadd, {0u, 0u}};
-            if (li.flags & kLeafRotOk) *orr++ = RotHit{li.vote_start, li.n_votes, li.valtoadd, 0u};
+    __syncthreads();
+    uint32_t* gout = b.grids + (size_t)frame * (kPosGridCells + kRotGridCells);
+    for (int i = tid; i < kPosGridCells; i += kGateThreads) {
+        const uint32_t v = s_grid[i];
+        if (v) atomicAdd(gout + i, v);
+    }
+    const uint32_t ntouched = s_ntouched;
+    if (ntouched <= (uint32_t)kTouchedCap) {
+        // a cell whose sum wrapped to 0 may be listed twice: the exchange makes the second visit add 0
+        for (uint32_t i = tid; i < ntouched; i += kGateThreads) {
+            const uint32_t c = kPosGridCells + s_touched[i];
+            const uint32_t v = atomicExch(&s_grid[c], 0u);
+            if (v) atomicAdd(gout + c, v);
+        }
+    } else {
+        for (int i = kPosGridCells + tid; i < kPosGridCells + kRotGridCells; i += kGateThreads) {
+            const uint32_t v = s_grid[i];
+            if (v) atomicAdd(gout + i, v);
         }
     }
 }
 
-// ================================================================ K4: votes + seeds + mean-shift
-// ONE persistent kernel does everything after the gate.  A work item is one accumulator of one
-// frame (centre or rotation — they are independent in the reference too, prediction.rs:469-472);
-// CTAs pull items from an atomic counter.  Per item:
-//   1. coarse pass   expand the frame's hits into the 20x20 (centre) or 20^3 (rotation) seed grid
-//                    in shared memory, arg-max -> seed            (prediction.rs:601-752, 437-460)
-//   2. box build     SparseArray3D<u32> (meanshift.rs:14-68) restricted to a dense kBox^3 cube of
-//                    cells around the current position, in an L2-resident per-CTA workspace:
-//                    plain u32 atomicAdd per in-box vote, no hashing, votes outside never touch memory
-//   3. mean-shift    meanshift.rs:328-407 in reference accumulation order on that cube.
-// A round moves the position by at most 10 cells, the cube leaves 14 cells of margin around the
-// 20^3 window; if the window would leave the cube, the cube is rebuilt around the current position
-// (counted in FrameState::rebuilds).  Results are therefore exactly those of the unbounded map.
-constexpr int kBox = 48;                      // cells per axis of the dense cube
+// ================================================================ K4a: seeds
+// One CTA per frame: arg-max of the two coarse grids -> mean-shift seeds (prediction.rs:694-752,
+// 437-460) and the origin of the frame's two accumulator cubes.
+constexpr int kBox = 48;                      // cells per axis of the dense accumulator cube
 constexpr int kBoxCells = kBox * kBox * kBox; // 110 592 cells = 432 KB
-constexpr int kVmThreads = 512;
-constexpr int kVmCtasPerSm = 2;               // 64 registers per thread: room for 4 vote records in flight
-constexpr int kVmWarps = kVmThreads / 32;
+constexpr int kSeedThreads = 256;
 constexpr int kMsHistory = 64;
-constexpr int kMsSegment = 2048;              // non-zero window cells summed per pass
-constexpr int kVmSmemBytes = kRotGridCells * 4 + 4 * kMsSegment * 4;
 
 struct Best {
     uint32_t val, idx;
@@ -489,411 +584,418 @@ __device__ Best block_argmax(const uint32_t* cells, int n, Best* s_red) {
     return r;
 }
 
-// Visits every centre vote of the frame: fn(nx, ny, nz, weight) with np = p3 - offset
-// (prediction.rs:647); votes with np.z < 0 are skipped (prediction.rs:650).  G lanes share a hit;
-// with G == 1 a thread loads up to four vote records before using them (memory-level parallelism:
-// these passes are bound by L2 latency, not bandwidth).
-template <int G, typename F>
-__device__ __forceinline__ void for_each_centre_vote(const CentreHit* __restrict__ hits, uint32_t n_hits,
-                                                     const float4* __restrict__ offsets, F&& fn) {
-    const uint32_t sub = threadIdx.x % G;
-    for (uint32_t hi = threadIdx.x / G; hi < n_hits; hi += kVmThreads / G) {
-        const uint4 ha = __ldg(reinterpret_cast<const uint4*>(hits + hi));
-        const uint2 hb = __ldg(reinterpret_cast<const uint2*>(hits + hi) + 2);
-        const float px = __uint_as_float(ha.x), py = __uint_as_float(ha.y), pz = __uint_as_float(ha.z);
-        const uint32_t v0 = ha.w, n = hb.x, wgt = hb.y;
-        if (G == 1) {
-            for (uint32_t k0 = 0; k0 < n; k0 += 4) {
-                float4 o[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k0 + u < n) o[u] = __ldg(offsets + v0 + k0 + u);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + u >= n) break;
-                    const float nx = __fsub_rn(px, o[u].x), ny = __fsub_rn(py, o[u].y), nz = __fsub_rn(pz, o[u].z);
-                    if (nz < 0.0f) continue;
-                    fn(nx, ny, nz, wgt);
-                }
+__global__ void __launch_bounds__(kSeedThreads) seed_kernel(FrameBuffers b, Geometry g, uint32_t iterations) {
+    __shared__ Best s_red[kSeedThreads / 32];
+    __shared__ unsigned long long s_sum[kSeedThreads / 32];
+    __shared__ uint32_t s_cnt[kSeedThreads / 32];
+    const uint32_t frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    FrameState* fs = b.fs + frame;
+    const uint32_t* grid = b.grids + (size_t)frame * (kPosGridCells + kRotGridCells);
+    const uint32_t guessed = fs->has_guess;
+
+    // ---- centre seed (prediction.rs:694-729, 750)
+    int32_t sm[3];
+    {
+        const Best bp = block_argmax(grid, kPosGridCells, s_red);
+        // z = mean of the non-zero depth in the winning grid part (prediction.rs:706-725)
+        const uint32_t gpw = g.w / kGuessGridParts, gph = g.h / kGuessGridParts;
+        const uint32_t cgx = bp.idx % kGuessGridParts, cgy = bp.idx / kGuessGridParts;
+        unsigned long long zs = 0;
+        uint32_t zc = 0;
+        const uint16_t* img = b.depth + (size_t)frame * g.h * g.w;
+        for (uint32_t i = tid; i < gpw * gph; i += kSeedThreads) {
+            const uint32_t v = img[(size_t)(gph * cgy + i / gpw) * g.w + gpw * cgx + i % gpw];
+            if (v > 0) {
+                zs += v;
+                zc += 1;
             }
-        } else {
-            for (uint32_t k = sub; k < n; k += G) {
-                const float4 o = __ldg(offsets + v0 + k);
-                const float nx = __fsub_rn(px, o.x), ny = __fsub_rn(py, o.y), nz = __fsub_rn(pz, o.z);
-                if (nz < 0.0f) continue;
-                fn(nx, ny, nz, wgt);
-            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            zs += __shfl_xor_sync(0xffffffffu, zs, d);
+            zc += __shfl_xor_sync(0xffffffffu, zc, d);
+        }
+        if (lane == 0) {
+            s_sum[warp] = zs;
+            s_cnt[warp] = zc;
+        }
+        __syncthreads();
+        zs = 0;
+        zc = 0;
+        for (int i = 0; i < kSeedThreads / 32; ++i) {
+            zs += s_sum[i];
+            zc += s_cnt[i];
+        }
+        const float meanz = zc > 0 ? (float)__ddiv_rn((double)zs, (double)zc) : 0.0f;
+        const float mxf = __fmul_rn(__fadd_rn((float)cgx, 0.5f), (float)gpw);  // :727-729
+        const float myf = __fmul_rn(__fadd_rn((float)cgy, 0.5f), (float)gph);
+        float m3[3];
+        img_to_space(g.Kinv, mxf, myf, meanz, m3);
+        for (int k = 0; k < 3; ++k) sm[k] = __float2int_rz(m3[k]);  // :750
+        if (guessed & 1u)  // prediction.rs:437-441
+            for (int k = 0; k < 3; ++k) sm[k] = __float2int_rz(fs->midp_guess[k]);
+    }
+    // ---- rotation seed (prediction.rs:733-747, 448-460)
+    int32_t sr[3];
+    {
+        const Best br = block_argmax(grid + kPosGridCells, kRotGridCells, s_red);  // :733-742
+        const uint32_t rc[3] = {br.idx % 20u, (br.idx % 400u) / 20u, br.idx / 400u};
+        for (int k = 0; k < 3; ++k) {
+            // :745-747, or the caller's guess :448-450; then :458-460
+            double deg = __ddiv_rn(__dadd_rn(__dmul_rn((double)rc[k], 360.0), 180.0), (double)kGuessGridParts);
+            if (guessed & 2u) deg = __dadd_rn(__ddiv_rn(__dmul_rn(fs->rot_guess[k], 180.0), 3.14159), 180.0);
+            sr[k] = __double2int_rz(__ddiv_rn(__dmul_rn(deg, (double)kRotGridParts), 360.0));
         }
     }
-}
-// Visits every rotation vote of the frame: fn(r1, r2, r3, weight), bins precomputed per vote.
-template <int G, typename F>
-__device__ __forceinline__ void for_each_rot_vote(const RotHit* __restrict__ hits, uint32_t n_hits,
-                                                  const uint32_t* __restrict__ rot_bins, F&& fn) {
-    const uint32_t sub = threadIdx.x % G;
-    for (uint32_t hi = threadIdx.x / G; hi < n_hits; hi += kVmThreads / G) {
-        const uint4 h = __ldg(reinterpret_cast<const uint4*>(hits + hi));  // vote_start, n_votes, valtoadd
-        if (G == 1) {
-            for (uint32_t k0 = 0; k0 < h.y; k0 += 4) {
-                uint32_t bins[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k0 + u < h.y) bins[u] = __ldg(rot_bins + h.x + k0 + u);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + u >= h.y) break;
-                    fn((int)(bins[u] & 0xffu), (int)((bins[u] >> 8) & 0xffu), (int)((bins[u] >> 16) & 0xffu), h.z);
-                }
-            }
-        } else {
-            for (uint32_t k = sub; k < h.y; k += G) {
-                const uint32_t bins = __ldg(rot_bins + h.x + k);
-                fn((int)(bins & 0xffu), (int)((bins >> 8) & 0xffu), (int)((bins >> 16) & 0xffu), h.z);
-            }
+    if (tid == 0) {
+        for (int k = 0; k < 3; ++k) {
+            fs->seed_mid[k] = sm[k];
+            fs->seed_rot[k] = sr[k];
+            // cube centred on the seed: 14 cells of margin around the 20^3 window
+            fs->box_org[0][k] = (int32_t)((uint32_t)sm[k] - (uint32_t)(kBox / 2));
+            fs->box_org[1][k] = (int32_t)((uint32_t)sr[k] - (uint32_t)(kBox / 2));
         }
+        fs->box_valid[0] = fs->box_valid[1] = iterations > 0 ? 1u : 0u;
     }
 }
 
+// ================================================================ K4b: accumulator cubes
+// SparseArray3D<u32> (meanshift.rs:14-68) restricted to a dense kBox^3 cube of cells per
+// (frame, accumulator), z fastest: plain u32 atomicAdd per in-cube vote, no hashing; votes outside
+// the cube never touch memory.  One thread (or G lanes) per gated patch x tree pair.
 __device__ __forceinline__ bool in_box(int x, int y, int z, const int32_t* org, uint32_t* idx) {
     const long long rx = (long long)x - org[0], ry = (long long)y - org[1], rz = (long long)z - org[2];
     if (rx < 0 || rx >= kBox || ry < 0 || ry >= kBox || rz < 0 || rz >= kBox) return false;
-    *idx = ((uint32_t)rz * kBox + (uint32_t)ry) * kBox + (uint32_t)rx;
+    *idx = ((uint32_t)rx * kBox + (uint32_t)ry) * kBox + (uint32_t)rz;
     return true;
 }
 
+// Adds the votes of pairs [first, first+step, ...) of one frame that fall into the cube(s).
+// which_mask: bit0 centre cube, bit1 rotation cube.
 template <int G>
-__global__ void __launch_bounds__(kVmThreads, kVmCtasPerSm) vote_meanshift_kernel(FrameBuffers b, Geometry g, ForestDev f,
-                                                                        uint32_t n_frames, uint32_t iterations,
-                                                                        uint32_t static_items) {
-    // dynamic shared memory (kVmSmemBytes): 64 KB of the 66 KB do not fit the 48 KB static limit
-    extern __shared__ __align__(16) uint8_t vm_smem[];
-    uint32_t* s_buf = reinterpret_cast<uint32_t*>(vm_smem);  // [8000] seed grid, later the window weights (f32 bits)
-    float(*s_terms)[kMsSegment] = reinterpret_cast<float(*)[kMsSegment]>(vm_smem + kRotGridCells * 4);  // [4][kMsSegment]
-                                                      // per-cell summands (num x,y,z, den) in reference order
-    __shared__ uint32_t s_mask[kKernelCells / 32];    // non-zero window cells, bit j of word c = ord c*32+j
-    __shared__ uint32_t s_off[kKernelCells / 32 + 1]; // rank of the first non-zero cell of every chunk
-    __shared__ int32_t s_hist[kMsHistory + 1][3];     // positions P_0 (seed), P_1, ... for cycle detection
-    __shared__ Best s_red[kVmWarps];
-    __shared__ unsigned long long s_sum[kVmWarps];
-    __shared__ uint32_t s_cnt[kVmWarps];
-    __shared__ int32_t s_pos[3], s_org[3];
-    __shared__ uint32_t s_flags, s_done, s_item;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint32_t* box = b.boxes + (size_t)blockIdx.x * kBoxCells;
-    constexpr uint32_t kChunks = kKernelCells / 32;  // 250
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = static_items ? blockIdx.x : atomicAdd(b.work_counter, 1u);
-        __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= 2u * n_frames) break;
-        const uint32_t frame = item >> 1, which = item & 1u;
-        FrameState* fs = b.fs + frame;
-        const size_t hit_base = (size_t)frame * g.P * g.n_trees;
-        const CentreHit* chits = b.chits + hit_base;
-        const RotHit* rhits = b.rhits + hit_base;
-        const uint32_t n_hits = which == 0 ? fs->n_chits : fs->n_rhits;
-        const bool guessed = (fs->has_guess >> which) & 1u;
-
-        // ------------------------------------------------------------ 1. seed
-        if (which == 0) {
-            int32_t sm[3] = {0, 0, 0};
-            if (!guessed || b.debug) {
-                // 20x20 grid, one private copy per warp to keep the shared atomics uncontended
-                for (int i = tid; i < kVmWarps * kPosGridCells; i += kVmThreads) s_buf[i] = 0;
-                __syncthreads();
-                uint32_t* mine = s_buf + warp * kPosGridCells;
-                for_each_centre_vote<G>(chits, n_hits, f.offsets, [&](float nx, float ny, float nz, uint32_t wgt) {
-                    const float np[3] = {nx, ny, nz};
-                    float p2[2];
-                    space_to_img(g.K, np, p2);  // prediction.rs:661
-                    // max!/min! macros (prediction.rs:19-25): plain comparisons, NaN -> 0.0
-                    const float mx = (p2[0] > 0.0f) ? p2[0] : 0.0f;
-                    const float x2d = (mx < (float)(g.w - 1)) ? mx : (float)(g.w - 1);
-                    const float my = (p2[1] > 0.0f) ? p2[1] : 0.0f;
-                    const float y2d = (my < (float)(g.h - 1)) ? my : (float)(g.h - 1);
-                    const uint32_t cx = __float2uint_rz(x2d) * kGuessGridParts / g.w;  // :671-674
-                    const uint32_t cy = __float2uint_rz(y2d) * kGuessGridParts / g.h;
-                    atomicAdd(&mine[cy * kGuessGridParts + cx], wgt);
-                });
-                __syncthreads();
-                for (int i = tid; i < kPosGridCells; i += kVmThreads) {
-                    uint32_t v = 0;
-                    for (int w2 = 0; w2 < kVmWarps; ++w2) v += s_buf[w2 * kPosGridCells + i];
-                    s_buf[kVmWarps * kPosGridCells + i] = v;  // 16*400 + 400 <= 8000
-                }
-                __syncthreads();
-                uint32_t* gridp = s_buf + kVmWarps * kPosGridCells;
-                uint32_t* gout = b.grids + (size_t)frame * (kPosGridCells + kRotGridCells);
-                for (int i = tid; i < kPosGridCells; i += kVmThreads) gout[i] = gridp[i];
-                const Best bp = block_argmax(gridp, kPosGridCells, s_red);
-                // z = mean of the non-zero depth in the winning grid part (prediction.rs:706-725)
-                const uint32_t gpw = g.w / kGuessGridParts, gph = g.h / kGuessGridParts;
-                const uint32_t cgx = bp.idx % kGuessGridParts, cgy = bp.idx / kGuessGridParts;
-                unsigned long long zs = 0;
-                uint32_t zc = 0;
-                const uint16_t* img = b.depth + (size_t)frame * g.h * g.w;
-                for (uint32_t i = tid; i < gpw * gph; i += kVmThreads) {
-                    const uint32_t v = img[(size_t)(gph * cgy + i / gpw) * g.w + gpw * cgx + i % gpw];
-                    if (v > 0) {
-                        zs += v;
-                        zc += 1;
-                    }
-                }
+__device__ __forceinline__ void accumulate_pairs(const float4* __restrict__ gated, uint32_t ngate, uint32_t T,
+                                                 const int32_t* __restrict__ leaf_f, uint32_t P, uint32_t first,
+                                                 uint32_t step, uint32_t sub, const ForestDev& f, uint32_t which_mask,
+                                                 const int32_t* org_c, uint32_t* cube_c, const int32_t* org_r,
+                                                 uint32_t* cube_r) {
+    const uint32_t npairs = ngate * T;
+    for (uint32_t i = first; i < npairs; i += step) {
+        const uint32_t t = i / ngate;
+        const float4 h = __ldg(gated + (i - t * ngate));
+        const int32_t L = leaf_f[(size_t)t * P + __float_as_uint(h.w)];
+        const LeafInfo li = f.leaf_info[L];
+        if (!(li.flags & kLeafVotes)) continue;
+        // Skip the leaf when the bounding box of its votes misses the cube.  Conservative, hence
+        // exact: p3 - o and the truncation are monotone, so every vote cell lies in
+        // [trunc(p3 - omax), trunc(p3 - omin)] per axis; rotation bins lie in [rmin, rmax].
+        const uint4 bb0 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L));
+        const uint4 bb1 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L) + 1);
+        bool do_c = (which_mask & 1u) && (li.flags & kLeafOffOk), do_r = (which_mask & 2u) && (li.flags & kLeafRotOk);
+        if (do_c) {
+            const float omin[3] = {__uint_as_float(bb0.x), __uint_as_float(bb0.y), __uint_as_float(bb0.z)};
+            const float omax[3] = {__uint_as_float(bb0.w), __uint_as_float(bb1.x), __uint_as_float(bb1.y)};
+            const float pc[3] = {h.x, h.y, h.z};
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    zs += __shfl_xor_sync(0xffffffffu, zs, d);
-                    zc += __shfl_xor_sync(0xffffffffu, zc, d);
+            for (int k = 0; k < 3; ++k) {
+                const long long lo = (long long)__float2int_rz(__fsub_rn(pc[k], omax[k])) - org_c[k];
+                const long long hi = (long long)__float2int_rz(__fsub_rn(pc[k], omin[k])) - org_c[k];
+                if (hi < 0 || lo >= kBox) do_c = false;
+            }
+        }
+        if (do_r) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int rmin = (int)((bb1.z >> (8 * k)) & 0xffu), rmax = (int)((bb1.w >> (8 * k)) & 0xffu);
+                if ((long long)rmax - org_r[k] < 0 || (long long)rmin - org_r[k] >= kBox) do_r = false;
+            }
+        }
+        if (do_c) {
+            for (uint32_t k0 = sub; k0 < li.n_votes; k0 += 4 * G) {
+                float4 o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u * G < li.n_votes) o[u] = __ldg(f.offsets + li.vote_start + k0 + u * G);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u * G >= li.n_votes) break;
+                    const float nx = __fsub_rn(h.x, o[u].x), ny = __fsub_rn(h.y, o[u].y), nz = __fsub_rn(h.z, o[u].z);
+                    if (nz < 0.0f) continue;  // prediction.rs:650
+                    uint32_t idx;  // mid[(x as i32, y as i32, z as i32)] += valtoadd  (prediction.rs:667)
+                    if (in_box(__float2int_rz(nx), __float2int_rz(ny), __float2int_rz(nz), org_c, &idx))
+                        atomicAdd(cube_c + idx, li.valtoadd);
+                }
+            }
+        }
+        if (do_r) {
+            for (uint32_t k0 = sub; k0 < li.n_votes; k0 += 4 * G) {
+                uint32_t bins[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u * G < li.n_votes) bins[u] = __ldg(f.rot_bins + li.vote_start + k0 + u * G);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u * G >= li.n_votes) break;
+                    uint32_t idx;  // rot[(r1, r2, r3)] += valtoadd  (prediction.rs:635)
+                    if (in_box((int)(bins[u] & 0xffu), (int)((bins[u] >> 8) & 0xffu), (int)((bins[u] >> 16) & 0xffu), org_r, &idx))
+                        atomicAdd(cube_r + idx, li.valtoadd);
+                }
+            }
+        }
+    }
+}
+
+constexpr int kBuildThreads = 256;
+template <int G>
+__global__ void __launch_bounds__(kBuildThreads) box_build_kernel(FrameBuffers b, Geometry g, ForestDev f) {
+    const uint32_t frame = blockIdx.y;
+    const FrameState* fs = b.fs + frame;
+    if (!fs->box_valid[0]) return;  // meanshift_iterations == 0: the accumulators are never read
+    const int32_t org_c[3] = {fs->box_org[0][0], fs->box_org[0][1], fs->box_org[0][2]};
+    const int32_t org_r[3] = {fs->box_org[1][0], fs->box_org[1][1], fs->box_org[1][2]};
+    uint32_t* cube_c = b.cubes + (size_t)(2u * frame) * kBoxCells;
+    accumulate_pairs<G>(b.gated + (size_t)frame * g.P, fs->n_gate, g.n_trees, b.leaf + (size_t)frame * g.n_trees * g.P, g.P,
+                        blockIdx.x * (kBuildThreads / G) + threadIdx.x / G, gridDim.x * (kBuildThreads / G),
+                        threadIdx.x % G, f, 3u, org_c, cube_c, org_r, cube_c + kBoxCells);
+}
+
+// ================================================================ K4c: mean-shift
+// MeanShift::meanshift (meanshift.rs:328-407) on the dense cube, one CTA per accumulator.  Per
+// round the sixteen warps read the 20^3 window (16 loads in flight per lane), rank its non-zero
+// cells in reference order (ballots + one cross-warp prefix) (x outermost, z innermost, offsets -10..+9: meanshift.rs:340-346),
+// stage the summands in shared memory at that rank and four lanes fold them into the f32
+// accumulators one after the other in exactly that order.  A round moves the position by at most
+// 10 cells and the cube leaves 14 cells of margin around the seed's window; if the window would
+// leave the cube, the cube is rebuilt around the current position from the frame's gated patches
+// (counted in FrameState::rebuilds), so the results stay exactly those of the unbounded map.
+constexpr int kMsThreads = 512;
+constexpr int kMsWarps = kMsThreads / 32;
+constexpr int kMsSegment = 1024;  // non-zero window cells summed per pass
+constexpr uint32_t kMsChunks = kKernelCells / 32;  // 250 steps of 32 cells
+constexpr int kMsLoads = (kKernelCells + kMsThreads - 1) / kMsThreads;  // 16 window cells per thread
+constexpr int kMsSmemBytes = kKernelCells * 4 + 4 * kMsSegment * 4;
+
+__device__ __forceinline__ void store_result(dh_result* r, uint32_t which, const int32_t* pos) {
+    if (which == 0) {  // prediction.rs:486-488
+        r->mid_point[0] = (float)pos[0];
+        r->mid_point[1] = (float)pos[1];
+        r->mid_point[2] = (float)pos[2];
+        r->_pad = 0;
+        r->bounding_box[0] = r->bounding_box[1] = r->bounding_box[2] = r->bounding_box[3] = 0;  // :491
+    } else {           // prediction.rs:477-482
+        for (int k = 0; k < 3; ++k)
+            r->rotation[k] = __dmul_rn(__ddiv_rn(__dsub_rn((double)pos[k], (double)kRotGridParts / 2.0),
+                                                 (double)(kRotGridParts / 2)),
+                                       3.14159);
+    }
+}
+
+// Clears one cube and re-accumulates the frame's votes around a new origin (whole CTA).
+__device__ __noinline__ void rebuild_cube(const float4* __restrict__ gated, uint32_t ngate, uint32_t T,
+                                          const int32_t* __restrict__ leaf_f, uint32_t P, const LeafInfo* leaf_info,
+                                          const LeafBox* leaf_box, const float4* offsets, const uint32_t* rot_bins,
+                                          uint32_t which, int32_t ox, int32_t oy, int32_t oz, uint32_t* box) {
+    const int32_t org[3] = {ox, oy, oz};
+    ForestDev f{};
+    f.leaf_info = leaf_info;
+    f.leaf_box = leaf_box;
+    f.offsets = offsets;
+    f.rot_bins = rot_bins;
+    uint4* bz = reinterpret_cast<uint4*>(box);
+    for (int i = threadIdx.x; i < kBoxCells / 4; i += kMsThreads) __stcg(bz + i, make_uint4(0u, 0u, 0u, 0u));
+    __threadfence();
+    __syncthreads();
+    accumulate_pairs<1>(gated, ngate, T, leaf_f, P, threadIdx.x, kMsThreads, 0u, f, 1u << which, org, box, org, box);
+    __threadfence();
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b, Geometry g, ForestDev f, uint32_t iterations) {
+    extern __shared__ __align__(16) uint8_t ms_smem[];
+    uint32_t* s_win = reinterpret_cast<uint32_t*>(ms_smem);  // [8000] window cells in reference order
+    float(*s_terms)[kMsSegment] = reinterpret_cast<float(*)[kMsSegment]>(ms_smem + kKernelCells * 4);  // [4][kMsSegment]
+                                                       // summands (num x,y,z, den) in reference order
+    __shared__ uint32_t s_mask[kMsChunks];             // non-zero window cells, bit j of word c = ord c*32+j
+    __shared__ uint32_t s_off[kMsChunks + 1];          // rank of the first non-zero cell of every chunk
+    __shared__ int32_t s_hist[kMsHistory + 1][3];      // positions P_0 (seed), P_1, ... for cycle detection
+    __shared__ int32_t s_pos[3], s_org[3];
+    __shared__ uint32_t s_flags, s_done;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t item = blockIdx.x, frame = item >> 1, which = item & 1u;
+    FrameState* fs = b.fs + frame;
+    uint32_t* box = b.cubes + (size_t)item * kBoxCells;
+    if (tid == 0) {
+        s_flags = 0;
+        s_done = 0;
+        const int32_t* seed = which == 0 ? fs->seed_mid : fs->seed_rot;
+        for (int k = 0; k < 3; ++k) {
+            s_pos[k] = s_hist[0][k] = seed[k];
+            s_org[k] = fs->box_org[which][k];
+        }
+    }
+    uint32_t rebuilds = 0;
+    uint32_t it = 0;
+    for (; it < iterations; ++it) {
+        __syncthreads();
+        const int32_t pos[3] = {s_pos[0], s_pos[1], s_pos[2]};
+        int32_t org[3] = {s_org[0], s_org[1], s_org[2]};
+        bool inside = true;
+        for (int k = 0; k < 3; ++k) {
+            const long long lo = (long long)pos[k] - 10 - org[k], hi = (long long)pos[k] + 9 - org[k];
+            if (lo < 0 || hi >= kBox) inside = false;
+        }
+        if (!inside) {
+            // rebuild the cube around the current position
+            ++rebuilds;
+            __syncthreads();
+            for (int k = 0; k < 3; ++k) org[k] = (int32_t)((uint32_t)pos[k] - (uint32_t)(kBox / 2));
+            if (tid == 0)
+                for (int k = 0; k < 3; ++k) s_org[k] = org[k];
+            rebuild_cube(b.gated + (size_t)frame * g.P, fs->n_gate, g.n_trees, b.leaf + (size_t)frame * g.n_trees * g.P, g.P,
+                         f.leaf_info, f.leaf_box, f.offsets, f.rot_bins, which, org[0], org[1], org[2], box);
+        }
+        // gather the 20^3 window into shared memory, all loads of a thread in flight at once.
+        // ord enumerates the cells in the reference loop order (x outermost, z innermost).
+        {
+            const uint32_t base = ((uint32_t)((long long)pos[0] - 10 - org[0]) * kBox + (uint32_t)((long long)pos[1] - 10 - org[1])) * kBox +
+                                  (uint32_t)((long long)pos[2] - 10 - org[2]);
+            uint32_t v[kMsLoads];
+#pragma unroll
+            for (int j = 0; j < kMsLoads; ++j) {
+                const uint32_t ord = (uint32_t)j * kMsThreads + tid;
+                v[j] = 0u;
+                if (ord < (uint32_t)kKernelCells) {
+                    const uint32_t xo = ord / 400u, yo = (ord / 20u) % 20u, zo = ord % 20u;
+                    v[j] = __ldcg(box + base + (xo * kBox + yo) * kBox + zo);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kMsLoads; ++j) {
+                const uint32_t ord = (uint32_t)j * kMsThreads + tid;
+                if (ord < (uint32_t)kKernelCells) s_win[ord] = v[j];
+            }
+        }
+        __syncthreads();
+        // non-zero mask of every 32-cell chunk, then (warp 0) the exclusive prefix of their populations
+        for (uint32_t c = warp; c < kMsChunks; c += kMsWarps) {
+            const uint32_t m = __ballot_sync(0xffffffffu, s_win[c * 32u + lane] != 0u);
+            if (lane == 0) s_mask[c] = m;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t run = 0;
+            for (uint32_t c0 = 0; c0 < kMsChunks; c0 += 32) {
+                const uint32_t c = c0 + lane;
+                const uint32_t n = c < kMsChunks ? (uint32_t)__popc(s_mask[c]) : 0u;
+                uint32_t incl = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += o;
+                }
+                if (c < kMsChunks) s_off[c] = run + incl - n;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) s_off[kMsChunks] = run;
+        }
+        __syncthreads();
+        const uint32_t nnz = s_off[kMsChunks];
+        float acc = 0.0f;
+        for (uint32_t seg = 0; seg < nnz; seg += kMsSegment) {
+            // every non-zero cell stages its four summands at its rank in reference order
+            for (uint32_t c = warp; c < kMsChunks; c += kMsWarps) {
+                if (s_off[c + 1] <= seg || s_off[c] >= seg + kMsSegment) continue;  // warp-uniform
+                const uint32_t m = s_mask[c];
+                if (!((m >> lane) & 1u)) continue;
+                const uint32_t r = s_off[c] + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                if (r < seg || r >= seg + kMsSegment) continue;
+                const uint32_t ord = c * 32u + lane;
+                const uint32_t xo = ord / 400u, yo = (ord / 20u) % 20u, zo = ord % 20u;
+                // influence * factor with kernel[(x+10, y+10, z+10)], dense index z*400 + y*20 + x
+                // (meanshift.rs:370-377, 78-88); then abs_pos * that
+                const float wgt = __fmul_rn(__ldg(f.ms_kernel + zo * 400u + yo * 20u + xo), (float)s_win[ord]);
+                s_terms[0][r - seg] = __fmul_rn((float)(int)((uint32_t)pos[0] + xo - 10u), wgt);
+                s_terms[1][r - seg] = __fmul_rn((float)(int)((uint32_t)pos[1] + yo - 10u), wgt);
+                s_terms[2][r - seg] = __fmul_rn((float)(int)((uint32_t)pos[2] + zo - 10u), wgt);
+                s_terms[3][r - seg] = wgt;
+            }
+            __syncthreads();
+            if (warp == 0 && lane < 4) {  // sequential f32 accumulation in reference order (meanshift.rs:337-380)
+                const uint32_t cnt = min((uint32_t)kMsSegment, nnz - seg);
+                const float4* t4 = reinterpret_cast<const float4*>(s_terms[lane]);
+                uint32_t i = 0;
+                if (cnt >= 8) {  // software-pipelined: the next eight summands load while these are added
+                    float4 a0 = t4[0], a1 = t4[1];
+                    for (; i + 16 <= cnt; i += 8) {
+                        const float4 n0 = t4[(i >> 2) + 2], n1 = t4[(i >> 2) + 3];
+                        acc = __fadd_rn(acc, a0.x); acc = __fadd_rn(acc, a0.y); acc = __fadd_rn(acc, a0.z); acc = __fadd_rn(acc, a0.w);
+                        acc = __fadd_rn(acc, a1.x); acc = __fadd_rn(acc, a1.y); acc = __fadd_rn(acc, a1.z); acc = __fadd_rn(acc, a1.w);
+                        a0 = n0;
+                        a1 = n1;
+                    }
+                    acc = __fadd_rn(acc, a0.x); acc = __fadd_rn(acc, a0.y); acc = __fadd_rn(acc, a0.z); acc = __fadd_rn(acc, a0.w);
+                    acc = __fadd_rn(acc, a1.x); acc = __fadd_rn(acc, a1.y); acc = __fadd_rn(acc, a1.z); acc = __fadd_rn(acc, a1.w);
+                    i += 8;
+                }
+                const float* t = s_terms[lane];
+                for (; i < cnt; ++i) acc = __fadd_rn(acc, t[i]);
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            const float den = __shfl_sync(0xffffffffu, acc, 3);
+            if (den == 0.0f) {  // "Breaking meanshift - zero sum" (meanshift.rs:385-388)
+                if (lane == 0) {
+                    s_flags |= 1u;
+                    s_done = 1;
+                }
+            } else {
+                const int np = __float2int_rz(__fdiv_rn(acc, den));  // meanshift.rs:391-394
+                const int nx = __shfl_sync(0xffffffffu, np, 0), ny = __shfl_sync(0xffffffffu, np, 1),
+                          nz = __shfl_sync(0xffffffffu, np, 2);
+                // Cycle detection (result-neutral): the update is a deterministic function of
+                // the position, so once P_{k+1} equals an earlier P_j the sequence is periodic
+                // with period k+1-j and P_iterations is read off the history (a fixed point is
+                // the period-1 case).
+                const uint32_t k1 = it + 1;
+                int found = -1;
+                if (k1 <= (uint32_t)kMsHistory) {
+                    for (uint32_t j = lane; j < k1; j += 32)
+                        if (s_hist[j][0] == nx && s_hist[j][1] == ny && s_hist[j][2] == nz) found = (int)j;
+                    found = __reduce_max_sync(0xffffffffu, found);
                 }
                 if (lane == 0) {
-                    s_sum[warp] = zs;
-                    s_cnt[warp] = zc;
-                }
-                __syncthreads();
-                zs = 0;
-                zc = 0;
-                for (int i = 0; i < kVmWarps; ++i) {
-                    zs += s_sum[i];
-                    zc += s_cnt[i];
-                }
-                const float meanz = zc > 0 ? (float)__ddiv_rn((double)zs, (double)zc) : 0.0f;
-                const float mxf = __fmul_rn(__fadd_rn((float)cgx, 0.5f), (float)gpw);  // :727-729
-                const float myf = __fmul_rn(__fadd_rn((float)cgy, 0.5f), (float)gph);
-                float m3[3];
-                img_to_space(g.Kinv, mxf, myf, meanz, m3);
-                for (int k = 0; k < 3; ++k) sm[k] = __float2int_rz(m3[k]);  // :750
-            }
-            if (guessed)  // prediction.rs:437-441
-                for (int k = 0; k < 3; ++k) sm[k] = __float2int_rz(fs->midp_guess[k]);
-            if (tid == 0)
-                for (int k = 0; k < 3; ++k) s_pos[k] = fs->seed_mid[k] = sm[k];
-        } else {
-            int32_t sr[3];
-            uint32_t rc[3] = {0u, 0u, 0u};
-            if (!guessed || b.debug) {
-                for (int i = tid; i < kRotGridCells; i += kVmThreads) s_buf[i] = 0;
-                __syncthreads();
-                for_each_rot_vote<G>(rhits, n_hits, f.rot_bins, [&](int r1, int r2, int r3, uint32_t wgt) {
-                    // rough = r * 20 / 120 (prediction.rs:630-636), dense index z*400 + y*20 + x
-                    const uint32_t q1 = (uint32_t)r1 * kGuessGridParts / kRotGridParts,
-                                   q2 = (uint32_t)r2 * kGuessGridParts / kRotGridParts,
-                                   q3 = (uint32_t)r3 * kGuessGridParts / kRotGridParts;
-                    atomicAdd(&s_buf[q3 * 400 + q2 * 20 + q1], wgt);
-                });
-                __syncthreads();
-                uint32_t* gout = b.grids + (size_t)frame * (kPosGridCells + kRotGridCells) + kPosGridCells;
-                for (int i = tid; i < kRotGridCells; i += kVmThreads) gout[i] = s_buf[i];
-                const Best br = block_argmax(s_buf, kRotGridCells, s_red);  // :733-742
-                rc[0] = br.idx % 20u;
-                rc[1] = (br.idx % 400u) / 20u;
-                rc[2] = br.idx / 400u;
-            }
-            for (int k = 0; k < 3; ++k) {
-                // :745-747, or the caller's guess :448-450; then :458-460
-                double deg = __ddiv_rn(__dadd_rn(__dmul_rn((double)rc[k], 360.0), 180.0), (double)kGuessGridParts);
-                if (guessed) deg = __dadd_rn(__ddiv_rn(__dmul_rn(fs->rot_guess[k], 180.0), 3.14159), 180.0);
-                sr[k] = __double2int_rz(__ddiv_rn(__dmul_rn(deg, (double)kRotGridParts), 360.0));
-            }
-            if (tid == 0)
-                for (int k = 0; k < 3; ++k) s_pos[k] = fs->seed_rot[k] = sr[k];
-        }
-        if (tid == 0) {
-            s_flags = 0;
-            s_done = 0;
-            s_org[0] = s_org[1] = s_org[2] = 0;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            s_hist[0][0] = s_pos[0]; s_hist[0][1] = s_pos[1]; s_hist[0][2] = s_pos[2];
-        }
-
-        // ------------------------------------------------------------ 2 + 3. box build, mean-shift rounds
-        bool have_box = false;
-        uint32_t rebuilds = 0;
-        uint32_t it = 0;
-        for (; it < iterations; ++it) {
-            __syncthreads();
-            const int32_t pos[3] = {s_pos[0], s_pos[1], s_pos[2]};
-            int32_t org[3] = {s_org[0], s_org[1], s_org[2]};
-            bool inside = have_box;
-            for (int k = 0; k < 3; ++k) {
-                const long long lo = (long long)pos[k] - 10 - org[k], hi = (long long)pos[k] + 9 - org[k];
-                if (lo < 0 || hi >= kBox) inside = false;
-            }
-            if (!inside) {
-                // (re)build the cube around the current position
-                if (have_box) ++rebuilds;
-                __syncthreads();
-                for (int k = 0; k < 3; ++k) org[k] = (int32_t)((uint32_t)pos[k] - (uint32_t)(kBox / 2));
-                if (tid == 0)
-                    for (int k = 0; k < 3; ++k) s_org[k] = org[k];
-                uint4* bz = reinterpret_cast<uint4*>(box);
-                for (int i = tid; i < kBoxCells / 4; i += kVmThreads) __stcg(bz + i, make_uint4(0u, 0u, 0u, 0u));
-                __threadfence();
-                __syncthreads();
-                if (which == 0) {
-                    for_each_centre_vote<G>(chits, n_hits, f.offsets, [&](float nx, float ny, float nz, uint32_t wgt) {
-                        uint32_t idx;  // mid[(x as i32, y as i32, z as i32)] += valtoadd  (prediction.rs:667)
-                        if (in_box(__float2int_rz(nx), __float2int_rz(ny), __float2int_rz(nz), org, &idx))
-                            atomicAdd(box + idx, wgt);
-                    });
-                } else {
-                    for_each_rot_vote<G>(rhits, n_hits, f.rot_bins, [&](int r1, int r2, int r3, uint32_t wgt) {
-                        uint32_t idx;  // rot[(r1, r2, r3)] += valtoadd  (prediction.rs:635)
-                        if (in_box(r1, r2, r3, org, &idx)) atomicAdd(box + idx, wgt);
-                    });
-                }
-                __threadfence();
-                __syncthreads();
-                have_box = true;
-            }
-            // gather the 20^3 window.  ord enumerates the cells in the reference loop order (x
-            // outermost, z innermost, offsets -10..+9: meanshift.rs:340-346); each warp owns whole
-            // 32-cell chunks so one ballot yields the chunk's non-zero mask.  Non-zero cells are
-            // replaced by their weight kernel[(x+10, y+10, z+10)] * (factor as f32)
-            // (meanshift.rs:370-377; dense kernel index z*400 + y*20 + x, meanshift.rs:78-88).
-            const uint32_t bx = (uint32_t)((long long)pos[0] - 10 - org[0]), by = (uint32_t)((long long)pos[1] - 10 - org[1]),
-                           bzz = (uint32_t)((long long)pos[2] - 10 - org[2]);
-            for (uint32_t c = warp; c < kChunks; c += kVmWarps) {
-                const uint32_t ord = c * 32 + lane;
-                const uint32_t xo = ord / 400u, yo = (ord / 20u) % 20u, zo = ord % 20u;
-                const uint32_t fct = __ldcg(box + ((bzz + zo) * kBox + (by + yo)) * kBox + (bx + xo));
-                const uint32_t m = __ballot_sync(0xffffffffu, fct != 0u);
-                if (lane == 0) s_mask[c] = m;
-                if (fct) s_buf[ord] = __float_as_uint(__fmul_rn(__ldg(f.ms_kernel + zo * 400u + yo * 20u + xo), (float)fct));
-            }
-            __syncthreads();
-            // Sequential f32 accumulation in reference order (meanshift.rs:337-380).  Only the chain
-            // of additions is inherently serial, so: (a) rank every non-zero cell in reference order
-            // (prefix sum over the chunk masks), (b) all threads compute the summands
-            // abs_pos * (influence * factor) and influence * factor into shared memory at that
-            // rank, (c) lanes 0..3 (num x, y, z, den) add them up one after the other.
-            if (warp == 0) {
-                uint32_t run = 0;
-                for (uint32_t c0 = 0; c0 < kChunks; c0 += 32) {
-                    const uint32_t c = c0 + lane;
-                    const uint32_t n = c < kChunks ? (uint32_t)__popc(s_mask[c]) : 0u;
-                    uint32_t incl = n;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= (uint32_t)d) incl += o;
+                    if (b.ms_trace && it < b.ms_trace_cap) {
+                        int32_t* tr = b.ms_trace + (((size_t)frame * 2 + which) * b.ms_trace_cap + it) * 3;
+                        tr[0] = nx; tr[1] = ny; tr[2] = nz;
                     }
-                    if (c < kChunks) s_off[c] = run + incl - n;
-                    run += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (lane == 0) s_off[kChunks] = run;
-            }
-            __syncthreads();
-            const uint32_t nnz = s_off[kChunks];
-            float acc = 0.0f;
-            for (uint32_t seg = 0; seg < nnz; seg += kMsSegment) {
-                for (uint32_t c = warp; c < kChunks; c += kVmWarps) {
-                    if (s_off[c + 1] <= seg || s_off[c] >= seg + kMsSegment) continue;  // warp-uniform
-                    const uint32_t m = s_mask[c];
-                    if ((m >> lane) & 1u) {
-                        const uint32_t r = s_off[c] + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                        if (r >= seg && r < seg + kMsSegment) {
-                            const uint32_t ord = c * 32 + lane;
-                            const float wgt = __uint_as_float(s_buf[ord]);
-                            const float fx = (float)(int)((uint32_t)pos[0] + (uint32_t)((int)(ord / 400u) - 10));
-                            const float fy = (float)(int)((uint32_t)pos[1] + (uint32_t)((int)((ord / 20u) % 20u) - 10));
-                            const float fz = (float)(int)((uint32_t)pos[2] + (uint32_t)((int)(ord % 20u) - 10));
-                            s_terms[0][r - seg] = __fmul_rn(fx, wgt);  // abs_pos * (influence * factor)
-                            s_terms[1][r - seg] = __fmul_rn(fy, wgt);
-                            s_terms[2][r - seg] = __fmul_rn(fz, wgt);
-                            s_terms[3][r - seg] = wgt;                 // influence * factor
+                    if (found >= 0) {
+                        const uint32_t j = (uint32_t)found, period = k1 - j;
+                        const uint32_t fin = j + (iterations - j) % period;  // index of P_iterations (< k1)
+                        s_pos[0] = s_hist[fin][0]; s_pos[1] = s_hist[fin][1]; s_pos[2] = s_hist[fin][2];
+                        s_done = 2;
+                    } else {
+                        s_pos[0] = nx; s_pos[1] = ny; s_pos[2] = nz;
+                        if (k1 <= (uint32_t)kMsHistory) {
+                            s_hist[k1][0] = nx; s_hist[k1][1] = ny; s_hist[k1][2] = nz;
                         }
                     }
                 }
-                __syncthreads();
-                if (warp == 0 && lane < 4) {
-                    const uint32_t cnt = min((uint32_t)kMsSegment, nnz - seg);
-                    const float* t = s_terms[lane];
-                    uint32_t i = 0;
-                    for (; i + 8 <= cnt; i += 8) {
-                        float v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) v[u] = t[i + u];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, v[u]);
-                    }
-                    for (; i < cnt; ++i) acc = __fadd_rn(acc, t[i]);
-                }
-                __syncthreads();
-            }
-            if (warp == 0) {
-                const float den = __shfl_sync(0xffffffffu, acc, 3);
-                if (den == 0.0f) {  // "Breaking meanshift - zero sum" (meanshift.rs:385-388)
-                    if (lane == 0) {
-                        s_flags |= 1u;
-                        s_done = 1;
-                    }
-                } else {
-                    const int np = __float2int_rz(__fdiv_rn(acc, den));  // meanshift.rs:391-394
-                    const int nx = __shfl_sync(0xffffffffu, np, 0), ny = __shfl_sync(0xffffffffu, np, 1),
-                              nz = __shfl_sync(0xffffffffu, np, 2);
-                    // Cycle detection (result-neutral): the update is a deterministic function of
-                    // the position, so once P_{k+1} equals an earlier P_j the sequence is periodic
-                    // with period k+1-j and P_iterations is read off the history (a fixed point is
-                    // the period-1 case).
-                    const uint32_t k1 = it + 1;
-                    int found = -1;
-                    if (k1 <= (uint32_t)kMsHistory) {
-                        for (uint32_t j = lane; j < k1; j += 32)
-                            if (s_hist[j][0] == nx && s_hist[j][1] == ny && s_hist[j][2] == nz) found = (int)j;
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) found = max(found, __shfl_xor_sync(0xffffffffu, found, d));
-                    }
-                    if (lane == 0) {
-                        if (b.ms_trace && it < b.ms_trace_cap) {
-                            int32_t* tr = b.ms_trace + (((size_t)frame * 2 + which) * b.ms_trace_cap + it) * 3;
-                            tr[0] = nx; tr[1] = ny; tr[2] = nz;
-                        }
-                        if (found >= 0) {
-                            const uint32_t j = (uint32_t)found, period = k1 - j;
-                            const uint32_t fin = j + (iterations - j) % period;  // index of P_iterations (< k1)
-                            s_pos[0] = s_hist[fin][0]; s_pos[1] = s_hist[fin][1]; s_pos[2] = s_hist[fin][2];
-                            s_done = 2;
-                        } else {
-                            s_pos[0] = nx; s_pos[1] = ny; s_pos[2] = nz;
-                            if (k1 <= (uint32_t)kMsHistory) {
-                                s_hist[k1][0] = nx; s_hist[k1][1] = ny; s_hist[k1][2] = nz;
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            if (s_done) {
-                if (s_done == 2) ++it;  // this round was executed
-                break;
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            fs->ms_iters[which] = it;
-            fs->ms_flags[which] = s_flags;
-            fs->rebuilds[which] = rebuilds;
-            fs->box_slot[which] = blockIdx.x;
-            for (int k = 0; k < 3; ++k) fs->box_org[which][k] = s_org[k];
-            fs->box_valid[which] = have_box ? 1u : 0u;
-            dh_result* r = b.results + frame;
-            if (which == 0) {  // prediction.rs:486-488
-                r->mid_point[0] = (float)s_pos[0];
-                r->mid_point[1] = (float)s_pos[1];
-                r->mid_point[2] = (float)s_pos[2];
-                r->_pad = 0;
-                r->bounding_box[0] = r->bounding_box[1] = r->bounding_box[2] = r->bounding_box[3] = 0;  // :491
-            } else {           // prediction.rs:477-482
-                for (int k = 0; k < 3; ++k)
-                    r->rotation[k] = __dmul_rn(__ddiv_rn(__dsub_rn((double)s_pos[k], (double)kRotGridParts / 2.0),
-                                                         (double)(kRotGridParts / 2)),
-                                               3.14159);
-            }
+        if (s_done) {
+            if (s_done == 2) ++it;  // this round was executed
+            break;
         }
-        if (static_items) break;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        fs->ms_iters[which] = it;
+        fs->ms_flags[which] = s_flags;
+        fs->rebuilds[which] = rebuilds;
+        for (int k = 0; k < 3; ++k) fs->box_org[which][k] = s_org[k];
+        const int32_t fin[3] = {s_pos[0], s_pos[1], s_pos[2]};
+        store_result(b.results + frame, which, fin);
     }
 }
 
@@ -905,7 +1007,9 @@ __global__ void __launch_bounds__(128) leaf_gate_kernel(const double* __restrict
                                                         const uint32_t* __restrict__ n_votes,
                                                         const float* __restrict__ offsets,
                                                         const double* __restrict__ rotations,
-                                                        LeafInfo* __restrict__ out, uint32_t n_leaves) {
+                                                        const uint32_t* __restrict__ rot_bins,
+                                                        LeafInfo* __restrict__ out, LeafBox* __restrict__ box_out,
+                                                        uint16_t* __restrict__ rot_coarse, uint32_t n_leaves) {
     const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_leaves) return;
     const uint32_t v0 = vote_start[l], n = n_votes[l];
@@ -960,8 +1064,37 @@ __global__ void __launch_bounds__(128) leaf_gate_kernel(const double* __restrict
             for (int k = 0; k < 3; ++k) tr = __fadd_rn(tr, __fdiv_rn(cov[k], dn1));
             if (tr <= kMaxVarianceOffset) li.flags |= kLeafOffOk;
         }
+        // the leaf casts votes at all: prob > 0 (prediction.rs:590), a non-zero weight, a spread gate open
+        if (leaf_prob[l] > 0.0 && li.valtoadd != 0u && (li.flags & (kLeafRotOk | kLeafOffOk))) li.flags |= kLeafVotes;
     }
     out[l] = li;
+    // bounding boxes of the leaf's votes (box_build skips leaves that cannot reach a cube) and
+    // the coarse rotation cell of every vote: rough = r * 20 / 120 per axis, dense index
+    // z*400 + y*20 + x (prediction.rs:630-636)
+    LeafBox bx;
+    for (int k = 0; k < 4; ++k) {
+        if (k < 3) bx.omin[k] = bx.omax[k] = 0.0f;
+        bx.rmin[k] = bx.rmax[k] = 0;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t bins = rot_bins[v0 + i];
+        uint32_t q[3];
+        for (int k = 0; k < 3; ++k) {
+            const float o = offsets[(size_t)(v0 + i) * 3 + k];
+            const uint8_t r = (uint8_t)((bins >> (8 * k)) & 0xffu);
+            if (i == 0 || o < bx.omin[k]) bx.omin[k] = o;
+            if (i == 0 || o > bx.omax[k]) bx.omax[k] = o;
+            if (!isfinite(o)) {
+                bx.omin[k] = -INFINITY;
+                bx.omax[k] = INFINITY;
+            }
+            if (i == 0 || r < bx.rmin[k]) bx.rmin[k] = r;
+            if (i == 0 || r > bx.rmax[k]) bx.rmax[k] = r;
+            q[k] = (uint32_t)r * kGuessGridParts / kRotGridParts;
+        }
+        rot_coarse[v0 + i] = (uint16_t)(q[2] * 400u + q[1] * 20u + q[0]);
+    }
+    box_out[l] = bx;
 }
 
 // ================================================================ next-row back-ends on the same front-end
@@ -1032,16 +1165,16 @@ __global__ void box_dump_kernel(FrameBuffers b, uint32_t frame, int which, int32
                                 unsigned long long* count) {
     const FrameState* fs = b.fs + frame;
     if (!fs->box_valid[which]) return;
-    const uint32_t* box = b.boxes + (size_t)fs->box_slot[which] * kBoxCells;
+    const uint32_t* box = b.cubes + ((size_t)frame * 2 + (uint32_t)which) * kBoxCells;
     const int32_t* org = fs->box_org[which];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)kBoxCells; i += gridDim.x * blockDim.x) {
         const uint32_t v = box[i];
         if (!v) continue;
         const unsigned long long o = atomicAdd(count, 1ull);
         if (keys_out) {
-            keys_out[o * 3 + 0] = org[0] + (int32_t)(i % kBox);
+            keys_out[o * 3 + 0] = org[0] + (int32_t)(i / (kBox * kBox));  // z fastest
             keys_out[o * 3 + 1] = org[1] + (int32_t)((i / kBox) % kBox);
-            keys_out[o * 3 + 2] = org[2] + (int32_t)(i / (kBox * kBox));
+            keys_out[o * 3 + 2] = org[2] + (int32_t)(i % kBox);
             vals_out[o] = v;
         }
     }
@@ -1120,38 +1253,51 @@ void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, size_t n_nodes, uint3
     plan_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(nodes, hot, n_nodes, tile_width);
 }
 
-void launch_gate(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
-    dim3 gr((g.P + 255) / 256, n_frames);
-    gate_kernel<<<gr, 256, 0, s>>>(b, g, f.leaf_prob, f.leaf_info);
-}
-
 uint32_t vote_box_cells() { return (uint32_t)kBoxCells; }
-uint32_t vote_ctas_per_sm() { return (uint32_t)kVmCtasPerSm; }
 uint32_t vote_box_dim() { return (uint32_t)kBox; }
 
-void launch_vote_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
-                           uint32_t iterations, uint32_t n_ctas, uint32_t lanes_per_hit, bool static_items,
-                           cudaStream_t s) {
+// The back end after the traversal, in launch order.  The coarse grids, the accumulator cubes
+// and the queue header must be zero when these run.  Each returns the kernels it launched.
+int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
+                       uint32_t lanes_per_hit, cudaStream_t s) {
+    if (!g.P) return 0;
+    dim3 gr((g.P + kGateThreads - 1) / kGateThreads, n_frames);
+    if (lanes_per_hit >= 32) gate_coarse_kernel<32><<<gr, kGateThreads, 0, s>>>(b, g, f);
+    else if (lanes_per_hit >= 8) gate_coarse_kernel<8><<<gr, kGateThreads, 0, s>>>(b, g, f);
+    else gate_coarse_kernel<1><<<gr, kGateThreads, 0, s>>>(b, g, f);
+    return 1;
+}
+
+int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
+                          uint32_t iterations, uint32_t lanes_per_hit, cudaStream_t s) {
+    seed_kernel<<<n_frames, kSeedThreads, 0, s>>>(b, g, iterations);
+    if (!g.P || !iterations) return 1;
+    // enough blocks per frame that a thread sees a handful of hits
+    const uint32_t per_frame =
+        std::max<uint32_t>(1u, std::min<uint32_t>(64u, (g.P * g.n_trees / 8u + kBuildThreads - 1) / kBuildThreads));
+    dim3 gr(per_frame, n_frames);
+    if (lanes_per_hit >= 32) box_build_kernel<32><<<gr, kBuildThreads, 0, s>>>(b, g, f);
+    else if (lanes_per_hit >= 8) box_build_kernel<8><<<gr, kBuildThreads, 0, s>>>(b, g, f);
+    else box_build_kernel<1><<<gr, kBuildThreads, 0, s>>>(b, g, f);
+    return 2;
+}
+
+int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t iterations,
+                     cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(vote_meanshift_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVmSmemBytes);
-        cudaFuncSetAttribute(vote_meanshift_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVmSmemBytes);
-        cudaFuncSetAttribute(vote_meanshift_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVmSmemBytes);
+        cudaFuncSetAttribute(meanshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes);
         configured = true;
     }
-    if (!static_items) cudaMemsetAsync(b.work_counter, 0, sizeof(uint32_t), s);
-    const uint32_t grid = static_items ? 2u * n_frames : n_ctas;
-    const uint32_t st = static_items ? 1u : 0u;
-    if (lanes_per_hit >= 32) vote_meanshift_kernel<32><<<grid, kVmThreads, kVmSmemBytes, s>>>(b, g, f, n_frames, iterations, st);
-    else if (lanes_per_hit >= 8) vote_meanshift_kernel<8><<<grid, kVmThreads, kVmSmemBytes, s>>>(b, g, f, n_frames, iterations, st);
-    else vote_meanshift_kernel<1><<<grid, kVmThreads, kVmSmemBytes, s>>>(b, g, f, n_frames, iterations, st);
+    meanshift_kernel<<<2u * n_frames, kMsThreads, kMsSmemBytes, s>>>(b, g, f, iterations);
+    return 1;
 }
 
 void launch_leaf_gates(const double* leaf_prob, const uint32_t* vote_start, const uint32_t* n_votes,
-                       const float* offsets, const double* rotations, LeafInfo* out, uint32_t n_leaves,
-                       cudaStream_t s) {
-    leaf_gate_kernel<<<(n_leaves + 127) / 128, 128, 0, s>>>(leaf_prob, vote_start, n_votes, offsets, rotations, out,
-                                                           n_leaves);
+                       const float* offsets, const double* rotations, const uint32_t* rot_bins, LeafInfo* out,
+                       LeafBox* box_out, uint16_t* rot_coarse, uint32_t n_leaves, cudaStream_t s) {
+    leaf_gate_kernel<<<(n_leaves + 127) / 128, 128, 0, s>>>(leaf_prob, vote_start, n_votes, offsets, rotations, rot_bins, out,
+                                                           box_out, rot_coarse, n_leaves);
 }
 
 void launch_mask(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint8_t* mask, cudaStream_t s) {

@@ -13,10 +13,10 @@ namespace dh {
 
 // Per-frame device bookkeeping, zeroed at the start of every pipeline pass.
 struct alignas(16) FrameState {
-    uint32_t n_chits;         // centre-voting patch x tree pairs appended to the hit list
-    uint32_t n_rhits;         // rotation-voting pairs
+    uint32_t n_chits;         // patch x tree pairs that cast centre votes
+    uint32_t n_rhits;         // patch x tree pairs that cast rotation votes
     uint32_t n_valid;         // non-background patches
-    uint32_t n_gate;          // patches with mean prob > 0.7
+    uint32_t n_gate;          // patches with mean prob > 0.7 = entries of the frame's gated-patch list
     unsigned long long n_mid_votes;  // centre votes the hits cast
     unsigned long long n_rot_votes;
     unsigned long long node_visits;
@@ -25,8 +25,7 @@ struct alignas(16) FrameState {
     uint32_t ms_iters[2];     // mean-shift rounds actually executed (centre, rotation)
     uint32_t ms_flags[2];     // bit0 zero-sum break
     uint32_t rebuilds[2];     // times the accumulator cube had to be rebuilt around a new position
-    uint32_t box_slot[2];     // workspace slot / origin of the last cube (debug export)
-    int32_t box_org[2][3];
+    int32_t box_org[2][3];    // origin of the accumulator cube (seed - 24, or the last rebuild)
     uint32_t box_valid[2];
     uint32_t has_guess;       // bit0 midp_guess, bit1 rot_guess supplied by the caller
     float midp_guess[3];
@@ -41,6 +40,7 @@ struct Geometry {
     uint32_t npx, npy, P;     // patches per row / column / frame
     uint32_t sat_pitch;       // elements per SAT row (multiple of 4)
     uint32_t n_trees;
+    uint32_t magic_w, magic_h;  // n / w == umulhi(n, magic_w) for n <= 20 * (w - 1), 0 = divide
     float K[9], Kinv[9];
 };
 
@@ -60,6 +60,8 @@ struct ForestDev {
     const LeafInfo* leaf_info;
     const float4* offsets;     // per vote: x, y, z (mm), w unused — one 16-byte load
     const uint32_t* rot_bins;  // per vote
+    const uint16_t* rot_coarse; // per vote: cell of the 20^3 rotation seed grid
+    const LeafBox* leaf_box;   // per leaf: bounding boxes of its votes
     const float* ms_kernel;    // 8000
     int32_t n_trees;
 };
@@ -70,12 +72,10 @@ struct FrameBuffers {
     int32_t* leaf;          // [F][T][P]
     float* p3;              // [F][P][3]
     uint8_t* gate;          // [F][P]
-    CentreHit* chits;       // [F][P*T]
-    RotHit* rhits;          // [F][P*T]
+    float4* gated;          // [F][P] gate-passing patches: p3 (prediction.rs:554) + patch index
     uint32_t* grids;        // [F][400 + 8000]
     FrameState* fs;         // [F]
-    uint32_t* boxes;        // [persistent CTAs][kBox^3] accumulator cubes
-    uint32_t* work_counter; // work-item counter of vote_meanshift_kernel
+    uint32_t* cubes;        // [F][2][kBox^3] accumulator cubes (centre, rotation), z fastest
     dh_result* results;     // [F]
     int32_t* ms_trace;      // [F][2][iters][3] or nullptr
     uint32_t ms_trace_cap;  // iterations per trace
@@ -86,16 +86,17 @@ void launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cud
 void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, size_t n_nodes, uint32_t tile_width, cudaStream_t s);
-void launch_gate(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s);
-void launch_vote_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
-                           uint32_t iterations, uint32_t n_ctas, uint32_t lanes_per_hit, bool static_items,
-                           cudaStream_t s);
+int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
+                       uint32_t lanes_per_hit, cudaStream_t s);
+int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
+                          uint32_t iterations, uint32_t lanes_per_hit, cudaStream_t s);
+int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t iterations,
+                     cudaStream_t s);
 uint32_t vote_box_cells();
-uint32_t vote_ctas_per_sm();
 uint32_t vote_box_dim();
 void launch_leaf_gates(const double* leaf_prob, const uint32_t* vote_start, const uint32_t* n_votes,
-                       const float* offsets, const double* rotations, LeafInfo* out, uint32_t n_leaves,
-                       cudaStream_t s);
+                       const float* offsets, const double* rotations, const uint32_t* rot_bins, LeafInfo* out,
+                       LeafBox* box_out, uint16_t* rot_coarse, uint32_t n_leaves, cudaStream_t s);
 void launch_mask(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint8_t* mask, cudaStream_t s);
 void launch_hough_image(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t* acc32,
                         uint16_t* out16, cudaStream_t s);

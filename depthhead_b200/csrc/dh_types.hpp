@@ -51,27 +51,17 @@ struct alignas(16) LeafInfo {
     uint32_t vote_start;  // first vote in the vote tables
     uint32_t n_votes;     // offsets.len() == rotations.len()
     uint32_t valtoadd;    // ((1000.0*prob) as usize / n) as u32
-    uint32_t flags;       // bit0 rot_ok (trace(cov rot) <= 400), bit1 off_ok (trace(cov off) <= 5200)
+    uint32_t flags;       // bit0 rot_ok (trace(cov rot) <= 400), bit1 off_ok (trace(cov off) <= 5200),
+                          // bit2 votes (prob > 0, valtoadd != 0 and bit0 | bit1)
 };
 static_assert(sizeof(LeafInfo) == 16, "LeafInfo must be 16 bytes");
-constexpr uint32_t kLeafRotOk = 1u, kLeafOffOk = 2u;
-
-// One voting patch x tree pair, split by accumulator.  The gate kernel copies the per-leaf
-// constants in, so the vote passes read hit -> votes with no further indirection.
-struct alignas(16) CentreHit {
-    float p3[3];          // back-projected patch centre (prediction.rs:554)
-    uint32_t vote_start;  // first offset vote of the leaf
-    uint32_t n_votes;
-    uint32_t valtoadd;
-    uint32_t pad[2];
+// Bounding boxes of a leaf's votes: offsets (mm) per axis and rotation bins per axis.  A
+// non-finite offset opens its axis to (-inf, +inf), so such a leaf is never skipped.
+struct alignas(32) LeafBox {
+    float omin[3], omax[3];
+    uint8_t rmin[4], rmax[4];  // [3] unused
 };
-static_assert(sizeof(CentreHit) == 32, "CentreHit must be 32 bytes (two 16-byte loads)");
-struct alignas(16) RotHit {
-    uint32_t vote_start;  // first rotation vote of the leaf
-    uint32_t n_votes;
-    uint32_t valtoadd;
-    uint32_t pad;
-};
-static_assert(sizeof(RotHit) == 16, "RotHit must be 16 bytes");
+static_assert(sizeof(LeafBox) == 32, "LeafBox must be one 32-byte sector");
+constexpr uint32_t kLeafRotOk = 1u, kLeafOffOk = 2u, kLeafVotes = 4u;
 
 }  // namespace dh

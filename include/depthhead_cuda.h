@@ -131,10 +131,11 @@ int dh_hough_image_raw(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uin
 #define DH_STAGE_H2D 0
 #define DH_STAGE_SAT 1
 #define DH_STAGE_TRAVERSE 2
-#define DH_STAGE_GATE 3
-#define DH_STAGE_VOTE_MEANSHIFT 4
-#define DH_STAGE_D2H 5
-#define DH_N_STAGES 6
+#define DH_STAGE_GATE 3      /* patch gate, hit list, coarse seed grids */
+#define DH_STAGE_VOTE 4      /* seeds + accumulator cubes */
+#define DH_STAGE_MEANSHIFT 5
+#define DH_STAGE_D2H 6
+#define DH_N_STAGES 7
 int dh_ctx_enable_stage_timing(dh_ctx* c, int on);
 int dh_ctx_stage_ms(dh_ctx* c, float ms[DH_N_STAGES]);
 /* Work counters of the last dh_predict/dh_predict_batch call:
