@@ -180,8 +180,6 @@ void Context::ensure_forest(const HostForest& hf) {
         df_serial_ = hf.serial;
         df_sigma_version_ = 0;
         df_n_leaves_ = NL;
-        const double avg = NL ? (double)NV / (double)NL : 0.0;
-        lanes_per_hit_ = avg >= 48.0 ? 32u : (avg >= 12.0 ? 8u : 1u);
     }
     const uint64_t sv = hf.sigma_version.load();
     if (df_sigma_version_ != sv) {
@@ -415,12 +413,12 @@ void Context::run_front(const FrameBuffers& b, uint32_t n, const FrameState* gue
 void Context::run_back(const FrameBuffers& b, uint32_t n, uint32_t iterations) {
     const Geometry& g = geom_;
     mark(DH_STAGE_GATE);
-    launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, lanes_per_hit_, stream_);
+    launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, stream_);
     stage_check("gate + coarse grids");
     mark(DH_STAGE_VOTE);
     // the accumulator cubes of this pass start empty
     if (iterations) DH_CUDA(cudaMemsetAsync(d_cubes_, 0, sizeof(uint32_t) * 2 * (size_t)vote_box_cells() * n, stream_));
-    launches_ += (uint64_t)launch_seed_and_cubes(b, g, fdev_, n, iterations, lanes_per_hit_, stream_);
+    launches_ += (uint64_t)launch_seed_and_cubes(b, g, fdev_, n, iterations, stream_);
     stage_check("seeds + accumulator cubes");
     mark(DH_STAGE_MEANSHIFT);
     launches_ += (uint64_t)launch_meanshift(b, g, fdev_, n, iterations, stream_);

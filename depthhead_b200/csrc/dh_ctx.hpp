@@ -95,7 +95,6 @@ private:
     LeafBox* df_leaf_box_ = nullptr;
     float* df_kernel_ = nullptr;
     ForestDev fdev_{};
-    uint32_t lanes_per_hit_ = 1;
 
     // scratch for one chunk of frames
     ScratchKey sk_;

@@ -388,7 +388,27 @@ __device__ __forceinline__ uint32_t coarse_pos_cell(const Geometry& g, float nx,
     const uint32_t cy = g.magic_h ? __umulhi(nyi, g.magic_h) : nyi / g.h;
     return cy * kGuessGridParts + cx;
 }
-template <int G>
+// Votes of 32 patch x tree pairs (one per lane) flattened over the lanes of the warp: lane l owns
+// votes [start_l, start_l + n_l) of the warp-wide numbering; the owner of vote v is the largest
+// lane whose start is <= v (lanes without votes share their successor's start and never win).
+__device__ __forceinline__ uint32_t flat_owner(uint32_t start, uint32_t v) {
+    uint32_t lo = 0;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const uint32_t cand = lo + (uint32_t)s;
+        if (__shfl_sync(0xffffffffu, start, cand) <= v) lo = cand;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (uint32_t)d) x += n;
+    }
+    return x;
+}
+
 __global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers b, Geometry g, ForestDev f) {
     __shared__ uint32_t s_grid[kPosGridCells + kRotGridCells];  // [0,400) centre, [400,8400) rotation
     __shared__ float4 s_gated[kGateThreads];                     // p3 + patch index of the CTA's gated patches
@@ -456,56 +476,70 @@ __global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers 
     if (tid < ngate) b.gated[(size_t)frame * g.P + s_base + tid] = s_gated[tid];
 
     // ---- phase B: pair = (tree, gated patch), neighbouring lanes = neighbouring gated patches.
-    // Consecutive centre votes of a thread mostly fall into the same 2-D cell, so equal cells are
-    // merged in a register before the shared atomic.
+    // A warp takes 32 pairs at a time and spreads their votes evenly over its lanes (flat_owner),
+    // so leaves with few, many or no votes cost the same per vote.  Consecutive centre votes of a
+    // lane mostly fall into the same 2-D cell, so equal cells are merged in a register before the
+    // shared atomic.
     uint32_t cur = 0xffffffffu, acc = 0;
     uint32_t cnt_c = 0, cnt_r = 0;
     unsigned long long nmid = 0, nrot = 0;
-    const uint32_t sub = tid % G;
     const uint32_t npairs = ngate * T;
-    for (uint32_t i = tid / G; i < npairs; i += kGateThreads / G) {
-        const uint32_t t = i / ngate;
-        const float4 h = s_gated[i - t * ngate];
-        const int32_t L = leaf_f[(size_t)t * g.P + __float_as_uint(h.w)];
-        const LeafInfo li = f.leaf_info[L];
-        if (!(li.flags & kLeafVotes)) continue;  // prob > 0 (prediction.rs:590), weight != 0, a spread gate open
-        if (li.flags & kLeafOffOk) {
-            if (sub == 0) { ++cnt_c; nmid += li.n_votes; }
-            for (uint32_t k0 = sub; k0 < li.n_votes; k0 += 4 * G) {
-                float4 o[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k0 + u * G < li.n_votes) o[u] = __ldg(f.offsets + li.vote_start + k0 + u * G);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + u * G >= li.n_votes) break;
+    for (uint32_t blk = (tid >> 5) * 32u; blk < npairs; blk += kGateThreads) {
+        const uint32_t i = blk + lane;
+        uint32_t n_c = 0, n_r = 0, v0 = 0, wgt = 0;
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < npairs) {
+            const uint32_t t = i / ngate;
+            h = s_gated[i - t * ngate];
+            const int32_t L = leaf_f[(size_t)t * g.P + __float_as_uint(h.w)];
+            const LeafInfo li = f.leaf_info[L];
+            if (li.flags & kLeafVotes) {  // prob > 0 (prediction.rs:590), weight != 0, a spread gate open
+                v0 = li.vote_start;
+                wgt = li.valtoadd;
+                if (li.flags & kLeafOffOk) { n_c = li.n_votes; ++cnt_c; nmid += li.n_votes; }
+                if (li.flags & kLeafRotOk) { n_r = li.n_votes; ++cnt_r; nrot += li.n_votes; }
+            }
+        }
+        {   // centre votes -> 20x20 grid
+            const uint32_t incl = warp_incl_scan(n_c, lane), start = incl - n_c;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            for (uint32_t vb = 0; vb < total; vb += 32u) {
+                const uint32_t v = min(vb + lane, total - 1u);
+                const uint32_t own = flat_owner(start, v);
+                const uint32_t k = v - __shfl_sync(0xffffffffu, start, own);
+                const uint32_t ov0 = __shfl_sync(0xffffffffu, v0, own), ow = __shfl_sync(0xffffffffu, wgt, own);
+                const float px = __shfl_sync(0xffffffffu, h.x, own), py = __shfl_sync(0xffffffffu, h.y, own),
+                            pz = __shfl_sync(0xffffffffu, h.z, own);
+                if (vb + lane < total) {
+                    const float4 o = __ldg(f.offsets + ov0 + k);
                     // np = p3 - offset (prediction.rs:647); np.z < 0 is skipped (:650)
-                    const float nx = __fsub_rn(h.x, o[u].x), ny = __fsub_rn(h.y, o[u].y), nz = __fsub_rn(h.z, o[u].z);
-                    if (nz < 0.0f) continue;
-                    const uint32_t cell = coarse_pos_cell(g, nx, ny, nz);
-                    if (cell == cur) {
-                        acc += li.valtoadd;
-                    } else {
-                        if (acc) atomicAdd(&s_grid[cur], acc);
-                        cur = cell;
-                        acc = li.valtoadd;
+                    const float nx = __fsub_rn(px, o.x), ny = __fsub_rn(py, o.y), nz = __fsub_rn(pz, o.z);
+                    if (!(nz < 0.0f)) {
+                        const uint32_t cell = coarse_pos_cell(g, nx, ny, nz);
+                        if (cell == cur) {
+                            acc += ow;
+                        } else {
+                            if (acc) atomicAdd(&s_grid[cur], acc);
+                            cur = cell;
+                            acc = ow;
+                        }
                     }
                 }
             }
         }
-        if (li.flags & kLeafRotOk) {
-            if (sub == 0) { ++cnt_r; nrot += li.n_votes; }
-            for (uint32_t k0 = sub; k0 < li.n_votes; k0 += 4 * G) {
-                uint32_t cell[4];  // rough = r * 20 / 120 per axis (prediction.rs:630-636), static per vote
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k0 + u * G < li.n_votes) cell[u] = __ldg(f.rot_coarse + li.vote_start + k0 + u * G);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + u * G >= li.n_votes) break;
-                    if (atomicAdd(&s_grid[kPosGridCells + cell[u]], li.valtoadd) == 0u) {
+        {   // rotation votes -> 20^3 grid; rough = r * 20 / 120 per axis (prediction.rs:630-636), static per vote
+            const uint32_t incl = warp_incl_scan(n_r, lane), start = incl - n_r;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            for (uint32_t vb = 0; vb < total; vb += 32u) {
+                const uint32_t v = min(vb + lane, total - 1u);
+                const uint32_t own = flat_owner(start, v);
+                const uint32_t k = v - __shfl_sync(0xffffffffu, start, own);
+                const uint32_t ov0 = __shfl_sync(0xffffffffu, v0, own), ow = __shfl_sync(0xffffffffu, wgt, own);
+                if (vb + lane < total) {
+                    const uint32_t cell = __ldg(f.rot_coarse + ov0 + k);
+                    if (atomicAdd(&s_grid[kPosGridCells + cell], ow) == 0u) {
                         const uint32_t slot = atomicAdd(&s_ntouched, 1u);
-                        if (slot < (uint32_t)kTouchedCap) s_touched[slot] = (uint16_t)cell[u];
+                        if (slot < (uint32_t)kTouchedCap) s_touched[slot] = (uint16_t)cell;
                     }
                 }
             }
@@ -670,74 +704,88 @@ __device__ __forceinline__ bool in_box(int x, int y, int z, const int32_t* org, 
     return true;
 }
 
-// Adds the votes of pairs [first, first+step, ...) of one frame that fall into the cube(s).
-// which_mask: bit0 centre cube, bit1 rotation cube.
-template <int G>
+// Adds the votes of one frame that fall into the cube(s).  Warp `first_warp` of `n_warps` takes
+// pairs 32 at a time (one per lane) and spreads their votes over its lanes (flat_owner).
+// which_mask: bit0 centre cube, bit1 rotation cube.  All 32 lanes of a warp must call.
 __device__ __forceinline__ void accumulate_pairs(const float4* __restrict__ gated, uint32_t ngate, uint32_t T,
-                                                 const int32_t* __restrict__ leaf_f, uint32_t P, uint32_t first,
-                                                 uint32_t step, uint32_t sub, const ForestDev& f, uint32_t which_mask,
+                                                 const int32_t* __restrict__ leaf_f, uint32_t P, uint32_t first_warp,
+                                                 uint32_t n_warps, const ForestDev& f, uint32_t which_mask,
                                                  const int32_t* org_c, uint32_t* cube_c, const int32_t* org_r,
                                                  uint32_t* cube_r) {
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t npairs = ngate * T;
-    for (uint32_t i = first; i < npairs; i += step) {
-        const uint32_t t = i / ngate;
-        const float4 h = __ldg(gated + (i - t * ngate));
-        const int32_t L = leaf_f[(size_t)t * P + __float_as_uint(h.w)];
-        const LeafInfo li = f.leaf_info[L];
-        if (!(li.flags & kLeafVotes)) continue;
-        // Skip the leaf when the bounding box of its votes misses the cube.  Conservative, hence
-        // exact: p3 - o and the truncation are monotone, so every vote cell lies in
-        // [trunc(p3 - omax), trunc(p3 - omin)] per axis; rotation bins lie in [rmin, rmax].
-        const uint4 bb0 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L));
-        const uint4 bb1 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L) + 1);
-        bool do_c = (which_mask & 1u) && (li.flags & kLeafOffOk), do_r = (which_mask & 2u) && (li.flags & kLeafRotOk);
-        if (do_c) {
-            const float omin[3] = {__uint_as_float(bb0.x), __uint_as_float(bb0.y), __uint_as_float(bb0.z)};
-            const float omax[3] = {__uint_as_float(bb0.w), __uint_as_float(bb1.x), __uint_as_float(bb1.y)};
-            const float pc[3] = {h.x, h.y, h.z};
+    for (uint32_t blk = first_warp * 32u; blk < npairs; blk += n_warps * 32u) {
+        const uint32_t i = blk + lane;
+        uint32_t n_c = 0, n_r = 0, v0 = 0, wgt = 0;
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < npairs) {
+            const uint32_t t = i / ngate;
+            h = __ldg(gated + (i - t * ngate));
+            const int32_t L = leaf_f[(size_t)t * P + __float_as_uint(h.w)];
+            const LeafInfo li = f.leaf_info[L];
+            if (li.flags & kLeafVotes) {
+                // Skip the leaf when the bounding box of its votes misses the cube.  Conservative,
+                // hence exact: p3 - o and the truncation are monotone, so every vote cell lies in
+                // [trunc(p3 - omax), trunc(p3 - omin)] per axis; rotation bins lie in [rmin, rmax].
+                const uint4 bb0 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L));
+                const uint4 bb1 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L) + 1);
+                bool do_c = (which_mask & 1u) && (li.flags & kLeafOffOk), do_r = (which_mask & 2u) && (li.flags & kLeafRotOk);
+                if (do_c) {
+                    const float omin[3] = {__uint_as_float(bb0.x), __uint_as_float(bb0.y), __uint_as_float(bb0.z)};
+                    const float omax[3] = {__uint_as_float(bb0.w), __uint_as_float(bb1.x), __uint_as_float(bb1.y)};
+                    const float pc[3] = {h.x, h.y, h.z};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const long long lo = (long long)__float2int_rz(__fsub_rn(pc[k], omax[k])) - org_c[k];
-                const long long hi = (long long)__float2int_rz(__fsub_rn(pc[k], omin[k])) - org_c[k];
-                if (hi < 0 || lo >= kBox) do_c = false;
+                    for (int k = 0; k < 3; ++k) {
+                        const long long lo = (long long)__float2int_rz(__fsub_rn(pc[k], omax[k])) - org_c[k];
+                        const long long hi = (long long)__float2int_rz(__fsub_rn(pc[k], omin[k])) - org_c[k];
+                        if (hi < 0 || lo >= kBox) do_c = false;
+                    }
+                }
+                if (do_r) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int rmin = (int)((bb1.z >> (8 * k)) & 0xffu), rmax = (int)((bb1.w >> (8 * k)) & 0xffu);
+                        if ((long long)rmax - org_r[k] < 0 || (long long)rmin - org_r[k] >= kBox) do_r = false;
+                    }
+                }
+                v0 = li.vote_start;
+                wgt = li.valtoadd;
+                if (do_c) n_c = li.n_votes;
+                if (do_r) n_r = li.n_votes;
             }
         }
-        if (do_r) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int rmin = (int)((bb1.z >> (8 * k)) & 0xffu), rmax = (int)((bb1.w >> (8 * k)) & 0xffu);
-                if ((long long)rmax - org_r[k] < 0 || (long long)rmin - org_r[k] >= kBox) do_r = false;
-            }
-        }
-        if (do_c) {
-            for (uint32_t k0 = sub; k0 < li.n_votes; k0 += 4 * G) {
-                float4 o[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k0 + u * G < li.n_votes) o[u] = __ldg(f.offsets + li.vote_start + k0 + u * G);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + u * G >= li.n_votes) break;
-                    const float nx = __fsub_rn(h.x, o[u].x), ny = __fsub_rn(h.y, o[u].y), nz = __fsub_rn(h.z, o[u].z);
-                    if (nz < 0.0f) continue;  // prediction.rs:650
-                    uint32_t idx;  // mid[(x as i32, y as i32, z as i32)] += valtoadd  (prediction.rs:667)
-                    if (in_box(__float2int_rz(nx), __float2int_rz(ny), __float2int_rz(nz), org_c, &idx))
-                        atomicAdd(cube_c + idx, li.valtoadd);
+        if (which_mask & 1u) {
+            const uint32_t incl = warp_incl_scan(n_c, lane), start = incl - n_c;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            for (uint32_t vb = 0; vb < total; vb += 32u) {
+                const uint32_t v = min(vb + lane, total - 1u);
+                const uint32_t own = flat_owner(start, v);
+                const uint32_t k = v - __shfl_sync(0xffffffffu, start, own);
+                const uint32_t ov0 = __shfl_sync(0xffffffffu, v0, own), ow = __shfl_sync(0xffffffffu, wgt, own);
+                const float px = __shfl_sync(0xffffffffu, h.x, own), py = __shfl_sync(0xffffffffu, h.y, own),
+                            pz = __shfl_sync(0xffffffffu, h.z, own);
+                if (vb + lane < total) {
+                    const float4 o = __ldg(f.offsets + ov0 + k);
+                    const float nx = __fsub_rn(px, o.x), ny = __fsub_rn(py, o.y), nz = __fsub_rn(pz, o.z);
+                    uint32_t idx;  // mid[(x as i32, y as i32, z as i32)] += valtoadd  (prediction.rs:650,667)
+                    if (!(nz < 0.0f) && in_box(__float2int_rz(nx), __float2int_rz(ny), __float2int_rz(nz), org_c, &idx))
+                        atomicAdd(cube_c + idx, ow);
                 }
             }
         }
-        if (do_r) {
-            for (uint32_t k0 = sub; k0 < li.n_votes; k0 += 4 * G) {
-                uint32_t bins[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k0 + u * G < li.n_votes) bins[u] = __ldg(f.rot_bins + li.vote_start + k0 + u * G);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + u * G >= li.n_votes) break;
+        if (which_mask & 2u) {
+            const uint32_t incl = warp_incl_scan(n_r, lane), start = incl - n_r;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            for (uint32_t vb = 0; vb < total; vb += 32u) {
+                const uint32_t v = min(vb + lane, total - 1u);
+                const uint32_t own = flat_owner(start, v);
+                const uint32_t k = v - __shfl_sync(0xffffffffu, start, own);
+                const uint32_t ov0 = __shfl_sync(0xffffffffu, v0, own), ow = __shfl_sync(0xffffffffu, wgt, own);
+                if (vb + lane < total) {
+                    const uint32_t bins = __ldg(f.rot_bins + ov0 + k);
                     uint32_t idx;  // rot[(r1, r2, r3)] += valtoadd  (prediction.rs:635)
-                    if (in_box((int)(bins[u] & 0xffu), (int)((bins[u] >> 8) & 0xffu), (int)((bins[u] >> 16) & 0xffu), org_r, &idx))
-                        atomicAdd(cube_r + idx, li.valtoadd);
+                    if (in_box((int)(bins & 0xffu), (int)((bins >> 8) & 0xffu), (int)((bins >> 16) & 0xffu), org_r, &idx))
+                        atomicAdd(cube_r + idx, ow);
                 }
             }
         }
@@ -745,7 +793,6 @@ __device__ __forceinline__ void accumulate_pairs(const float4* __restrict__ gate
 }
 
 constexpr int kBuildThreads = 256;
-template <int G>
 __global__ void __launch_bounds__(kBuildThreads) box_build_kernel(FrameBuffers b, Geometry g, ForestDev f) {
     const uint32_t frame = blockIdx.y;
     const FrameState* fs = b.fs + frame;
@@ -753,9 +800,9 @@ __global__ void __launch_bounds__(kBuildThreads) box_build_kernel(FrameBuffers b
     const int32_t org_c[3] = {fs->box_org[0][0], fs->box_org[0][1], fs->box_org[0][2]};
     const int32_t org_r[3] = {fs->box_org[1][0], fs->box_org[1][1], fs->box_org[1][2]};
     uint32_t* cube_c = b.cubes + (size_t)(2u * frame) * kBoxCells;
-    accumulate_pairs<G>(b.gated + (size_t)frame * g.P, fs->n_gate, g.n_trees, b.leaf + (size_t)frame * g.n_trees * g.P, g.P,
-                        blockIdx.x * (kBuildThreads / G) + threadIdx.x / G, gridDim.x * (kBuildThreads / G),
-                        threadIdx.x % G, f, 3u, org_c, cube_c, org_r, cube_c + kBoxCells);
+    accumulate_pairs(b.gated + (size_t)frame * g.P, fs->n_gate, g.n_trees, b.leaf + (size_t)frame * g.n_trees * g.P, g.P,
+                     blockIdx.x * (kBuildThreads / 32) + (threadIdx.x >> 5), gridDim.x * (kBuildThreads / 32), f, 3u, org_c,
+                     cube_c, org_r, cube_c + kBoxCells);
 }
 
 // ================================================================ K4c: mean-shift
@@ -804,7 +851,7 @@ __device__ __noinline__ void rebuild_cube(const float4* __restrict__ gated, uint
     for (int i = threadIdx.x; i < kBoxCells / 4; i += kMsThreads) __stcg(bz + i, make_uint4(0u, 0u, 0u, 0u));
     __threadfence();
     __syncthreads();
-    accumulate_pairs<1>(gated, ngate, T, leaf_f, P, threadIdx.x, kMsThreads, 0u, f, 1u << which, org, box, org, box);
+    accumulate_pairs(gated, ngate, T, leaf_f, P, threadIdx.x >> 5, kMsThreads / 32, f, 1u << which, org, box, org, box);
     __threadfence();
     __syncthreads();
 }
@@ -1258,27 +1305,22 @@ uint32_t vote_box_dim() { return (uint32_t)kBox; }
 
 // The back end after the traversal, in launch order.  The coarse grids, the accumulator cubes
 // and the queue header must be zero when these run.  Each returns the kernels it launched.
-int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
-                       uint32_t lanes_per_hit, cudaStream_t s) {
+int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
     if (!g.P) return 0;
     dim3 gr((g.P + kGateThreads - 1) / kGateThreads, n_frames);
-    if (lanes_per_hit >= 32) gate_coarse_kernel<32><<<gr, kGateThreads, 0, s>>>(b, g, f);
-    else if (lanes_per_hit >= 8) gate_coarse_kernel<8><<<gr, kGateThreads, 0, s>>>(b, g, f);
-    else gate_coarse_kernel<1><<<gr, kGateThreads, 0, s>>>(b, g, f);
+    gate_coarse_kernel<<<gr, kGateThreads, 0, s>>>(b, g, f);
     return 1;
 }
 
 int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
-                          uint32_t iterations, uint32_t lanes_per_hit, cudaStream_t s) {
+                          uint32_t iterations, cudaStream_t s) {
     seed_kernel<<<n_frames, kSeedThreads, 0, s>>>(b, g, iterations);
     if (!g.P || !iterations) return 1;
     // enough blocks per frame that a thread sees a handful of hits
     const uint32_t per_frame =
         std::max<uint32_t>(1u, std::min<uint32_t>(64u, (g.P * g.n_trees / 8u + kBuildThreads - 1) / kBuildThreads));
     dim3 gr(per_frame, n_frames);
-    if (lanes_per_hit >= 32) box_build_kernel<32><<<gr, kBuildThreads, 0, s>>>(b, g, f);
-    else if (lanes_per_hit >= 8) box_build_kernel<8><<<gr, kBuildThreads, 0, s>>>(b, g, f);
-    else box_build_kernel<1><<<gr, kBuildThreads, 0, s>>>(b, g, f);
+    box_build_kernel<<<gr, kBuildThreads, 0, s>>>(b, g, f);
     return 2;
 }
 

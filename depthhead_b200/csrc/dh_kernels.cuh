@@ -86,10 +86,9 @@ void launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cud
 void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, size_t n_nodes, uint32_t tile_width, cudaStream_t s);
-int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
-                       uint32_t lanes_per_hit, cudaStream_t s);
+int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
-                          uint32_t iterations, uint32_t lanes_per_hit, cudaStream_t s);
+                          uint32_t iterations, cudaStream_t s);
 int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t iterations,
                      cudaStream_t s);
 uint32_t vote_box_cells();
