@@ -302,10 +302,13 @@ def main():
     while len(sampler.lines) < 2 and time.perf_counter() - t_wait < 3.0:
         step_device()
     sampler.begin_region()
-    ctx.enable_stage_timing(True)
-    ms_dev, wall_dev, stage, counters, out_dev = timed(step_device, args.steps, with_stages=True)
-    ctx.enable_stage_timing(False)
+    ms_dev, wall_dev, _, counters, out_dev = timed(step_device, args.steps)
     ms_e2e, wall_e2e, _, _, out_host = timed(step_host, args.steps)
+    # per-stage times (and the roofline of the traversal kernel): the same steps again with the
+    # pipeline serialised on one stream, CUDA events between the stages
+    ctx.enable_stage_timing(True)
+    ms_ser, _, stage, counters_ser, _ = timed(step_device, args.steps, with_stages=True)
+    ctx.enable_stage_timing(False)
     # the timed regions last ~0.2 s: extend the sampled window with identical untimed steps so the
     # clock record has enough samples under the same load
     t_wait = time.perf_counter()
@@ -320,7 +323,7 @@ def main():
 
     # ---- roofline of the dominant kernel (traversal), from this rank's live stage timers
     peak, peak_src = measured_peak_gbs()
-    dev_chunk = args.chunk or 1024  # library default for device-resident input
+    dev_chunk = args.chunk or 256  # library default for device-resident input
     launches = max(1, (n + dev_chunk - 1) // dev_chunk) * args.steps
     trav_ms = stage.get("traverse", 0.0)
     alg_bytes = counters["node_visits"] * BYTES_PER_NODE_VISIT + counters["evals"] * BYTES_PER_LEAF_HEADER
@@ -356,6 +359,8 @@ def main():
                 "wall_ms_per_step": wall_e2e / args.steps},
         "gpu_launches": int(counters["launches"]),
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+        "stage_timing": "separate pass of the same steps with the pipeline lanes serialised on one stream "
+                        "(%.3f ms per step); the timed `value` pass overlaps chunks on %s lanes" % (ms_ser / args.steps, os.environ.get("DH_LANES", "2")),
         "wall_ms_per_step": wall_dev / args.steps,
         "work_per_step": {k: counters[k] // args.steps for k in ("frames", "valid_patches", "evals", "node_visits", "gate_patches", "hits", "centre_votes", "rot_votes", "meanshift_iters", "cube_rebuilds")},
         "roofline": roofline, "clocks": clocks,

@@ -75,6 +75,12 @@ Context::Context(int device) : device_(device) {
     DH_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     DH_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     stream_ = own_stream_;
+    max_lanes_ = (int)std::min<uint32_t>(kMaxLanes, env_u32("DH_LANES", 2));
+    DH_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxLanes; ++i) {
+        DH_CUDA(cudaEventCreateWithFlags(&lanes_[i].done, cudaEventDisableTiming));
+        if (i > 0) DH_CUDA(cudaStreamCreateWithFlags(&lanes_[i].own, cudaStreamNonBlocking));
+    }
     for (int i = 0; i < 2; ++i) {
         DH_CUDA(cudaEventCreateWithFlags(&ev_copied_[i], cudaEventDisableTiming));
         DH_CUDA(cudaEventCreateWithFlags(&ev_consumed_[i], cudaEventDisableTiming));
@@ -105,6 +111,11 @@ Context::~Context() {
         if (ev_copied_[i]) cudaEventDestroy(ev_copied_[i]);
         if (ev_consumed_[i]) cudaEventDestroy(ev_consumed_[i]);
     }
+    for (int i = 0; i < kMaxLanes; ++i) {
+        if (lanes_[i].done) cudaEventDestroy(lanes_[i].done);
+        if (lanes_[i].own) cudaStreamDestroy(lanes_[i].own);
+    }
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (own_stream_) cudaStreamDestroy(own_stream_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
 }
@@ -204,20 +215,55 @@ void Context::ensure_forest(const HostForest& hf) {
 }
 
 // ------------------------------------------------------------------------------------------------ scratch
+void Context::free_lane(Lane& L) {
+    dev_free(L.sat);
+    dev_free(L.leaf);
+    dev_free(L.p3);
+    dev_free(L.gate);
+    dev_free(L.gated);
+    dev_free(L.cubes);
+    dev_free(L.grids);
+    dev_free(L.fs);
+    dev_free(L.results);
+    dev_free(L.ms_trace);
+    L.allocated = false;
+}
+
 void Context::free_scratch() {
     for (int i = 0; i < 2; ++i) dev_free(d_depth_[i]);
     staging_elems_ = 0;
-    dev_free(d_sat_);
-    dev_free(d_leaf_);
-    dev_free(d_p3_);
-    dev_free(d_gate_);
-    dev_free(d_gated_);
-    dev_free(d_cubes_);
-    dev_free(d_grids_);
-    dev_free(d_fs_);
-    dev_free(d_results_);
-    dev_free(d_ms_trace_);
+    for (int i = 0; i < kMaxLanes; ++i) free_lane(lanes_[i]);
     sk_ = ScratchKey();
+}
+
+void Context::alloc_lane(Lane& L) {
+    const Geometry& g = geom_;
+    const size_t F = sk_.frames, P = std::max<uint32_t>(g.P, 1u), T = g.n_trees;
+    const uint32_t w = g.w, h = g.h;
+    dev_alloc(L.sat, F * (size_t)(h + 1) * g.sat_pitch);
+    DH_CUDA(cudaMemsetAsync(L.sat, 0, F * (size_t)(h + 1) * g.sat_pitch * sizeof(uint32_t), stream_));  // row 0 stays 0
+    dev_alloc(L.leaf, F * P * T);
+    dev_alloc(L.p3, F * P * 3);
+    dev_alloc(L.gate, F * P);
+    dev_alloc(L.gated, F * P);
+    dev_alloc(L.cubes, F * 2 * (size_t)vote_box_cells());
+    dev_alloc(L.grids, F * (size_t)(kPosGridCells + kRotGridCells));
+    dev_alloc(L.fs, F);
+    dev_alloc(L.results, F);
+    if (sk_.trace_iters) dev_alloc(L.ms_trace, F * 2 * (size_t)sk_.trace_iters * 3);
+    if (g.P) {
+        // TMA descriptor over the SAT scratch: [F][h+1][pitch] u32, box = one tile
+        const cuuint64_t gdim[3] = {(cuuint64_t)(w + 1), (cuuint64_t)(h + 1), (cuuint64_t)F};
+        const cuuint64_t gstr[2] = {(cuuint64_t)g.sat_pitch * 4u, (cuuint64_t)g.sat_pitch * 4u * (h + 1)};
+        const cuuint32_t box[3] = {tiles_.tw, tiles_.th, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        CUresult r = get_encode_fn()(&L.sat_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, L.sat, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) throw ModelError(DH_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    }
+    DH_CUDA(cudaStreamSynchronize(stream_));
+    L.allocated = true;
 }
 
 TilePlan Context::plan_tiles(const Geometry& g) const {
@@ -252,13 +298,13 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
 
 uint32_t Context::pick_chunk(uint32_t n_frames, int depth_loc) const {
     // Host input: small chunks so the H2D copy of chunk c+1 hides behind the kernels of chunk c
-    // and the first kernels start early.  Device input: large chunks, so the persistent
-    // vote/mean-shift kernel has many work items per CTA and the launch tails are amortised.
-    uint32_t c = chunk_frames_ ? chunk_frames_ : (depth_loc == DH_DEPTH_DEVICE ? 1024u : 128u);
+    // and the first kernels start early.  Device input: chunks large enough to fill the GPU
+    // several times over, small enough that a batch spreads over all pipeline lanes.
+    uint32_t c = chunk_frames_ ? chunk_frames_ : (depth_loc == DH_DEPTH_DEVICE ? 256u : 128u);
     return std::max<uint32_t>(1u, std::min<uint32_t>(c, std::max<uint32_t>(n_frames, 1u)));
 }
 
-void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9]) {
+void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9], int n_lanes) {
     const uint32_t sw = hf.subimage_width, sh = hf.subimage_height, stride = hf.stepwidth.load();
     if (stride == 0) throw ModelError(DH_E_SHAPE, "stepwidth 0: the reference's sliding window never advances");
     if (w < sw || h < sh)
@@ -302,32 +348,11 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
         g.magic_w = magic(w);
         g.magic_h = magic(h);
         if ((uint64_t)g.P * g.n_trees > 0x7fffffffull) throw ModelError(DH_E_SHAPE, "too many patch x tree pairs per frame");
-        const size_t F = cap, P = std::max<uint32_t>(g.P, 1u), T = g.n_trees;
-        dev_alloc(d_sat_, F * (size_t)(h + 1) * g.sat_pitch);
-        DH_CUDA(cudaMemsetAsync(d_sat_, 0, F * (size_t)(h + 1) * g.sat_pitch * sizeof(uint32_t), stream_));  // row 0 stays 0
-        dev_alloc(d_leaf_, F * P * T);
-        dev_alloc(d_p3_, F * P * 3);
-        dev_alloc(d_gate_, F * P);
-        dev_alloc(d_gated_, F * P);
-        dev_alloc(d_cubes_, F * 2 * (size_t)vote_box_cells());
-        dev_alloc(d_grids_, F * (size_t)(kPosGridCells + kRotGridCells));
-        dev_alloc(d_fs_, F);
-        dev_alloc(d_results_, F);
-        if (k.trace_iters) dev_alloc(d_ms_trace_, F * 2 * (size_t)k.trace_iters * 3);
-        if (g.P) {
-            tiles_ = plan_tiles(g);
-            // TMA descriptor over the SAT scratch: [F][h+1][pitch] u32, box = one tile
-            const cuuint64_t gdim[3] = {(cuuint64_t)(w + 1), (cuuint64_t)(h + 1), (cuuint64_t)F};
-            const cuuint64_t gstr[2] = {(cuuint64_t)g.sat_pitch * 4u, (cuuint64_t)g.sat_pitch * 4u * (h + 1)};
-            const cuuint32_t box[3] = {tiles_.tw, tiles_.th, 1u};
-            const cuuint32_t estr[3] = {1u, 1u, 1u};
-            CUresult r = get_encode_fn()(&sat_map_, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_sat_, gdim, gstr, box, estr,
-                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) throw ModelError(DH_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-        }
+        if (g.P) tiles_ = plan_tiles(g);
         sk_ = k;
     }
+    for (int i = 0; i < std::max(1, std::min(n_lanes, kMaxLanes)); ++i)
+        if (!lanes_[i].allocated) alloc_lane(lanes_[i]);
     std::memcpy(g.K, K, sizeof(float) * 9);
     mat3_inverse_f32(K, g.Kinv);
 }
@@ -344,19 +369,19 @@ void Context::ensure_staging(int slots) {
         if (!d_depth_[i]) dev_alloc(d_depth_[i], staging_elems_);
 }
 
-FrameBuffers Context::buffers(const uint16_t* depth) const {
+FrameBuffers Context::buffers(const Lane& L, const uint16_t* depth) const {
     FrameBuffers b{};
     b.depth = depth;
-    b.sat = d_sat_;
-    b.leaf = d_leaf_;
-    b.p3 = d_p3_;
-    b.gate = d_gate_;
-    b.gated = d_gated_;
-    b.grids = d_grids_;
-    b.fs = d_fs_;
-    b.cubes = d_cubes_;
-    b.results = d_results_;
-    b.ms_trace = d_ms_trace_;
+    b.sat = L.sat;
+    b.leaf = L.leaf;
+    b.p3 = L.p3;
+    b.gate = L.gate;
+    b.gated = L.gated;
+    b.grids = L.grids;
+    b.fs = L.fs;
+    b.cubes = L.cubes;
+    b.results = L.results;
+    b.ms_trace = L.ms_trace;
     b.ms_trace_cap = sk_.trace_iters;
     b.debug = debug_ ? 1u : 0u;
     return b;
@@ -386,51 +411,56 @@ void Context::mark(int stage_begin_of) {
 
 // ------------------------------------------------------------------------------------------------ one pass
 // Front end shared by every entry point: SAT + traversal (+ zeroed per-frame state).
-void Context::run_front(const FrameBuffers& b, uint32_t n, const FrameState* guess_state) {
+void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameState* guess_state) {
     const Geometry& g = geom_;
-    DH_CUDA(cudaMemsetAsync(d_fs_, 0, sizeof(FrameState) * n, stream_));
-    DH_CUDA(cudaMemsetAsync(d_grids_, 0, sizeof(uint32_t) * (size_t)(kPosGridCells + kRotGridCells) * n, stream_));
+    cudaStream_t st = L.stream;
+    DH_CUDA(cudaMemsetAsync(L.fs, 0, sizeof(FrameState) * n, st));
+    DH_CUDA(cudaMemsetAsync(L.grids, 0, sizeof(uint32_t) * (size_t)(kPosGridCells + kRotGridCells) * n, st));
     if (guess_state) {
         *h_fs_ = *guess_state;
-        DH_CUDA(cudaMemcpyAsync(d_fs_, h_fs_, sizeof(FrameState), cudaMemcpyHostToDevice, stream_));
+        DH_CUDA(cudaMemcpyAsync(L.fs, h_fs_, sizeof(FrameState), cudaMemcpyHostToDevice, st));
     }
     if (g.P && hot_tw_ != tiles_.tw) {  // node table for this tile plan (once per forest x plan)
         launch_plan_nodes(df_nodes_, df_hot_, df_n_nodes_, tiles_.tw, stream_);
+        DH_CUDA(cudaStreamSynchronize(stream_));
         hot_tw_ = tiles_.tw;
     }
     mark(DH_STAGE_SAT);
-    launch_sat(b, g, n, stream_);
+    launch_sat(b, g, n, st);
     launches_ += 2;
     stage_check("sat");
     mark(DH_STAGE_TRAVERSE);
     if (g.P) {
-        launch_traverse(sat_map_, b, g, tiles_, fdev_, n, stream_);
+        launch_traverse(L.sat_map, b, g, tiles_, fdev_, n, st);
         launches_ += 1;
         stage_check("traverse");
     }
 }
 
-void Context::run_back(const FrameBuffers& b, uint32_t n, uint32_t iterations) {
+void Context::run_back(Lane& L, const FrameBuffers& b, uint32_t n, uint32_t iterations) {
     const Geometry& g = geom_;
+    cudaStream_t st = L.stream;
     mark(DH_STAGE_GATE);
-    launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, stream_);
+    launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, st);
     stage_check("gate + coarse grids");
     mark(DH_STAGE_VOTE);
     // the accumulator cubes of this pass start empty
-    if (iterations) DH_CUDA(cudaMemsetAsync(d_cubes_, 0, sizeof(uint32_t) * 2 * (size_t)vote_box_cells() * n, stream_));
-    launches_ += (uint64_t)launch_seed_and_cubes(b, g, fdev_, n, iterations, stream_);
+    if (iterations) DH_CUDA(cudaMemsetAsync(L.cubes, 0, sizeof(uint32_t) * 2 * (size_t)vote_box_cells() * n, st));
+    launches_ += (uint64_t)launch_seed_and_cubes(b, g, fdev_, n, iterations, st);
     stage_check("seeds + accumulator cubes");
     mark(DH_STAGE_MEANSHIFT);
-    launches_ += (uint64_t)launch_meanshift(b, g, fdev_, n, iterations, stream_);
+    launches_ += (uint64_t)launch_meanshift(b, g, fdev_, n, iterations, st);
     stage_check("mean-shift");
     mark(DH_STAGE_D2H);
-    launch_counters(b, g, n, d_counters_, stream_);
+    launch_counters(b, g, n, d_counters_, st);
     launches_ += 1;
     DH_CUDA(cudaGetLastError());
 }
 
 void Context::begin_call() {
     DH_CUDA(cudaSetDevice(device_));
+    lanes_[0].stream = stream_;
+    for (int i = 1; i < kMaxLanes; ++i) lanes_[i].stream = lanes_[i].own;
     launches_ = 0;
     ev_used_ = 0;
     marks_.clear();
@@ -478,11 +508,11 @@ void Context::predict(const HostForest& hf, const uint16_t* depth, uint32_t w, u
         for (int k = 0; k < 3; ++k) gs.rot_guess[k] = rot_guess[k];
     }
     {
-        FrameBuffers b = buffers(d_depth_[0]);
-        run_front(b, 1, &gs);
-        run_back(b, 1, iterations);
+        FrameBuffers b = buffers(lanes_[0], d_depth_[0]);
+        run_front(lanes_[0], b, 1, &gs);
+        run_back(lanes_[0], b, 1, iterations);
     }
-    DH_CUDA(cudaMemcpyAsync(out, d_results_, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
+    DH_CUDA(cudaMemcpyAsync(out, lanes_[0].results, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
     mark(-1);
     end_call();
     have_debug_ = debug_;
@@ -498,24 +528,32 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
         return;
     }
     ensure_forest(hf);
-    ensure_scratch(hf, w, h, pick_chunk(n, depth_loc), K);
+    // Chunks go round-robin over the lanes.  Stage timing needs the kernels of a pass back to
+    // back on one stream, so it runs single-lane.
+    const uint32_t want_chunk = pick_chunk(n, depth_loc);
+    const int n_lanes = timing_ ? 1 : (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)max_lanes_, (n + want_chunk - 1) / want_chunk));
+    ensure_scratch(hf, w, h, want_chunk, K, n_lanes);
     const uint32_t iterations = hf.meanshift_iterations.load();
     const uint32_t F = call_chunk_;
     const uint32_t n_chunks = (n + F - 1) / F;
     const size_t frame_px = (size_t)w * h;
-    // pinned staging for results and per-chunk pool state
+    // pinned staging for the results
     if (h_results_cap_ < n) {
         if (h_results_) cudaFreeHost(h_results_);
         h_results_ = nullptr;
         DH_CUDA(cudaHostAlloc((void**)&h_results_, sizeof(dh_result) * n, cudaHostAllocDefault));
         h_results_cap_ = n;
     }
+    // fork: the other lanes (and the copy stream) start after everything already queued on the caller's stream
+    DH_CUDA(cudaEventRecord(ev_fork_, stream_));
+    for (int i = 1; i < n_lanes; ++i) DH_CUDA(cudaStreamWaitEvent(lanes_[i].stream, ev_fork_, 0));
     auto enqueue_chunk = [&](uint32_t c, const uint16_t* d_depth) {
+        Lane& L = lanes_[c % (uint32_t)n_lanes];
         const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
-        FrameBuffers b = buffers(d_depth);
-        run_front(b, nc, nullptr);
-        run_back(b, nc, iterations);
-        DH_CUDA(cudaMemcpyAsync(h_results_ + f0, d_results_, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, stream_));
+        FrameBuffers b = buffers(L, d_depth);
+        run_front(L, b, nc, nullptr);
+        run_back(L, b, nc, iterations);
+        DH_CUDA(cudaMemcpyAsync(h_results_ + f0, L.results, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, L.stream));
     };
     if (depth_loc != DH_DEPTH_DEVICE) ensure_staging(2);
     if (depth_loc == DH_DEPTH_DEVICE) {
@@ -524,8 +562,10 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
         // double-buffered staging: the copy of chunk c+1 overlaps the kernels of chunk c
         for (uint32_t c = 0; c < n_chunks; ++c) {
             const int slot = (int)(c & 1u);
+            Lane& L = lanes_[c % (uint32_t)n_lanes];
             const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
             if (c >= 2) DH_CUDA(cudaStreamWaitEvent(copy_stream_, ev_consumed_[slot], 0));
+            else DH_CUDA(cudaStreamWaitEvent(copy_stream_, ev_fork_, 0));
             cudaEvent_t t0 = nullptr, t1 = nullptr;
             if (timing_) {
                 t0 = next_event();
@@ -539,9 +579,15 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
                 copy_marks_.push_back({t0, t1});
             }
             DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
-            DH_CUDA(cudaStreamWaitEvent(stream_, ev_copied_[slot], 0));
+            DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
             enqueue_chunk(c, d_depth_[slot]);
-            DH_CUDA(cudaEventRecord(ev_consumed_[slot], stream_));
+            DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
+        }
+    }
+    if (n_lanes > 1) {  // join: the caller's stream continues after every lane
+        for (int i = 1; i < n_lanes; ++i) {
+            DH_CUDA(cudaEventRecord(lanes_[i].done, lanes_[i].stream));
+            DH_CUDA(cudaStreamWaitEvent(stream_, lanes_[i].done, 0));
         }
     }
     mark(-1);
@@ -558,8 +604,8 @@ void Context::predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t
     ensure_scratch(hf, w, h, 1, K);
     ensure_staging(1);
     DH_CUDA(cudaMemcpyAsync(d_depth_[0], depth, (size_t)w * h * sizeof(uint16_t), cudaMemcpyHostToDevice, stream_));
-    FrameBuffers b = buffers(d_depth_[0]);
-    run_front(b, 1, nullptr);
+    FrameBuffers b = buffers(lanes_[0], d_depth_[0]);
+    run_front(lanes_[0], b, 1, nullptr);
     if (aux8_cap_ < (size_t)w * h) {
         dev_free(d_aux8_);
         dev_alloc(d_aux8_, (size_t)w * h);
@@ -584,8 +630,8 @@ void Context::hough_image_raw(const HostForest& hf, const uint16_t* depth, uint3
     ensure_scratch(hf, w, h, 1, K);
     ensure_staging(1);
     DH_CUDA(cudaMemcpyAsync(d_depth_[0], depth, (size_t)w * h * sizeof(uint16_t), cudaMemcpyHostToDevice, stream_));
-    FrameBuffers b = buffers(d_depth_[0]);
-    run_front(b, 1, nullptr);
+    FrameBuffers b = buffers(lanes_[0], d_depth_[0]);
+    run_front(lanes_[0], b, 1, nullptr);
     const size_t px = (size_t)w * h;
     if (aux32_cap_ < px) {
         dev_free(d_aux32_);
@@ -621,22 +667,22 @@ void Context::debug_leaf(int32_t* leaf) {
     require_debug();
     const size_t P = geom_.P, T = geom_.n_trees;
     std::vector<int32_t> tmp(P * T);
-    DH_CUDA(cudaMemcpy(tmp.data(), d_leaf_, P * T * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    DH_CUDA(cudaMemcpy(tmp.data(), lanes_[0].leaf, P * T * sizeof(int32_t), cudaMemcpyDeviceToHost));
     for (size_t t = 0; t < T; ++t)  // device layout [T][P] -> exported [P][T]
         for (size_t p = 0; p < P; ++p) leaf[p * T + t] = tmp[t * P + p];
 }
 void Context::debug_patches(float* p3, uint8_t* gate) {
     require_debug();
     const size_t P = geom_.P;
-    if (gate) DH_CUDA(cudaMemcpy(gate, d_gate_, P, cudaMemcpyDeviceToHost));
-    if (p3) DH_CUDA(cudaMemcpy(p3, d_p3_, P * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (gate) DH_CUDA(cudaMemcpy(gate, lanes_[0].gate, P, cudaMemcpyDeviceToHost));
+    if (p3) DH_CUDA(cudaMemcpy(p3, lanes_[0].p3, P * 3 * sizeof(float), cudaMemcpyDeviceToHost));
 }
 void Context::debug_seeds(uint32_t* guess_pos, uint32_t* guess_rot, int32_t* seed_mid, int32_t* seed_rot) {
     require_debug();
-    if (guess_pos) DH_CUDA(cudaMemcpy(guess_pos, d_grids_, kPosGridCells * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (guess_rot) DH_CUDA(cudaMemcpy(guess_rot, d_grids_ + kPosGridCells, kRotGridCells * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (guess_pos) DH_CUDA(cudaMemcpy(guess_pos, lanes_[0].grids, kPosGridCells * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (guess_rot) DH_CUDA(cudaMemcpy(guess_rot, lanes_[0].grids + kPosGridCells, kRotGridCells * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     FrameState fs;
-    DH_CUDA(cudaMemcpy(&fs, d_fs_, sizeof(fs), cudaMemcpyDeviceToHost));
+    DH_CUDA(cudaMemcpy(&fs, lanes_[0].fs, sizeof(fs), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 3; ++k) {
         if (seed_mid) seed_mid[k] = fs.seed_mid[k];
         if (seed_rot) seed_rot[k] = fs.seed_rot[k];
@@ -651,13 +697,13 @@ void Context::debug_votes(int which, int32_t* keys, uint32_t* vals, uint64_t* n,
     int32_t* d_keys = nullptr;
     uint32_t* d_vals = nullptr;
     FrameState fs;
-    DH_CUDA(cudaMemcpy(&fs, d_fs_, sizeof(fs), cudaMemcpyDeviceToHost));
+    DH_CUDA(cudaMemcpy(&fs, lanes_[0].fs, sizeof(fs), cudaMemcpyDeviceToHost));
     const size_t cells = vote_box_cells();
     if (keys) {
         dev_alloc(d_keys, cells * 3);
         dev_alloc(d_vals, cells);
     }
-    FrameBuffers b = buffers(d_depth_[0]);
+    FrameBuffers b = buffers(lanes_[0], d_depth_[0]);
     launch_box_dump(b, 0, which, d_keys, d_vals, d_count, stream_);
     DH_CUDA(cudaStreamSynchronize(stream_));
     unsigned long long cnt = 0;
@@ -678,12 +724,12 @@ void Context::debug_meanshift(int which, int32_t* pos, uint32_t* n_iter) {
     require_debug();
     if (which < 0 || which > 1) throw ModelError(DH_E_ARG, "which must be 0 (centre) or 1 (rotation)");
     FrameState fs;
-    DH_CUDA(cudaMemcpy(&fs, d_fs_, sizeof(fs), cudaMemcpyDeviceToHost));
+    DH_CUDA(cudaMemcpy(&fs, lanes_[0].fs, sizeof(fs), cudaMemcpyDeviceToHost));
     const uint32_t ran = std::min<uint32_t>(fs.ms_iters[which], sk_.trace_iters);
     const uint32_t room = n_iter ? *n_iter : 0;
     const uint32_t cnt = std::min(ran, room);
-    if (pos && cnt && d_ms_trace_)
-        DH_CUDA(cudaMemcpy(pos, d_ms_trace_ + (size_t)which * sk_.trace_iters * 3, (size_t)cnt * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (pos && cnt && lanes_[0].ms_trace)
+        DH_CUDA(cudaMemcpy(pos, lanes_[0].ms_trace + (size_t)which * sk_.trace_iters * 3, (size_t)cnt * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (n_iter) *n_iter = ran;
     last_ms_flags_[which] = fs.ms_flags[which];
 }

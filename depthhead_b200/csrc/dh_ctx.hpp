@@ -13,6 +13,28 @@
 
 namespace dh {
 
+// One pipeline lane: a stream plus the per-chunk scratch its kernels work in.  Chunks of a batch
+// go round-robin over the lanes, so kernels of different chunks (HBM-bound summed-area tables,
+// shared-memory-bound traversal, issue-bound voting, latency-bound mean-shift) overlap on the GPU.
+struct Lane {
+    cudaStream_t stream = nullptr;  // lane 0: the context's stream; others: their own
+    cudaStream_t own = nullptr;
+    cudaEvent_t done = nullptr;
+    uint32_t* sat = nullptr;        // [F][h+1][pitch]
+    int32_t* leaf = nullptr;        // [F][T][P]
+    float* p3 = nullptr;            // [F][P][3]   (debug export)
+    uint8_t* gate = nullptr;        // [F][P]      (debug export)
+    float4* gated = nullptr;        // [F][P]
+    uint32_t* grids = nullptr;      // [F][400 + 8000]
+    FrameState* fs = nullptr;       // [F]
+    dh_result* results = nullptr;   // [F]
+    int32_t* ms_trace = nullptr;    // [F][2][iters][3] (debug export)
+    uint32_t* cubes = nullptr;      // [F][2][kBox^3]
+    CUtensorMap sat_map{};
+    bool allocated = false;
+};
+constexpr int kMaxLanes = 4;
+
 struct ScratchKey {
     uint32_t w = 0, h = 0, sw = 0, sh = 0, stride = 0, n_trees = 0, frames = 0, trace_iters = 0;
     bool same_shape(const ScratchKey& o) const {
@@ -57,14 +79,16 @@ public:
 private:
     void ensure_forest(const HostForest& hf);
     void free_forest();
-    void ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9]);
+    void ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9], int n_lanes = 1);
+    void alloc_lane(Lane& L);
+    void free_lane(Lane& L);
     void ensure_staging(int slots);
     uint32_t pick_chunk(uint32_t n_frames, int depth_loc) const;
     void free_scratch();
     TilePlan plan_tiles(const Geometry& g) const;
-    FrameBuffers buffers(const uint16_t* depth) const;
-    void run_front(const FrameBuffers& b, uint32_t n, const FrameState* guess_state);
-    void run_back(const FrameBuffers& b, uint32_t n, uint32_t iterations);
+    FrameBuffers buffers(const Lane& L, const uint16_t* depth) const;
+    void run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameState* guess_state);
+    void run_back(Lane& L, const FrameBuffers& b, uint32_t n, uint32_t iterations);
     void begin_call();
     void end_call();
     cudaEvent_t next_event();
@@ -100,21 +124,13 @@ private:
     ScratchKey sk_;
     Geometry geom_{};
     TilePlan tiles_{};
-    CUtensorMap sat_map_{};
+    Lane lanes_[kMaxLanes];
+    int max_lanes_ = 2;           // DH_LANES
+    cudaEvent_t ev_fork_ = nullptr;
     uint32_t chunk_frames_ = 0;   // 0 = adaptive
     uint32_t call_chunk_ = 1;
     uint16_t* d_depth_[2] = {nullptr, nullptr};
     size_t staging_elems_ = 0;
-    uint32_t* d_sat_ = nullptr;
-    int32_t* d_leaf_ = nullptr;
-    float* d_p3_ = nullptr;
-    uint8_t* d_gate_ = nullptr;
-    float4* d_gated_ = nullptr;           // gate-passing patches [F][P]
-    uint32_t* d_cubes_ = nullptr;         // accumulator cubes [F][2][kBox^3]
-    uint32_t* d_grids_ = nullptr;
-    FrameState* d_fs_ = nullptr;
-    dh_result* d_results_ = nullptr;
-    int32_t* d_ms_trace_ = nullptr;
     unsigned long long* d_counters_ = nullptr;
     uint32_t* d_aux32_ = nullptr;
     uint16_t* d_aux16_ = nullptr;
