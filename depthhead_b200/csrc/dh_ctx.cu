@@ -131,6 +131,8 @@ void Context::synchronize() {
 void Context::free_forest() {
     dev_free(df_nodes_);
     dev_free(df_hot_);
+    if (hot_tex_) cudaDestroyTextureObject(hot_tex_);
+    hot_tex_ = 0;
     hot_tw_ = 0;
     dev_free(df_roots_);
     dev_free(df_leaf_prob_);
@@ -152,6 +154,16 @@ void Context::ensure_forest(const HostForest& hf) {
         dev_alloc(df_nodes_, NN);
         dev_alloc(df_hot_, NN);
         df_n_nodes_ = NN;
+        if (env_u32("DH_TEX", 1) && NN && NN * 2 < (1ull << 27)) {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = df_hot_;
+            rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+            rd.res.linear.sizeInBytes = NN * sizeof(HotNode);
+            cudaTextureDesc td{};
+            td.readMode = cudaReadModeElementType;
+            DH_CUDA(cudaCreateTextureObject(&hot_tex_, &rd, &td, nullptr));
+        }
         dev_alloc(df_roots_, (size_t)hf.n_trees);
         dev_alloc(df_leaf_prob_, NL);
         dev_alloc(df_leaf_info_, NL);
@@ -203,6 +215,7 @@ void Context::ensure_forest(const HostForest& hf) {
     }
     fdev_.nodes = df_nodes_;
     fdev_.hot = df_hot_;
+    fdev_.hot_tex = hot_tex_;
     fdev_.roots = df_roots_;
     fdev_.leaf_prob = df_leaf_prob_;
     fdev_.leaf_info = df_leaf_info_;

@@ -108,6 +108,7 @@ private:
     NodeRec* df_nodes_ = nullptr;
     HotNode* df_hot_ = nullptr;            // df_nodes_ prepared for tile width hot_tw_ (plan_nodes_kernel)
     uint32_t hot_tw_ = 0;
+    cudaTextureObject_t hot_tex_ = 0;
     size_t df_n_nodes_ = 0;
     int32_t* df_roots_ = nullptr;
     double* df_leaf_prob_ = nullptr;

@@ -210,8 +210,9 @@ __device__ __noinline__ bool binarize_ieee(const NodeRec* __restrict__ nodes, in
 // compacted (ballot) so that every lane of the traversal loop owns a live patch x tree pair; lanes
 // of a warp are neighbouring patches of the same tree, so the upper levels read the same node
 // record (broadcast) and nearby taps.
-template <int kThreads>
+template <int kThreads, bool kTex>
 __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constant__ CUtensorMap sat_map,
+                                                            cudaTextureObject_t hot_tex,
                                                             const HotNode* __restrict__ hot,
                                                             const NodeRec* __restrict__ nodes,
                                                             const int32_t* __restrict__ roots, int32_t* __restrict__ leaf,
@@ -322,8 +323,14 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
         const uint32_t o = org_a + ly * g.stride * tw4 + lx * g.stride * 4u;
         int32_t node = __ldg(roots + t);
         while (node >= 0) {
-            const uint4 A = __ldg(hot4 + 2 * (size_t)node);      // rect taps, pixel counts
-            const uint4 B = __ldg(hot4 + 2 * (size_t)node + 1);  // children, threshold * c1 * c2
+            uint4 A, B;  // A: rect taps, pixel counts;  B: children, threshold * c1 * c2
+            if (kTex) {
+                A = tex1Dfetch<uint4>(hot_tex, 2 * node);
+                B = tex1Dfetch<uint4>(hot_tex, 2 * node + 1);
+            } else {
+                A = __ldg(hot4 + 2 * (size_t)node);
+                B = __ldg(hot4 + 2 * (size_t)node + 1);
+            }
             // SubImage::average_value_in_rect (types.rs:317-339) via four SAT taps per rectangle
             const uint32_t a00 = o + ((A.x & 0xffffu) << 2), aw = __byte_perm(A.x, 0u, 0x4442) << 2, ah = (A.x >> 24) * tw4;
             const uint32_t b00 = o + ((A.y & 0xffffu) << 2), bw = __byte_perm(A.y, 0u, 0x4442) << 2, bh = (A.y >> 24) * tw4;
@@ -1275,7 +1282,7 @@ uint32_t traverse_smem_bytes(uint32_t tw, uint32_t th, uint32_t patches_per_tile
 
 int traverse_kernel_attrs(int* regs, int* max_smem) {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, traverse_kernel<kTraverseThreads>);
+    cudaError_t e = cudaFuncGetAttributes(&a, traverse_kernel<kTraverseThreads, false>);
     if (e != cudaSuccess) return (int)e;
     if (regs) *regs = a.numRegs;
     if (max_smem) *max_smem = a.maxDynamicSharedSizeBytes;
@@ -1286,13 +1293,19 @@ void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Ge
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
     static int configured_smem = -1;
     if ((int)tp.smem_bytes > configured_smem) {
-        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)tp.smem_bytes);
         configured_smem = (int)tp.smem_bytes;
     }
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
-    traverse_kernel<kTraverseThreads><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, f.hot, f.nodes, f.roots, b.leaf, b.sat,
-                                                                                  b.fs, g, tp);
+    if (f.hot_tex)
+        traverse_kernel<kTraverseThreads, true><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.nodes, f.roots,
+                                                                                          b.leaf, b.sat, b.fs, g, tp);
+    else
+        traverse_kernel<kTraverseThreads, false><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.nodes, f.roots,
+                                                                                           b.leaf, b.sat, b.fs, g, tp);
 }
 
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, size_t n_nodes, uint32_t tile_width, cudaStream_t s) {

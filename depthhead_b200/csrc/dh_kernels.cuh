@@ -55,6 +55,7 @@ struct TilePlan {
 struct ForestDev {
     const NodeRec* nodes;
     const HotNode* hot;        // nodes prepared for the current tile plan (plan_nodes_kernel)
+    cudaTextureObject_t hot_tex;  // the same table as a uint4 texture (0 = fetch through the LSU path)
     const int32_t* roots;
     const double* leaf_prob;
     const LeafInfo* leaf_info;
