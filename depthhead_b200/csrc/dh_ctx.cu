@@ -131,6 +131,7 @@ void Context::synchronize() {
 void Context::free_forest() {
     dev_free(df_nodes_);
     dev_free(df_hot_);
+    dev_free(df_uni_);
     if (hot_tex_) cudaDestroyTextureObject(hot_tex_);
     hot_tex_ = 0;
     hot_tw_ = 0;
@@ -154,12 +155,21 @@ void Context::ensure_forest(const HostForest& hf) {
         dev_alloc(df_nodes_, NN);
         dev_alloc(df_hot_, NN);
         df_n_nodes_ = NN;
-        if (env_u32("DH_TEX", 1) && NN && NN * 2 < (1ull << 27)) {
+        // Node fetches go through the texture path when the table fits a 1-D texture (2^27
+        // texels); forests whose rectangles all have one size get the 16-byte box-sum nodes.
+        uni_rw_ = uni_rh_ = 0;
+        const bool use_tex = env_u32("DH_TEX", 1) != 0;
+        if (use_tex && NN && env_u32("DH_UNIFORM", 1) && hf.uniform_rw && NN < (1ull << 27)) {
+            dev_alloc(df_uni_, NN);
+            uni_rw_ = hf.uniform_rw;
+            uni_rh_ = hf.uniform_rh;
+        }
+        if (use_tex && NN && (df_uni_ || NN * 2 < (1ull << 27))) {
             cudaResourceDesc rd{};
             rd.resType = cudaResourceTypeLinear;
-            rd.res.linear.devPtr = df_hot_;
+            rd.res.linear.devPtr = df_uni_ ? (void*)df_uni_ : (void*)df_hot_;
             rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
-            rd.res.linear.sizeInBytes = NN * sizeof(HotNode);
+            rd.res.linear.sizeInBytes = df_uni_ ? NN * sizeof(UniNode) : NN * sizeof(HotNode);
             cudaTextureDesc td{};
             td.readMode = cudaReadModeElementType;
             DH_CUDA(cudaCreateTextureObject(&hot_tex_, &rd, &td, nullptr));
@@ -216,6 +226,9 @@ void Context::ensure_forest(const HostForest& hf) {
     fdev_.nodes = df_nodes_;
     fdev_.hot = df_hot_;
     fdev_.hot_tex = hot_tex_;
+    fdev_.uni = df_uni_;
+    fdev_.uni_rw = uni_rw_;
+    fdev_.uni_rh = uni_rh_;
     fdev_.roots = df_roots_;
     fdev_.leaf_prob = df_leaf_prob_;
     fdev_.leaf_info = df_leaf_info_;
@@ -434,7 +447,7 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
         DH_CUDA(cudaMemcpyAsync(L.fs, h_fs_, sizeof(FrameState), cudaMemcpyHostToDevice, st));
     }
     if (g.P && hot_tw_ != tiles_.tw) {  // node table for this tile plan (once per forest x plan)
-        launch_plan_nodes(df_nodes_, df_hot_, df_n_nodes_, tiles_.tw, stream_);
+        launch_plan_nodes(df_nodes_, df_hot_, df_uni_, df_n_nodes_, tiles_.tw, stream_);
         DH_CUDA(cudaStreamSynchronize(stream_));
         hot_tw_ = tiles_.tw;
     }

@@ -109,6 +109,8 @@ private:
     HotNode* df_hot_ = nullptr;            // df_nodes_ prepared for tile width hot_tw_ (plan_nodes_kernel)
     uint32_t hot_tw_ = 0;
     cudaTextureObject_t hot_tex_ = 0;
+    UniNode* df_uni_ = nullptr;            // uniform-rectangle forests: box-sum nodes for tile width hot_tw_
+    uint32_t uni_rw_ = 0, uni_rh_ = 0;
     size_t df_n_nodes_ = 0;
     int32_t* df_roots_ = nullptr;
     double* df_leaf_prob_ = nullptr;

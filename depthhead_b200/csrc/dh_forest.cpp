@@ -314,6 +314,18 @@ HostForest* flatten_forest(const RawForest& raw) {
         hf->tree_node_off.push_back((int64_t)hf->nodes.size());
     }
     hf->max_depth = max_depth;
+    if (!hf->nodes.empty()) {
+        const NodeRec& n0r = hf->nodes[0];
+        uint32_t rw = (uint32_t)(n0r.r[2] - n0r.r[0]), rh = (uint32_t)(n0r.r[3] - n0r.r[1]);
+        for (const NodeRec& n : hf->nodes)
+            for (int k = 0; k < 2; ++k)
+                if ((uint32_t)(n.r[k * 4 + 2] - n.r[k * 4 + 0]) != rw || (uint32_t)(n.r[k * 4 + 3] - n.r[k * 4 + 1]) != rh) rw = rh = 0;
+        // rectangle sums must fit i32 (rw*rh*65535 < 2^31) for the single-precision filter
+        if (rw && rh && rw * rh <= 32768u) {
+            hf->uniform_rw = rw;
+            hf->uniform_rh = rh;
+        }
+    }
 
     // ---- leaves and votes
     hf->leaf_prob = raw.prob;

@@ -48,6 +48,11 @@ struct HostForest {
 
     int32_t n_trees = 0;
     int32_t max_depth = 0;                 // longest root->leaf path in nodes (for work estimates)
+    // Every feature rectangle of every node has this size (0 = sizes differ).  True for forests
+    // trained by the reference: houghforest.rs:230-234 draws both rectangles with one scale factor
+    // (hough_tree_trainer.rs:165 sets min = max = 0.3 -> 24x24 inside 80x80).  Enables the
+    // box-sum traversal (two taps per node instead of eight).
+    uint32_t uniform_rw = 0, uniform_rh = 0;
     std::vector<NodeRec> nodes;            // BFS order per tree, trees back to back
     std::vector<int32_t> roots;            // per tree: >=0 global node index, <0 ~global leaf id
     std::vector<int64_t> tree_node_off, tree_leaf_off;

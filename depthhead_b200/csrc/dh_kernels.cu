@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128) sat_cols_kernel(uint32_t* __restrict__ sa
 // ================================================================ K2: forest traversal
 // Node table prepared for one tile plan: see HotNode (dh_types.hpp).
 __global__ void __launch_bounds__(256) plan_nodes_kernel(const NodeRec* __restrict__ nodes, HotNode* __restrict__ hot,
-                                                         size_t n, uint32_t tw) {
+                                                         UniNode* __restrict__ uni, size_t n, uint32_t tw) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const NodeRec r = nodes[i];
@@ -176,6 +176,14 @@ __global__ void __launch_bounds__(256) plan_nodes_kernel(const NodeRec* __restri
     h.child[1] = r.child[1];
     h.thr_scaled = r.thr_scaled;
     hot[i] = h;
+    if (uni) {  // all rectangles have one size: c[0] == c[1] == the common pixel count
+        UniNode u;
+        u.taps = (h.r1 & 0xffffu) | (h.r2 << 16);
+        u.child[0] = r.child[0];
+        u.child[1] = r.child[1];
+        u.thr_count = (float)__dmul_rn(r.threshold, (double)c[0]);
+        uni[i] = u;
+    }
 }
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -187,6 +195,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
@@ -210,14 +221,17 @@ __device__ __noinline__ bool binarize_ieee(const NodeRec* __restrict__ nodes, in
 // compacted (ballot) so that every lane of the traversal loop owns a live patch x tree pair; lanes
 // of a warp are neighbouring patches of the same tree, so the upper levels read the same node
 // record (broadcast) and nearby taps.
-template <int kThreads, bool kTex>
+// kMode 0: general rectangles, nodes through the LSU path; 1: general, nodes through the texture
+// path; 2: uniform rectangles (box-sum tile, UniNode through the texture path).
+template <int kThreads, int kMode>
 __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constant__ CUtensorMap sat_map,
                                                             cudaTextureObject_t hot_tex,
                                                             const HotNode* __restrict__ hot,
                                                             const NodeRec* __restrict__ nodes,
                                                             const int32_t* __restrict__ roots, int32_t* __restrict__ leaf,
                                                             const uint32_t* __restrict__ sat,
-                                                            FrameState* __restrict__ fs, Geometry g, TilePlan tp) {
+                                                            FrameState* __restrict__ fs, Geometry g, TilePlan tp,
+                                                            uint32_t uni_rw, uint32_t uni_rh) {
     extern __shared__ uint8_t smem_raw[];
     // 128-byte aligned tile (TMA destination), then the barrier, then the compacted patch list;
     // everything is addressed through 32-bit shared-window addresses
@@ -312,6 +326,36 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
     __syncthreads();
     const uint32_t nlive = s_nlive;
 
+    if (kMode == 2 && nlive) {
+        // ---- uniform rectangles: turn the SAT tile into box sums in place,
+        //      B[y][x] = S[y+rh][x+rw] - S[y][x+rw] - S[y+rh][x] + S[y][x]  (types.rs:317-339 for the
+        //      rw x rh rectangle at (x, y)), so that a rectangle is ONE tap.  Rows go in waves of one
+        //      per warp: a wave reads, barrier, writes; later waves only touch rows below.
+        const uint32_t rw4 = uni_rw * 4u, rh4 = uni_rh * tw4;
+        const uint32_t n_rows = tp.th - uni_rh, n_cols = tp.tw - uni_rw;  // B is defined for y < n_rows, x < n_cols
+        constexpr int kPerLane = 8;  // tile width <= 256
+        for (uint32_t r0 = 0; r0 < n_rows; r0 += kThreads / 32) {
+            const uint32_t r = r0 + (tid >> 5);
+            const uint32_t row_a = tile_a + r * tw4;
+            uint32_t v[kPerLane];
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) {
+                const uint32_t x = (uint32_t)j * 32u + (tid & 31u);
+                if (r < n_rows && x < n_cols) {
+                    const uint32_t a = row_a + x * 4u;
+                    v[j] = lds_u32(a + rh4 + rw4) - lds_u32(a + rw4) - lds_u32(a + rh4) + lds_u32(a);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) {
+                const uint32_t x = (uint32_t)j * 32u + (tid & 31u);
+                if (r < n_rows && x < n_cols) sts_u32(row_a + x * 4u, v[j]);
+            }
+        }
+        __syncthreads();
+    }
+
     // ---- root -> leaf walks: item = (tree, live patch); lanes = neighbouring live patches
     uint32_t visits = 0;
     const uint32_t items = nlive * (uint32_t)T;
@@ -322,9 +366,28 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
         const uint32_t lx = lp % tp.tpx, ly = lp / tp.tpx;
         const uint32_t o = org_a + ly * g.stride * tw4 + lx * g.stride * 4u;
         int32_t node = __ldg(roots + t);
+        if (kMode == 2) {
+            while (node >= 0) {
+                const uint4 U = tex1Dfetch<uint4>(hot_tex, node);  // taps, child[0], child[1], threshold * count
+                const uint32_t s1 = lds_u32(o + ((U.x & 0xffffu) << 2)), s2 = lds_u32(o + ((U.x >> 16) << 2));
+                // binarize (houghforest.rs:185-193) for equal pixel counts c: avg1 - avg2 > thr  <=>
+                // (s1 - s2) / c > thr.  Single-precision filter: d = float(s1 - s2) - thr*c carries an
+                // absolute error below (|s1 - s2| + |thr*c|) * 2^-22 + 1 (two roundings to f32, one of
+                // the subtraction, and the < 0.01 the reference's own roundings can move the exact
+                // quotient in units of 1/c), so outside that band its sign IS the reference's
+                // answer; inside it (and for NaN) the IEEE-division path decides.
+                const float nf = (float)(int32_t)(s1 - s2), tc = __uint_as_float(U.w);
+                const float d = __fsub_rn(nf, tc);
+                const float band = __fmaf_rn(__fadd_rn(fabsf(nf), fabsf(tc)), 2.384185791015625e-07f, 4.0f);
+                int32_t next = d > 0.0f ? (int)U.z : (int)U.y;
+                if (!(fabsf(d) > band)) next = binarize_ieee(nodes, node, s1, s2) ? (int)U.z : (int)U.y;
+                node = next;
+                ++visits;
+            }
+        } else
         while (node >= 0) {
             uint4 A, B;  // A: rect taps, pixel counts;  B: children, threshold * c1 * c2
-            if (kTex) {
+            if (kMode == 1) {
                 A = tex1Dfetch<uint4>(hot_tex, 2 * node);
                 B = tex1Dfetch<uint4>(hot_tex, 2 * node + 1);
             } else {
@@ -1282,7 +1345,7 @@ uint32_t traverse_smem_bytes(uint32_t tw, uint32_t th, uint32_t patches_per_tile
 
 int traverse_kernel_attrs(int* regs, int* max_smem) {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, traverse_kernel<kTraverseThreads, false>);
+    cudaError_t e = cudaFuncGetAttributes(&a, traverse_kernel<kTraverseThreads, 0>);
     if (e != cudaSuccess) return (int)e;
     if (regs) *regs = a.numRegs;
     if (max_smem) *max_smem = a.maxDynamicSharedSizeBytes;
@@ -1293,24 +1356,26 @@ void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Ge
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
     static int configured_smem = -1;
     if ((int)tp.smem_bytes > configured_smem) {
-        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)tp.smem_bytes);
-        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         configured_smem = (int)tp.smem_bytes;
     }
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
-    if (f.hot_tex)
-        traverse_kernel<kTraverseThreads, true><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.nodes, f.roots,
-                                                                                          b.leaf, b.sat, b.fs, g, tp);
+    if (f.uni && f.hot_tex)
+        traverse_kernel<kTraverseThreads, 2><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.nodes, f.roots, b.leaf,
+                                                                                       b.sat, b.fs, g, tp, f.uni_rw, f.uni_rh);
+    else if (f.hot_tex)
+        traverse_kernel<kTraverseThreads, 1><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.nodes, f.roots, b.leaf,
+                                                                                       b.sat, b.fs, g, tp, 0u, 0u);
     else
-        traverse_kernel<kTraverseThreads, false><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.nodes, f.roots,
-                                                                                           b.leaf, b.sat, b.fs, g, tp);
+        traverse_kernel<kTraverseThreads, 0><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.nodes, f.roots, b.leaf, b.sat,
+                                                                                       b.fs, g, tp, 0u, 0u);
 }
 
-void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, size_t n_nodes, uint32_t tile_width, cudaStream_t s) {
+void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width, cudaStream_t s) {
     if (n_nodes == 0) return;
-    plan_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(nodes, hot, n_nodes, tile_width);
+    plan_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(nodes, hot, uni, n_nodes, tile_width);
 }
 
 uint32_t vote_box_cells() { return (uint32_t)kBoxCells; }

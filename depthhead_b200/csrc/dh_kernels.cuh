@@ -56,6 +56,8 @@ struct ForestDev {
     const NodeRec* nodes;
     const HotNode* hot;        // nodes prepared for the current tile plan (plan_nodes_kernel)
     cudaTextureObject_t hot_tex;  // the same table as a uint4 texture (0 = fetch through the LSU path)
+    const UniNode* uni;        // uniform-rectangle forests: 16-byte nodes for the box-sum traversal (or nullptr)
+    uint32_t uni_rw, uni_rh;   // the common rectangle size
     const int32_t* roots;
     const double* leaf_prob;
     const LeafInfo* leaf_info;
@@ -86,7 +88,7 @@ struct FrameBuffers {
 void launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s);
 void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s);
-void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, size_t n_nodes, uint32_t tile_width, cudaStream_t s);
+void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width, cudaStream_t s);
 int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
                           uint32_t iterations, cudaStream_t s);

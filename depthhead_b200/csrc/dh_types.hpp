@@ -55,6 +55,17 @@ struct alignas(16) LeafInfo {
                           // bit2 votes (prob > 0, valtoadd != 0 and bit0 | bit1)
 };
 static_assert(sizeof(LeafInfo) == 16, "LeafInfo must be 16 bytes");
+// Node of a forest whose feature rectangles all have one size (HostForest::uniform_rw/rh): the
+// traversal turns its shared-memory tile into box sums, so a rectangle is ONE tap.  16 bytes =
+// one texture fetch.  thr_count = threshold * pixel count, rounded to f32 (the filter widens its
+// band accordingly; near-ties fall back to NodeRec and IEEE division).
+struct alignas(16) UniNode {
+    uint32_t taps;     // off00 of rectangle 1 | off00 of rectangle 2 << 16  (y0 * tile_width + x0)
+    int32_t child[2];
+    float thr_count;
+};
+static_assert(sizeof(UniNode) == 16, "UniNode must be 16 bytes");
+
 // Bounding boxes of a leaf's votes: offsets (mm) per axis and rotation bins per axis.  A
 // non-finite offset opens its axis to (-inf, +inf), so such a leaf is never skipped.
 struct alignas(32) LeafBox {
