@@ -159,12 +159,13 @@ void Context::ensure_forest(const HostForest& hf) {
         // texels); forests whose rectangles all have one size get the 16-byte box-sum nodes.
         uni_rw_ = uni_rh_ = 0;
         const bool use_tex = env_u32("DH_TEX", 1) != 0;
-        if (use_tex && NN && env_u32("DH_UNIFORM", 1) && hf.uniform_rw && NN < (1ull << 27)) {
+        const bool uni_ldg = env_u32("DH_UNI_LDG", 0) != 0;
+        if (NN && env_u32("DH_UNIFORM", 1) && hf.uniform_rw && (uni_ldg || (use_tex && NN < (1ull << 27)))) {
             dev_alloc(df_uni_, NN);
             uni_rw_ = hf.uniform_rw;
             uni_rh_ = hf.uniform_rh;
         }
-        if (use_tex && NN && (df_uni_ || NN * 2 < (1ull << 27))) {
+        if (use_tex && NN && !(df_uni_ && uni_ldg) && (df_uni_ || NN * 2 < (1ull << 27))) {
             cudaResourceDesc rd{};
             rd.resType = cudaResourceTypeLinear;
             rd.res.linear.devPtr = df_uni_ ? (void*)df_uni_ : (void*)df_hot_;
@@ -295,7 +296,8 @@ void Context::alloc_lane(Lane& L) {
 TilePlan Context::plan_tiles(const Geometry& g) const {
     // Choose the patch tile that minimises total shared-memory fill traffic per frame, subject to
     // the tile (plus bookkeeping) fitting `limit` bytes so that several CTAs share an SM.
-    const uint32_t limits[3] = {75000u, 113000u, smem_optin_ > 2048u ? smem_optin_ - 1024u : smem_optin_};
+    const uint32_t big = env_u32("DH_TRAV_THREADS", 1024) >= 1024 ? 1u : 0u;
+    const uint32_t limits[3] = {big ? 113000u : 75000u, 113000u, smem_optin_ > 2048u ? smem_optin_ - 1024u : smem_optin_};
     for (uint32_t limit : limits) {
         TilePlan best{};
         double best_cost = 1e300;
@@ -314,7 +316,7 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
                 const double cost = (double)tiles_x * tiles_y * ((double)tw * th * 4.0 + 8192.0);
                 if (cost < best_cost) {
                     best_cost = cost;
-                    best = TilePlan{tpx, tpy, tiles_x, tiles_y, tw, th, bytes, 512u};
+                    best = TilePlan{tpx, tpy, tiles_x, tiles_y, tw, th, bytes, (big && limit <= 113000u) ? 1024u : 512u};
                 }
             }
         if (best.tpx) return best;
@@ -457,6 +459,8 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
     stage_check("sat");
     mark(DH_STAGE_TRAVERSE);
     if (g.P) {
+        // leaf ids start at -1 (background); the traversal writes the non-background patches only
+        DH_CUDA(cudaMemsetAsync(L.leaf, 0xFF, sizeof(int32_t) * (size_t)n * g.n_trees * g.P, st));
         launch_traverse(L.sat_map, b, g, tiles_, fdev_, n, st);
         launches_ += 1;
         stage_check("traverse");

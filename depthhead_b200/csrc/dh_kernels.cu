@@ -222,11 +222,13 @@ __device__ __noinline__ bool binarize_ieee(const NodeRec* __restrict__ nodes, in
 // of a warp are neighbouring patches of the same tree, so the upper levels read the same node
 // record (broadcast) and nearby taps.
 // kMode 0: general rectangles, nodes through the LSU path; 1: general, nodes through the texture
-// path; 2: uniform rectangles (box-sum tile, UniNode through the texture path).
+// path; 2: uniform rectangles (box-sum tile, UniNode through the texture path); 3: the same with
+// UniNode through the LSU path.
 template <int kThreads, int kMode>
-__global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constant__ CUtensorMap sat_map,
+__global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_kernel(const __grid_constant__ CUtensorMap sat_map,
                                                             cudaTextureObject_t hot_tex,
                                                             const HotNode* __restrict__ hot,
+                                                            const UniNode* __restrict__ uni,
                                                             const NodeRec* __restrict__ nodes,
                                                             const int32_t* __restrict__ roots, int32_t* __restrict__ leaf,
                                                             const uint32_t* __restrict__ sat,
@@ -274,14 +276,7 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
         }
     }
     __syncthreads();
-    if (s_empty) {  // prediction.rs:567-571 fails for every patch of the tile
-        for (uint32_t i = tid; i < npt * (uint32_t)T; i += kThreads) {
-            const uint32_t lp = i % npt, t = i / npt;
-            const uint32_t gx = px0 + lp % tp.tpx, gy = py0 + lp / tp.tpx;
-            if (gx < g.npx && gy < g.npy) leaf_f[(size_t)t * g.P + gy * g.npx + gx] = -1;
-        }
-        return;
-    }
+    if (s_empty) return;  // prediction.rs:567-571 fails for every patch of the tile: their leaf ids stay -1
     {
         asm volatile(
             "{\n"
@@ -302,16 +297,15 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
     uint32_t my_valid = 0;
     for (uint32_t lp = tid; lp < ((npt + 31u) & ~31u); lp += kThreads) {
         bool ok = false;
+        uint32_t packed = 0;
         if (lp < npt) {
             const uint32_t lx = lp % tp.tpx, ly = lp / tp.tpx;
             const uint32_t gx = px0 + lx, gy = py0 + ly;
             if (gx < g.npx && gy < g.npy) {
-                const uint32_t gp = gy * g.npx + gx;
                 const uint32_t o = org_a + ly * g.stride * tw4 + lx * g.stride * 4u;
                 const uint32_t sum = lds_u32(o + g.sh * tw4 + g.sw * 4u) - lds_u32(o + g.sw * 4u) - lds_u32(o + g.sh * tw4) + lds_u32(o);
-                ok = sum != 0u;
-                if (!ok)
-                    for (int t = 0; t < T; ++t) leaf_f[(size_t)t * g.P + gp] = -1;
+                ok = sum != 0u;  // background patches keep the -1 the leaf buffer was filled with
+                packed = lx | (ly << 8);
             }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, ok);
@@ -319,14 +313,14 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
         if ((tid & 31u) == 0 && m) basei = atomicAdd(&s_nlive, (uint32_t)__popc(m));
         basei = __shfl_sync(0xffffffffu, basei, 0);
         if (ok) {
-            sts_u16(live_a + 2u * (basei + __popc(m & ((1u << (tid & 31u)) - 1u))), lp);
+            sts_u16(live_a + 2u * (basei + __popc(m & ((1u << (tid & 31u)) - 1u))), packed);
             ++my_valid;
         }
     }
     __syncthreads();
     const uint32_t nlive = s_nlive;
 
-    if (kMode == 2 && nlive) {
+    if (kMode >= 2 && nlive) {
         // ---- uniform rectangles: turn the SAT tile into box sums in place,
         //      B[y][x] = S[y+rh][x+rw] - S[y][x+rw] - S[y+rh][x] + S[y][x]  (types.rs:317-339 for the
         //      rw x rh rectangle at (x, y)), so that a rectangle is ONE tap.  Rows go in waves of one
@@ -360,15 +354,18 @@ __global__ void __launch_bounds__(kThreads) traverse_kernel(const __grid_constan
     uint32_t visits = 0;
     const uint32_t items = nlive * (uint32_t)T;
     const uint4* hot4 = reinterpret_cast<const uint4*>(hot);
+    // it / nlive by multiply-high (exact while it * nlive < 2^32)
+    const uint32_t nl_magic = (nlive >= 2u && (unsigned long long)items * nlive < (1ull << 32)) ? (uint32_t)((1ull << 32) / nlive) + 1u : 0u;
     for (uint32_t it = tid; it < items; it += kThreads) {
-        const uint32_t t = it / nlive;
+        const uint32_t t = nl_magic ? __umulhi(it, nl_magic) : it / nlive;
         const uint32_t lp = lds_u16(live_a + 2u * (it - t * nlive));
-        const uint32_t lx = lp % tp.tpx, ly = lp / tp.tpx;
+        const uint32_t lx = lp & 0xffu, ly = lp >> 8;
         const uint32_t o = org_a + ly * g.stride * tw4 + lx * g.stride * 4u;
         int32_t node = __ldg(roots + t);
-        if (kMode == 2) {
+        if (kMode >= 2) {
             while (node >= 0) {
-                const uint4 U = tex1Dfetch<uint4>(hot_tex, node);  // taps, child[0], child[1], threshold * count
+                // taps, child[0], child[1], threshold * count
+                const uint4 U = kMode == 2 ? tex1Dfetch<uint4>(hot_tex, node) : __ldg(reinterpret_cast<const uint4*>(uni) + node);
                 const uint32_t s1 = lds_u32(o + ((U.x & 0xffffu) << 2)), s2 = lds_u32(o + ((U.x >> 16) << 2));
                 // binarize (houghforest.rs:185-193) for equal pixel counts c: avg1 - avg2 > thr  <=>
                 // (s1 - s2) / c > thr.  Single-precision filter: d = float(s1 - s2) - thr*c carries an
@@ -1352,25 +1349,36 @@ int traverse_kernel_attrs(int* regs, int* max_smem) {
     return 0;
 }
 
-void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
-                     const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
+template <int kThreads>
+static void launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
+                              const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
     static int configured_smem = -1;
     if ((int)tp.smem_bytes > configured_smem) {
-        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
-        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
-        cudaFuncSetAttribute(traverse_kernel<kTraverseThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         configured_smem = (int)tp.smem_bytes;
     }
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
     if (f.uni && f.hot_tex)
-        traverse_kernel<kTraverseThreads, 2><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.nodes, f.roots, b.leaf,
-                                                                                       b.sat, b.fs, g, tp, f.uni_rw, f.uni_rh);
+        traverse_kernel<kThreads, 2><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat,
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh);
+    else if (f.uni)
+        traverse_kernel<kThreads, 3><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat, b.fs, g,
+                                                                       tp, f.uni_rw, f.uni_rh);
     else if (f.hot_tex)
-        traverse_kernel<kTraverseThreads, 1><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.nodes, f.roots, b.leaf,
-                                                                                       b.sat, b.fs, g, tp, 0u, 0u);
+        traverse_kernel<kThreads, 1><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat,
+                                                                       b.fs, g, tp, 0u, 0u);
     else
-        traverse_kernel<kTraverseThreads, 0><<<gr, kTraverseThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.nodes, f.roots, b.leaf, b.sat,
-                                                                                       b.fs, g, tp, 0u, 0u);
+        traverse_kernel<kThreads, 0><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat, b.fs, g,
+                                                                       tp, 0u, 0u);
+}
+
+void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
+                     const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
+    if (tp.threads >= 1024) launch_traverse_t<1024>(sat_map, b, g, tp, f, n_frames, s);
+    else launch_traverse_t<512>(sat_map, b, g, tp, f, n_frames, s);
 }
 
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width, cudaStream_t s) {
