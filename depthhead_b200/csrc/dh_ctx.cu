@@ -53,6 +53,12 @@ uint32_t env_u32(const char* name, uint32_t dflt) {
     long x = std::strtol(v, nullptr, 10);
     return x > 0 ? (uint32_t)x : dflt;
 }
+// on/off switch: "0" turns it off
+bool env_flag(const char* name, bool dflt) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    return std::strtol(v, nullptr, 10) != 0;
+}
 
 }  // namespace
 
@@ -158,9 +164,9 @@ void Context::ensure_forest(const HostForest& hf) {
         // Node fetches go through the texture path when the table fits a 1-D texture (2^27
         // texels); forests whose rectangles all have one size get the 16-byte box-sum nodes.
         uni_rw_ = uni_rh_ = 0;
-        const bool use_tex = env_u32("DH_TEX", 1) != 0;
-        const bool uni_ldg = env_u32("DH_UNI_LDG", 0) != 0;
-        if (NN && env_u32("DH_UNIFORM", 1) && hf.uniform_rw && (uni_ldg || (use_tex && NN < (1ull << 27)))) {
+        const bool use_tex = env_flag("DH_TEX", true);
+        const bool uni_ldg = env_flag("DH_UNI_LDG", false);
+        if (NN && env_flag("DH_UNIFORM", true) && hf.uniform_rw && (uni_ldg || (use_tex && NN < (1ull << 27)))) {
             dev_alloc(df_uni_, NN);
             uni_rw_ = hf.uniform_rw;
             uni_rh_ = hf.uniform_rh;
@@ -244,6 +250,7 @@ void Context::ensure_forest(const HostForest& hf) {
 // ------------------------------------------------------------------------------------------------ scratch
 void Context::free_lane(Lane& L) {
     dev_free(L.sat);
+    dev_free(L.band_u);
     dev_free(L.leaf);
     dev_free(L.p3);
     dev_free(L.gate);
@@ -269,6 +276,8 @@ void Context::alloc_lane(Lane& L) {
     const uint32_t w = g.w, h = g.h;
     dev_alloc(L.sat, F * (size_t)(h + 1) * g.sat_pitch);
     DH_CUDA(cudaMemsetAsync(L.sat, 0, F * (size_t)(h + 1) * g.sat_pitch * sizeof(uint32_t), stream_));  // row 0 stays 0
+    if (w + 1 <= 1024 && env_flag("DH_SAT_BANDS", true))
+        dev_alloc(L.band_u, F * (size_t)((h + sat_band_rows() - 1) / sat_band_rows()) * (w + 1));
     dev_alloc(L.leaf, F * P * T);
     dev_alloc(L.p3, F * P * 3);
     dev_alloc(L.gate, F * P);
@@ -401,6 +410,7 @@ FrameBuffers Context::buffers(const Lane& L, const uint16_t* depth) const {
     FrameBuffers b{};
     b.depth = depth;
     b.sat = L.sat;
+    b.band_u = L.band_u;
     b.leaf = L.leaf;
     b.p3 = L.p3;
     b.gate = L.gate;
@@ -454,8 +464,7 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
         hot_tw_ = tiles_.tw;
     }
     mark(DH_STAGE_SAT);
-    launch_sat(b, g, n, st);
-    launches_ += 2;
+    launches_ += (uint64_t)launch_sat(b, g, n, st);
     stage_check("sat");
     mark(DH_STAGE_TRAVERSE);
     if (g.P) {

@@ -21,6 +21,7 @@ struct Lane {
     cudaStream_t own = nullptr;
     cudaEvent_t done = nullptr;
     uint32_t* sat = nullptr;        // [F][h+1][pitch]
+    uint32_t* band_u = nullptr;     // [F][bands][w+1]
     int32_t* leaf = nullptr;        // [F][T][P]
     float* p3 = nullptr;            // [F][P][3]   (debug export)
     uint8_t* gate = nullptr;        // [F][P]      (debug export)

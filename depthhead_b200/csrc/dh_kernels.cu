@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace dh {
 
@@ -150,6 +151,128 @@ __global__ void __launch_bounds__(128) sat_cols_kernel(uint32_t* __restrict__ sa
     for (; y < h; ++y) {
         acc += col[(size_t)y * pitch];
         col[(size_t)y * pitch] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- banded single-pass variant
+// For images up to 1023 pixels wide the table is produced with two reads of the depth and ONE
+// write of the table (the two-pass variant above reads and writes the table twice): the frame is cut into bands of kSatBandRows
+// rows.  Pass A: per band, the column sums of its rows and their exclusive scan along x, i.e. the
+// band's contribution U_b[x] to every table row below it.  Pass B: per band, thread x keeps
+// S[y][x] for its column in a register: S[y+1][x] = S[y][x] + (sum of row y left of x), the row
+// prefix coming from a block-wide scan of the row, eight rows per barrier.
+constexpr int kSatBandRows = 32;
+constexpr int kSatBatch = 8;
+
+// exclusive block-wide scan of one value per thread; `tot` (one slot per warp) is scratch
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* tot, uint32_t lane, uint32_t warp, uint32_t n_warps) {
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += n;
+    }
+    if (lane == 31) tot[warp] = incl;
+    __syncthreads();
+    uint32_t t = lane < n_warps ? tot[lane] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, t, d);
+        if (lane >= (uint32_t)d) t += n;
+    }
+    const uint32_t carry = __shfl_sync(0xffffffffu, t, (warp + 31u) & 31u);  // inclusive total of the warps before
+    return (warp ? carry : 0u) + incl - v;
+}
+
+__global__ void __launch_bounds__(1024) sat_band_sums_kernel(const uint16_t* __restrict__ depth, uint32_t* __restrict__ band_u,
+                                                             uint32_t w, uint32_t h, uint32_t n_bands) {
+    __shared__ uint32_t s_tot[32];
+    const uint32_t frame = blockIdx.y, band = blockIdx.x, x = threadIdx.x;
+    const uint32_t y0 = band * kSatBandRows, y1 = min(h, y0 + kSatBandRows);
+    const uint16_t* img = depth + (size_t)frame * h * w;
+    uint32_t cs = 0;
+    if (x < w) {
+        uint32_t y = y0;
+        for (; y + 8 <= y1; y += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(img + (size_t)(y + j) * w + x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cs += v[j];
+        }
+        for (; y < y1; ++y) cs += __ldg(img + (size_t)y * w + x);
+    }
+    const uint32_t u = block_excl_scan(cs, s_tot, x & 31u, x >> 5, blockDim.x >> 5);
+    if (x <= w) band_u[((size_t)frame * n_bands + band) * (w + 1) + x] = u;
+}
+
+// Pass B.  One CTA per band of 32 rows, one warp per row: the row's exclusive prefix sums go to
+// shared memory (8 pixels per lane per step, one 16-byte load, warp-shuffle scan of the lane
+// totals); then one thread per column walks down the band adding them up and writes the table.
+__global__ void __launch_bounds__(kSatBandRows * 32) sat_band_kernel(const uint16_t* __restrict__ depth,
+                                                                     const uint32_t* __restrict__ band_u,
+                                                                     uint32_t* __restrict__ sat, uint32_t w, uint32_t h,
+                                                                     uint32_t pitch, uint32_t n_bands) {
+    extern __shared__ __align__(16) uint32_t s_rows[];  // [kSatBandRows][spitch] exclusive row prefixes, positions 0..w
+    const uint32_t spitch = (w + 1 + 8) & ~7u;          // every 8-wide store stays inside its row
+    const uint32_t frame = blockIdx.y, band = blockIdx.x, tid = threadIdx.x;
+    const uint32_t lane = tid & 31u, r = tid >> 5;
+    const uint32_t y0 = band * kSatBandRows, y1 = min(h, y0 + kSatBandRows);
+    const uint16_t* img = depth + (size_t)frame * h * w;
+    if (y0 + r < y1) {
+        const uint16_t* row = img + (size_t)(y0 + r) * w;
+        uint32_t* srow = s_rows + r * spitch;
+        const bool vec_ok = ((w & 7u) == 0u) && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0u);
+        uint32_t carry = 0;
+        for (uint32_t seg = 0; seg <= w; seg += 256) {  // positions 0..w inclusive
+            const uint32_t x = seg + lane * 8;
+            uint32_t v[8];
+            if (vec_ok && x + 8 <= w) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + x));
+                v[0] = q.x & 0xffffu; v[1] = q.x >> 16; v[2] = q.y & 0xffffu; v[3] = q.y >> 16;
+                v[4] = q.z & 0xffffu; v[5] = q.z >> 16; v[6] = q.w & 0xffffu; v[7] = q.w >> 16;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = (x + j < w) ? (uint32_t)__ldg(row + x + j) : 0u;
+            }
+            uint32_t e[8];
+            uint32_t tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                e[j] = tot;
+                tot += v[j];
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += n;
+            }
+            const uint32_t base = carry + incl - tot;
+            if (x <= w) {  // spitch leaves room for the whole 8-wide store
+                *reinterpret_cast<uint4*>(srow + x) = make_uint4(base + e[0], base + e[1], base + e[2], base + e[3]);
+                *reinterpret_cast<uint4*>(srow + x + 4) = make_uint4(base + e[4], base + e[5], base + e[6], base + e[7]);
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    uint32_t* out = sat + (size_t)frame * (h + 1) * pitch;
+    for (uint32_t x = tid; x <= w; x += kSatBandRows * 32) {
+        // S[y0][x]: everything above this band and left of x
+        uint32_t acc = 0;
+        const uint32_t* u = band_u + (size_t)frame * n_bands * (w + 1) + x;
+        uint32_t b2 = 0;
+        for (; b2 + 4 <= band; b2 += 4) {  // four loads in flight
+            const uint32_t u0 = __ldg(u + (size_t)b2 * (w + 1)), u1 = __ldg(u + (size_t)(b2 + 1) * (w + 1)),
+                           u2 = __ldg(u + (size_t)(b2 + 2) * (w + 1)), u3 = __ldg(u + (size_t)(b2 + 3) * (w + 1));
+            acc += u0 + u1 + u2 + u3;
+        }
+        for (; b2 < band; ++b2) acc += __ldg(u + (size_t)b2 * (w + 1));
+        for (uint32_t y = y0; y < y1; ++y) {
+            acc += s_rows[(y - y0) * spitch + x];
+            out[(size_t)(y + 1) * pitch + x] = acc;
+        }
     }
 }
 
@@ -1328,11 +1451,29 @@ constexpr int kTraverseThreads = 512;
 using namespace dev;
 
 // ================================================================ launch wrappers
-void launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s) {
+int launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s) {
+    if (b.band_u && g.w + 1 <= 1024) {
+        int launches = 0;
+        // banded pass: per-band column-sum scans, then the table
+        const uint32_t n_bands = (g.h + kSatBandRows - 1) / kSatBandRows;
+        const uint32_t threads = (g.w + 1 + 31) & ~31u;
+        const uint32_t smem = kSatBandRows * ((g.w + 1 + 8) & ~7u) * 4u;
+        static uint32_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(sat_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+        dim3 gr(n_bands, n_frames);
+        sat_band_sums_kernel<<<gr, threads, 0, s>>>(b.depth, b.band_u, g.w, g.h, n_bands);
+        sat_band_kernel<<<gr, kSatBandRows * 32, smem, s>>>(b.depth, b.band_u, b.sat, g.w, g.h, g.sat_pitch, n_bands);
+        launches += 2;
+        return launches;
+    }
     dim3 gr((g.h + kSatRowWarps - 1) / kSatRowWarps, n_frames);
     sat_rows_kernel<<<gr, kSatRowWarps * 32, 0, s>>>(b.depth, b.sat, g.w, g.h, g.sat_pitch);
     dim3 gc((g.w + 1 + 127) / 128, n_frames);
     sat_cols_kernel<<<gc, 128, 0, s>>>(b.sat, g.w, g.h, g.sat_pitch);
+    return 2;
 }
 
 uint32_t traverse_smem_bytes(uint32_t tw, uint32_t th, uint32_t patches_per_tile) {
@@ -1386,6 +1527,7 @@ void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t 
     plan_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(nodes, hot, uni, n_nodes, tile_width);
 }
 
+uint32_t sat_band_rows() { return (uint32_t)kSatBandRows; }
 uint32_t vote_box_cells() { return (uint32_t)kBoxCells; }
 uint32_t vote_box_dim() { return (uint32_t)kBox; }
 

@@ -72,6 +72,7 @@ struct ForestDev {
 struct FrameBuffers {
     const uint16_t* depth;  // [F][h][w]
     uint32_t* sat;          // [F][h+1][pitch]
+    uint32_t* band_u;       // [F][bands][w+1] per-band column-sum scans of the banded SAT pass (or nullptr)
     int32_t* leaf;          // [F][T][P]
     float* p3;              // [F][P][3]
     uint8_t* gate;          // [F][P]
@@ -85,7 +86,7 @@ struct FrameBuffers {
     uint32_t debug;         // 1: compute the seed grids even when the caller supplied seeds
 };
 
-void launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s);
+int launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s);
 void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width, cudaStream_t s);
@@ -94,6 +95,7 @@ int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const Forest
                           uint32_t iterations, cudaStream_t s);
 int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t iterations,
                      cudaStream_t s);
+uint32_t sat_band_rows();
 uint32_t vote_box_cells();
 uint32_t vote_box_dim();
 void launch_leaf_gates(const double* leaf_prob, const uint32_t* vote_start, const uint32_t* n_votes,

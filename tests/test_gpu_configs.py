@@ -1,0 +1,190 @@
+"""GPU parity for the remaining BASELINE.json configs and for every kernel variant.
+
+configs[2] (Biwi-shaped sequence sharded by frame), configs[3] (large forest: 50 trees, depth 20,
+dense stride-1 sampling) and configs[4] (vote-heavy: a million votes per frame) are run against
+the oracle at sizes it finishes in seconds, and at (or near) full size through size-independent
+properties: batch == single frame, chunking / sharding independence, permutation equivariance,
+work-counter identities.  The variant test forces each fallback kernel (LSU node fetch, general
+rectangles instead of box sums, two-pass summed-area table, 512-thread traversal, one lane) and
+repeats the stage-by-stage comparison.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from depthhead_b200 import Context, HoughPrediction, IntrinsicMatrix, synth
+from test_gpu_parity import _compare_frame
+
+pytestmark = pytest.mark.gpu
+
+K = IntrinsicMatrix.default_kinect_intrinsic()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _small_frames(n, h, w, seed):
+    """crops of the synthetic 640x480 frames around the person (keeps non-background content)"""
+    full = synth.make_frames(n, seed=seed)
+    y0, x0 = (480 - h) // 2, (640 - w) // 2
+    return np.ascontiguousarray(full[:, y0:y0 + h, x0:x0 + w])
+
+
+VARIANTS = [
+    {"DH_TEX": "0"},                                # general rectangles need the LSU path when the texture is off
+    {"DH_UNIFORM": "0"},                            # general 8-tap traversal on a uniform forest
+    {"DH_UNIFORM": "0", "DH_TEX": "0"},
+    {"DH_UNI_LDG": "1"},                            # box sums, nodes through the LSU path
+    {"DH_SAT_BANDS": "0"},                          # two-pass summed-area table
+    {"DH_TRAV_THREADS": "512"},                     # 512-thread traversal tiles
+    {"DH_LANES": "1"},
+    {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},
+]
+
+
+@pytest.mark.parametrize("env", VARIANTS, ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
+def test_kernel_variants(monkeypatch, env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c = Context(0)  # the switches are read when a context uploads a model / sizes its scratch
+    try:
+        for kw in (dict(seed=3, n_trees=4, max_depth=7), dict(seed=5, n_trees=3, max_depth=8, stop_prob=0.2, ragged_rects=True)):
+            arr = synth.make_forest(**kw)
+            js = synth.forest_to_json(arr, stepwidth=6)
+            hp = HoughPrediction.from_json(js)
+            of = oracle.OracleForest.from_json(js)
+            frames = synth.make_frames(5, seed=21)
+            _compare_frame(c, hp, of, frames[0])
+            out = hp.predict_batch(frames, K, ctx=c)
+            for i, d in enumerate(frames):
+                tr = of.predict(d, synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+                assert np.array_equal(out["mid_point"][i], tr.mid_point) and np.array_equal(out["rotation"][i], tr.rotation)
+    finally:
+        c.close()
+
+
+def test_config3_large_forest_dense_stride_vs_oracle(ctx):
+    """configs[3] shape — many sparse deep trees, stride 1 — on a cropped frame the oracle can afford."""
+    arr = synth.make_forest(seed=9, n_trees=50, max_depth=20, stop_prob=0.3)
+    hp = HoughPrediction.from_arrays(arr, stepwidth=1)
+    of = oracle.OracleForest(arr, 1, 80, 80, 8.0, 20)
+    for d in _small_frames(2, 128, 160, seed=5):
+        _compare_frame(ctx, hp, of, d)
+
+
+def test_config3_large_forest_full_size_properties(ctx):
+    """50 trees, depth 20, stride 1 on full 640x480 frames: 224 000 patches x 50 trees per frame."""
+    arr = synth.make_forest(seed=9, n_trees=50, max_depth=20, stop_prob=0.3)
+    hp = HoughPrediction.from_arrays(arr, stepwidth=1)
+    frames = synth.make_frames(3, seed=8)
+    a = hp.predict_batch(frames, K, ctx=ctx)
+    cnt = ctx.counters()
+    assert cnt["patches"] == 3 * 224000
+    assert cnt["evals"] == cnt["valid_patches"] * 50
+    assert cnt["evals"] <= cnt["node_visits"] <= cnt["evals"] * 20
+    ctx.set_chunk_frames(2)
+    b = hp.predict_batch(frames[::-1].copy(), K, ctx=ctx)
+    ctx.set_chunk_frames(0)
+    assert np.array_equal(a["mid_point"], b["mid_point"][::-1]) and np.array_equal(a["rotation"], b["rotation"][::-1])
+    for i in range(3):
+        s = hp.predict_parameter_parallel(frames[i], K, ctx=ctx)
+        assert np.array_equal(s.mid_point, a["mid_point"][i]) and np.array_equal(s.rotation, a["rotation"][i])
+
+
+def test_config4_vote_heavy_vs_oracle(ctx):
+    """configs[4] shape — leaves with 32..128 votes — on a cropped frame, every stage compared."""
+    arr = synth.make_forest(seed=13, n_trees=10, max_depth=8, votes_lo=32, votes_hi=128)
+    hp = HoughPrediction.from_arrays(arr, stepwidth=2)
+    of = oracle.OracleForest(arr, 2, 80, 80, 8.0, 20)
+    for d in _small_frames(2, 160, 200, seed=6):
+        _compare_frame(ctx, hp, of, d)
+
+
+def test_config4_vote_heavy_full_size(ctx):
+    """stride 1, 10 trees, 32..128 votes per leaf on full frames: over a million votes per frame
+    through the coarse-grid, cube and mean-shift kernels; one frame checked against the oracle."""
+    arr = synth.make_forest(seed=13, n_trees=10, max_depth=8, votes_lo=32, votes_hi=128)
+    hp = HoughPrediction.from_arrays(arr, stepwidth=1)
+    frames = synth.make_frames(3, seed=12)
+    a = hp.predict_batch(frames, K, ctx=ctx)
+    cnt = ctx.counters()
+    assert (cnt["centre_votes"] + cnt["rot_votes"]) / 3 >= 1_000_000
+    perm = np.array([2, 0, 1])
+    b = hp.predict_batch(frames[perm], K, ctx=ctx)
+    assert np.array_equal(b["mid_point"], a["mid_point"][perm]) and np.array_equal(b["rotation"], a["rotation"][perm])
+    of = oracle.OracleForest(arr, 1, 80, 80, 8.0, 20)
+    tr = of.predict(frames[1], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+    assert np.array_equal(a["mid_point"][1], tr.mid_point) and np.array_equal(a["rotation"][1], tr.rotation)
+
+
+def test_config2_sequence_sharded_by_frame(ctx):
+    """configs[2]: a Biwi-shaped sequence cut into contiguous shards (depthhead_b200.shard) gives
+    byte-identical results to the unsharded run, shard by shard, for 1/2/4/8-way splits."""
+    from depthhead_b200 import shard
+    arr = synth.make_forest(seed=1, n_trees=10, max_depth=12)
+    hp = HoughPrediction.from_arrays(arr, stepwidth=5)
+    n = 37
+    frames = synth.make_frames(n, seed=3, sequence=True)
+    whole = hp.predict_batch(frames, K, ctx=ctx)
+    for world in (2, 4, 8):
+        parts = []
+        for rank in range(world):
+            lo, hi = shard.shard_range(n, rank, world)
+            parts.append(hp.predict_batch(frames[lo:hi], K, ctx=ctx) if hi > lo else whole[:0])
+        got = np.concatenate(parts)
+        assert got.tobytes() == whole.tobytes()
+    of = oracle.OracleForest(arr, 5, 80, 80, 8.0, 20)
+    for i in (0, 18, 36):
+        tr = of.predict(frames[i], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+        assert np.array_equal(whole["mid_point"][i], tr.mid_point) and np.array_equal(whole["rotation"][i], tr.rotation)
+
+
+def _ramp_forest(n_trees=6):
+    """Trees without nodes (a single leaf each) whose centre votes pile up exponentially along x:
+    cell x of [0, 32) receives about 1.25^x votes per patch.  Mean-shift seeded at the thin end
+    climbs the ramp by several cells per round, far more than the 14 cells of margin around the
+    seed's window."""
+    mult = np.maximum(1, np.round(1.25 ** np.arange(32))).astype(np.int64)
+    xs = np.repeat(np.arange(32), mult)                      # one entry per vote
+    per = int(np.ceil(len(xs) / n_trees))
+    assert per <= 1000                                       # valtoadd = 1000 / n must stay >= 1
+    offsets, rotations, vote_off = [], [], [0]
+    for t in range(n_trees):
+        part = xs[t * per:(t + 1) * per]
+        if len(part) < 2:
+            part = np.array([31, 31])
+        o = np.zeros((len(part), 3), np.float32)
+        o[:, 0] = -part.astype(np.float32) - 0.5             # np = p3 - o lands in cell trunc(p3.x) + x
+        offsets.append(o)
+        rotations.append(np.tile(np.array([[9.0, -12.0, 3.0]]), (len(part), 1)))
+        vote_off.append(vote_off[-1] + len(part))
+    z = np.zeros(n_trees + 1, np.int64)
+    return dict(n_trees=n_trees, tree_node_off=z, tree_leaf_off=np.arange(n_trees + 1, dtype=np.int64),
+                rects=np.zeros((0, 8), np.int64), threshold=np.zeros(0), child=np.zeros((0, 2), np.int32),
+                prob=np.ones(n_trees), vote_off=np.asarray(vote_off, np.int64),
+                offsets=np.ascontiguousarray(np.concatenate(offsets)),
+                rotations=np.ascontiguousarray(np.concatenate(rotations)), sub_w=80, sub_h=80, max_depth=0)
+
+
+def test_drifting_mean_shift_rebuilds_the_cube(ctx):
+    """The window walks out of the seed-centred accumulator cube: the cube is rebuilt around the
+    current position (more than once) and the trajectory still matches the oracle round by round."""
+    arr = _ramp_forest()
+    js = synth.forest_to_json(arr, stepwidth=5, meanshift_iterations=30)
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    d = np.full((90, 90), 1000, np.uint16)                   # 2 x 2 patches, all valid, p3 ~ (-500, -357, 1000)
+    tr = of.predict(d, synth.KINECT_K, mode=oracle.MODE_SAT, keep=True)
+    x0 = int(tr.mid_keys[:, 0].min())
+    y0, z0 = int(tr.mid_keys[0, 1]), int(tr.mid_keys[0, 2])
+    total = 0
+    for start in (x0 - 6, x0 + 2):
+        guess = [float(start), float(y0), float(z0)]
+        res, t2 = _compare_frame(ctx, hp, of, d, midp_guess=guess, rot_guess=[0.15, -0.2, 0.05])
+        assert abs(int(res.mid_point[0]) - start) > 14       # the position really left the first cube
+        total += ctx.counters()["cube_rebuilds"]
+    assert total >= 2
