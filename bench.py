@@ -226,6 +226,7 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
@@ -323,7 +324,7 @@ def main():
 
     # ---- roofline of the dominant kernel (traversal), from this rank's live stage timers
     peak, peak_src = measured_peak_gbs()
-    dev_chunk = args.chunk or 256  # library default for device-resident input
+    dev_chunk = args.chunk or 512  # library default for device-resident input
     launches = max(1, (n + dev_chunk - 1) // dev_chunk) * args.steps
     trav_ms = stage.get("traverse", 0.0)
     alg_bytes = counters["node_visits"] * BYTES_PER_NODE_VISIT + counters["evals"] * BYTES_PER_LEAF_HEADER

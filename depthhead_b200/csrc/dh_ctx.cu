@@ -94,7 +94,7 @@ Context::Context(int device) : device_(device) {
     dev_alloc(d_counters_, DH_N_COUNTERS);
     DH_CUDA(cudaHostAlloc((void**)&h_fs_, sizeof(FrameState), cudaHostAllocDefault));
     DH_CUDA(cudaHostAlloc((void**)&h_counters_, sizeof(unsigned long long) * DH_N_COUNTERS, cudaHostAllocDefault));
-    chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 0);  // 0 = adaptive (128 for host input, 1024 for device input)
+    chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 0);  // 0 = adaptive (128 for host input, 512 for device input)
     debug_sync_ = env_u32("DH_DEBUG_SYNC", 0) != 0;
     std::memset(stage_ms_, 0, sizeof(stage_ms_));
     std::memset(counters_, 0, sizeof(counters_));
@@ -337,7 +337,7 @@ uint32_t Context::pick_chunk(uint32_t n_frames, int depth_loc) const {
     // Host input: small chunks so the H2D copy of chunk c+1 hides behind the kernels of chunk c
     // and the first kernels start early.  Device input: chunks large enough to fill the GPU
     // several times over, small enough that a batch spreads over all pipeline lanes.
-    uint32_t c = chunk_frames_ ? chunk_frames_ : (depth_loc == DH_DEPTH_DEVICE ? 256u : 128u);
+    uint32_t c = chunk_frames_ ? chunk_frames_ : (depth_loc == DH_DEPTH_DEVICE ? 512u : 128u);
     return std::max<uint32_t>(1u, std::min<uint32_t>(c, std::max<uint32_t>(n_frames, 1u)));
 }
 
