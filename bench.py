@@ -329,19 +329,25 @@ def main():
     trav_ms = stage.get("traverse", 0.0)
     alg_bytes = counters["node_visits"] * BYTES_PER_NODE_VISIT + counters["evals"] * BYTES_PER_LEAF_HEADER
     achieved = alg_bytes / (trav_ms / 1000.0) / 1e9 if trav_ms > 0 else None
-    traffic = None
+    traffic, pipes = None, None
     tpath = os.path.join(ROOT, "profiles", "traverse_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            # captured on a 512-frame launch; scale to this run's launch size
+            traffic = tj.get("dram_bytes_per_launch") * (min(dev_chunk, n) / float(tj.get("frames_per_launch", 512)))
+            pipes = tj.get("pipe_utilisation_pct")
         except Exception:
             traffic = None
     roofline = {"kernel": "traverse_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / launches, "launches": launches,
                 "avg_launch_ms": trav_ms / launches,
-                "note": "algorithmic bytes are served from shared memory (SAT taps) and L2 (node records), "
-                        "not HBM: a fraction above 1 is expected; see DESIGN.md"}
+                "ncu_pipe_utilisation_pct": pipes,
+                "note": "algorithmic bytes (SURVEY 8d: 56 B per node visit + 16 B per evaluation) are served from "
+                        "shared memory (taps) and L1/L2 (node records), not HBM, so the fraction exceeds 1; `traffic` "
+                        "is the DRAM traffic of one launch from ncu (profiles/r01_v3_summary.md); the kernel is bound "
+                        "by the latency of its dependent fetch->tap->compare chain, see DESIGN.md"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
