@@ -1,26 +1,7 @@
-# INTEGRATION — binding `libdepthhead_cuda.so` from depthhead (Rust)
+// Mirrors INTEGRATION.md.  Not compiled in the build image (no cargo / rustc there); the same C ABI
+// is exercised by depthhead_b200/capi.py in the test-suite.
+extern crate image;
 
-The reference is a Rust crate (2015 edition). Its prediction entry points
-(`src/hough/prediction.rs:376-409`) are replaced by the C ABI in `include/depthhead_cuda.h`. A
-maintainer adds a small crate `depthhead-cuda` next to `depthhead` with the `extern "C"` block and
-safe wrapper below (also kept as files under `rust/depthhead-cuda/`). **This Rust source could not be compiled in the build image** (no `cargo` /
-`rustc`); the same ABI is exercised by the Python ctypes binding (`depthhead_b200/capi.py`) in the
-test-suite, and `tests/test_capi_cpu.py` checks that the library exports every symbol of the header.
-
-## `depthhead-cuda/build.rs`
-
-```rust
-fn main() {
-    // directory holding libdepthhead_cuda.so (built by `python -m depthhead_b200._build`)
-    let dir = std::env::var("DEPTHHEAD_CUDA_LIB_DIR").expect("set DEPTHHEAD_CUDA_LIB_DIR");
-    println!("cargo:rustc-link-search=native={}", dir);
-    println!("cargo:rustc-link-lib=dylib=depthhead_cuda");
-}
-```
-
-## `depthhead-cuda/src/lib.rs`
-
-```rust
 //! Drop-in for depthhead's `HoughPrediction` prediction path on an NVIDIA B200.
 use std::ffi::CStr;
 use std::os::raw::{c_char, c_int, c_void};
@@ -145,36 +126,3 @@ impl HoughPrediction {
 impl Drop for HoughPrediction {
     fn drop(&mut self) { unsafe { dh_ctx_free(self.ctx); dh_forest_free(self.forest); } }
 }
-```
-
-## Call-site change in depthhead
-
-`examples/live_prediction.rs:166-173` loads the forest and `:76,86` calls
-`forest.predict_parameter_parallel(img, &intrinsic, guess_mid, guess_rot)`. With the shim:
-
-```rust
-// before: let forest: HoughPrediction = serde_json::from_str(&text)?;
-let forest = depthhead_cuda::HoughPrediction::from_json_on(&text, 0)?;
-let res = forest.predict_parameter_parallel(&img, &depthhead_cuda::IntrinsicMatrix::default_kinect_intrinsic(), None, None);
-```
-
-## Ownership, threading, errors
-
-* The caller owns every input and output buffer; nothing is retained past a call. `dh_forest*` is
-  immutable after load (shareable across threads and GPUs; each context uploads its own device
-  copy lazily); `dh_ctx*` is single-threaded: one per GPU per host thread.
-* Every function returns `int` (0 ok, `DH_E_JSON/-1`, `DH_E_SHAPE/-2`, `DH_E_CUDA/-3`,
-  `DH_E_ARG/-4`, `DH_E_STATE/-5`); `dh_last_error()` is thread-local; nothing unwinds across the ABI.
-* Degenerate shapes (`w < subimage_width`, stepwidth 0) are `DH_E_SHAPE` instead of the reference's
-  u32 underflow / endless loop; forests the reference would panic on are rejected at load.
-* Multi-GPU: one process (or thread) per GPU, each with its own `dh_ctx`, frames split in
-  contiguous blocks, results concatenated on the host — there is no collective.
-
-## Python (what the tests use)
-
-```python
-from depthhead_b200 import HoughPrediction, IntrinsicMatrix, Context
-hp  = HoughPrediction.from_json(open("forest.json").read())
-res = hp.predict_parameter_parallel(depth_u16_hw, IntrinsicMatrix.default_kinect_intrinsic())
-out = hp.predict_batch(frames_u16_nhw, IntrinsicMatrix.default_kinect_intrinsic(), ctx=Context(0))
-```
