@@ -251,6 +251,7 @@ void Context::ensure_forest(const HostForest& hf) {
 void Context::free_lane(Lane& L) {
     dev_free(L.sat);
     dev_free(L.band_u);
+    dev_free(L.box);
     dev_free(L.leaf);
     dev_free(L.p3);
     dev_free(L.gate);
@@ -274,10 +275,14 @@ void Context::alloc_lane(Lane& L) {
     const Geometry& g = geom_;
     const size_t F = sk_.frames, P = std::max<uint32_t>(g.P, 1u), T = g.n_trees;
     const uint32_t w = g.w, h = g.h;
-    dev_alloc(L.sat, F * (size_t)(h + 1) * g.sat_pitch);
-    DH_CUDA(cudaMemsetAsync(L.sat, 0, F * (size_t)(h + 1) * g.sat_pitch * sizeof(uint32_t), stream_));  // row 0 stays 0
-    if (w + 1 <= 1024 && env_flag("DH_SAT_BANDS", true))
-        dev_alloc(L.band_u, F * (size_t)((h + sat_band_rows() - 1) / sat_band_rows()) * (w + 1));
+    if (g.rw) {
+        dev_alloc(L.box, F * (size_t)g.box_h * g.box_pitch);
+    } else {
+        dev_alloc(L.sat, F * (size_t)(h + 1) * g.sat_pitch);
+        DH_CUDA(cudaMemsetAsync(L.sat, 0, F * (size_t)(h + 1) * g.sat_pitch * sizeof(uint32_t), stream_));  // row 0 stays 0
+        if (w + 1 <= 1024 && env_flag("DH_SAT_BANDS", true))
+            dev_alloc(L.band_u, F * (size_t)((h + sat_band_rows() - 1) / sat_band_rows()) * (w + 1));
+    }
     dev_alloc(L.leaf, F * P * T);
     dev_alloc(L.p3, F * P * 3);
     dev_alloc(L.gate, F * P);
@@ -288,12 +293,14 @@ void Context::alloc_lane(Lane& L) {
     dev_alloc(L.results, F);
     if (sk_.trace_iters) dev_alloc(L.ms_trace, F * 2 * (size_t)sk_.trace_iters * 3);
     if (g.P) {
-        // TMA descriptor over the SAT scratch: [F][h+1][pitch] u32, box = one tile
-        const cuuint64_t gdim[3] = {(cuuint64_t)(w + 1), (cuuint64_t)(h + 1), (cuuint64_t)F};
-        const cuuint64_t gstr[2] = {(cuuint64_t)g.sat_pitch * 4u, (cuuint64_t)g.sat_pitch * 4u * (h + 1)};
+        // TMA descriptor over the SAT scratch [F][h+1][pitch] u32 (or the box-sum image
+        // [F][box_h][box_pitch]), box = one tile; out-of-range elements read as zero
+        const cuuint64_t gdim[3] = {(cuuint64_t)(g.rw ? g.box_w : w + 1), (cuuint64_t)(g.rw ? g.box_h : h + 1), (cuuint64_t)F};
+        const cuuint64_t row_bytes = (cuuint64_t)(g.rw ? g.box_pitch : g.sat_pitch) * 4u;
+        const cuuint64_t gstr[2] = {row_bytes, row_bytes * (g.rw ? g.box_h : h + 1)};
         const cuuint32_t box[3] = {tiles_.tw, tiles_.th, 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
-        CUresult r = get_encode_fn()(&L.sat_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, L.sat, gdim, gstr, box, estr,
+        CUresult r = get_encode_fn()(&L.sat_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, g.rw ? L.box : L.sat, gdim, gstr, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) throw ModelError(DH_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -315,8 +322,9 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
                 // the TMA origin is rounded down to 4 elements (16 B); unless every tile origin is
                 // already aligned, the window needs up to 3 extra columns
                 const uint32_t slack = ((tpx * g.stride) & 3u) ? 3u : 0u;
-                const uint32_t tw = ((tpx - 1) * g.stride + g.sw + 1 + slack + 3) & ~3u;
-                const uint32_t th = (tpy - 1) * g.stride + g.sh + 1;
+                // summed-area table: sw + 1 taps per patch row; box-sum image: sw - rw + 1
+                const uint32_t tw = ((tpx - 1) * g.stride + g.sw + 1 - g.rw + slack + 3) & ~3u;
+                const uint32_t th = (tpy - 1) * g.stride + g.sh + 1 - g.rh;
                 if (tw > 256 || th > 256) continue;  // TMA box limit per dimension
                 const uint32_t bytes = traverse_smem_bytes(tw, th, tpx * tpy);
                 if (bytes > limit) continue;
@@ -360,6 +368,10 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
         cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(cap, budget / per_frame));
     }
     ScratchKey k{w, h, sw, sh, stride, (uint32_t)hf.n_trees, cap, debug_ ? hf.meanshift_iterations.load() : 0u};
+    if (df_uni_ && env_flag("DH_BOX_IMAGE", true) && box_image_supported(w, h, sw, sh, uni_rw_, uni_rh_)) {
+        k.rw = uni_rw_;
+        k.rh = uni_rh_;
+    }
     call_chunk_ = cap;  // frames per pass of this call (the scratch may be larger)
     Geometry& g = geom_;
     if (!k.same_shape(sk_) || k.frames > sk_.frames) {
@@ -376,6 +388,13 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
         g.npy = span_y == 0 ? 0 : (span_y + stride - 1) / stride;
         g.P = g.npx * g.npy;
         g.sat_pitch = (w + 1 + 3) & ~3u;
+        g.rw = k.rw;
+        g.rh = k.rh;
+        if (g.rw) {
+            g.box_w = w - g.rw + 1;
+            g.box_h = h - g.rh + 1;
+            g.box_pitch = (g.box_w + 3) & ~3u;
+        }
         g.n_trees = (uint32_t)hf.n_trees;
         // exact division by multiply-high: floor(n / d) == umulhi(n, floor(2^32 / d) + 1) whenever n * d < 2^32
         auto magic = [](uint32_t d) -> uint32_t {
@@ -411,6 +430,7 @@ FrameBuffers Context::buffers(const Lane& L, const uint16_t* depth) const {
     b.depth = depth;
     b.sat = L.sat;
     b.band_u = L.band_u;
+    b.box = L.box;
     b.leaf = L.leaf;
     b.p3 = L.p3;
     b.gate = L.gate;
@@ -464,7 +484,7 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
         hot_tw_ = tiles_.tw;
     }
     mark(DH_STAGE_SAT);
-    launches_ += (uint64_t)launch_sat(b, g, n, st);
+    launches_ += (uint64_t)(g.rw ? launch_box_image(b, g, n, n_sms_, st) : launch_sat(b, g, n, st));
     stage_check("sat");
     mark(DH_STAGE_TRAVERSE);
     if (g.P) {

@@ -22,6 +22,7 @@ struct Lane {
     cudaEvent_t done = nullptr;
     uint32_t* sat = nullptr;        // [F][h+1][pitch]
     uint32_t* band_u = nullptr;     // [F][bands][w+1]
+    uint32_t* box = nullptr;        // [F][h-rh+1][pitch] box-sum image (replaces sat/band_u in box-image mode)
     int32_t* leaf = nullptr;        // [F][T][P]
     float* p3 = nullptr;            // [F][P][3]   (debug export)
     uint8_t* gate = nullptr;        // [F][P]      (debug export)
@@ -38,9 +39,10 @@ constexpr int kMaxLanes = 4;
 
 struct ScratchKey {
     uint32_t w = 0, h = 0, sw = 0, sh = 0, stride = 0, n_trees = 0, frames = 0, trace_iters = 0;
+    uint32_t rw = 0, rh = 0;  // box-image mode: the forest's common rectangle size (0 = summed-area-table mode)
     bool same_shape(const ScratchKey& o) const {
         return w == o.w && h == o.h && sw == o.sw && sh == o.sh && stride == o.stride && n_trees == o.n_trees &&
-               trace_iters == o.trace_iters;
+               trace_iters == o.trace_iters && rw == o.rw && rh == o.rh;
     }
 };
 

@@ -276,6 +276,134 @@ __global__ void __launch_bounds__(kSatBandRows * 32) sat_band_kernel(const uint1
     }
 }
 
+// ---------------------------------------------------------------- K1b: box-sum image
+// Forests whose feature rectangles all have one size rw x rh (what the reference's trainer
+// produces: houghforest.rs:230-234) never need a general summed-area table: the node test reads
+// B[y][x] = sum of the rw x rh rectangle whose top-left pixel is (x, y) (types.rs:317-339 for that
+// rectangle), one tap per rectangle.  This kernel writes B straight from the depth image: one
+// read of the depth, one write of B, no intermediate table.
+//
+// The unit of work is a WARP: it owns a strip of at most 256 input columns (8 per lane, one
+// 16-byte load per lane per row, fetched four rows ahead) and sweeps down a band of rows with the
+// rh-row window sums of its columns in registers: acc += row r, acc -= row r - rh + 1, the
+// departing row coming from a lane-private ring of the last rh rows in shared memory (16 bytes
+// per lane per row, no synchronisation).  Per output row the window sums are turned into
+// exclusive prefix sums along x (shuffle scan), staged in a warp-private row of shared memory, and
+// B[y][x] = P[x + rw] - P[x] goes out with 16-byte stores.  No block-level barrier; all arithmetic
+// in u32 (rw*rh*65535 < 2^31 is checked at load; prefix sums may wrap, differences are exact).
+constexpr int kBoxWarps = 2;                    // independent units per CTA
+constexpr int kBoxThreads = kBoxWarps * 32;
+constexpr int kBoxStripIn = 256;                // input columns per strip: 8 per lane
+constexpr int kBoxRowPitch = 272;               // P[0..256] + the slack the last active lane may read
+constexpr int kBoxAhead = 4;                    // rows fetched ahead
+
+__device__ __forceinline__ uint4 box_fetch(const uint16_t* __restrict__ row, uint32_t w, uint32_t x, bool vec_ok, bool on) {
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (!on) return q;
+    if (vec_ok) return __ldg(reinterpret_cast<const uint4*>(row + x));
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (x + j < w) ? (uint32_t)__ldg(row + x + j) : 0u;
+    return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+}
+template <bool kAdd>
+__device__ __forceinline__ void box_apply(uint32_t acc[8], const uint4 q) {
+    const uint32_t v[8] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16, q.z & 0xffffu, q.z >> 16, q.w & 0xffffu, q.w >> 16};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = kAdd ? acc[j] + v[j] : acc[j] - v[j];
+}
+
+__global__ void __launch_bounds__(kBoxThreads) box_image_kernel(const uint16_t* __restrict__ depth, uint32_t* __restrict__ box,
+                                                                uint32_t w, uint32_t h, uint32_t rw, uint32_t rh, uint32_t bw,
+                                                                uint32_t bh, uint32_t bpitch, uint32_t strip_out, uint32_t n_strips,
+                                                                uint32_t band_rows, uint32_t n_bands, uint32_t n_units) {
+    extern __shared__ __align__(16) uint32_t s_box[];  // [kBoxWarps][2][kBoxRowPitch] prefix rows, then [kBoxWarps][rh][32] uint4 pixel rings
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t unit = blockIdx.x * kBoxWarps + warp;
+    if (unit >= n_units) return;
+    const uint32_t strip = unit % n_strips;
+    unit /= n_strips;
+    const uint32_t band = unit % n_bands, frame = unit / n_bands;
+    const uint32_t c0 = strip * strip_out, c1 = min(bw, c0 + strip_out);  // output columns (c0 is a multiple of 8)
+    const uint32_t y0 = band * band_rows, y1 = min(bh, y0 + band_rows);   // output rows
+    if (c0 >= c1 || y0 >= y1) return;
+    const uint32_t x_end = c1 + rw - 1u;          // one past the last input column (<= w)
+    const uint32_t r_end = y1 + rh - 1u;          // one past the last input row (<= h)
+    const uint16_t* img = depth + (size_t)frame * h * w;
+    const bool vec_ok = ((w & 7u) == 0u) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0u);
+    const uint32_t my_x = c0 + lane * 8u;
+    const bool lane_in = my_x < x_end;            // the lane holds input pixels
+    const bool lane_out = my_x < c1;              // the lane holds output columns
+    const bool q_vec = (rw & 3u) == 0u;
+    uint32_t* sp0 = s_box + warp * 2u * kBoxRowPitch + lane * 8u;
+    uint4* ring = reinterpret_cast<uint4*>(s_box + kBoxWarps * 2u * kBoxRowPitch) + (size_t)warp * rh * 32u + lane;
+    uint32_t* out = box + ((size_t)frame * bh + y0) * bpitch + my_x;
+    const uint16_t* row_nxt = img + (size_t)y0 * w;   // next input row to fetch
+    uint32_t acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0u;
+    uint4 q[kBoxAhead];
+#pragma unroll
+    for (int k = 0; k < kBoxAhead; ++k) {
+        q[k] = box_fetch(row_nxt, w, my_x, vec_ok, lane_in && y0 + (uint32_t)k < r_end);
+        row_nxt += w;
+    }
+    uint32_t buf = 0, slot = 0;                   // slot = (r - y0) mod rh
+    for (uint32_t r0 = y0; r0 < r_end; r0 += kBoxAhead) {
+#pragma unroll
+        for (int k = 0; k < kBoxAhead; ++k) {
+            const uint32_t r = r0 + (uint32_t)k;
+            if (r >= r_end) break;
+            const uint4 cur = q[k];
+            q[k] = box_fetch(row_nxt, w, my_x, vec_ok, lane_in && r + kBoxAhead < r_end);
+            row_nxt += w;
+            ring[slot * 32u] = cur;               // row r takes the place of row r - rh (left the window last round)
+            if (++slot == rh) slot = 0;
+            box_apply<true>(acc, cur);
+            if (r + 1u >= y0 + rh) {              // the window [r - rh + 1, r] is complete
+                // exclusive prefix sums of the window sums along x
+                uint32_t e[8], tot = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    e[j] = tot;
+                    tot += acc[j];
+                }
+                uint32_t incl = tot;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += n;
+                }
+                const uint32_t base = incl - tot;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) e[j] += base;
+                uint32_t* sp = sp0 + buf * kBoxRowPitch;
+                *reinterpret_cast<uint4*>(sp) = make_uint4(e[0], e[1], e[2], e[3]);
+                *reinterpret_cast<uint4*>(sp + 4) = make_uint4(e[4], e[5], e[6], e[7]);
+                if (lane == 31u) sp[8] = incl;  // P[256]
+                const uint4 old = ring[slot * 32u];  // row r - rh + 1 leaves the window
+                __syncwarp();
+                if (lane_out) {
+                    uint32_t t[8];
+                    if (q_vec) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(sp + rw), b2 = *reinterpret_cast<const uint4*>(sp + rw + 4);
+                        t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b2.x; t[5] = b2.y; t[6] = b2.z; t[7] = b2.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) t[j] = sp[rw + j];
+                    }
+                    // columns at or beyond bw are row padding (never read); beyond the pitch nothing is stored
+                    if (my_x < bpitch) *reinterpret_cast<uint4*>(out) = make_uint4(t[0] - e[0], t[1] - e[1], t[2] - e[2], t[3] - e[3]);
+                    if (my_x + 4u < bpitch) *reinterpret_cast<uint4*>(out + 4) = make_uint4(t[4] - e[4], t[5] - e[5], t[6] - e[6], t[7] - e[7]);
+                }
+                out += bpitch;
+                buf ^= 1u;
+                box_apply<false>(acc, old);
+            }
+        }
+    }
+}
+
 // ================================================================ K2: forest traversal
 // Node table prepared for one tile plan: see HotNode (dh_types.hpp).
 __global__ void __launch_bounds__(256) plan_nodes_kernel(const NodeRec* __restrict__ nodes, HotNode* __restrict__ hot,
@@ -346,7 +474,9 @@ __device__ __noinline__ bool binarize_ieee(const NodeRec* __restrict__ nodes, in
 // record (broadcast) and nearby taps.
 // kMode 0: general rectangles, nodes through the LSU path; 1: general, nodes through the texture
 // path; 2: uniform rectangles (box-sum tile, UniNode through the texture path); 3: the same with
-// UniNode through the LSU path.
+// UniNode through the LSU path; 4 and 5: as 2 and 3, but the TMA load brings a window of the
+// box-sum image (box_image_kernel) instead of the summed-area table, so the tile needs no
+// conversion and is (sw - rw + 1)-ish wide instead of (sw + 1)-ish.
 template <int kThreads, int kMode>
 __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_kernel(const __grid_constant__ CUtensorMap sat_map,
                                                             cudaTextureObject_t hot_tex,
@@ -382,20 +512,42 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1u) : "memory");
         fence_mbar_init();
         s_nlive = 0;
-        // window of the tile's patches: [x0, x1) x [y0, y1).  Its pixel sum is < 2^32 (<= 256*256
-        // pixels), so the modular four-tap difference is zero iff every patch is background.
+    }
+    if (tid < 32u) {
+        // window of the tile's patches: [x0, x1) x [y0, y1); every patch of the tile is background
+        // (prediction.rs:567-571) iff no pixel of the window is set
         const uint32_t lastx = min(px0 + tp.tpx, g.npx) - 1u, lasty = min(py0 + tp.tpy, g.npy) - 1u;
         const uint32_t x1 = lastx * g.stride + g.sw, y1 = lasty * g.stride + g.sh;
-        const uint32_t* S = sat + (size_t)frame * (g.h + 1) * g.sat_pitch;
-        const uint32_t sum = __ldg(S + (size_t)y1 * g.sat_pitch + x1) - __ldg(S + (size_t)y0 * g.sat_pitch + x1) -
-                             __ldg(S + (size_t)y1 * g.sat_pitch + x0) + __ldg(S + (size_t)y0 * g.sat_pitch + x0);
-        s_empty = sum == 0u;
-        if (sum != 0u) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(tile_bytes) : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(tile_a),
-                "l"(&sat_map), "r"((int)ax0), "r"((int)y0), "r"((int)frame), "r"(bar_a)
-                : "memory");
+        bool any;
+        if (kMode >= 4) {
+            // covered by rw x rh rectangles of the box-sum image (the last one of a row / column
+            // is pulled back inside the window; sums are non-negative, so overlap is harmless)
+            const uint32_t nkx = (x1 - x0 + uni_rw - 1u) / uni_rw, nky = (y1 - y0 + uni_rh - 1u) / uni_rh;
+            const uint32_t* B = sat + (size_t)frame * g.box_h * g.box_pitch;
+            uint32_t acc = 0;
+            for (uint32_t i = tid; i < nkx * nky; i += 32u) {
+                const uint32_t kx = i % nkx, ky = i / nkx;
+                const uint32_t bx = min(x0 + kx * uni_rw, x1 - uni_rw), by = min(y0 + ky * uni_rh, y1 - uni_rh);
+                acc |= __ldg(B + (size_t)by * g.box_pitch + bx);
+            }
+            any = __any_sync(0xffffffffu, acc != 0u);
+        } else {
+            // the window's pixel sum is < 2^32 (<= 256*256 pixels), so the modular four-tap
+            // difference of the summed-area table is zero iff every pixel is
+            const uint32_t* S = sat + (size_t)frame * (g.h + 1) * g.sat_pitch;
+            const uint32_t sum = __ldg(S + (size_t)y1 * g.sat_pitch + x1) - __ldg(S + (size_t)y0 * g.sat_pitch + x1) -
+                                 __ldg(S + (size_t)y1 * g.sat_pitch + x0) + __ldg(S + (size_t)y0 * g.sat_pitch + x0);
+            any = sum != 0u;
+        }
+        if (tid == 0) {
+            s_empty = !any;
+            if (any) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(tile_bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(tile_a),
+                    "l"(&sat_map), "r"((int)ax0), "r"((int)y0), "r"((int)frame), "r"(bar_a)
+                    : "memory");
+            }
         }
     }
     __syncthreads();
@@ -426,7 +578,16 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
             const uint32_t gx = px0 + lx, gy = py0 + ly;
             if (gx < g.npx && gy < g.npy) {
                 const uint32_t o = org_a + ly * g.stride * tw4 + lx * g.stride * 4u;
-                const uint32_t sum = lds_u32(o + g.sh * tw4 + g.sw * 4u) - lds_u32(o + g.sw * 4u) - lds_u32(o + g.sh * tw4) + lds_u32(o);
+                uint32_t sum;
+                if (kMode >= 4) {  // the patch covered by rw x rh rectangles, the last ones pulled back inside
+                    sum = 0;
+                    for (uint32_t vy = 0; vy < g.sh; vy += uni_rh) {
+                        const uint32_t ra = o + min(vy, g.sh - uni_rh) * tw4;
+                        for (uint32_t vx = 0; vx < g.sw; vx += uni_rw) sum |= lds_u32(ra + min(vx, g.sw - uni_rw) * 4u);
+                    }
+                } else {
+                    sum = lds_u32(o + g.sh * tw4 + g.sw * 4u) - lds_u32(o + g.sw * 4u) - lds_u32(o + g.sh * tw4) + lds_u32(o);
+                }
                 ok = sum != 0u;  // background patches keep the -1 the leaf buffer was filled with
                 packed = lx | (ly << 8);
             }
@@ -443,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
     __syncthreads();
     const uint32_t nlive = s_nlive;
 
-    if (kMode >= 2 && nlive) {
+    if ((kMode == 2 || kMode == 3) && nlive) {
         // ---- uniform rectangles: turn the SAT tile into box sums in place,
         //      B[y][x] = S[y+rh][x+rw] - S[y][x+rw] - S[y+rh][x] + S[y][x]  (types.rs:317-339 for the
         //      rw x rh rectangle at (x, y)), so that a rectangle is ONE tap.  Rows go in waves of one
@@ -488,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
         if (kMode >= 2) {
             while (node >= 0) {
                 // taps, child[0], child[1], threshold * count
-                const uint4 U = kMode == 2 ? tex1Dfetch<uint4>(hot_tex, node) : __ldg(reinterpret_cast<const uint4*>(uni) + node);
+                const uint4 U = (kMode == 2 || kMode == 4) ? tex1Dfetch<uint4>(hot_tex, node) : __ldg(reinterpret_cast<const uint4*>(uni) + node);
                 const uint32_t s1 = lds_u32(o + ((U.x & 0xffffu) << 2)), s2 = lds_u32(o + ((U.x >> 16) << 2));
                 // binarize (houghforest.rs:185-193) for equal pixel counts c: avg1 - avg2 > thr  <=>
                 // (s1 - s2) / c > thr.  Single-precision filter: d = float(s1 - s2) - thr*c carries an
@@ -1476,6 +1637,40 @@ int launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cuda
     return 2;
 }
 
+// Box-sum image mode needs: rectangles no larger than 128 per side (strips of 256 input columns
+// per warp; prefix sums of 256 window sums stay well-defined) and a patch that a handful of rectangles cover
+// (the background test of a patch ORs ceil(sw/rw) * ceil(sh/rh) taps).
+bool box_image_supported(uint32_t w, uint32_t h, uint32_t sw, uint32_t sh, uint32_t rw, uint32_t rh) {
+    if (!rw || !rh || rw > 128u || rh > 128u || rw > sw || rh > sh || w < rw || h < rh) return false;
+    return ((sw + rw - 1u) / rw) * ((sh + rh - 1u) / rh) <= 64u;
+}
+
+int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, int n_sms, cudaStream_t s) {
+    const uint32_t smem = (uint32_t)kBoxWarps * (2u * kBoxRowPitch * 4u + g.rh * 512u);
+    static uint32_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(box_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    // strips: a multiple of 8 output columns each, at most 257 - rw (column c reads P[c + rw] <= P[256])
+    const uint32_t max_out = ((uint32_t)kBoxStripIn + 1u - g.rw) & ~7u;
+    const uint32_t n_strips = (g.box_w + max_out - 1u) / max_out;
+    const uint32_t strip_out = (((g.box_w + n_strips - 1u) / n_strips) + 7u) & ~7u;
+    // bands: a band re-reads the rh - 1 rows above it, so as few as possible, but enough that the
+    // warps of one launch fill the GPU once; never shorter than rh rows
+    const uint32_t ctas_per_sm = std::max<uint32_t>(1u, std::min<uint32_t>(16u, (227u * 1024u) / (smem + 1024u)));
+    const uint32_t slots = (uint32_t)n_sms * ctas_per_sm * kBoxWarps;
+    const uint32_t units = n_strips * n_frames;
+    uint32_t n_bands = std::max<uint32_t>(1u, std::min<uint32_t>(slots / units, std::max<uint32_t>(1u, g.box_h / g.rh)));
+    const uint32_t band_rows = (g.box_h + n_bands - 1u) / n_bands;
+    n_bands = (g.box_h + band_rows - 1u) / band_rows;
+    const uint32_t n_units = n_strips * n_bands * n_frames;
+    box_image_kernel<<<(n_units + kBoxWarps - 1u) / kBoxWarps, kBoxThreads, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h,
+                                                                                      g.box_pitch, strip_out, n_strips, band_rows, n_bands,
+                                                                                      n_units);
+    return 1;
+}
+
 uint32_t traverse_smem_bytes(uint32_t tw, uint32_t th, uint32_t patches_per_tile) {
     const uint32_t tile_bytes = (tw * th * 4u + 15u) & ~15u;
     return 128u + tile_bytes + 16u + ((patches_per_tile + 31u) & ~31u) * 2u + 64u;
@@ -1499,10 +1694,18 @@ static void launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b,
         cudaFuncSetAttribute(traverse_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kThreads, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kThreads, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         configured_smem = (int)tp.smem_bytes;
     }
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
-    if (f.uni && f.hot_tex)
+    if (f.uni && g.rw && f.hot_tex)
+        traverse_kernel<kThreads, 4><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh);
+    else if (f.uni && g.rw)
+        traverse_kernel<kThreads, 5><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box, b.fs, g,
+                                                                       tp, f.uni_rw, f.uni_rh);
+    else if (f.uni && f.hot_tex)
         traverse_kernel<kThreads, 2><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat,
                                                                        b.fs, g, tp, f.uni_rw, f.uni_rh);
     else if (f.uni)

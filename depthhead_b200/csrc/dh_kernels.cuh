@@ -41,13 +41,19 @@ struct Geometry {
     uint32_t sat_pitch;       // elements per SAT row (multiple of 4)
     uint32_t n_trees;
     uint32_t magic_w, magic_h;  // n / w == umulhi(n, magic_w) for n <= 20 * (w - 1), 0 = divide
+    // box-sum image mode (forests whose feature rectangles all have one size rw x rh): the front
+    // end writes B[y][x] = sum of the rw x rh rectangle at (x, y) instead of a summed-area table.
+    uint32_t rw, rh;          // 0 = summed-area-table mode
+    uint32_t box_w, box_h;    // w - rw + 1, h - rh + 1
+    uint32_t box_pitch;       // elements per row of B (multiple of 4)
     float K[9], Kinv[9];
 };
 
 struct TilePlan {
     uint32_t tpx, tpy;        // patches per tile
     uint32_t tiles_x, tiles_y;
-    uint32_t tw, th;          // SAT tile extent in elements (tw multiple of 4)
+    uint32_t tw, th;          // extent of the shared-memory tile in elements (tw multiple of 4): summed-area
+                              // table window, or box-sum image window in box-image mode
     uint32_t smem_bytes;
     uint32_t threads;
 };
@@ -73,6 +79,7 @@ struct FrameBuffers {
     const uint16_t* depth;  // [F][h][w]
     uint32_t* sat;          // [F][h+1][pitch]
     uint32_t* band_u;       // [F][bands][w+1] per-band column-sum scans of the banded SAT pass (or nullptr)
+    uint32_t* box;          // [F][box_h][box_pitch] box-sum image (box-image mode, else nullptr)
     int32_t* leaf;          // [F][T][P]
     float* p3;              // [F][P][3]
     uint8_t* gate;          // [F][P]
@@ -87,6 +94,8 @@ struct FrameBuffers {
 };
 
 int launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s);
+int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, int n_sms, cudaStream_t s);
+bool box_image_supported(uint32_t w, uint32_t h, uint32_t sw, uint32_t sh, uint32_t rw, uint32_t rh);
 void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width, cudaStream_t s);

@@ -39,7 +39,9 @@ VARIANTS = [
     {"DH_UNIFORM": "0"},                            # general 8-tap traversal on a uniform forest
     {"DH_UNIFORM": "0", "DH_TEX": "0"},
     {"DH_UNI_LDG": "1"},                            # box sums, nodes through the LSU path
-    {"DH_SAT_BANDS": "0"},                          # two-pass summed-area table
+    {"DH_SAT_BANDS": "0", "DH_BOX_IMAGE": "0"},     # two-pass summed-area table
+    {"DH_BOX_IMAGE": "0"},                          # uniform forest on the summed-area table (box sums made in the tile)
+    {"DH_BOX_IMAGE": "0", "DH_UNI_LDG": "1"},
     {"DH_TRAV_THREADS": "512"},                     # 512-thread traversal tiles
     {"DH_LANES": "1"},
     {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},
@@ -65,6 +67,40 @@ def test_kernel_variants(monkeypatch, env):
                 assert np.array_equal(out["mid_point"][i], tr.mid_point) and np.array_equal(out["rotation"][i], tr.rotation)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("sub,scale,stride,hw", [
+    ((80, 80), 0.3, 5, (480, 640)),     # the trained shape: 24x24 rectangles in 80x80 patches
+    ((80, 80), 0.3, 7, (203, 331)),     # width not a multiple of 8: scalar pixel loads, ragged strips
+    ((64, 48), 0.5, 4, (150, 296)),     # 32x24 rectangles, 2x2 taps cover a patch
+    ((40, 56), 0.13, 3, (97, 120)),     # 5x7 rectangles: 8x8 = 64 taps per background test
+    ((96, 96), 0.9, 9, (200, 264)),     # 86x86 rectangles: long ring, narrow box image
+])
+def test_box_image_shapes(ctx, sub, scale, stride, hw):
+    """box-sum image front end (box_image_kernel + traversal modes 4/5) on rectangle / patch / image
+    shapes that exercise strips, bands, the scalar load path and the tap cover of the background test"""
+    arr = synth.make_forest(seed=17, n_trees=3, max_depth=6, sub_w=sub[0], sub_h=sub[1], rect_scale=scale)
+    js = synth.forest_to_json(arr, stepwidth=stride)
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    frames = _small_frames(3, hw[0], hw[1], seed=5) if hw != (480, 640) else synth.make_frames(2, seed=5)
+    for d in frames:
+        _compare_frame(ctx, hp, of, d)
+    assert ctx.counters()["launches"] > 0
+    # a frame of isolated pixels: most tiles are background, single set pixels decide patches
+    rng = np.random.default_rng(3)
+    d = np.zeros(hw, np.uint16)
+    ys, xs = rng.integers(0, hw[0], 12), rng.integers(0, hw[1], 12)
+    d[ys, xs] = rng.integers(1, 65535, 12)
+    _compare_frame(ctx, hp, of, d)
+    # saturated frame: every rectangle sum at its maximum
+    _compare_frame(ctx, hp, of, np.full(hw, 65535, np.uint16))
+    # many frames at once: bands and strips of a batch
+    batch = np.stack([frames[i % len(frames)] for i in range(9)])
+    out = hp.predict_batch(batch, K, ctx=ctx)
+    for i, dd in enumerate(batch):
+        tr = of.predict(dd, synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+        assert np.array_equal(out["mid_point"][i], tr.mid_point) and np.array_equal(out["rotation"][i], tr.rotation)
 
 
 def test_config3_large_forest_dense_stride_vs_oracle(ctx):
