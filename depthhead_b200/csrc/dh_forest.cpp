@@ -320,8 +320,8 @@ HostForest* flatten_forest(const RawForest& raw) {
         for (const NodeRec& n : hf->nodes)
             for (int k = 0; k < 2; ++k)
                 if ((uint32_t)(n.r[k * 4 + 2] - n.r[k * 4 + 0]) != rw || (uint32_t)(n.r[k * 4 + 3] - n.r[k * 4 + 1]) != rh) rw = rh = 0;
-        // rectangle sums must fit i32 (rw*rh*65535 < 2^31) for the single-precision filter
-        if (rw && rh && rw * rh <= 32768u) {
+        // twice the difference of two rectangle sums must fit i32 (rw*rh*65535 < 2^30) for the integer node test
+        if (rw && rh && rw * rh <= 16383u) {
             hf->uniform_rw = rw;
             hf->uniform_rh = rh;
         }

@@ -432,7 +432,24 @@ __global__ void __launch_bounds__(256) plan_nodes_kernel(const NodeRec* __restri
         u.taps = (h.r1 & 0xffffu) | (h.r2 << 16);
         u.child[0] = r.child[0];
         u.child[1] = r.child[1];
-        u.thr_count = (float)__dmul_rn(r.threshold, (double)c[0]);
+        // Decision value E for d2 = 2*(s1 - s2), |s1 - s2| < 2^30 (rw*rh <= 16383 is checked at
+        // load).  The reference compares fl(fl(s1/c) - fl(s2/c)) > thr; its three roundings move
+        // the left side by < 2.2e-11 (|s/c| <= 65535, eps = 2^-53), so whenever the real numbers
+        // differ by more than that, (s1 - s2) > thr*c decides.  y = fl(thr*c) is within 1.2e-7 of
+        // thr*c for |y| < 2^30.  If y is further than 1e-3 from every integer, no integer s1 - s2
+        // comes closer than 9e-4 to thr*c (5.5e-8 after the division by c): the answer is
+        // s1 - s2 > floor(y), E = 2*floor(y) + 1 (odd: never equal to d2).  Otherwise only
+        // s1 - s2 == m = rint(y) can be a tie: E = 2*m, d2 > E decides the rest and d2 == E goes
+        // to the IEEE-division path.  NaN thresholds never pass (E = INT_MAX).
+        const double y = __dmul_rn(r.threshold, (double)c[0]);
+        int32_t E;
+        if (!(y < 1073741824.0)) E = 0x7fffffff;            // y >= 2^30 or NaN: never greater
+        else if (y <= -1073741824.0) E = -0x7fffffff;       // always greater
+        else {
+            const double m = rint(y);
+            E = fabs(__dsub_rn(y, m)) <= 1e-3 ? 2 * (int32_t)m : 2 * (int32_t)floor(y) + 1;
+        }
+        u.e2 = E;
         uni[i] = u;
     }
 }
@@ -569,7 +586,6 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
     // ---- background test (prediction.rs:567-571: mean over the whole patch > 0  <=>  sum != 0)
     const uint32_t tw4 = tp.tw * 4u;
     const uint32_t org_a = tile_a + dx * 4u;  // patch (0,0) of the tile
-    uint32_t my_valid = 0;
     for (uint32_t lp = tid; lp < ((npt + 31u) & ~31u); lp += kThreads) {
         bool ok = false;
         uint32_t packed = 0;
@@ -589,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
                     sum = lds_u32(o + g.sh * tw4 + g.sw * 4u) - lds_u32(o + g.sw * 4u) - lds_u32(o + g.sh * tw4) + lds_u32(o);
                 }
                 ok = sum != 0u;  // background patches keep the -1 the leaf buffer was filled with
-                packed = lx | (ly << 8);
+                packed = (ly * g.stride * tp.tw + lx * g.stride) | ((lx | (ly << 8)) << 16);  // origin word offset (< 65536) | patch
             }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, ok);
@@ -597,12 +613,12 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
         if ((tid & 31u) == 0 && m) basei = atomicAdd(&s_nlive, (uint32_t)__popc(m));
         basei = __shfl_sync(0xffffffffu, basei, 0);
         if (ok) {
-            sts_u16(live_a + 2u * (basei + __popc(m & ((1u << (tid & 31u)) - 1u))), packed);
-            ++my_valid;
+            sts_u32(live_a + 4u * (basei + __popc(m & ((1u << (tid & 31u)) - 1u))), packed);
         }
     }
     __syncthreads();
     const uint32_t nlive = s_nlive;
+    if (tid == 0 && nlive) atomicAdd(&fs[frame].n_valid, nlive);
 
     if ((kMode == 2 || kMode == 3) && nlive) {
         // ---- uniform rectangles: turn the SAT tile into box sums in place,
@@ -642,26 +658,22 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
     const uint32_t nl_magic = (nlive >= 2u && (unsigned long long)items * nlive < (1ull << 32)) ? (uint32_t)((1ull << 32) / nlive) + 1u : 0u;
     for (uint32_t it = tid; it < items; it += kThreads) {
         const uint32_t t = nl_magic ? __umulhi(it, nl_magic) : it / nlive;
-        const uint32_t lp = lds_u16(live_a + 2u * (it - t * nlive));
-        const uint32_t lx = lp & 0xffu, ly = lp >> 8;
-        const uint32_t o = org_a + ly * g.stride * tw4 + lx * g.stride * 4u;
+        const uint32_t lp = lds_u32(live_a + 4u * (it - t * nlive));
+        const uint32_t lx = (lp >> 16) & 0xffu, ly = lp >> 24;
+        const uint32_t o = org_a + ((lp & 0xffffu) << 2);
         int32_t node = __ldg(roots + t);
         if (kMode >= 2) {
             while (node >= 0) {
                 // taps, child[0], child[1], threshold * count
                 const uint4 U = (kMode == 2 || kMode == 4) ? tex1Dfetch<uint4>(hot_tex, node) : __ldg(reinterpret_cast<const uint4*>(uni) + node);
                 const uint32_t s1 = lds_u32(o + ((U.x & 0xffffu) << 2)), s2 = lds_u32(o + ((U.x >> 16) << 2));
-                // binarize (houghforest.rs:185-193) for equal pixel counts c: avg1 - avg2 > thr  <=>
-                // (s1 - s2) / c > thr.  Single-precision filter: d = float(s1 - s2) - thr*c carries an
-                // absolute error below (|s1 - s2| + |thr*c|) * 2^-22 + 1 (two roundings to f32, one of
-                // the subtraction, and the < 0.01 the reference's own roundings can move the exact
-                // quotient in units of 1/c), so outside that band its sign IS the reference's
-                // answer; inside it (and for NaN) the IEEE-division path decides.
-                const float nf = (float)(int32_t)(s1 - s2), tc = __uint_as_float(U.w);
-                const float d = __fsub_rn(nf, tc);
-                const float band = __fmaf_rn(__fadd_rn(fabsf(nf), fabsf(tc)), 2.384185791015625e-07f, 4.0f);
-                int32_t next = d > 0.0f ? (int)U.z : (int)U.y;
-                if (!(fabsf(d) > band)) next = binarize_ieee(nodes, node, s1, s2) ? (int)U.z : (int)U.y;
+                // binarize (houghforest.rs:185-193) for equal pixel counts c: avg1 - avg2 > thr, decided
+                // on integers.  U.w = E (plan_nodes_kernel): the answer is 2*(s1 - s2) > E, and only
+                // 2*(s1 - s2) == E (an exact tie up to the reference's own roundings, possible for
+                // even E only) takes the IEEE-division path.
+                const int32_t d2 = (int32_t)(s1 - s2) << 1, E = (int32_t)U.w;
+                int32_t next = d2 > E ? (int)U.z : (int)U.y;
+                if (d2 == E) next = binarize_ieee(nodes, node, s1, s2) ? (int)U.z : (int)U.y;
                 node = next;
                 ++visits;
             }
@@ -701,14 +713,8 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
 
     // ---- per-frame counters (measured mean depth feeds the roofline arithmetic)
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        visits += __shfl_xor_sync(0xffffffffu, visits, d);
-        my_valid += __shfl_xor_sync(0xffffffffu, my_valid, d);
-    }
-    if ((tid & 31u) == 0) {
-        if (visits) atomicAdd(&fs[frame].node_visits, (unsigned long long)visits);
-        if (my_valid) atomicAdd(&fs[frame].n_valid, my_valid);
-    }
+    for (int d = 16; d > 0; d >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, d);
+    if ((tid & 31u) == 0 && visits) atomicAdd(&fs[frame].node_visits, (unsigned long long)visits);
 }
 
 // ================================================================ K3: patch gate + coarse seed grids
@@ -764,7 +770,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers 
     __shared__ uint32_t s_grid[kPosGridCells + kRotGridCells];  // [0,400) centre, [400,8400) rotation
     __shared__ float4 s_gated[kGateThreads];                     // p3 + patch index of the CTA's gated patches
     __shared__ uint16_t s_touched[kTouchedCap];                  // rotation cells this CTA made non-zero
-    __shared__ uint32_t s_ngate, s_base, s_ntouched;
+    __shared__ uint32_t s_ngate, s_base, s_ntouched, s_next;
     const uint32_t frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31u;
     const uint32_t p = blockIdx.x * kGateThreads + tid;
     const uint32_t T = g.n_trees;
@@ -773,6 +779,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers 
     if (tid == 0) {
         s_ngate = 0;
         s_ntouched = 0;
+        s_next = 0;
     }
     __syncthreads();
 
@@ -835,7 +842,12 @@ __global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers 
     uint32_t cnt_c = 0, cnt_r = 0;
     unsigned long long nmid = 0, nrot = 0;
     const uint32_t npairs = ngate * T;
-    for (uint32_t blk = (tid >> 5) * 32u; blk < npairs; blk += kGateThreads) {
+    // batches of 32 pairs are handed out through a shared counter: their vote counts differ a lot
+    for (;;) {
+        uint32_t blk = 0;
+        if (lane == 0) blk = atomicAdd(&s_next, 32u);
+        blk = __shfl_sync(0xffffffffu, blk, 0);
+        if (blk >= npairs) break;
         const uint32_t i = blk + lane;
         uint32_t n_c = 0, n_r = 0, v0 = 0, wgt = 0;
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1673,7 +1685,7 @@ int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames
 
 uint32_t traverse_smem_bytes(uint32_t tw, uint32_t th, uint32_t patches_per_tile) {
     const uint32_t tile_bytes = (tw * th * 4u + 15u) & ~15u;
-    return 128u + tile_bytes + 16u + ((patches_per_tile + 31u) & ~31u) * 2u + 64u;
+    return 128u + tile_bytes + 16u + ((patches_per_tile + 31u) & ~31u) * 4u + 64u;
 }
 
 int traverse_kernel_attrs(int* regs, int* max_smem) {

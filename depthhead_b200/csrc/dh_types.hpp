@@ -56,13 +56,13 @@ struct alignas(16) LeafInfo {
 };
 static_assert(sizeof(LeafInfo) == 16, "LeafInfo must be 16 bytes");
 // Node of a forest whose feature rectangles all have one size (HostForest::uniform_rw/rh): the
-// traversal turns its shared-memory tile into box sums, so a rectangle is ONE tap.  16 bytes =
-// one texture fetch.  thr_count = threshold * pixel count, rounded to f32 (the filter widens its
-// band accordingly; near-ties fall back to NodeRec and IEEE division).
+// traversal reads box sums, so a rectangle is ONE tap.  16 bytes = one texture fetch.  e2 encodes
+// the threshold for the integer node test 2*(s1 - s2) > e2 (plan_nodes_kernel); an exact
+// 2*(s1 - s2) == e2 falls back to NodeRec and IEEE division.
 struct alignas(16) UniNode {
     uint32_t taps;     // off00 of rectangle 1 | off00 of rectangle 2 << 16  (y0 * tile_width + x0)
     int32_t child[2];
-    float thr_count;
+    int32_t e2;
 };
 static_assert(sizeof(UniNode) == 16, "UniNode must be 16 bytes");
 
