@@ -284,18 +284,17 @@ __global__ void __launch_bounds__(kSatBandRows * 32) sat_band_kernel(const uint1
 // read of the depth, one write of B, no intermediate table.
 //
 // The unit of work is a WARP: it owns a strip of at most 256 input columns (8 per lane, one
-// 16-byte load per lane per row, fetched four rows ahead) and sweeps down a band of rows with the
+// 16-byte load per lane per row, fetched eight rows ahead) and sweeps down a band of rows with the
 // rh-row window sums of its columns in registers: acc += row r, acc -= row r - rh + 1, the
 // departing row coming from a lane-private ring of the last rh rows in shared memory (16 bytes
 // per lane per row, no synchronisation).  Per output row the window sums are turned into
 // exclusive prefix sums along x (shuffle scan), staged in a warp-private row of shared memory, and
 // B[y][x] = P[x + rw] - P[x] goes out with 16-byte stores.  No block-level barrier; all arithmetic
 // in u32 (rw*rh*65535 < 2^31 is checked at load; prefix sums may wrap, differences are exact).
-constexpr int kBoxWarps = 2;                    // independent units per CTA
-constexpr int kBoxThreads = kBoxWarps * 32;
+constexpr int kBoxMaxWarps = 8;                 // warps per CTA = strips of one (frame, band), when there are at most 8
 constexpr int kBoxStripIn = 256;                // input columns per strip: 8 per lane
 constexpr int kBoxRowPitch = 272;               // P[0..256] + the slack the last active lane may read
-constexpr int kBoxAhead = 4;                    // rows fetched ahead
+constexpr int kBoxAhead = 8;                    // rows fetched ahead
 
 __device__ __forceinline__ uint4 box_fetch(const uint16_t* __restrict__ row, uint32_t w, uint32_t x, bool vec_ok, bool on) {
     uint4 q = make_uint4(0u, 0u, 0u, 0u);
@@ -313,13 +312,15 @@ __device__ __forceinline__ void box_apply(uint32_t acc[8], const uint4 q) {
     for (int j = 0; j < 8; ++j) acc[j] = kAdd ? acc[j] + v[j] : acc[j] - v[j];
 }
 
-__global__ void __launch_bounds__(kBoxThreads) box_image_kernel(const uint16_t* __restrict__ depth, uint32_t* __restrict__ box,
+__global__ void __launch_bounds__(kBoxMaxWarps * 32) box_image_kernel(const uint16_t* __restrict__ depth, uint32_t* __restrict__ box,
                                                                 uint32_t w, uint32_t h, uint32_t rw, uint32_t rh, uint32_t bw,
                                                                 uint32_t bh, uint32_t bpitch, uint32_t strip_out, uint32_t n_strips,
                                                                 uint32_t band_rows, uint32_t n_bands, uint32_t n_units) {
-    extern __shared__ __align__(16) uint32_t s_box[];  // [kBoxWarps][2][kBoxRowPitch] prefix rows, then [kBoxWarps][rh][32] uint4 pixel rings
+    extern __shared__ __align__(16) uint32_t s_box[];  // [warps][2][kBoxRowPitch] prefix rows, then [warps][rh][32] uint4 pixel rings
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t unit = blockIdx.x * kBoxWarps + warp;
+    const uint32_t n_warps = blockDim.x >> 5;  // the strips of one (frame, band) sit in one CTA: their reads and writes
+                                               // of a row are adjacent in memory and happen at about the same time
+    uint32_t unit = blockIdx.x * n_warps + warp;
     if (unit >= n_units) return;
     const uint32_t strip = unit % n_strips;
     unit /= n_strips;
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(kBoxThreads) box_image_kernel(const uint16_t* 
     const bool lane_out = my_x < c1;              // the lane holds output columns
     const bool q_vec = (rw & 3u) == 0u;
     uint32_t* sp0 = s_box + warp * 2u * kBoxRowPitch + lane * 8u;
-    uint4* ring = reinterpret_cast<uint4*>(s_box + kBoxWarps * 2u * kBoxRowPitch) + (size_t)warp * rh * 32u + lane;
+    uint4* ring = reinterpret_cast<uint4*>(s_box + n_warps * 2u * kBoxRowPitch) + (size_t)warp * rh * 32u + lane;
     uint32_t* out = box + ((size_t)frame * bh + y0) * bpitch + my_x;
     const uint16_t* row_nxt = img + (size_t)y0 * w;   // next input row to fetch
     uint32_t acc[8];
@@ -1658,28 +1659,30 @@ bool box_image_supported(uint32_t w, uint32_t h, uint32_t sw, uint32_t sh, uint3
 }
 
 int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, int n_sms, cudaStream_t s) {
-    const uint32_t smem = (uint32_t)kBoxWarps * (2u * kBoxRowPitch * 4u + g.rh * 512u);
+    // strips: a multiple of 8 output columns each, at most 257 - rw (column c reads P[c + rw] <= P[256])
+    const uint32_t max_out = ((uint32_t)kBoxStripIn + 1u - g.rw) & ~7u;
+    const uint32_t n_strips = (g.box_w + max_out - 1u) / max_out;
+    const uint32_t strip_out = (((g.box_w + n_strips - 1u) / n_strips) + 7u) & ~7u;
+    const uint32_t per_warp = 2u * kBoxRowPitch * 4u + g.rh * 512u;
+    uint32_t wpc = n_strips <= (uint32_t)kBoxMaxWarps ? n_strips : 2u;  // warps per CTA
+    while (wpc > 1u && wpc * per_warp > 100u * 1024u) --wpc;           // tall rectangles: long pixel rings
+    const uint32_t smem = wpc * per_warp;
     static uint32_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(box_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    // strips: a multiple of 8 output columns each, at most 257 - rw (column c reads P[c + rw] <= P[256])
-    const uint32_t max_out = ((uint32_t)kBoxStripIn + 1u - g.rw) & ~7u;
-    const uint32_t n_strips = (g.box_w + max_out - 1u) / max_out;
-    const uint32_t strip_out = (((g.box_w + n_strips - 1u) / n_strips) + 7u) & ~7u;
     // bands: a band re-reads the rh - 1 rows above it, so as few as possible, but enough that the
     // warps of one launch fill the GPU once; never shorter than rh rows
     const uint32_t ctas_per_sm = std::max<uint32_t>(1u, std::min<uint32_t>(16u, (227u * 1024u) / (smem + 1024u)));
-    const uint32_t slots = (uint32_t)n_sms * ctas_per_sm * kBoxWarps;
+    const uint32_t slots = (uint32_t)n_sms * ctas_per_sm * wpc;
     const uint32_t units = n_strips * n_frames;
     uint32_t n_bands = std::max<uint32_t>(1u, std::min<uint32_t>(slots / units, std::max<uint32_t>(1u, g.box_h / g.rh)));
     const uint32_t band_rows = (g.box_h + n_bands - 1u) / n_bands;
     n_bands = (g.box_h + band_rows - 1u) / band_rows;
     const uint32_t n_units = n_strips * n_bands * n_frames;
-    box_image_kernel<<<(n_units + kBoxWarps - 1u) / kBoxWarps, kBoxThreads, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h,
-                                                                                      g.box_pitch, strip_out, n_strips, band_rows, n_bands,
-                                                                                      n_units);
+    box_image_kernel<<<(n_units + wpc - 1u) / wpc, wpc * 32u, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h,
+                                                                        g.box_pitch, strip_out, n_strips, band_rows, n_bands, n_units);
     return 1;
 }
 
