@@ -13,6 +13,8 @@ JSON format), patch stride 5.
            the kernels run on, max over ranks)
   e2e      the same metric through the C ABI with pinned HOST buffers: every step copies its
            frames host->device and its results device->host inside the timed region
+  e2e_biwi the same frames handed over as Biwi run-length coded depth files (the database's own
+           format, src/db_reader/biwi.rs:81-103) and expanded on the GPU: the compressed bytes cross PCIe
   roofline the traversal kernel: algorithmic bytes (56 B per node visit + 16 B per patch x tree
            leaf header) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline   the C++ oracle (a restatement of the reference, NOT the Rust binary) timed on
@@ -267,6 +269,15 @@ def main():
     def step_host():
         return hp.predict_batch(host_np, K, ctx=ctx)
 
+    # the same frames as Biwi depth files in one pinned blob (encoded once, outside every timed region)
+    from depthhead_b200 import biwi
+    blob_np, offsets = biwi.pack_files([biwi.encode_depth(f) for f in frames])
+    blob_pinned = torch.from_numpy(blob_np).pin_memory()
+    blob_host = blob_pinned.numpy()
+
+    def step_biwi():
+        return biwi.predict_files(hp, blob_host, offsets, W, H, K, ctx=ctx)
+
     def timed(fn, steps, with_stages=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stage = {}
@@ -298,6 +309,7 @@ def main():
         step_device()
     for _ in range(min(args.warmup, 2)):
         step_host()
+        step_biwi()
     # keep the GPU under the same load until nvidia-smi is producing samples (untimed)
     t_wait = time.perf_counter()
     while len(sampler.lines) < 2 and time.perf_counter() - t_wait < 3.0:
@@ -305,6 +317,7 @@ def main():
     sampler.begin_region()
     ms_dev, wall_dev, _, counters, out_dev = timed(step_device, args.steps)
     ms_e2e, wall_e2e, _, _, out_host = timed(step_host, args.steps)
+    ms_biwi, wall_biwi, _, _, out_biwi = timed(step_biwi, args.steps)
     # per-stage times (and the roofline of the traversal kernel): the same steps again with the
     # pipeline serialised on one stream, CUDA events between the stages
     ctx.enable_stage_timing(True)
@@ -317,6 +330,7 @@ def main():
         step_device()
     clocks = sampler.stop()
     assert np.array_equal(out_dev["mid_point"], out_host["mid_point"]) and np.array_equal(out_dev["rotation"], out_host["rotation"])
+    assert np.array_equal(out_dev["mid_point"], out_biwi["mid_point"]) and np.array_equal(out_dev["rotation"], out_biwi["rotation"])
 
     total_frames = n * world * args.steps
     value = total_frames / (ms_dev / 1000.0)
@@ -346,8 +360,17 @@ def main():
                 "ncu_pipe_utilisation_pct": pipes,
                 "note": "algorithmic bytes (SURVEY 8d: 56 B per node visit + 16 B per evaluation) are served from "
                         "shared memory (taps) and L1/L2 (node records), not HBM, so the fraction exceeds 1; `traffic` "
-                        "is the DRAM traffic of one launch from ncu (profiles/r01_v3_summary.md); the kernel is bound "
-                        "by the latency of its dependent fetch->tap->compare chain, see DESIGN.md"}
+                        "is the DRAM traffic of one launch from ncu (profiles/); what binds the kernel is the L1TEX "
+                        "data pipe (shared-memory taps + node fetches: lsu + tex wavefronts fill it), see DESIGN.md"}
+    # the HBM-bound kernel of the step: the front end (box-sum image, or summed-area table for
+    # forests with mixed rectangle sizes) reads the depth once and writes its table once
+    fe_ms = stage.get("sat", 0.0)
+    fe_bytes_frame = W * H * 2 + (W - 24 + 1) * (H - 24 + 1) * 4
+    fe_achieved = fe_bytes_frame * counters["frames"] / (fe_ms / 1000.0) / 1e9 if fe_ms > 0 else None
+    roofline_front = {"kernel": "box_image_kernel", "bound": "hbm", "achieved": fe_achieved, "peak": peak, "unit": "GB/s",
+                      "frac": (fe_achieved / peak) if fe_achieved else None,
+                      "algorithmic_bytes_per_frame": fe_bytes_frame, "avg_launch_ms": fe_ms / launches,
+                      "note": "614400 B of depth read + 617x457 box sums x 4 B written per frame (24x24 rectangles)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -357,20 +380,24 @@ def main():
                    "forest": "%d trees, depth %d, %d nodes, %d leaves, %d votes; loaded from %s in %.1f s"
                              % (N_TREES, MAX_DEPTH, hp.n_nodes, hp.n_leaves, hp.n_votes, model_src, t_load),
                    "sharding": "frames by rank, forest replicated, no collective on the data path",
-                   "l2": "inputs (%.0f MB per step) and the summed-area scratch exceed the 126 MB L2; no flush" % (frames.nbytes / 1e6)},
+                   "l2": "inputs (%.0f MB per step) and the box-sum scratch exceed the 126 MB L2; no flush" % (frames.nbytes / 1e6)},
         "evals_per_s": counters["evals"] * world / (ms_dev / 1000.0),
         "patch_tree_evals_per_frame": counters["evals"] / max(1, counters["frames"]),
         "mean_visited_depth": counters["node_visits"] / max(1, counters["evals"]),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
                 "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": ms_e2e / args.steps,
                 "wall_ms_per_step": wall_e2e / args.steps},
+        "e2e_biwi": {"value": total_frames / (ms_biwi / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": int(offsets[-1]),
+                     "d2h_bytes_per_step": int(out_biwi.nbytes), "ms_per_step": ms_biwi / args.steps,
+                     "wall_ms_per_step": wall_biwi / args.steps, "compression": float(frames.nbytes) / float(offsets[-1]),
+                     "note": "same frames as Biwi run-length coded depth files (biwi.rs:81-103), expanded on the GPU"},
         "gpu_launches": int(counters["launches"]),
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
         "stage_timing": "separate pass of the same steps with the pipeline lanes serialised on one stream "
                         "(%.3f ms per step); the timed `value` pass overlaps chunks on %s lanes" % (ms_ser / args.steps, os.environ.get("DH_LANES", "2")),
         "wall_ms_per_step": wall_dev / args.steps,
         "work_per_step": {k: counters[k] // args.steps for k in ("frames", "valid_patches", "evals", "node_visits", "gate_patches", "hits", "centre_votes", "rot_votes", "meanshift_iters", "cube_rebuilds")},
-        "roofline": roofline, "clocks": clocks,
+        "roofline": roofline, "roofline_front_end": roofline_front, "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)

@@ -72,6 +72,11 @@ SIGNATURES = {
     "dh_ctx_synchronize": (C.c_int, [_vp]),
     "dh_predict": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, C.POINTER(dh_result)]),
     "dh_predict_batch": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, C.c_int, _vp]),
+    "dh_biwi_depth_dims": (C.c_int, [_vp, C.c_size_t, C.POINTER(_u32), C.POINTER(_u32)]),
+    "dh_biwi_decode_depth": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, C.c_int]),
+    "dh_predict_batch_biwi": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "dh_biwi_parse_cal": (C.c_int, [C.c_char_p, C.c_size_t, _vp]),
+    "dh_biwi_parse_pose": (C.c_int, [_vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "dh_predict_mask": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "dh_hough_image_raw": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "dh_ctx_enable_stage_timing": (C.c_int, [_vp, C.c_int]),

@@ -193,6 +193,39 @@ int dh_predict_batch(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint3
         c->cx->predict_batch(*f->hf, depth, n, w, h, K, depth_loc, out);
     });
 }
+int dh_biwi_depth_dims(const uint8_t* file, size_t len, uint32_t* w, uint32_t* h) {
+    return guarded([&] {
+        REQUIRE(file && w && h, "dh_biwi_depth_dims: NULL argument");
+        dh::biwi_depth_dims(file, len, w, h);
+    });
+}
+int dh_biwi_decode_depth(dh_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w, uint32_t h,
+                         uint16_t* out, int out_loc) {
+    return guarded([&] {
+        REQUIRE(c && (n == 0 || (blob && offsets && out)), "dh_biwi_decode_depth: NULL argument");
+        REQUIRE(out_loc == DH_DEPTH_HOST || out_loc == DH_DEPTH_DEVICE, "dh_biwi_decode_depth: bad out_loc");
+        c->cx->biwi_decode(blob, offsets, n, w, h, out, out_loc);
+    });
+}
+int dh_predict_batch_biwi(dh_ctx* c, const dh_forest* f, const uint8_t* blob, const uint64_t* offsets, uint32_t n,
+                          uint32_t w, uint32_t h, const float K[9], dh_result* out) {
+    return guarded([&] {
+        REQUIRE(c && f && K && (n == 0 || (blob && offsets && out)), "dh_predict_batch_biwi: NULL argument");
+        c->cx->predict_batch_biwi(*f->hf, blob, offsets, n, w, h, K, out);
+    });
+}
+int dh_biwi_parse_cal(const char* text, size_t len, float K[9]) {
+    return guarded([&] {
+        REQUIRE(text && K, "dh_biwi_parse_cal: NULL argument");
+        dh::biwi_parse_cal(text, len, K);
+    });
+}
+int dh_biwi_parse_pose(const uint8_t* file, size_t len, const float K[9], float pos3d[3], float pos2d[2], float rot[3]) {
+    return guarded([&] {
+        REQUIRE(file && K && pos3d && pos2d && rot, "dh_biwi_parse_pose: NULL argument");
+        dh::biwi_parse_pose(file, len, K, pos3d, pos2d, rot);
+    });
+}
 int dh_predict_mask(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask) {
     return guarded([&] {
         REQUIRE(c && f && depth && mask, "dh_predict_mask: NULL argument");

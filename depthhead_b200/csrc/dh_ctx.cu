@@ -106,6 +106,10 @@ Context::~Context() {
     free_scratch();
     free_forest();
     dev_free(d_counters_);
+    for (int i = 0; i < 2; ++i) dev_free(d_blob_[i]);
+    dev_free(d_offsets_);
+    dev_free(d_status_);
+    if (h_status_) cudaFreeHost(h_status_);
     dev_free(d_aux32_);
     dev_free(d_aux16_);
     dev_free(d_aux8_);
@@ -580,6 +584,104 @@ void Context::predict(const HostForest& hf, const uint16_t* depth, uint32_t w, u
 
 void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h,
                             const float K[9], int depth_loc, dh_result* out) {
+    run_batch(hf, depth, nullptr, nullptr, n, w, h, K, depth_loc, out);
+}
+
+void Context::predict_batch_biwi(const HostForest& hf, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w,
+                                 uint32_t h, const float K[9], dh_result* out) {
+    run_batch(hf, nullptr, blob, offsets, n, w, h, K, DH_DEPTH_HOST, out);
+}
+
+// Device copies of the file offsets and room for the compressed bytes of one chunk per slot.
+void Context::ensure_biwi(const uint64_t* offsets, uint32_t n, uint32_t chunk, int slots) {
+    for (uint32_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i]) throw ModelError(DH_E_ARG, "Biwi offsets are not monotone at frame " + std::to_string(i));
+        if (offsets[i] & 3u) throw ModelError(DH_E_ARG, "Biwi frame " + std::to_string(i) + " does not start at a multiple of 4 bytes");
+        if (offsets[i + 1] - offsets[i] > 0xfffffff0ull) throw ModelError(DH_E_ARG, "Biwi frame " + std::to_string(i) + " is larger than 4 GB");
+    }
+    size_t need = 0;
+    for (uint32_t f0 = 0; f0 < n; f0 += chunk) need = std::max<size_t>(need, (size_t)(offsets[std::min(n, f0 + chunk)] - offsets[f0]));
+    need += 64;  // the decode kernel reads whole 4-byte words
+    if (need > blob_cap_) {
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        DH_CUDA(cudaStreamSynchronize(copy_stream_));
+        for (int i = 0; i < 2; ++i) dev_free(d_blob_[i]);
+        blob_cap_ = need;
+    }
+    for (int i = 0; i < slots && i < 2; ++i)
+        if (!d_blob_[i]) dev_alloc(d_blob_[i], blob_cap_);
+    if ((size_t)n + 1 > biwi_frames_cap_) {
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        dev_free(d_offsets_);
+        dev_free(d_status_);
+        if (h_status_) cudaFreeHost(h_status_);
+        h_status_ = nullptr;
+        biwi_frames_cap_ = (size_t)n + 1;
+        dev_alloc(d_offsets_, biwi_frames_cap_);
+        dev_alloc(d_status_, biwi_frames_cap_);
+        DH_CUDA(cudaHostAlloc((void**)&h_status_, sizeof(uint32_t) * biwi_frames_cap_, cudaHostAllocDefault));
+    }
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "offset width");
+    DH_CUDA(cudaMemcpyAsync(d_offsets_, offsets, sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, stream_));
+}
+
+void Context::check_biwi_status(uint32_t n) {
+    DH_CUDA(cudaMemcpyAsync(h_status_, d_status_, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream_));
+    DH_CUDA(cudaStreamSynchronize(stream_));
+    for (uint32_t i = 0; i < n; ++i)
+        if (h_status_[i]) {
+            static const char* what[] = {"", "is truncated (the reference fails with UnexpectedEof, biwi.rs:90-96)",
+                                         "has a run past the last pixel (the reference panics, biwi.rs:92,97)",
+                                         "has a header that differs from the requested width x height"};
+            throw ModelError(DH_E_ARG, "Biwi frame " + std::to_string(i) + " " + what[std::min<uint32_t>(h_status_[i], 3u)]);
+        }
+}
+
+void Context::biwi_decode(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w, uint32_t h, uint16_t* out,
+                          int out_loc) {
+    begin_call();
+    have_debug_ = false;
+    if (n == 0) {
+        end_call();
+        return;
+    }
+    if ((uint64_t)w * h == 0 || (uint64_t)w * h > 0x7fffffffull) throw ModelError(DH_E_SHAPE, "Biwi frame of 0 or more than 2^31 pixels");
+    const size_t frame_px = (size_t)w * h;
+    const uint32_t chunk = std::max<uint32_t>(1u, (uint32_t)std::min<uint64_t>(n, (1ull << 30) / (frame_px * 2)));
+    ensure_biwi(offsets, n, chunk, 1);
+    uint16_t* d_out = out;
+    uint16_t* tmp = nullptr;
+    if (out_loc != DH_DEPTH_DEVICE) {
+        dev_alloc(tmp, (size_t)chunk * frame_px);
+        d_out = tmp;
+    }
+    try {
+        for (uint32_t f0 = 0; f0 < n; f0 += chunk) {
+            const uint32_t nc = std::min(chunk, n - f0);
+            uint16_t* dst = out_loc == DH_DEPTH_DEVICE ? d_out + (size_t)f0 * frame_px : d_out;
+            DH_CUDA(cudaMemcpyAsync(d_blob_[0], blob + offsets[f0], (size_t)(offsets[f0 + nc] - offsets[f0]), cudaMemcpyHostToDevice, stream_));
+            DH_CUDA(cudaMemsetAsync(dst, 0, (size_t)nc * frame_px * sizeof(uint16_t), stream_));
+            launch_biwi_decode(d_blob_[0], d_offsets_ + f0, offsets[f0], nc, w, h, dst, d_status_ + f0, stream_);
+            launches_ += 1;
+            DH_CUDA(cudaGetLastError());
+            if (out_loc != DH_DEPTH_DEVICE)
+                DH_CUDA(cudaMemcpyAsync(out + (size_t)f0 * frame_px, dst, (size_t)nc * frame_px * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream_));
+            DH_CUDA(cudaStreamSynchronize(stream_));  // d_blob_[0] (and tmp) are reused by the next chunk
+        }
+        check_biwi_status(n);
+    } catch (...) {
+        cudaStreamSynchronize(stream_);
+        dev_free(tmp);
+        end_call();
+        throw;
+    }
+    dev_free(tmp);
+    mark(-1);
+    end_call();
+}
+
+void Context::run_batch(const HostForest& hf, const uint16_t* depth, const uint8_t* blob, const uint64_t* offsets, uint32_t n,
+                        uint32_t w, uint32_t h, const float K[9], int depth_loc, dh_result* out) {
     begin_call();
     have_debug_ = false;
     if (n == 0) {
@@ -589,7 +691,9 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
     ensure_forest(hf);
     // Chunks go round-robin over the lanes.  Stage timing needs the kernels of a pass back to
     // back on one stream, so it runs single-lane.
-    const uint32_t want_chunk = pick_chunk(n, depth_loc);
+    // Biwi input: the run-length expansion is latency-bound (one thread per frame walks the run
+    // headers), so its chunks are larger: more frames in flight per launch
+    const uint32_t want_chunk = (blob && !chunk_frames_) ? std::min<uint32_t>(256u, n) : pick_chunk(n, depth_loc);
     const int n_lanes = timing_ ? 1 : (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)max_lanes_, (n + want_chunk - 1) / want_chunk));
     ensure_scratch(hf, w, h, want_chunk, K, n_lanes);
     const uint32_t iterations = hf.meanshift_iterations.load();
@@ -603,6 +707,8 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
         DH_CUDA(cudaHostAlloc((void**)&h_results_, sizeof(dh_result) * n, cudaHostAllocDefault));
         h_results_cap_ = n;
     }
+    if (depth_loc != DH_DEPTH_DEVICE) ensure_staging(2);
+    if (blob) ensure_biwi(offsets, n, F, 2);
     // fork: the other lanes (and the copy stream) start after everything already queued on the caller's stream
     DH_CUDA(cudaEventRecord(ev_fork_, stream_));
     for (int i = 1; i < n_lanes; ++i) DH_CUDA(cudaStreamWaitEvent(lanes_[i].stream, ev_fork_, 0));
@@ -614,11 +720,11 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
         run_back(L, b, nc, iterations);
         DH_CUDA(cudaMemcpyAsync(h_results_ + f0, L.results, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, L.stream));
     };
-    if (depth_loc != DH_DEPTH_DEVICE) ensure_staging(2);
     if (depth_loc == DH_DEPTH_DEVICE) {
         for (uint32_t c = 0; c < n_chunks; ++c) enqueue_chunk(c, depth + (size_t)c * F * frame_px);
     } else {
-        // double-buffered staging: the copy of chunk c+1 overlaps the kernels of chunk c
+        // double-buffered staging: the copy of chunk c+1 overlaps the kernels of chunk c.  Biwi
+        // input: the COMPRESSED bytes are copied, and the lane expands them into the staging slot.
         for (uint32_t c = 0; c < n_chunks; ++c) {
             const int slot = (int)(c & 1u);
             Lane& L = lanes_[c % (uint32_t)n_lanes];
@@ -631,14 +737,24 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
                 t1 = next_event();
                 DH_CUDA(cudaEventRecord(t0, copy_stream_));
             }
-            DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
-                                    cudaMemcpyHostToDevice, copy_stream_));
+            if (blob)
+                DH_CUDA(cudaMemcpyAsync(d_blob_[slot], blob + offsets[f0], (size_t)(offsets[f0 + nc] - offsets[f0]), cudaMemcpyHostToDevice,
+                                        copy_stream_));
+            else
+                DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
+                                        cudaMemcpyHostToDevice, copy_stream_));
             if (timing_) {
                 DH_CUDA(cudaEventRecord(t1, copy_stream_));
                 copy_marks_.push_back({t0, t1});
             }
             DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
             DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
+            if (blob) {
+                mark(DH_STAGE_H2D);  // the expansion counts as input transfer
+                DH_CUDA(cudaMemsetAsync(d_depth_[slot], 0, (size_t)nc * frame_px * sizeof(uint16_t), L.stream));
+                launch_biwi_decode(d_blob_[slot], d_offsets_ + f0, offsets[f0], nc, w, h, d_depth_[slot], d_status_ + f0, L.stream);
+                launches_ += 1;
+            }
             enqueue_chunk(c, d_depth_[slot]);
             DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
         }
@@ -652,6 +768,7 @@ void Context::predict_batch(const HostForest& hf, const uint16_t* depth, uint32_
     mark(-1);
     DH_CUDA(cudaStreamSynchronize(stream_));
     end_call();
+    if (blob) check_biwi_status(n);
     std::memcpy(out, h_results_, sizeof(dh_result) * n);
 }
 

@@ -65,6 +65,10 @@ public:
                  const float* midp_guess, const double* rot_guess, dh_result* out);
     void predict_batch(const HostForest& hf, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h,
                        const float K[9], int depth_loc, dh_result* out);
+    // Biwi run-length coded frames (biwi.rs:81-103): blob/offsets in host memory, see depthhead_cuda.h
+    void biwi_decode(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w, uint32_t h, uint16_t* out, int out_loc);
+    void predict_batch_biwi(const HostForest& hf, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w, uint32_t h,
+                            const float K[9], dh_result* out);
     void predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask);
     void hough_image_raw(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
                          uint16_t* votes);
@@ -86,6 +90,10 @@ private:
     void alloc_lane(Lane& L);
     void free_lane(Lane& L);
     void ensure_staging(int slots);
+    void ensure_biwi(const uint64_t* offsets, uint32_t n, uint32_t chunk, int slots);
+    void check_biwi_status(uint32_t n);
+    void run_batch(const HostForest& hf, const uint16_t* depth, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w,
+                   uint32_t h, const float K[9], int depth_loc, dh_result* out);
     uint32_t pick_chunk(uint32_t n_frames, int depth_loc) const;
     void free_scratch();
     TilePlan plan_tiles(const Geometry& g) const;
@@ -138,6 +146,13 @@ private:
     uint16_t* d_depth_[2] = {nullptr, nullptr};
     size_t staging_elems_ = 0;
     unsigned long long* d_counters_ = nullptr;
+    // Biwi input: compressed bytes of a chunk (two slots), file offsets, per-frame decode status
+    uint8_t* d_blob_[2] = {nullptr, nullptr};
+    size_t blob_cap_ = 0;
+    unsigned long long* d_offsets_ = nullptr;
+    uint32_t* d_status_ = nullptr;
+    uint32_t* h_status_ = nullptr;
+    size_t biwi_frames_cap_ = 0;
     uint32_t* d_aux32_ = nullptr;
     uint16_t* d_aux16_ = nullptr;
     uint8_t* d_aux8_ = nullptr;

@@ -79,4 +79,9 @@ void mat3_inverse_f32(const float k[9], float inv[9]);
 // FullArray3D::build_kernel(20, sigma) (meanshift.rs:228-252): 8000 f32, index z*400+y*20+x.
 void build_meanshift_kernel(float sigma, float* out8000);
 
+// Biwi side files (dh_biwi.cpp; src/db_reader/biwi.rs:27-86)
+void biwi_depth_dims(const uint8_t* file, size_t len, uint32_t* w, uint32_t* h);
+void biwi_parse_cal(const char* text, size_t len, float K[9]);
+void biwi_parse_pose(const uint8_t* file, size_t len, const float K[9], float pos3d[3], float pos2d[2], float rot[3]);
+
 }  // namespace dh

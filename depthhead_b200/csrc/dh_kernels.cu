@@ -1571,6 +1571,131 @@ __global__ void narrow_u16_kernel(const uint32_t* __restrict__ in, uint16_t* __r
     if (i < n) out[i] = (uint16_t)(in[i] & 0xffffu);
 }
 
+// ================================================================ Biwi run-length decode
+// read_depth (biwi.rs:81-103): [u32 w][u32 h] then, until w*h pixels are covered,
+// [u32 n_empty][u32 n_full][n_full x u16].  The position of a run header depends on every header
+// before it, so one thread has to walk them; everything else is parallel.  One CTA per frame:
+// the file is staged through shared memory in 16 KB pieces (coalesced 4-byte loads), thread 0
+// walks the headers of a piece inside shared memory (~30 cycles per run instead of a global-memory
+// round trip) and lists the runs (cut into segments of at most 512 pixels), then the warps copy
+// the segments' pixels from the staged bytes to the frame.  The frame was zeroed beforehand, so
+// empty runs cost nothing.  Damaged files set the frame's status: 1 truncated (the reference's
+// UnexpectedEof), 2 a run past the last pixel (its `unwrap` panic), 3 header is not w x h.
+constexpr int kRleThreads = 256;
+constexpr int kRlePieceWords = 4096;   // 16 KB of file per round
+constexpr int kRleSegs = 1024;         // segments listed per round
+constexpr int kRleSegPixels = 512;
+
+__global__ void __launch_bounds__(kRleThreads) biwi_decode_kernel(const uint8_t* __restrict__ blob,
+                                                                  const unsigned long long* __restrict__ offsets,
+                                                                  unsigned long long blob_base, uint32_t w, uint32_t h,
+                                                                  uint16_t* __restrict__ out, uint32_t* __restrict__ status) {
+    __shared__ __align__(16) uint32_t s_piece[kRlePieceWords + 2];
+    __shared__ uint32_t s_seg_src[kRleSegs];   // byte offset of the segment's pixels inside the file
+    __shared__ uint32_t s_seg_dst[kRleSegs];   // first pixel
+    __shared__ uint16_t s_seg_n[kRleSegs];
+    __shared__ uint32_t s_nseg, s_pos, s_p, s_err, s_done, s_run_left, s_run_src, s_run_dst;
+    const uint32_t frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned long long o0 = offsets[frame] - blob_base, o1 = offsets[frame + 1] - blob_base;
+    const uint8_t* file = blob + o0;                  // 4-byte aligned (checked on the host)
+    const uint32_t len = (uint32_t)(o1 - o0);
+    const uint32_t npx = w * h;
+    uint16_t* dst = out + (size_t)frame * npx;
+    if (tid == 0) {
+        s_err = 0;
+        s_done = 0;
+        s_pos = 8;         // byte position of the next run header
+        s_p = 0;           // pixels covered so far
+        s_run_left = 0;    // pixels of a full run still to be listed (a run longer than one round's list)
+        if (len < 8) s_err = 1;
+        else if (reinterpret_cast<const uint32_t*>(file)[0] != w || reinterpret_cast<const uint32_t*>(file)[1] != h) s_err = 3;
+        if (npx == 0) s_done = 1;
+    }
+    __syncthreads();
+    while (!s_err && !s_done) {
+        // ---- stage the piece that starts at the next header
+        const uint32_t base = s_pos & ~3u;
+        const uint32_t avail = min((uint32_t)kRlePieceWords + 2u, (len - base + 3u) / 4u);  // words we may touch (padding to 4 is readable:
+                                                                                           // the next file or the blob's tail padding)
+        for (uint32_t i = tid; i < avail; i += kRleThreads) s_piece[i] = __ldg(reinterpret_cast<const uint32_t*>(file + base) + i);
+        __syncthreads();
+        // ---- thread 0: walk the headers inside the piece.  The loop is the serial part of the
+        //      decode, so it only follows the chain (three independent shared-memory loads, two
+        //      funnel shifts for headers on odd 2-byte positions) and notes where each run's
+        //      pixels are; cutting long runs into segments happens after it.
+        if (tid == 0) {
+            uint32_t pos = s_pos, p = s_p, nseg = 0, err = 0;
+            uint32_t left = s_run_left, rsrc = s_run_src, rdst = s_run_dst;
+            const uint32_t piece_end = base + (uint32_t)kRlePieceWords * 4u;
+            for (;;) {
+                while (left && nseg < (uint32_t)kRleSegs) {  // cut the current full run into segments
+                    const uint32_t n = min(left, (uint32_t)kRleSegPixels);
+                    s_seg_src[nseg] = rsrc;
+                    s_seg_dst[nseg] = rdst;
+                    s_seg_n[nseg] = (uint16_t)n;
+                    ++nseg;
+                    rsrc += 2u * n;
+                    rdst += n;
+                    left -= n;
+                }
+                if (left || nseg >= (uint32_t)kRleSegs) break;   // list full
+                // fast path: runs that fit one segment, as long as headers stay inside the piece
+                while (p < npx && pos + 8u <= piece_end && pos + 8u <= len && nseg < (uint32_t)kRleSegs) {
+                    const uint32_t wi = (pos - base) >> 2, sh = (pos & 2u) << 3;
+                    const uint32_t w0 = s_piece[wi], w1 = s_piece[wi + 1], w2 = s_piece[wi + 2];
+                    const uint32_t ne = __funnelshift_r(w0, w1, sh), nf = __funnelshift_r(w1, w2, sh);
+                    // `it.next().unwrap()` past the last pixel panics (biwi.rs:92,97)
+                    if (ne > npx - p || nf > npx - p - ne) { err = 2; break; }
+                    if ((unsigned long long)pos + 8ull + 2ull * nf > (unsigned long long)len) { err = 1; break; }
+                    const uint32_t d0 = p + ne;
+                    p = d0 + nf;
+                    if (nf > (uint32_t)kRleSegPixels) {  // long run: the segment cutter above takes it
+                        left = nf;
+                        rsrc = pos + 8u;
+                        rdst = d0;
+                        pos += 8u + 2u * nf;
+                        break;
+                    }
+                    s_seg_src[nseg] = pos + 8u;
+                    s_seg_dst[nseg] = d0;
+                    s_seg_n[nseg] = (uint16_t)nf;
+                    nseg += nf ? 1u : 0u;
+                    pos += 8u + 2u * nf;
+                }
+                if (err || left) { if (err) break; else continue; }
+                if (p >= npx) break;                              // biwi.rs:89 `while p < width*height`
+                if (nseg >= (uint32_t)kRleSegs) break;
+                if (pos + 8u > len) { err = 1; break; }           // read_u32 hits the end of the file
+                break;                                            // next header is outside this piece
+            }
+            s_pos = pos;
+            s_p = p;
+            s_nseg = nseg;
+            s_run_left = left;
+            s_run_src = rsrc;
+            s_run_dst = rdst;
+            if (err) s_err = err;
+            else if (p >= npx && !left) s_done = 1;
+        }
+        __syncthreads();
+        // ---- the warps copy the listed segments: pixels are 2-byte aligned in the file
+        const uint32_t nseg = s_nseg;
+        for (uint32_t sgi = warp; sgi < nseg; sgi += kRleThreads / 32) {
+            const uint32_t src = s_seg_src[sgi], d0 = s_seg_dst[sgi], n = s_seg_n[sgi];
+            const uint16_t* px = reinterpret_cast<const uint16_t*>(file + src);
+            const bool staged = src >= base && src + 2u * n <= base + avail * 4u;  // whole segment inside the staged piece
+            for (uint32_t i = lane; i < n; i += 32u) {
+                uint16_t v;
+                if (staged) v = reinterpret_cast<const uint16_t*>(s_piece)[((src - base) >> 1) + i];
+                else v = __ldg(px + i);
+                dst[d0 + i] = v;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) status[frame] = s_err;
+}
+
 // ================================================================ debug: dump one accumulator cube
 __global__ void box_dump_kernel(FrameBuffers b, uint32_t frame, int which, int32_t* keys_out, uint32_t* vals_out,
                                 unsigned long long* count) {
@@ -1804,6 +1929,11 @@ void launch_counters(const FrameBuffers& b, const Geometry& g, uint32_t n_frames
                      cudaStream_t s) {
     const uint32_t blocks = (n_frames + 255) / 256;
     counters_kernel<<<blocks, 256, 0, s>>>(b.fs, n_frames, out, g.P, g.n_trees);
+}
+
+void launch_biwi_decode(const uint8_t* blob, const unsigned long long* offsets, unsigned long long blob_base, uint32_t n, uint32_t w,
+                        uint32_t h, uint16_t* out, uint32_t* status, cudaStream_t s) {
+    if (n) biwi_decode_kernel<<<n, kRleThreads, 0, s>>>(blob, offsets, blob_base, w, h, out, status);
 }
 
 void launch_box_dump(const FrameBuffers& b, uint32_t frame, int which, int32_t* keys, uint32_t* vals,

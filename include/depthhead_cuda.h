@@ -15,6 +15,10 @@
  *   src/hough/prediction.rs:259-267   struct PredictionResult                  -> dh_result
  *   src/hough/prediction.rs:850-905   predict_mask                             -> dh_predict_mask
  *   src/hough/prediction.rs:760-841   build_hough_image (votes, before blur)   -> dh_hough_image_raw
+ *   src/db_reader/biwi.rs:81-103      read_depth (run-length coded depth file)  -> dh_biwi_depth_dims,
+ *                                                                                 dh_biwi_decode_depth, dh_predict_batch_biwi
+ *   src/db_reader/biwi.rs:27-60       read_cal (depth.cal -> IntrinsicMatrix)   -> dh_biwi_parse_cal
+ *   src/db_reader/biwi.rs:63-77       read_gt (ground-truth pose file)          -> dh_biwi_parse_pose
  */
 #ifndef DEPTHHEAD_CUDA_H
 #define DEPTHHEAD_CUDA_H
@@ -124,6 +128,33 @@ int dh_predict_mask(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32
 /* build_hough_image before its gaussian blur (prediction.rs:760-841): votes[h][w] u16 to host. */
 int dh_hough_image_raw(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h,
                        const float K[9], uint16_t* votes);
+
+/* ------------------------------------------------------------------ Biwi Kinect Head Pose wire formats */
+/* read_depth (biwi.rs:81-103): u32 width, u32 height, then until width*height pixels are covered
+ * [u32 n_empty][u32 n_full][n_full x u16], all little-endian; pixels of empty runs are 0.  The
+ * compressed files of n frames are handed over as ONE blob: frame i occupies bytes
+ * [offsets[i], offsets[i+1]) (offsets: n+1 entries, each a multiple of 4; padding between files is
+ * fine), so that the COMPRESSED bytes cross PCIe and the runs are expanded on the GPU.
+ * A file the reference would fail on (truncated: UnexpectedEof; a run past the last pixel: panic)
+ * or whose header differs from w x h gives DH_E_ARG naming the first bad frame. */
+
+/* header of one file: width and height (host-only, no GPU needed) */
+int dh_biwi_depth_dims(const uint8_t* file, size_t len, uint32_t* w, uint32_t* h);
+/* Expand n frames to out[n][h][w] u16; blob and offsets in host memory; out_loc says whether `out`
+ * is host or device memory (DH_DEPTH_HOST / DH_DEPTH_DEVICE). */
+int dh_biwi_decode_depth(dh_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w, uint32_t h,
+                         uint16_t* out, int out_loc);
+/* read_depth + predict_parameter_parallel(img, K, None, None) for n frames: what
+ * examples/db_evaluate.rs:296 does per file, with the decode on the GPU. */
+int dh_predict_batch_biwi(dh_ctx* c, const dh_forest* f, const uint8_t* blob, const uint64_t* offsets, uint32_t n,
+                          uint32_t w, uint32_t h, const float K[9], dh_result* out);
+/* read_cal (biwi.rs:27-60): the first three lines of depth.cal, three numbers each (tokens
+ * matching \d+[\.\d+]* exactly as the reference's regex, so a sign is not part of a number), to
+ * a row-major 3x3 matrix.  Host-only. */
+int dh_biwi_parse_cal(const char* text, size_t len, float K[9]);
+/* read_gt (biwi.rs:63-77): six little-endian f32 (position mm, rotation), plus the position
+ * projected with K (space_to_img_coord).  Host-only. */
+int dh_biwi_parse_pose(const uint8_t* file, size_t len, const float K[9], float pos3d[3], float pos2d[2], float rot[3]);
 
 /* ------------------------------------------------------------------ measurement */
 /* Per-stage device time (CUDA events on the context's stream) of the LAST dh_predict_batch call,

@@ -94,6 +94,12 @@ def lib():
     L.orc_rect_average.argtypes = [vp, u32, u32, vp, vp, C.c_int]
     L.orc_leaf_static.argtypes = [vp, C.c_int64, vp, vp, vp]
     L.orc_num_threads.restype = C.c_int
+    L.orc_biwi_read_depth.restype = C.c_int
+    L.orc_biwi_read_depth.argtypes = [vp, u64, vp, u64, vp, vp]
+    L.orc_biwi_read_gt.restype = C.c_int
+    L.orc_biwi_read_gt.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.orc_biwi_read_cal.restype = C.c_int
+    L.orc_biwi_read_cal.argtypes = [C.c_char_p, u64, vp]
     _lib = L
     return L
 
@@ -311,3 +317,50 @@ class OracleForest:
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+# ----------------------------------------------------------------------------- Biwi wire formats
+class BiwiError(RuntimeError):
+    """code 1: UnexpectedEof / Unsupported Calibration-File, 2: panic or ParseFloatError, 3: see message"""
+
+    def __init__(self, code: int, what: str):
+        super().__init__("%s (code %d)" % (what, code))
+        self.code = code
+
+
+def biwi_read_depth(data: bytes) -> np.ndarray:
+    """read_depth (src/db_reader/biwi.rs:81-103) -> [h, w] uint16."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    if buf.size < 8:
+        raise BiwiError(1, "read_depth: UnexpectedEof in the header")
+    w, h = (int(x) for x in np.frombuffer(buf[:8].tobytes(), "<u4"))
+    npx = (w * h) & 0xFFFFFFFF
+    if npx > (1 << 28):
+        raise BiwiError(3, "read_depth: oracle refuses frames over 2^28 pixels")
+    out = np.zeros(max(npx, 1), np.uint16)
+    wo, ho = C.c_uint32(0), C.c_uint32(0)
+    rc = lib().orc_biwi_read_depth(_p(buf), buf.size, _p(out), out.size, C.byref(wo), C.byref(ho))
+    if rc:
+        raise BiwiError(rc, "read_depth: " + {1: "UnexpectedEof", 2: "run past the last pixel (panic)", 3: "buffer"}[rc])
+    return out[:npx].reshape(h, w)
+
+
+def biwi_read_gt(data: bytes, K) -> tuple:
+    """read_gt (biwi.rs:63-77) -> (pos3d[3], pos2d[2], rot[3]) float32."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    k = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
+    p3, p2, rot = np.zeros(3, np.float32), np.zeros(2, np.float32), np.zeros(3, np.float32)
+    rc = lib().orc_biwi_read_gt(_p(buf) if buf.size else None, buf.size, _p(k), _p(p3), _p(p2), _p(rot))
+    if rc:
+        raise BiwiError(rc, "read_gt: UnexpectedEof")
+    return p3, p2, rot
+
+
+def biwi_read_cal(text: str | bytes) -> np.ndarray:
+    """read_cal (biwi.rs:27-60) -> 3x3 float32."""
+    b = text.encode() if isinstance(text, str) else bytes(text)
+    K = np.zeros(9, np.float32)
+    rc = lib().orc_biwi_read_cal(b, len(b), _p(K))
+    if rc:
+        raise BiwiError(rc, "read_cal: " + {1: "Unsupported Calibration-File", 2: "ParseFloatError", 3: "fourth number on a line (panic)"}[rc])
+    return K.reshape(3, 3)

@@ -1086,4 +1086,111 @@ int orc_num_threads() {
 #endif
 }
 
+// ---------------------------------------------------------------------------- Biwi wire formats
+// src/db_reader/biwi.rs restated.  Return codes: 0 ok, 1 the reader ran out of bytes (io::Error
+// UnexpectedEof in the reference), 2 a run writes past the last pixel (`it.next().unwrap()` panics,
+// biwi.rs:92,97), 3 caller's buffer too small (not a reference condition).
+struct ByteReader {  // byteorder::ReadBytesExt over a slice, little endian
+    const uint8_t* p;
+    size_t len, pos;
+    bool u32(uint32_t* v) {
+        if (pos + 4 > len) { pos = len; return false; }
+        *v = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24);
+        pos += 4;
+        return true;
+    }
+    bool u16(uint16_t* v) {
+        if (pos + 2 > len) { pos = len; return false; }
+        *v = (uint16_t)(p[pos] | (p[pos + 1] << 8));
+        pos += 2;
+        return true;
+    }
+};
+
+// read_depth, biwi.rs:81-103
+int orc_biwi_read_depth(const uint8_t* file, uint64_t len, uint16_t* out, uint64_t cap_px, uint32_t* w_out, uint32_t* h_out) {
+    ByteReader r{file, (size_t)len, 0};
+    uint32_t width, height;
+    if (!r.u32(&width)) return 1;                       // :83
+    if (!r.u32(&height)) return 1;                      // :84
+    *w_out = width;
+    *h_out = height;
+    const uint64_t npx = (uint64_t)(uint32_t)(width * height);  // `(width * height) as usize`: u32 product (:89)
+    if (npx > cap_px) return 3;
+    for (uint64_t i = 0; i < npx; ++i) out[i] = 0;      // DepthImage::new (:86)
+    uint64_t p = 0, it = 0;                             // it: pixels_mut() iterator position
+    while (p < npx) {                                   // :89
+        uint32_t num_empty, num_nonempty;
+        if (!r.u32(&num_empty)) return 1;               // :90
+        for (uint32_t k = 0; k < num_empty; ++k) {      // :91-93
+            if (it >= npx) return 2;
+            out[it++] = 0;
+        }
+        if (!r.u32(&num_nonempty)) return 1;            // :94
+        for (uint32_t k = 0; k < num_nonempty; ++k) {   // :95-98
+            uint16_t v;
+            if (!r.u16(&v)) return 1;
+            if (it >= npx) return 2;
+            out[it++] = v;
+        }
+        p += (uint64_t)num_empty + (uint64_t)num_nonempty;  // :99
+    }
+    return 0;
+}
+
+// read_gt, biwi.rs:63-77 (+ space_to_img_coord, types.rs:424-428)
+int orc_biwi_read_gt(const uint8_t* file, uint64_t len, const float* K, float* pos3d, float* pos2d, float* rot) {
+    ByteReader r{file, (size_t)len, 0};
+    float res[6];
+    for (int i = 0; i < 6; ++i) {
+        uint32_t u;
+        if (!r.u32(&u)) return 1;
+        std::memcpy(&res[i], &u, 4);
+    }
+    Intrinsic k;
+    std::memcpy(k.k, K, sizeof(float) * 9);
+    const float p3[3] = {res[0], res[1], res[2]};
+    float p2[2];
+    space_to_img_coord(k, p3, p2);
+    for (int i = 0; i < 3; ++i) {
+        pos3d[i] = res[i];
+        rot[i] = res[3 + i];
+    }
+    pos2d[0] = p2[0];
+    pos2d[1] = p2[1];
+    return 0;
+}
+
+// read_cal, biwi.rs:27-60.  Return: 0 ok, 1 "Unsupported Calibration-File", 2 ParseFloatError,
+// 3 a fourth match on a line (index out of bounds panic at :45).
+int orc_biwi_read_cal(const char* text, uint64_t len, float* K) {
+    auto digit = [](char c) { return c >= '0' && c <= '9'; };
+    size_t pos = 0;
+    for (int j = 0; j < 3; ++j) {
+        size_t e = pos;
+        while (e < len && text[e] != '\n') ++e;          // read_line
+        int found = 0;
+        size_t i = pos;
+        while (i < e) {                                  // FLOAT.captures_iter: (\d+[\.\d+]*)
+            if (!digit(text[i])) { ++i; continue; }
+            size_t k = i;
+            while (k < e && digit(text[k])) ++k;
+            while (k < e && (digit(text[k]) || text[k] == '.' || text[k] == '+')) ++k;
+            if (found == 3) return 3;                    // res[j][3] = ..  (:45)
+            // f32::from_str: digits [ '.' digits ] for a token made of these characters
+            std::string tok(text + i, k - i);
+            size_t d = 0;
+            while (d < tok.size() && digit(tok[d])) ++d;
+            if (d < tok.size() && tok[d] == '.') { ++d; while (d < tok.size() && digit(tok[d])) ++d; }
+            if (d != tok.size()) return 2;
+            K[j * 3 + found] = strtof(tok.c_str(), nullptr);
+            ++found;
+            i = k;
+        }
+        if (found != 3) return 1;                        // :53-55
+        pos = e < len ? e + 1 : len;
+    }
+    return 0;
+}
+
 }  // extern "C"
