@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
 // non-zero cells are then added to the frame's grids in global memory.  Everything that is
 // constant per leaf (valtoadd, spread gates) was precomputed by leaf_gate_kernel.
 constexpr int kGateThreads = 256;
-constexpr int kTouchedCap = 4096;
+constexpr int kTouchedCap = 1024;
 
 // 2-D projection of one centre vote onto the 20x20 seed grid (prediction.rs:661-675)
 __device__ __forceinline__ uint32_t coarse_pos_cell(const Geometry& g, float nx, float ny, float nz) {
@@ -758,6 +758,16 @@ __device__ __forceinline__ uint32_t flat_owner(uint32_t start, uint32_t v) {
     }
     return lo;
 }
+// Votes of 32 patch x tree pairs (one per lane) spread evenly over the lanes of the warp: in the
+// warp-wide numbering, lane l's pair owns votes [start_l, start_l + n_l).  The pairs that have votes
+// are compacted, in lane order, into warp-private slots of shared memory (32 bytes: start, first
+// vote, weight, patch centre); a window of 32 votes then finds its owners with one warp-wide OR:
+// every pair whose first vote falls into the window sets that bit, and vote j belongs to slot
+// (pairs that began before the window) + popc(bits <= j) - 1.
+struct alignas(16) PairSlot {
+    uint4 a;    // start, first vote of the leaf, weight, unused
+    float4 h;   // p3 (prediction.rs:554) + patch index
+};
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -767,10 +777,41 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane) {
     return x;
 }
 
+// Calls body(vote index, weight, p3) once per vote of the warp's 32 pairs, 32 votes at a time.
+// n: votes of this lane's pair (0 = none), v0: its first vote.  All 32 lanes must call.
+template <typename Body>
+__device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t wgt, const float4 h, PairSlot* slots,
+                                              uint32_t lane, Body&& body) {
+    const uint32_t has = __ballot_sync(0xffffffffu, n > 0u);
+    if (!has) return;
+    const uint32_t incl = warp_incl_scan(n, lane), start = incl - n;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();  // the previous call's readers are done with the slots
+    if (n > 0u) {
+        PairSlot* mine = slots + __popc(has & ((1u << lane) - 1u));
+        mine->a = make_uint4(start, v0, wgt, 0u);
+        mine->h = h;
+    }
+    __syncwarp();
+    uint32_t before = 0;  // pairs whose votes begin before the window
+    for (uint32_t vb = 0; vb < total; vb += 32u) {
+        const uint32_t rel = start - vb;
+        const uint32_t begins = __reduce_or_sync(0xffffffffu, (n > 0u && rel < 32u) ? (1u << rel) : 0u);
+        const uint32_t k = before + (uint32_t)__popc(begins & (0xffffffffu >> (31u - lane))) - 1u;
+        before += (uint32_t)__popc(begins);
+        if (vb + lane < total) {
+            const uint4 a = slots[k].a;
+            const float4 c = slots[k].h;
+            body(a.y + (vb + lane - a.x), a.z, c);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers b, Geometry g, ForestDev f) {
     __shared__ uint32_t s_grid[kPosGridCells + kRotGridCells];  // [0,400) centre, [400,8400) rotation
     __shared__ float4 s_gated[kGateThreads];                     // p3 + patch index of the CTA's gated patches
     __shared__ uint16_t s_touched[kTouchedCap];                  // rotation cells this CTA made non-zero
+    __shared__ PairSlot s_slots[kGateThreads / 32][32];         // vote spreading, one set per warp
     __shared__ uint32_t s_ngate, s_base, s_ntouched, s_next;
     const uint32_t frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31u;
     const uint32_t p = blockIdx.x * kGateThreads + tid;
@@ -835,11 +876,8 @@ __global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers 
     if (tid < ngate) b.gated[(size_t)frame * g.P + s_base + tid] = s_gated[tid];
 
     // ---- phase B: pair = (tree, gated patch), neighbouring lanes = neighbouring gated patches.
-    // A warp takes 32 pairs at a time and spreads their votes evenly over its lanes (flat_owner),
-    // so leaves with few, many or no votes cost the same per vote.  Consecutive centre votes of a
-    // lane mostly fall into the same 2-D cell, so equal cells are merged in a register before the
-    // shared atomic.
-    uint32_t cur = 0xffffffffu, acc = 0;
+    // A warp takes 32 pairs at a time and spreads their votes evenly over its lanes (for_each_vote),
+    // so leaves with few, many or no votes cost the same per vote.
     uint32_t cnt_c = 0, cnt_r = 0;
     unsigned long long nmid = 0, nrot = 0;
     const uint32_t npairs = ngate * T;
@@ -864,52 +902,22 @@ __global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers 
                 if (li.flags & kLeafRotOk) { n_r = li.n_votes; ++cnt_r; nrot += li.n_votes; }
             }
         }
-        {   // centre votes -> 20x20 grid
-            const uint32_t incl = warp_incl_scan(n_c, lane), start = incl - n_c;
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            for (uint32_t vb = 0; vb < total; vb += 32u) {
-                const uint32_t v = min(vb + lane, total - 1u);
-                const uint32_t own = flat_owner(start, v);
-                const uint32_t k = v - __shfl_sync(0xffffffffu, start, own);
-                const uint32_t ov0 = __shfl_sync(0xffffffffu, v0, own), ow = __shfl_sync(0xffffffffu, wgt, own);
-                const float px = __shfl_sync(0xffffffffu, h.x, own), py = __shfl_sync(0xffffffffu, h.y, own),
-                            pz = __shfl_sync(0xffffffffu, h.z, own);
-                if (vb + lane < total) {
-                    const float4 o = __ldg(f.offsets + ov0 + k);
-                    // np = p3 - offset (prediction.rs:647); np.z < 0 is skipped (:650)
-                    const float nx = __fsub_rn(px, o.x), ny = __fsub_rn(py, o.y), nz = __fsub_rn(pz, o.z);
-                    if (!(nz < 0.0f)) {
-                        const uint32_t cell = coarse_pos_cell(g, nx, ny, nz);
-                        if (cell == cur) {
-                            acc += ow;
-                        } else {
-                            if (acc) atomicAdd(&s_grid[cur], acc);
-                            cur = cell;
-                            acc = ow;
-                        }
-                    }
-                }
+        // centre votes -> 20x20 grid
+        for_each_vote(n_c, v0, wgt, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, const float4& c) {
+            const float4 o = __ldg(f.offsets + vote);
+            // np = p3 - offset (prediction.rs:647); np.z < 0 is skipped (:650)
+            const float nx = __fsub_rn(c.x, o.x), ny = __fsub_rn(c.y, o.y), nz = __fsub_rn(c.z, o.z);
+            if (!(nz < 0.0f)) atomicAdd(&s_grid[coarse_pos_cell(g, nx, ny, nz)], ow);
+        });
+        // rotation votes -> 20^3 grid; rough = r * 20 / 120 per axis (prediction.rs:630-636), static per vote
+        for_each_vote(n_r, v0, wgt, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, const float4&) {
+            const uint32_t cell = __ldg(f.rot_coarse + vote);
+            if (atomicAdd(&s_grid[kPosGridCells + cell], ow) == 0u) {
+                const uint32_t slot = atomicAdd(&s_ntouched, 1u);
+                if (slot < (uint32_t)kTouchedCap) s_touched[slot] = (uint16_t)cell;
             }
-        }
-        {   // rotation votes -> 20^3 grid; rough = r * 20 / 120 per axis (prediction.rs:630-636), static per vote
-            const uint32_t incl = warp_incl_scan(n_r, lane), start = incl - n_r;
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            for (uint32_t vb = 0; vb < total; vb += 32u) {
-                const uint32_t v = min(vb + lane, total - 1u);
-                const uint32_t own = flat_owner(start, v);
-                const uint32_t k = v - __shfl_sync(0xffffffffu, start, own);
-                const uint32_t ov0 = __shfl_sync(0xffffffffu, v0, own), ow = __shfl_sync(0xffffffffu, wgt, own);
-                if (vb + lane < total) {
-                    const uint32_t cell = __ldg(f.rot_coarse + ov0 + k);
-                    if (atomicAdd(&s_grid[kPosGridCells + cell], ow) == 0u) {
-                        const uint32_t slot = atomicAdd(&s_ntouched, 1u);
-                        if (slot < (uint32_t)kTouchedCap) s_touched[slot] = (uint16_t)cell;
-                    }
-                }
-            }
-        }
+        });
     }
-    if (acc) atomicAdd(&s_grid[cur], acc);
     // per-frame counters, one atomic per warp
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
