@@ -312,6 +312,10 @@ __device__ __forceinline__ void box_apply(uint32_t acc[8], const uint4 q) {
     for (int j = 0; j < 8; ++j) acc[j] = kAdd ? acc[j] + v[j] : acc[j] - v[j];
 }
 
+// kWhole: rw is a multiple of 8, i.e. a rectangle row is a suffix of one lane's 8 columns, rw/8 - 1
+// whole lanes and a prefix of one more lane: B comes straight out of shuffles, without the prefix
+// sums over the whole warp and their trip through shared memory.
+template <bool kWhole>
 __global__ void __launch_bounds__(kBoxMaxWarps * 32) box_image_kernel(const uint16_t* __restrict__ depth, uint32_t* __restrict__ box,
                                                                 uint32_t w, uint32_t h, uint32_t rw, uint32_t rh, uint32_t bw,
                                                                 uint32_t bh, uint32_t bpitch, uint32_t strip_out, uint32_t n_strips,
@@ -362,40 +366,56 @@ __global__ void __launch_bounds__(kBoxMaxWarps * 32) box_image_kernel(const uint
             if (++slot == rh) slot = 0;
             box_apply<true>(acc, cur);
             if (r + 1u >= y0 + rh) {              // the window [r - rh + 1, r] is complete
-                // exclusive prefix sums of the window sums along x
+                const uint4 old = ring[slot * 32u];  // row r - rh + 1 leaves the window
+                // exclusive prefix sums of the lane's 8 window sums
                 uint32_t e[8], tot = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     e[j] = tot;
                     tot += acc[j];
                 }
-                uint32_t incl = tot;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= (uint32_t)d) incl += n;
-                }
-                const uint32_t base = incl - tot;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) e[j] += base;
-                uint32_t* sp = sp0 + buf * kBoxRowPitch;
-                *reinterpret_cast<uint4*>(sp) = make_uint4(e[0], e[1], e[2], e[3]);
-                *reinterpret_cast<uint4*>(sp + 4) = make_uint4(e[4], e[5], e[6], e[7]);
-                if (lane == 31u) sp[8] = incl;  // P[256]
-                const uint4 old = ring[slot * 32u];  // row r - rh + 1 leaves the window
-                __syncwarp();
-                if (lane_out) {
+                if (kWhole) {
+                    // B[8l + j] = (T_l - e_l[j]) + T_{l+1} + .. + T_{l+k-1} + e_{l+k}[j],  k = rw / 8
+                    const uint32_t k = rw >> 3;
+                    uint32_t whole = tot;
+                    for (uint32_t i = 1; i < k; ++i) whole += __shfl_down_sync(0xffffffffu, tot, i);
                     uint32_t t[8];
-                    if (q_vec) {
-                        const uint4 a = *reinterpret_cast<const uint4*>(sp + rw), b2 = *reinterpret_cast<const uint4*>(sp + rw + 4);
-                        t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b2.x; t[5] = b2.y; t[6] = b2.z; t[7] = b2.w;
-                    } else {
+                    t[0] = whole;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) t[j] = sp[rw + j];
+                    for (int j = 1; j < 8; ++j) t[j] = whole - e[j] + __shfl_down_sync(0xffffffffu, e[j], k);
+                    if (lane_out) {
+                        // columns at or beyond bw are row padding (never read); beyond the pitch nothing is stored
+                        if (my_x < bpitch) *reinterpret_cast<uint4*>(out) = make_uint4(t[0], t[1], t[2], t[3]);
+                        if (my_x + 4u < bpitch) *reinterpret_cast<uint4*>(out + 4) = make_uint4(t[4], t[5], t[6], t[7]);
                     }
-                    // columns at or beyond bw are row padding (never read); beyond the pitch nothing is stored
-                    if (my_x < bpitch) *reinterpret_cast<uint4*>(out) = make_uint4(t[0] - e[0], t[1] - e[1], t[2] - e[2], t[3] - e[3]);
-                    if (my_x + 4u < bpitch) *reinterpret_cast<uint4*>(out + 4) = make_uint4(t[4] - e[4], t[5] - e[5], t[6] - e[6], t[7] - e[7]);
+                } else {
+                    // general width: prefix sums over the whole warp, staged in shared memory
+                    uint32_t incl = tot;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= (uint32_t)d) incl += n;
+                    }
+                    const uint32_t base = incl - tot;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) e[j] += base;
+                    uint32_t* sp = sp0 + buf * kBoxRowPitch;
+                    *reinterpret_cast<uint4*>(sp) = make_uint4(e[0], e[1], e[2], e[3]);
+                    *reinterpret_cast<uint4*>(sp + 4) = make_uint4(e[4], e[5], e[6], e[7]);
+                    if (lane == 31u) sp[8] = incl;  // P[256]
+                    __syncwarp();
+                    if (lane_out) {
+                        uint32_t t[8];
+                        if (q_vec) {
+                            const uint4 a = *reinterpret_cast<const uint4*>(sp + rw), b2 = *reinterpret_cast<const uint4*>(sp + rw + 4);
+                            t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b2.x; t[5] = b2.y; t[6] = b2.z; t[7] = b2.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) t[j] = sp[rw + j];
+                        }
+                        if (my_x < bpitch) *reinterpret_cast<uint4*>(out) = make_uint4(t[0] - e[0], t[1] - e[1], t[2] - e[2], t[3] - e[3]);
+                        if (my_x + 4u < bpitch) *reinterpret_cast<uint4*>(out + 4) = make_uint4(t[4] - e[4], t[5] - e[5], t[6] - e[6], t[7] - e[7]);
+                    }
                 }
                 out += bpitch;
                 buf ^= 1u;
@@ -1802,7 +1822,8 @@ int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames
     const uint32_t smem = wpc * per_warp;
     static uint32_t configured = 0;
     if (smem > configured) {
-        cudaFuncSetAttribute(box_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(box_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(box_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     // bands: a band re-reads the rh - 1 rows above it, so as few as possible, but enough that the
@@ -1814,8 +1835,13 @@ int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames
     const uint32_t band_rows = (g.box_h + n_bands - 1u) / n_bands;
     n_bands = (g.box_h + band_rows - 1u) / band_rows;
     const uint32_t n_units = n_strips * n_bands * n_frames;
-    box_image_kernel<<<(n_units + wpc - 1u) / wpc, wpc * 32u, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h,
-                                                                        g.box_pitch, strip_out, n_strips, band_rows, n_bands, n_units);
+    static const bool allow_whole = !(std::getenv("DH_BOX_WHOLE") && std::atoi(std::getenv("DH_BOX_WHOLE")) == 0);
+    if ((g.rw & 7u) == 0u && allow_whole)
+        box_image_kernel<true><<<(n_units + wpc - 1u) / wpc, wpc * 32u, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h,
+                                                                                  g.box_pitch, strip_out, n_strips, band_rows, n_bands, n_units);
+    else
+        box_image_kernel<false><<<(n_units + wpc - 1u) / wpc, wpc * 32u, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h,
+                                                                                   g.box_pitch, strip_out, n_strips, band_rows, n_bands, n_units);
     return 1;
 }
 
