@@ -37,6 +37,15 @@ extern "C" {
                         k: *const f32, depth_loc: c_int, out: *mut DhResult) -> c_int;
     fn dh_predict_mask(c: *mut DhCtx, f: *const DhForest, depth: *const u16, w: u32, h: u32,
                        mask: *mut u8) -> c_int;
+    // Biwi wire formats (src/db_reader/biwi.rs:27-103)
+    fn dh_biwi_depth_dims(file: *const u8, len: usize, w: *mut u32, h: *mut u32) -> c_int;
+    fn dh_biwi_decode_depth(c: *mut DhCtx, blob: *const u8, offsets: *const u64, n: u32, w: u32, h: u32,
+                            out: *mut u16, out_loc: c_int) -> c_int;
+    fn dh_predict_batch_biwi(c: *mut DhCtx, f: *const DhForest, blob: *const u8, offsets: *const u64, n: u32,
+                             w: u32, h: u32, k: *const f32, out: *mut DhResult) -> c_int;
+    fn dh_biwi_parse_cal(text: *const c_char, len: usize, k: *mut f32) -> c_int;
+    fn dh_biwi_parse_pose(file: *const u8, len: usize, k: *const f32, pos3d: *mut f32, pos2d: *mut f32,
+                          rot: *mut f32) -> c_int;
 }
 
 #[derive(Debug)]
@@ -125,4 +134,61 @@ impl HoughPrediction {
 }
 impl Drop for HoughPrediction {
     fn drop(&mut self) { unsafe { dh_ctx_free(self.ctx); dh_forest_free(self.forest); } }
+}
+
+/// src/db_reader/biwi.rs: the three file formats on the way to the prediction path.
+pub mod biwi {
+    use super::*;
+    /// Compressed depth files of one sequence, packed for the GPU: every file starts at a multiple
+    /// of 16 bytes of `blob`; `offsets` has one more entry than there are files.
+    pub struct PackedFiles { pub blob: Vec<u8>, pub offsets: Vec<u64>, pub width: u32, pub height: u32 }
+    impl PackedFiles {
+        pub fn new(files: &[Vec<u8>]) -> Result<Self, Error> {
+            let (mut w, mut h) = (0u32, 0u32);
+            if let Some(first) = files.first() {
+                check(unsafe { dh_biwi_depth_dims(first.as_ptr(), first.len(), &mut w, &mut h) })?;
+            }
+            let (mut blob, mut offsets) = (Vec::new(), Vec::with_capacity(files.len() + 1));
+            for f in files {
+                offsets.push(blob.len() as u64);
+                blob.extend_from_slice(f);
+                while blob.len() % 16 != 0 { blob.push(0); }
+            }
+            offsets.push(blob.len() as u64);
+            blob.extend_from_slice(&[0u8; 16]);
+            Ok(PackedFiles { blob, offsets, width: w, height: h })
+        }
+    }
+    /// read_cal (biwi.rs:27-60)
+    pub fn read_cal(text: &str) -> Result<IntrinsicMatrix, Error> {
+        let mut k = [[0f32; 3]; 3];
+        check(unsafe { dh_biwi_parse_cal(text.as_ptr() as *const c_char, text.len(), k.as_mut_ptr() as *mut f32) })?;
+        Ok(IntrinsicMatrix(k))
+    }
+    /// read_gt (biwi.rs:63-77): (pos3d, pos2d, rot)
+    pub fn read_gt(file: &[u8], k: &IntrinsicMatrix) -> Result<([f32; 3], [f32; 2], [f32; 3]), Error> {
+        let (mut p3, mut p2, mut rot) = ([0f32; 3], [0f32; 2], [0f32; 3]);
+        check(unsafe { dh_biwi_parse_pose(file.as_ptr(), file.len(), k.0.as_ptr() as *const f32, p3.as_mut_ptr(),
+                                          p2.as_mut_ptr(), rot.as_mut_ptr()) })?;
+        Ok((p3, p2, rot))
+    }
+    impl HoughPrediction {
+        /// read_depth (biwi.rs:81-103) for every file, expanded on the GPU: n images back to back
+        pub fn read_depth(&self, files: &PackedFiles) -> Result<Vec<u16>, Error> {
+            let n = (files.offsets.len() - 1) as u32;
+            let mut out = vec![0u16; n as usize * files.width as usize * files.height as usize];
+            check(unsafe { dh_biwi_decode_depth(self.ctx, files.blob.as_ptr(), files.offsets.as_ptr(), n, files.width,
+                                                files.height, out.as_mut_ptr(), 0 /* DH_DEPTH_HOST */) })?;
+            Ok(out)
+        }
+        /// what examples/db_evaluate.rs:296 does per file — read_depth + predict_parameter(img, K, None,
+        /// None) — for a whole sequence, the compressed bytes crossing PCIe
+        pub fn predict_files(&self, files: &PackedFiles, k: &IntrinsicMatrix) -> Result<Vec<DhResult>, Error> {
+            let n = (files.offsets.len() - 1) as u32;
+            let mut out = vec![DhResult::default(); n as usize];
+            check(unsafe { dh_predict_batch_biwi(self.ctx, self.forest, files.blob.as_ptr(), files.offsets.as_ptr(), n,
+                                                 files.width, files.height, k.0.as_ptr() as *const f32, out.as_mut_ptr()) })?;
+            Ok(out)
+        }
+    }
 }
