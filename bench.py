@@ -329,6 +329,18 @@ def main():
     while len(sampler.lines) - sampler.mark < 8 and time.perf_counter() - t_wait < 2.0:
         step_device()
     clocks = sampler.stop()
+    # the reference's live use (examples/live_prediction.rs:76,86): ONE frame per call, host buffer in,
+    # result out, previous result as the next seed — wall-clock latency of dh_predict
+    lat = []
+    res = hp.predict_parameter_parallel(host_np[0], K, ctx=ctx)
+    for i in range(60):
+        f = host_np[i % n]
+        t0 = time.perf_counter()
+        res = hp.predict_parameter_parallel(f, K, res.mid_point, res.rotation, ctx=ctx)
+        lat.append((time.perf_counter() - t0) * 1000.0)
+    lat = sorted(lat[10:])
+    single = {"median_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "calls": len(lat),
+              "note": "dh_predict wall clock: one 640x480 host frame in, pose out, seeded with the previous pose"}
     assert np.array_equal(out_dev["mid_point"], out_host["mid_point"]) and np.array_equal(out_dev["rotation"], out_host["rotation"])
     assert np.array_equal(out_dev["mid_point"], out_biwi["mid_point"]) and np.array_equal(out_dev["rotation"], out_biwi["rotation"])
 
@@ -391,6 +403,7 @@ def main():
                      "d2h_bytes_per_step": int(out_biwi.nbytes), "ms_per_step": ms_biwi / args.steps,
                      "wall_ms_per_step": wall_biwi / args.steps, "compression": float(frames.nbytes) / float(offsets[-1]),
                      "note": "same frames as Biwi run-length coded depth files (biwi.rs:81-103), expanded on the GPU"},
+        "single_frame_latency": single,
         "gpu_launches": int(counters["launches"]),
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
         "stage_timing": "separate pass of the same steps with the pipeline lanes serialised on one stream "
