@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdepthhead_cuda.so")
-SOURCES = ["dh_kernels.cu", "dh_ctx.cu", "dh_capi.cu", "dh_forest.cpp", "dh_biwi.cpp"]
+SOURCES = ["dh_kernels.cu", "dh_ctx.cu", "dh_capi.cu", "dh_forest.cpp", "dh_biwi.cpp", "dh_train.cu"]
 HEADERS = ["dh_kernels.cuh", "dh_ctx.hpp", "dh_forest.hpp", "dh_json.hpp", "dh_types.hpp",
            os.path.join("..", "..", "include", "depthhead_cuda.h")]
 

@@ -37,6 +37,16 @@ RESULT_DTYPE = np.dtype([("mid_point", np.float32, 3), ("_pad", np.uint32), ("ro
 assert RESULT_DTYPE.itemsize == C.sizeof(dh_result) == 56
 
 
+class dh_split_stats(C.Structure):
+    _fields_ = [("n", C.c_uint32 * 2), ("n_pos", C.c_uint32 * 2), ("det_off", C.c_double * 2), ("det_rot", C.c_double * 2),
+                ("impurity", C.c_double)]
+
+
+SPLIT_DTYPE = np.dtype([("n", np.uint32, 2), ("n_pos", np.uint32, 2), ("det_off", np.float64, 2), ("det_rot", np.float64, 2),
+                        ("impurity", np.float64)], align=True)
+assert SPLIT_DTYPE.itemsize == C.sizeof(dh_split_stats) == 56
+
+
 class dh_forest_arrays(C.Structure):
     _fields_ = [("stepwidth", C.c_uint32), ("subimage_width", C.c_uint32), ("subimage_height", C.c_uint32),
                 ("meanshift_iterations", C.c_uint32), ("gaussian_sigma", C.c_float), ("n_trees", C.c_int32),
@@ -77,6 +87,10 @@ SIGNATURES = {
     "dh_predict_batch_biwi": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "dh_biwi_parse_cal": (C.c_int, [C.c_char_p, C.c_size_t, _vp]),
     "dh_biwi_parse_pose": (C.c_int, [_vp, C.c_size_t, _vp, _vp, _vp, _vp]),
+    "dh_trainset_create": (C.c_int, [_vp, _vp, _u64, _u32, _u32, _u32, _u32, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "dh_trainset_free": (None, [_vp]),
+    "dh_train_score_level": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _u32, _u64, C.c_double, _vp]),
+    "dh_train_split_level": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dh_predict_mask": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "dh_hough_image_raw": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "dh_ctx_enable_stage_timing": (C.c_int, [_vp, C.c_int]),

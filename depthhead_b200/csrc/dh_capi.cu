@@ -226,6 +226,40 @@ int dh_biwi_parse_pose(const uint8_t* file, size_t len, const float K[9], float 
         dh::biwi_parse_pose(file, len, K, pos3d, pos2d, rot);
     });
 }
+struct dh_trainset {
+    dh::TrainSet* ts;
+};
+int dh_trainset_create(dh_ctx* c, const uint16_t* patches, uint64_t n, uint32_t sw, uint32_t sh, uint32_t rw, uint32_t rh,
+                       const uint8_t* is_object, const float* offsets, const double* rotations, dh_trainset** out) {
+    return guarded([&] {
+        REQUIRE(c && patches && is_object && offsets && rotations && out, "dh_trainset_create: NULL argument");
+        *out = nullptr;
+        dh::TrainSet* ts = c->cx->trainset_create(patches, n, sw, sh, rw, rh, is_object, offsets, rotations);
+        *out = new dh_trainset{ts};
+    });
+}
+void dh_trainset_free(dh_trainset* t) {
+    if (!t) return;
+    dh::trainset_free(t->ts);
+    delete t;
+}
+int dh_train_score_level(dh_ctx* c, const dh_trainset* t, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
+                         const int32_t* cand_rects, const double* cand_thr, uint32_t m, uint64_t depth, double steepness,
+                         dh_split_stats* out) {
+    return guarded([&] {
+        REQUIRE(c && t && node_off && (n_nodes == 0 || m == 0 || (sample_idx && cand_rects && cand_thr && out)),
+                "dh_train_score_level: NULL argument");
+        REQUIRE(steepness == steepness && steepness != 0.0, "dh_train_score_level: steepness must be a non-zero number");
+        c->cx->train_score_level(*t->ts, sample_idx, node_off, n_nodes, cand_rects, cand_thr, m, depth, steepness, out);
+    });
+}
+int dh_train_split_level(dh_ctx* c, const dh_trainset* t, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
+                         const int32_t* rects, const double* thr, uint8_t* bits) {
+    return guarded([&] {
+        REQUIRE(c && t && node_off && (n_nodes == 0 || (sample_idx && rects && thr && bits)), "dh_train_split_level: NULL argument");
+        c->cx->train_split_level(*t->ts, sample_idx, node_off, n_nodes, rects, thr, bits);
+    });
+}
 int dh_predict_mask(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask) {
     return guarded([&] {
         REQUIRE(c && f && depth && mask, "dh_predict_mask: NULL argument");

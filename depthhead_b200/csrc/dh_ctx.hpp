@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <memory>
 #include <utility>
 #include <vector>
 
@@ -36,6 +37,9 @@ struct Lane {
     bool allocated = false;
 };
 constexpr int kMaxLanes = 4;
+
+struct TrainSet;  // dh_train.cu
+void trainset_free(TrainSet* t);
 
 struct ScratchKey {
     uint32_t w = 0, h = 0, sw = 0, sh = 0, stride = 0, n_trees = 0, frames = 0, trace_iters = 0;
@@ -69,6 +73,14 @@ public:
     void biwi_decode(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w, uint32_t h, uint16_t* out, int out_loc);
     void predict_batch_biwi(const HostForest& hf, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w, uint32_t h,
                             const float K[9], dh_result* out);
+    // training: split scoring (dh_train.cu; houghforest.rs:250-295)
+    TrainSet* trainset_create(const uint16_t* patches, uint64_t n, uint32_t sw, uint32_t sh, uint32_t rw, uint32_t rh,
+                              const uint8_t* is_object, const float* offsets, const double* rotations);
+    void train_score_level(const TrainSet& ts, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
+                           const int32_t* cand_rects, const double* cand_thr, uint32_t m, uint64_t depth, double steepness,
+                           dh_split_stats* out);
+    void train_split_level(const TrainSet& ts, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
+                           const int32_t* rects, const double* thr, uint8_t* bits);
     void predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask);
     void hough_image_raw(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
                          uint16_t* votes);

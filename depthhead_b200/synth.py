@@ -23,13 +23,18 @@ KINECT_K = np.array([[560.0, 0.0, 320.0], [0.0, 560.0, 240.0], [0.0, 0.0, 1.0]],
 
 # ----------------------------------------------------------------------------- frames
 def make_frames(n: int, seed: int = 0, w: int = 640, h: int = 480, sequence: bool = False,
-                start_index: int = 0) -> np.ndarray:
+                start_index: int = 0, with_truth: bool = False):
     """n synthetic depth frames [n,h,w] u16.  One "person": a head ellipsoid (semi-axes
     ~75x100x90 mm) at depth z0~U[700,1200] mm, a torso slab below it, +-3 mm noise, 1-2 %
     dropout to 0.  Frame i depends only on (seed, start_index+i), so shards generated on
     different ranks are identical to the corresponding slice of a single-process run.
-    sequence=True: smooth pose trajectories in "sessions" of 625 frames (BIWI-shaped)."""
+    sequence=True: smooth pose trajectories in "sessions" of 625 frames (BIWI-shaped).
+    with_truth=True: also the ground truth a Biwi annotation carries (db_reader/reader.rs
+    DepthTrue): head centre [n,3] f32 mm, rotation [n,3] f32 (the ellipsoid has no orientation:
+    a smooth function of the position stands in), head mask [n,h,w] u8."""
     out = np.zeros((n, h, w), np.uint16)
+    centres = np.zeros((n, 3), np.float32)
+    masks = np.zeros((n, h, w), np.uint8) if with_truth else None
     fx, fy, cx, cy = 560.0 * w / 640.0, 560.0 * h / 480.0, w / 2.0, h / 2.0
     for i in range(n):
         gi = start_index + i
@@ -74,10 +79,16 @@ def make_frames(n: int, seed: int = 0, w: int = 640, h: int = 480, sequence: boo
             d = hz - c * np.sqrt(np.where(inside, q, 0.0)) + rng.uniform(-3, 3, q.shape)
             reg = img[v0:v1, u0:u1]
             reg[inside] = np.clip(d, 1, 65535).astype(np.uint16)[inside]
+            if with_truth:
+                masks[i, v0:v1, u0:u1][inside] = 255
+        centres[i] = (hx, hy, hz)
         # dropout: 1-2 % of pixels to 0
         frac = rng.uniform(0.01, 0.02)
         drop = rng.random((h, w)) < frac
         img[drop] = 0
+    if with_truth:
+        rots = np.stack([centres[:, 0] / 8.0, centres[:, 1] / 4.0, (centres[:, 2] - 950.0) / 16.0], 1).astype(np.float32)
+        return out, centres, rots, masks
     return out
 
 

@@ -19,6 +19,8 @@
  *                                                                                 dh_biwi_decode_depth, dh_predict_batch_biwi
  *   src/db_reader/biwi.rs:27-60       read_cal (depth.cal -> IntrinsicMatrix)   -> dh_biwi_parse_cal
  *   src/db_reader/biwi.rs:63-77       read_gt (ground-truth pose file)          -> dh_biwi_parse_pose
+ *   src/hough/houghforest.rs:250-295  HoughTreeFunctions::impurity (training)   -> dh_train_score_level
+ *   src/hough/houghforest.rs:185-193  binarize of the chosen split (training)   -> dh_train_split_level
  */
 #ifndef DEPTHHEAD_CUDA_H
 #define DEPTHHEAD_CUDA_H
@@ -155,6 +157,39 @@ int dh_biwi_parse_cal(const char* text, size_t len, float K[9]);
 /* read_gt (biwi.rs:63-77): six little-endian f32 (position mm, rotation), plus the position
  * projected with K (space_to_img_coord).  Host-only. */
 int dh_biwi_parse_pose(const uint8_t* file, size_t len, const float K[9], float pos3d[3], float pos2d[2], float rot[3]);
+
+/* ------------------------------------------------------------------ training: split scoring */
+/* The reference grows its trees with stamm's train_forest_parallel (an external crate), which
+ * calls HoughTreeFunctions::impurity (houghforest.rs:250-295) for every candidate NodeParam of
+ * every node.  These entry points evaluate that for all nodes of one tree level on the GPU; the
+ * loop that grows the tree stays with the caller (depthhead_b200/train.py mirrors HoughLearning). */
+typedef struct dh_trainset dh_trainset;  /* training samples resident on one GPU */
+/* n samples: patches[n][sh][sw] u16 (the cropped sub-images of prediction.rs:223-226),
+ * is_object[n] (Truth::Object or NoObject), offsets[n][3] f32 mm and rotations[n][3] f64 of the
+ * Object samples (ignored for the others).  rw x rh: the one rectangle size every candidate
+ * feature will have (subrect_feature_scale of hough_tree_trainer.rs:165 applied to the sub-image). */
+int dh_trainset_create(dh_ctx* c, const uint16_t* patches, uint64_t n, uint32_t sw, uint32_t sh, uint32_t rw, uint32_t rh,
+                       const uint8_t* is_object, const float* offsets, const double* rotations, dh_trainset** out);
+void dh_trainset_free(dh_trainset* t);
+/* per candidate: side 0 = binarize Zero, side 1 = One.  det_*: determinants of the covariance
+ * matrices of the side's Object offsets / rotations (NaN with fewer than two of them); impurity:
+ * houghforest.rs:250-295, NaN where the reference itself aborts (an empty side: its
+ * assert!(res.is_finite()); a determinant sum below -0.001: its unreachable!()). */
+typedef struct dh_split_stats {
+    uint32_t n[2], n_pos[2];
+    double det_off[2], det_rot[2];
+    double impurity;
+} dh_split_stats;
+/* One tree level: node k owns sample_idx[node_off[k] .. node_off[k+1]) (indices into the training
+ * set, in set order); cand_rects[n_nodes][m][8] (r1 x0,y0,x1,y1, r2 ..; bottomright exclusive) and
+ * cand_thr[n_nodes][m] are its m candidates; out[n_nodes][m]. */
+int dh_train_score_level(dh_ctx* c, const dh_trainset* t, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
+                         const int32_t* cand_rects, const double* cand_thr, uint32_t m, uint64_t depth, double steepness,
+                         dh_split_stats* out);
+/* binarize (houghforest.rs:185-193) of ONE chosen NodeParam per node over the node's samples:
+ * bits[node_off[n_nodes]] (1 = One). */
+int dh_train_split_level(dh_ctx* c, const dh_trainset* t, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
+                         const int32_t* rects, const double* thr, uint8_t* bits);
 
 /* ------------------------------------------------------------------ measurement */
 /* Per-stage device time (CUDA events on the context's stream) of the LAST dh_predict_batch call,

@@ -94,6 +94,13 @@ def lib():
     L.orc_rect_average.argtypes = [vp, u32, u32, vp, vp, C.c_int]
     L.orc_leaf_static.argtypes = [vp, C.c_int64, vp, vp, vp]
     L.orc_num_threads.restype = C.c_int
+    L.orc_train_binarize.argtypes = [vp, u32, u32, vp, u64, vp, f64, vp]
+    L.orc_train_impurity.restype = f64
+    L.orc_train_impurity.argtypes = [vp, vp, vp, vp, u64, vp, u64, u64, f64, vp, vp]
+    L.orc_train_impurity_from_stats.restype = f64
+    L.orc_train_impurity_from_stats.argtypes = [vp, u64, f64, vp]
+    L.orc_train_early_stop.restype = C.c_int
+    L.orc_train_early_stop.argtypes = [vp, vp, u64, u64, u64, u64]
     L.orc_biwi_read_depth.restype = C.c_int
     L.orc_biwi_read_depth.argtypes = [vp, u64, vp, u64, vp, vp]
     L.orc_biwi_read_gt.restype = C.c_int
@@ -364,3 +371,41 @@ def biwi_read_cal(text: str | bytes) -> np.ndarray:
     if rc:
         raise BiwiError(rc, "read_cal: " + {1: "Unsupported Calibration-File", 2: "ParseFloatError", 3: "fourth number on a line (panic)"}[rc])
     return K.reshape(3, 3)
+
+
+# ----------------------------------------------------------------------------- training callbacks
+SIDE_DTYPE = np.dtype([("n", np.uint64), ("n_pos", np.uint64), ("det_off", np.float64), ("det_rot", np.float64)])
+
+
+def train_binarize(patches: np.ndarray, idx, rects8, threshold: float) -> np.ndarray:
+    """binarize (houghforest.rs:185-193) of one NodeParam on the samples idx -> u8 bits."""
+    p = np.ascontiguousarray(patches, np.uint16)
+    i = np.ascontiguousarray(idx, np.uint32)
+    r = np.ascontiguousarray(rects8, np.int32).reshape(8)
+    bits = np.zeros(len(i), np.uint8)
+    lib().orc_train_binarize(_p(p), p.shape[2], p.shape[1], _p(i), len(i), _p(r), float(threshold), _p(bits))
+    return bits
+
+
+def train_impurity(is_object, offsets, rotations, left, right, depth: int, steepness: float):
+    """impurity (houghforest.rs:250-295) -> (value, per-side stats SIDE_DTYPE[2], hit_unreachable)."""
+    o = np.ascontiguousarray(is_object, np.uint8)
+    of = np.ascontiguousarray(offsets, np.float32)
+    ro = np.ascontiguousarray(rotations, np.float64)
+    le, ri = np.ascontiguousarray(left, np.uint32), np.ascontiguousarray(right, np.uint32)
+    st = np.zeros(2, SIDE_DTYPE)
+    bad = C.c_int(0)
+    v = lib().orc_train_impurity(_p(o), _p(of), _p(ro), _p(le), len(le), _p(ri), len(ri), int(depth), float(steepness), _p(st),
+                                 C.byref(bad))
+    return float(v), st, bool(bad.value)
+
+
+def train_impurity_from_stats(stats, depth: int, steepness: float) -> float:
+    st = np.ascontiguousarray(stats, SIDE_DTYPE)
+    return float(lib().orc_train_impurity_from_stats(_p(st), int(depth), float(steepness), None))
+
+
+def train_early_stop(is_object, idx, depth: int, max_depth: int, min_subset_size: int) -> bool:
+    o = np.ascontiguousarray(is_object, np.uint8)
+    i = np.ascontiguousarray(idx, np.uint32)
+    return bool(lib().orc_train_early_stop(_p(o), _p(i), len(i), int(depth), int(max_depth), int(min_subset_size)))

@@ -1193,4 +1193,110 @@ int orc_biwi_read_cal(const char* text, uint64_t len, float* K) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------- training callbacks
+// HoughTreeFunctions as TreeLearnFunctions (houghforest.rs:196-311).  The trainer that calls them is
+// stamm's (not vendored: UNPINNED); these are the depthhead-owned pieces it calls.
+
+// binarize (houghforest.rs:185-193) of a candidate NodeParam on training samples: patches
+// [n][sh][sw] u16 (InMutSubImage crops, prediction.rs:223-226), rect = x, y, w, h per rectangle.
+void orc_train_binarize(const uint16_t* patches, uint32_t sw, uint32_t sh, const uint32_t* idx, uint64_t n_idx,
+                        const int32_t* rects /*8: r1 x0,y0,x1,y1, r2 ..*/, double threshold, uint8_t* bits) {
+    Rect sub = rect_new(0, 0, sw, sh);
+    Rect r1 = rect_new((uint32_t)rects[0], (uint32_t)rects[1], (uint32_t)(rects[2] - rects[0]), (uint32_t)(rects[3] - rects[1]));
+    Rect r2 = rect_new((uint32_t)rects[4], (uint32_t)rects[5], (uint32_t)(rects[6] - rects[4]), (uint32_t)(rects[7] - rects[5]));
+    for (uint64_t k = 0; k < n_idx; ++k) {
+        Image img{patches + (size_t)idx[k] * sw * sh, sw, sh};
+        const double a1 = average_value_in_rect(img, sub, r1), a2 = average_value_in_rect(img, sub, r2);
+        bits[k] = (a1 - a2 > threshold) ? 1 : 0;
+    }
+}
+
+struct OrcSideStats {  // what the GPU scorer reports per (candidate, side)
+    uint64_t n, n_pos;
+    double det_off, det_rot;  // determinants of the two covariance matrices (NaN for fewer than two positives)
+};
+
+static inline double rs_ln(double x) { return x == 0.0 ? 0.0 : std::log(x); }  // ln! (houghforest.rs:18-20)
+
+// entropy (houghforest.rs:258-264)
+static double train_entropy(const uint8_t* is_obj, const uint32_t* idx, uint64_t n) {
+    uint64_t positives = 0;
+    for (uint64_t k = 0; k < n; ++k) positives += is_obj[idx[k]] ? 1 : 0;
+    const double prob = (double)positives / (double)n;  // rel!
+    return prob * rs_ln(prob) + (1.0 - prob) * rs_ln(1.0 - prob);
+}
+// regression_log (houghforest.rs:265-284); *bad = 1 where the reference hits unreachable!()
+static double train_regression_log(const uint8_t* is_obj, const float* offsets, const double* rotations, const uint32_t* idx,
+                                   uint64_t n, OrcSideStats* st, int* bad) {
+    std::vector<double> off, rot;
+    for (uint64_t k = 0; k < n; ++k)
+        if (is_obj[idx[k]]) {
+            for (int c = 0; c < 3; ++c) {
+                off.push_back((double)offsets[(size_t)idx[k] * 3 + c]);   // x.0[c] as f64
+                rot.push_back(rotations[(size_t)idx[k] * 3 + c]);
+            }
+        }
+    st->n = n;
+    st->n_pos = off.size() / 3;
+    st->det_off = st->det_rot = std::numeric_limits<double>::quiet_NaN();
+    if (off.empty()) return 0.0;
+    double mo[3], co[9], mr[3], cr[9];
+    estimate_mean_cov<double, 3>(off.data(), off.size() / 3, mo, co);
+    estimate_mean_cov<double, 3>(rot.data(), rot.size() / 3, mr, cr);
+    st->det_off = mat3_det<double>(co);
+    st->det_rot = mat3_det<double>(cr);
+    const double x = st->det_off + st->det_rot;
+    if (x > 0.0) return std::log(x);
+    if (x < -0.001) { *bad = 1; return 0.0; }
+    return 0.0;
+}
+// impurity (houghforest.rs:250-295).  Returns NaN-free values only for non-empty sides (an empty
+// side makes the reference's assert!(res.is_finite()) fire: rel!(0, 0) is NaN).
+double orc_train_impurity(const uint8_t* is_obj, const float* offsets, const double* rotations, const uint32_t* left,
+                          uint64_t nl, const uint32_t* right, uint64_t nr, uint64_t depth, double steepness,
+                          OrcSideStats* stats /*[2] or NULL*/, int* bad) {
+    OrcSideStats st[2];
+    int b = 0;
+    const uint64_t count = nl + nr;
+    const double left_factor = (double)nl / (double)count, right_factor = (double)nr / (double)count;
+    const double impurity = -(left_factor * train_entropy(is_obj, left, nl) + right_factor * train_entropy(is_obj, right, nr));
+    const double rl = train_regression_log(is_obj, offsets, rotations, left, nl, &st[0], &b);
+    const double rr = train_regression_log(is_obj, offsets, rotations, right, nr, &st[1], &b);
+    const double regression_uncert = left_factor * rl + right_factor * rr;
+    const double e_factor = -((double)depth / steepness);
+    const double f = std::exp(e_factor);
+    if (stats) { stats[0] = st[0]; stats[1] = st[1]; }
+    if (bad) *bad = b;
+    return impurity + (1.0 - f) * regression_uncert;
+}
+// the same combination from per-side statistics (what the product does with the GPU's numbers)
+double orc_train_impurity_from_stats(const OrcSideStats* st /*[2]*/, uint64_t depth, double steepness, int* bad) {
+    auto entropy = [](const OrcSideStats& s) {
+        const double prob = (double)s.n_pos / (double)s.n;
+        return prob * rs_ln(prob) + (1.0 - prob) * rs_ln(1.0 - prob);
+    };
+    auto reglog = [&](const OrcSideStats& s) {
+        if (s.n_pos == 0) return 0.0;
+        const double x = s.det_off + s.det_rot;
+        if (x > 0.0) return std::log(x);
+        if (x < -0.001 && bad) *bad = 1;
+        return 0.0;
+    };
+    const uint64_t count = st[0].n + st[1].n;
+    const double lf = (double)st[0].n / (double)count, rf = (double)st[1].n / (double)count;
+    const double impurity = -(lf * entropy(st[0]) + rf * entropy(st[1]));
+    const double reg = lf * reglog(st[0]) + rf * reglog(st[1]);
+    const double f = std::exp(-((double)depth / steepness));
+    return impurity + (1.0 - f) * reg;
+}
+// early_stop (houghforest.rs:302-311)
+int orc_train_early_stop(const uint8_t* is_obj, const uint32_t* idx, uint64_t n, uint64_t depth, uint64_t max_depth,
+                         uint64_t min_subset_size) {
+    bool all_neg = true;
+    for (uint64_t k = 0; k < n; ++k)
+        if (is_obj[idx[k]]) all_neg = false;
+    if (all_neg) return 1;
+    return (depth >= max_depth || n < min_subset_size) ? 1 : 0;
+}
+
 }  // extern "C"
