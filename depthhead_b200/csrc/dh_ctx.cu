@@ -645,7 +645,7 @@ void Context::biwi_decode(const uint8_t* blob, const uint64_t* offsets, uint32_t
         end_call();
         return;
     }
-    if ((uint64_t)w * h == 0 || (uint64_t)w * h > 0x7fffffffull) throw ModelError(DH_E_SHAPE, "Biwi frame of 0 or more than 2^31 pixels");
+    if ((uint64_t)w * h == 0 || (uint64_t)w * h > 0x3fffffffull) throw ModelError(DH_E_SHAPE, "Biwi frame of 0 or more than 2^30 pixels");
     const size_t frame_px = (size_t)w * h;
     const uint32_t chunk = std::max<uint32_t>(1u, (uint32_t)std::min<uint64_t>(n, (1ull << 30) / (frame_px * 2)));
     ensure_biwi(offsets, n, chunk, 1);

@@ -1602,124 +1602,177 @@ __global__ void narrow_u16_kernel(const uint32_t* __restrict__ in, uint16_t* __r
 // ================================================================ Biwi run-length decode
 // read_depth (biwi.rs:81-103): [u32 w][u32 h] then, until w*h pixels are covered,
 // [u32 n_empty][u32 n_full][n_full x u16].  The position of a run header depends on every header
-// before it, so one thread has to walk them; everything else is parallel.  One CTA per frame:
-// the file is staged through shared memory in 16 KB pieces (coalesced 4-byte loads), thread 0
-// walks the headers of a piece inside shared memory (~30 cycles per run instead of a global-memory
-// round trip) and lists the runs (cut into segments of at most 512 pixels), then the warps copy
-// the segments' pixels from the staged bytes to the frame.  The frame was zeroed beforehand, so
-// empty runs cost nothing.  Damaged files set the frame's status: 1 truncated (the reference's
-// UnexpectedEof), 2 a run past the last pixel (its `unwrap` panic), 3 header is not w x h.
+// before it, so ONE thread has to follow the chain; everything else is parallel.  One CTA per
+// frame, the file staged through shared memory in 16 KB pieces (coalesced 4-byte loads); per piece
+//   1. thread 0 follows the chain inside shared memory and only notes the header positions
+//      (load n_full, store the position, advance);
+//   2. all threads: a block-wide prefix sum of n_empty + n_full (saturating at w*h + 1) gives
+//      every run its first pixel; the reference's failure conditions are checked per run, the
+//      first failing run deciding; runs longer than 2048 pixels are set aside;
+//   3. the warps copy the runs' pixels (from the staged bytes where they lie inside the piece),
+//      the long runs with the whole CTA.
+// The frame was zeroed beforehand, so empty runs cost nothing.  Damaged files set the frame's
+// status: 1 truncated (the reference's UnexpectedEof), 2 a run past the last pixel (its `unwrap`
+// panic; also reported when the same run is truncated as well), 3 header is not w x h.
 constexpr int kRleThreads = 256;
-constexpr int kRlePieceWords = 4096;   // 16 KB of file per round
-constexpr int kRleSegs = 1024;         // segments listed per round
-constexpr int kRleSegPixels = 512;
+constexpr int kRlePieceWords = 4096;    // 16 KB of file per round
+constexpr int kRleRuns = 2048;          // a piece holds at most 2048 headers
+constexpr int kRlePerThread = kRleRuns / kRleThreads;
+constexpr uint32_t kRleLongRun = 2048;  // pixels: longer runs are copied by the whole CTA
+constexpr uint32_t kRleLongCap = 16;    // a 16 KB piece cannot start more than 4 of them
+
+__device__ __forceinline__ uint32_t rle_u32(const uint16_t* p16, uint32_t i) { return (uint32_t)p16[i] | ((uint32_t)p16[i + 1] << 16); }
 
 __global__ void __launch_bounds__(kRleThreads) biwi_decode_kernel(const uint8_t* __restrict__ blob,
                                                                   const unsigned long long* __restrict__ offsets,
                                                                   unsigned long long blob_base, uint32_t w, uint32_t h,
                                                                   uint16_t* __restrict__ out, uint32_t* __restrict__ status) {
     __shared__ __align__(16) uint32_t s_piece[kRlePieceWords + 2];
-    __shared__ uint32_t s_seg_src[kRleSegs];   // byte offset of the segment's pixels inside the file
-    __shared__ uint32_t s_seg_dst[kRleSegs];   // first pixel
-    __shared__ uint16_t s_seg_n[kRleSegs];
-    __shared__ uint32_t s_nseg, s_pos, s_p, s_err, s_done, s_run_left, s_run_src, s_run_dst;
+    __shared__ uint32_t s_run_pos[kRleRuns];   // byte position of the run's header inside the file
+    __shared__ uint32_t s_run_p[kRleRuns];     // pixels covered before the run (saturating at npx + 1)
+    __shared__ uint32_t s_warp_tot[kRleThreads / 32];
+    __shared__ uint32_t s_long[kRleLongCap];
+    __shared__ uint32_t s_nrun, s_pos, s_p, s_nlong, s_err, s_done, s_end_run, s_bad_run;
     const uint32_t frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const unsigned long long o0 = offsets[frame] - blob_base, o1 = offsets[frame + 1] - blob_base;
     const uint8_t* file = blob + o0;                  // 4-byte aligned (checked on the host)
     const uint32_t len = (uint32_t)(o1 - o0);
-    const uint32_t npx = w * h;
+    const uint32_t npx = w * h, cap = npx + 1u;       // npx <= 2^30 (checked on the host): sums of two capped values fit u32
     uint16_t* dst = out + (size_t)frame * npx;
+    const uint16_t* piece16 = reinterpret_cast<const uint16_t*>(s_piece);
     if (tid == 0) {
         s_err = 0;
-        s_done = 0;
+        s_done = npx == 0u ? 1u : 0u;
         s_pos = 8;         // byte position of the next run header
         s_p = 0;           // pixels covered so far
-        s_run_left = 0;    // pixels of a full run still to be listed (a run longer than one round's list)
-        if (len < 8) s_err = 1;
+        if (len < 8u) s_err = 1;
         else if (reinterpret_cast<const uint32_t*>(file)[0] != w || reinterpret_cast<const uint32_t*>(file)[1] != h) s_err = 3;
-        if (npx == 0) s_done = 1;
     }
-    __syncthreads();
-    while (!s_err && !s_done) {
+    for (;;) {
+        __syncthreads();
+        if (s_err || s_done) break;
+        const uint32_t pos0 = s_pos, p0 = s_p;
+        if (pos0 > len || len - pos0 < 8u) {          // read_u32 of the next header hits the end of the file (biwi.rs:90,94)
+            if (tid == 0) s_err = 1;
+            continue;
+        }
         // ---- stage the piece that starts at the next header
-        const uint32_t base = s_pos & ~3u;
-        const uint32_t avail = min((uint32_t)kRlePieceWords + 2u, (len - base + 3u) / 4u);  // words we may touch (padding to 4 is readable:
-                                                                                           // the next file or the blob's tail padding)
+        const uint32_t base = pos0 & ~3u;
+        const uint32_t avail = min((uint32_t)kRlePieceWords + 2u, (len - base + 3u) / 4u);  // padding up to 4 bytes is readable
         for (uint32_t i = tid; i < avail; i += kRleThreads) s_piece[i] = __ldg(reinterpret_cast<const uint32_t*>(file + base) + i);
-        __syncthreads();
-        // ---- thread 0: walk the headers inside the piece.  The loop is the serial part of the
-        //      decode, so it only follows the chain (three independent shared-memory loads, two
-        //      funnel shifts for headers on odd 2-byte positions) and notes where each run's
-        //      pixels are; cutting long runs into segments happens after it.
         if (tid == 0) {
-            uint32_t pos = s_pos, p = s_p, nseg = 0, err = 0;
-            uint32_t left = s_run_left, rsrc = s_run_src, rdst = s_run_dst;
-            const uint32_t piece_end = base + (uint32_t)kRlePieceWords * 4u;
-            for (;;) {
-                while (left && nseg < (uint32_t)kRleSegs) {  // cut the current full run into segments
-                    const uint32_t n = min(left, (uint32_t)kRleSegPixels);
-                    s_seg_src[nseg] = rsrc;
-                    s_seg_dst[nseg] = rdst;
-                    s_seg_n[nseg] = (uint16_t)n;
-                    ++nseg;
-                    rsrc += 2u * n;
-                    rdst += n;
-                    left -= n;
+            s_nlong = 0;
+            s_end_run = 0xffffffffu;
+            s_bad_run = 0xffffffffu;
+        }
+        __syncthreads();
+        // ---- 1. thread 0 follows the chain (headers are only 2-byte aligned: n_full is read as two halves)
+        if (tid == 0) {
+            uint32_t pos = pos0, n = 0;
+            const uint32_t lim = min(base + (uint32_t)kRlePieceWords * 4u, len);  // a header must end inside the piece and the file
+            while (pos + 8u <= lim && n < (uint32_t)kRleRuns) {
+                const uint32_t nf = rle_u32(piece16, (pos - base + 4u) >> 1);
+                s_run_pos[n++] = pos;
+                if (nf > ((len - pos - 8u) >> 1)) {   // its pixels run past the end of the file: the chain ends here
+                    pos = 0xffffffffu;
+                    break;
                 }
-                if (left || nseg >= (uint32_t)kRleSegs) break;   // list full
-                // fast path: runs that fit one segment, as long as headers stay inside the piece
-                while (p < npx && pos + 8u <= piece_end && pos + 8u <= len && nseg < (uint32_t)kRleSegs) {
-                    const uint32_t wi = (pos - base) >> 2, sh = (pos & 2u) << 3;
-                    const uint32_t w0 = s_piece[wi], w1 = s_piece[wi + 1], w2 = s_piece[wi + 2];
-                    const uint32_t ne = __funnelshift_r(w0, w1, sh), nf = __funnelshift_r(w1, w2, sh);
-                    // `it.next().unwrap()` past the last pixel panics (biwi.rs:92,97)
-                    if (ne > npx - p || nf > npx - p - ne) { err = 2; break; }
-                    if ((unsigned long long)pos + 8ull + 2ull * nf > (unsigned long long)len) { err = 1; break; }
-                    const uint32_t d0 = p + ne;
-                    p = d0 + nf;
-                    if (nf > (uint32_t)kRleSegPixels) {  // long run: the segment cutter above takes it
-                        left = nf;
-                        rsrc = pos + 8u;
-                        rdst = d0;
-                        pos += 8u + 2u * nf;
-                        break;
-                    }
-                    s_seg_src[nseg] = pos + 8u;
-                    s_seg_dst[nseg] = d0;
-                    s_seg_n[nseg] = (uint16_t)nf;
-                    nseg += nf ? 1u : 0u;
-                    pos += 8u + 2u * nf;
-                }
-                if (err || left) { if (err) break; else continue; }
-                if (p >= npx) break;                              // biwi.rs:89 `while p < width*height`
-                if (nseg >= (uint32_t)kRleSegs) break;
-                if (pos + 8u > len) { err = 1; break; }           // read_u32 hits the end of the file
-                break;                                            // next header is outside this piece
+                pos += 8u + 2u * nf;
             }
+            s_nrun = n;
             s_pos = pos;
-            s_p = p;
-            s_nseg = nseg;
-            s_run_left = left;
-            s_run_src = rsrc;
-            s_run_dst = rdst;
-            if (err) s_err = err;
-            else if (p >= npx && !left) s_done = 1;
         }
         __syncthreads();
-        // ---- the warps copy the listed segments: pixels are 2-byte aligned in the file
-        const uint32_t nseg = s_nseg;
-        for (uint32_t sgi = warp; sgi < nseg; sgi += kRleThreads / 32) {
-            const uint32_t src = s_seg_src[sgi], d0 = s_seg_dst[sgi], n = s_seg_n[sgi];
-            const uint16_t* px = reinterpret_cast<const uint16_t*>(file + src);
-            const bool staged = src >= base && src + 2u * n <= base + avail * 4u;  // whole segment inside the staged piece
-            for (uint32_t i = lane; i < n; i += 32u) {
-                uint16_t v;
-                if (staged) v = reinterpret_cast<const uint16_t*>(s_piece)[((src - base) >> 1) + i];
-                else v = __ldg(px + i);
-                dst[d0 + i] = v;
+        const uint32_t nrun = s_nrun;
+        // ---- 2. first pixel of every run: block-wide exclusive scan of n_empty + n_full
+        uint32_t loc[kRlePerThread], tot = 0;
+#pragma unroll
+        for (int j = 0; j < kRlePerThread; ++j) {
+            const uint32_t r = tid * kRlePerThread + (uint32_t)j;
+            uint32_t c = 0;
+            if (r < nrun) {
+                const uint32_t hp = (s_run_pos[r] - base) >> 1;
+                c = min(min(rle_u32(piece16, hp), cap) + min(rle_u32(piece16, hp + 2u), cap), cap);
+            }
+            loc[j] = tot;
+            tot = min(tot + c, cap);
+        }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl = min(incl + nb, cap);
+        }
+        if (lane == 31u) s_warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t before = p0;
+        for (uint32_t k = 0; k < warp; ++k) before = min(before + s_warp_tot[k], cap);
+        // exclusive prefix of this lane inside the warp: redo it from the neighbour's inclusive value (saturation forbids a subtraction)
+        const uint32_t left = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane) before = min(before + left, cap);
+#pragma unroll
+        for (int j = 0; j < kRlePerThread; ++j) {
+            const uint32_t r = tid * kRlePerThread + (uint32_t)j;
+            if (r < nrun) s_run_p[r] = min(before + loc[j], cap);
+        }
+        __syncthreads();
+        // ---- the reference's events per run, in its order; the first run at or past the last pixel ends the frame
+        for (uint32_t r = tid; r < nrun; r += kRleThreads) {
+            const uint32_t p = s_run_p[r];
+            if (p >= npx) {                           // biwi.rs:89: the loop ended before this header would be read
+                atomicMin(&s_end_run, r);
+                continue;
+            }
+            const uint32_t pos = s_run_pos[r], hp = (pos - base) >> 1;
+            const uint32_t ne = rle_u32(piece16, hp), nf = rle_u32(piece16, hp + 2u);
+            const uint32_t room = npx - p;
+            uint32_t e = 0;
+            if (ne > room || nf > room - ne) e = 2;                    // `it.next().unwrap()` past the last pixel (biwi.rs:92,97)
+            else if (nf > ((len - pos - 8u) >> 1)) e = 1;              // read_u16 hits the end of the file (biwi.rs:96)
+            if (e) atomicMin(&s_bad_run, (r << 2) | e);
+            else if (nf > kRleLongRun) {
+                const uint32_t k = atomicAdd(&s_nlong, 1u);
+                if (k < kRleLongCap) s_long[k] = r;
             }
         }
         __syncthreads();
+        const uint32_t end_run = min(nrun, s_end_run);
+        const bool failed = s_bad_run != 0xffffffffu && (s_bad_run >> 2) < end_run;
+        // ---- 3. copy: one warp per run; pixels are 2-byte aligned in the file
+        if (!failed) {
+            for (uint32_t r = warp; r < end_run; r += kRleThreads / 32) {
+                const uint32_t pos = s_run_pos[r], hp = (pos - base) >> 1;
+                const uint32_t ne = rle_u32(piece16, hp), nf = rle_u32(piece16, hp + 2u);
+                if (nf > kRleLongRun) continue;
+                const uint32_t src = pos + 8u, d0 = s_run_p[r] + ne;
+                const bool staged = src + 2u * nf <= base + avail * 4u;  // whole run inside the staged piece
+                const uint16_t* px = reinterpret_cast<const uint16_t*>(file + src);
+                const uint32_t so = (src - base) >> 1;
+                for (uint32_t i = lane; i < nf; i += 32u) dst[d0 + i] = staged ? piece16[so + i] : __ldg(px + i);
+            }
+            const uint32_t nlong = min(s_nlong, kRleLongCap);
+            for (uint32_t k = 0; k < nlong; ++k) {
+                const uint32_t r = s_long[k];
+                if (r >= end_run) continue;
+                const uint32_t pos = s_run_pos[r], hp = (pos - base) >> 1;
+                const uint32_t ne = rle_u32(piece16, hp), nf = rle_u32(piece16, hp + 2u);
+                const uint16_t* px = reinterpret_cast<const uint16_t*>(file + pos + 8u);
+                const uint32_t d0 = s_run_p[r] + ne;
+                for (uint32_t i = tid; i < nf; i += kRleThreads) dst[d0 + i] = __ldg(px + i);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (failed) s_err = s_bad_run & 3u;
+            else if (s_end_run != 0xffffffffu) s_done = 1;
+            else {
+                // pixels covered after this round's runs
+                uint32_t p = p0;
+                for (uint32_t k = 0; k < kRleThreads / 32; ++k) p = min(p + s_warp_tot[k], cap);
+                s_p = p;
+                if (p >= npx) s_done = 1;
+            }
+        }
     }
     if (tid == 0) status[frame] = s_err;
 }
