@@ -693,7 +693,7 @@ void Context::run_batch(const HostForest& hf, const uint16_t* depth, const uint8
     // back on one stream, so it runs single-lane.
     // Biwi input: the run-length expansion is latency-bound (one thread per frame walks the run
     // headers), so its chunks are larger: more frames in flight per launch
-    const uint32_t want_chunk = (blob && !chunk_frames_) ? std::min<uint32_t>(256u, n) : pick_chunk(n, depth_loc);
+    const uint32_t want_chunk = (blob && !chunk_frames_) ? std::min<uint32_t>(512u, n) : pick_chunk(n, depth_loc);
     const int n_lanes = timing_ ? 1 : (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)max_lanes_, (n + want_chunk - 1) / want_chunk));
     ensure_scratch(hf, w, h, want_chunk, K, n_lanes);
     const uint32_t iterations = hf.meanshift_iterations.load();
