@@ -212,6 +212,14 @@ class HoughPrediction:
         capi.check(capi.load().dh_forest_from_arrays(C.byref(a), C.byref(h)))
         return cls(h)
 
+    def to_json(self) -> str:
+        """serde_json::to_string(&HoughPrediction) (what hough_tree_trainer.rs:182 writes)."""
+        need = C.c_size_t(0)
+        capi.check(capi.load().dh_forest_to_json(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        capi.check(capi.load().dh_forest_to_json(self._h, buf, need.value, C.byref(need)))
+        return buf.raw[:need.value].decode("utf-8")
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             capi.load().dh_forest_free(self._h)

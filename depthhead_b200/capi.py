@@ -47,6 +47,13 @@ SPLIT_DTYPE = np.dtype([("n", np.uint32, 2), ("n_pos", np.uint32, 2), ("det_off"
 assert SPLIT_DTYPE.itemsize == C.sizeof(dh_split_stats) == 56
 
 
+class dh_train_params(C.Structure):
+    _fields_ = [("stepwidth", C.c_uint32), ("subimage_width", C.c_uint32), ("subimage_height", C.c_uint32),
+                ("max_depth", C.c_uint32), ("n_trees", C.c_uint32), ("subset_per_tree", C.c_uint32),
+                ("subrect_feature_scale", C.c_double), ("features_per_node", C.c_uint32), ("min_subset_size", C.c_uint32),
+                ("steepness", C.c_double), ("gaussian_sigma", C.c_float), ("_pad", C.c_uint32), ("seed", C.c_uint64)]
+
+
 class dh_forest_arrays(C.Structure):
     _fields_ = [("stepwidth", C.c_uint32), ("subimage_width", C.c_uint32), ("subimage_height", C.c_uint32),
                 ("meanshift_iterations", C.c_uint32), ("gaussian_sigma", C.c_float), ("n_trees", C.c_int32),
@@ -91,6 +98,8 @@ SIGNATURES = {
     "dh_trainset_free": (None, [_vp]),
     "dh_train_score_level": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _u32, _u64, C.c_double, _vp]),
     "dh_train_split_level": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp]),
+    "dh_train_forest": (C.c_int, [_vp, C.POINTER(dh_train_params), _vp, _u64, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "dh_forest_to_json": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dh_predict_mask": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "dh_hough_image_raw": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "dh_ctx_enable_stage_timing": (C.c_int, [_vp, C.c_int]),

@@ -260,6 +260,23 @@ int dh_train_split_level(dh_ctx* c, const dh_trainset* t, const uint32_t* sample
         c->cx->train_split_level(*t->ts, sample_idx, node_off, n_nodes, rects, thr, bits);
     });
 }
+int dh_train_forest(dh_ctx* c, const dh_train_params* p, const uint16_t* patches, uint64_t n, const uint8_t* is_object,
+                    const float* offsets, const double* rotations, dh_forest** out) {
+    return guarded([&] {
+        REQUIRE(c && p && patches && is_object && offsets && rotations && out, "dh_train_forest: NULL argument");
+        *out = nullptr;
+        std::unique_ptr<dh::HostForest> hf(c->cx->train_forest(*p, patches, n, is_object, offsets, rotations));
+        *out = new dh_forest{std::move(hf)};
+    });
+}
+int dh_forest_to_json(const dh_forest* f, char* buf, size_t cap, size_t* needed) {
+    return guarded([&] {
+        REQUIRE(f && needed && (cap == 0 || buf), "dh_forest_to_json: NULL argument");
+        const std::string js = dh::forest_to_json(*f->hf);
+        *needed = js.size();
+        if (cap) std::memcpy(buf, js.data(), std::min(cap, js.size()));
+    });
+}
 int dh_predict_mask(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask) {
     return guarded([&] {
         REQUIRE(c && f && depth && mask, "dh_predict_mask: NULL argument");

@@ -79,6 +79,8 @@ public:
     void train_score_level(const TrainSet& ts, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
                            const int32_t* cand_rects, const double* cand_thr, uint32_t m, uint64_t depth, double steepness,
                            dh_split_stats* out);
+    HostForest* train_forest(const dh_train_params& tp, const uint16_t* patches, uint64_t n, const uint8_t* is_object,
+                             const float* offsets, const double* rotations);
     void train_split_level(const TrainSet& ts, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
                            const int32_t* rects, const double* thr, uint8_t* bits);
     void predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask);

@@ -16,6 +16,7 @@
 // no nodes is the single leaf 0.  Only parse_forest_container() knows this layout.
 #include "dh_forest.hpp"
 
+#include <charconv>
 #include <cmath>
 #include <cstring>
 #include <deque>
@@ -387,4 +388,85 @@ void build_meanshift_kernel(float sigma, float* out) {
     }
 }
 
+}  // namespace dh
+
+// ------------------------------------------------------------------------------------------------ writer
+namespace dh {
+namespace {
+template <typename T>
+void put_float(std::string& o, T v) {
+    if (!std::isfinite(v)) { o += "null"; return; }   // serde_json writes non-finite floats as null
+    char buf[40];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v);  // shortest representation that round-trips
+    std::string t(buf, r.ptr);
+    if (t.find_first_of(".eEn") == std::string::npos) t += ".0";  // serde_json/ryu always mark a float: 8 -> 8.0
+    o += t;
+}
+void put_u(std::string& o, uint64_t v) { o += std::to_string(v); }
+void put_rect(std::string& o, const uint8_t* r) {
+    o += "{\"topleft\":["; put_u(o, r[0]); o += ','; put_u(o, r[1]);
+    o += "],\"bottomright\":["; put_u(o, r[2]); o += ','; put_u(o, r[3]); o += "]}";
+}
+}  // namespace
+
+std::string forest_to_json(const HostForest& hf) {
+    std::string o;
+    o.reserve(64 + hf.n_nodes() * 160 + hf.n_leaves() * 48 + hf.n_votes() * 90);
+    o += "{\"stepwidth\":"; put_u(o, hf.stepwidth.load());
+    o += ",\"subimage_width\":"; put_u(o, hf.subimage_width);
+    o += ",\"subimage_height\":"; put_u(o, hf.subimage_height);
+    o += ",\"gaussian_sigma\":"; put_float(o, hf.gaussian_sigma);
+    o += ",\"forest\":{\"trees\":[";
+    for (int32_t t = 0; t < hf.n_trees; ++t) {
+        if (t) o += ',';
+        const int64_t n0 = hf.tree_node_off[(size_t)t], n1 = hf.tree_node_off[(size_t)t + 1];
+        const int64_t l0 = hf.tree_leaf_off[(size_t)t], l1 = hf.tree_leaf_off[(size_t)t + 1];
+        o += "{\"functions\":{\"input_size\":{\"topleft\":[0,0],\"bottomright\":[";
+        put_u(o, hf.subimage_width); o += ','; put_u(o, hf.subimage_height);
+        o += "]},\"min_subrect_factor\":"; put_float(o, hf.fn_min_subrect_factor);
+        o += ",\"max_subrect_factor\":"; put_float(o, hf.fn_max_subrect_factor);
+        o += ",\"number_of_gen_features\":"; put_u(o, hf.fn_number_of_gen_features);
+        o += ",\"steepness\":"; put_float(o, hf.fn_steepness);
+        o += ",\"max_depth\":"; put_u(o, hf.fn_max_depth);
+        o += ",\"min_subset_size\":"; put_u(o, hf.fn_min_subset_size);
+        o += "},\"nodes\":[";
+        for (int64_t n = n0; n < n1; ++n) {
+            if (n > n0) o += ',';
+            const NodeRec& r = hf.nodes[(size_t)n];
+            o += "{\"param\":{\"r1\":"; put_rect(o, r.r);
+            o += ",\"r2\":"; put_rect(o, r.r + 4);
+            o += ",\"threshold\":"; put_float(o, r.threshold);
+            o += "},\"children\":[";
+            for (int b = 0; b < 2; ++b) {
+                if (b) o += ',';
+                const int32_t c = r.child[b];  // >= 0 global node, < 0 ~global leaf -> tree-local
+                o += std::to_string(c >= 0 ? (int64_t)c - n0 : ~((int64_t)(~c) - l0));
+            }
+            o += "]}";
+        }
+        o += "],\"leaves\":[";
+        for (int64_t l = l0; l < l1; ++l) {
+            if (l > l0) o += ',';
+            o += "{\"prob\":"; put_float(o, hf.leaf_prob[(size_t)l]);
+            const uint32_t v0 = hf.leaf_vote_start[(size_t)l], nv = hf.leaf_n_votes[(size_t)l];
+            o += ",\"offsets\":[";
+            for (uint32_t v = 0; v < nv; ++v) {
+                if (v) o += ',';
+                o += '['; put_float(o, hf.offsets[(size_t)(v0 + v) * 3]); o += ','; put_float(o, hf.offsets[(size_t)(v0 + v) * 3 + 1]);
+                o += ','; put_float(o, hf.offsets[(size_t)(v0 + v) * 3 + 2]); o += ']';
+            }
+            o += "],\"rotations\":[";
+            for (uint32_t v = 0; v < nv; ++v) {
+                if (v) o += ',';
+                o += '['; put_float(o, hf.rotations[(size_t)(v0 + v) * 3]); o += ','; put_float(o, hf.rotations[(size_t)(v0 + v) * 3 + 1]);
+                o += ','; put_float(o, hf.rotations[(size_t)(v0 + v) * 3 + 2]); o += ']';
+            }
+            o += "]}";
+        }
+        o += "]}";
+    }
+    o += "]},\"meanshift_iterations\":"; put_u(o, hf.meanshift_iterations.load());
+    o += '}';
+    return o;
+}
 }  // namespace dh

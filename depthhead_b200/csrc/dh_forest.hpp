@@ -64,6 +64,10 @@ struct HostForest {
     std::vector<uint32_t> rot_bins;        // per vote: r1 | r2<<8 | r3<<16, each in [0,120)
     uint32_t max_votes_per_leaf = 0;
     uint64_t serial = 0;                   // unique id: contexts key their device copy on it
+    // HoughTreeFunctions (houghforest.rs:89-122) written into the document by forest_to_json; the
+    // prediction path never reads them.  Set by the trainer; defaults are the reference trainer's.
+    double fn_min_subrect_factor = 0.3, fn_max_subrect_factor = 0.3, fn_steepness = 5.0;
+    uint64_t fn_number_of_gen_features = 2000, fn_max_depth = 15, fn_min_subset_size = 20;
 
     size_t n_nodes() const { return nodes.size(); }
     size_t n_leaves() const { return leaf_prob.size(); }
@@ -73,6 +77,10 @@ struct HostForest {
 // Validates (everything the reference would panic / loop forever on becomes an error) and
 // re-lays the nodes out in BFS order.  Throws ModelError.
 HostForest* flatten_forest(const RawForest& raw);
+
+// serde_json::to_string(&HoughPrediction) (hough_tree_trainer.rs:182 `tojson`): the document
+// parse_hough_prediction_json reads, floats in shortest round-trip form like serde_json (ryu).
+std::string forest_to_json(const HostForest& hf);
 
 // Mat3::inv (meancov_estimation.rs:344-352), f32, adjugate / det.
 void mat3_inverse_f32(const float k[9], float inv[9]);

@@ -309,6 +309,199 @@ void Context::train_split_level(const TrainSet& ts, const uint32_t* sample_idx, 
     DH_CUDA_T(cudaStreamSynchronize(stream_));
 }
 
+// ---------------------------------------------------------------------------------------------- tree growing
+// Stand-in for stamm 0.2.0's `train_forest_parallel` (not vendored), stated in DESIGN.md section 9 and
+// mirrored line by line by depthhead_b200/train.py: counter-based random numbers, subsets drawn
+// without replacement in drawn order, breadth-first growth from depth 0, candidates on which the
+// reference's impurity aborts are skipped, the smallest impurity wins (first of equals), samples
+// keep their order through a split, children[bit] receives the side with binarize == bit.
+namespace {
+struct CounterRng {  // draw k = splitmix64(seed + k * golden), k = 1, 2, ..; uniform [0,1) = top 53 bits
+    uint64_t seed, k = 0;
+    explicit CounterRng(uint64_t s) : seed(s) {}
+    double next() {
+        ++k;
+        uint64_t z = seed + k * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    }
+    std::vector<uint32_t> permutation(uint64_t n) {  // Fisher-Yates from the back
+        std::vector<uint32_t> a(n);
+        for (uint64_t i = 0; i < n; ++i) a[i] = (uint32_t)i;
+        for (uint64_t i = n; i-- > 1;) {
+            const uint64_t j = (uint64_t)(next() * (double)(i + 1));
+            std::swap(a[i], a[j]);
+        }
+        return a;
+    }
+};
+
+// Rect::scale_and_replace (types.rs:82-91) of Rect(0, 0, w, h): x0, y0, x1, y1
+void scale_and_replace(uint32_t w, uint32_t h, double scale, double rx, double ry, int32_t out[4]) {
+    if (scale > 1.0) { out[0] = 0; out[1] = 0; out[2] = (int32_t)w; out[3] = (int32_t)h; return; }
+    const double nw = (double)w * scale, nh = (double)h * scale;
+    const double nx = 0.0 + rx * ((double)w - nw), ny = 0.0 + ry * ((double)h - nh);
+    const uint32_t x = (uint32_t)nx, y = (uint32_t)ny;  // `as u32`: truncation (values are in range)
+    out[0] = (int32_t)x; out[1] = (int32_t)y; out[2] = (int32_t)(x + (uint32_t)nw); out[3] = (int32_t)(y + (uint32_t)nh);
+}
+}  // namespace
+
+HostForest* Context::train_forest(const dh_train_params& tp, const uint16_t* patches, uint64_t n, const uint8_t* is_object,
+                                  const float* offsets, const double* rotations) {
+    // HoughTreeFunctions::new returns None for these (houghforest.rs:143-147); a factor of 0 makes
+    // random_subrect_iterator(..).unwrap() panic (types.rs:106-110)
+    const double sc = tp.subrect_feature_scale;
+    if (!(sc > 0.0) || sc > 1.0 || tp.features_per_node == 0 || !(tp.steepness > 0.0))
+        throw ModelError(DH_E_ARG, "Bad parameter for learning Houghforest");
+    if (tp.n_trees == 0 || tp.subimage_width == 0 || tp.subimage_height == 0 || tp.stepwidth == 0)
+        throw ModelError(DH_E_ARG, "dh_train_forest: zero trees / sub-image / stepwidth");
+    const uint32_t sw = tp.subimage_width, sh = tp.subimage_height;
+    const uint32_t rw = (uint32_t)((double)sw * sc), rh = (uint32_t)((double)sh * sc);
+    std::unique_ptr<TrainSet, void (*)(TrainSet*)> ts(trainset_create(patches, n, sw, sh, rw, rh, is_object, offsets, rotations), trainset_free);
+    CounterRng rng(tp.seed);
+    const uint32_t M = tp.features_per_node;
+
+    RawForest raw;
+    raw.stepwidth = tp.stepwidth; raw.subimage_width = sw; raw.subimage_height = sh;
+    raw.meanshift_iterations = 20;  // prediction.rs:232
+    raw.gaussian_sigma = tp.gaussian_sigma;
+    raw.n_trees = (int32_t)tp.n_trees;
+
+    struct Slot { int32_t rect[8]; double thr; int32_t child[2]; bool is_node = false; int64_t leaf = -1; };
+    for (uint32_t t = 0; t < tp.n_trees; ++t) {
+        std::vector<uint32_t> subset = rng.permutation(n);
+        if (subset.size() > tp.subset_per_tree) subset.resize(tp.subset_per_tree);
+        std::vector<Slot> slots(1);
+        std::vector<std::pair<uint32_t, std::vector<uint32_t>>> frontier;
+        frontier.emplace_back(0u, std::move(subset));
+        std::vector<std::pair<uint32_t, std::vector<uint32_t>>> leaf_sets;  // (slot, samples) in creation order
+        for (uint64_t depth = 0; !frontier.empty(); ++depth) {
+            // early_stop (houghforest.rs:302-311), else param_set (:227-246): five draws per candidate
+            std::vector<size_t> split;            // indices into frontier
+            std::vector<int32_t> cand_rects;
+            std::vector<double> cand_thr;
+            for (size_t f = 0; f < frontier.size(); ++f) {
+                const std::vector<uint32_t>& idx = frontier[f].second;
+                bool any_obj = false;
+                for (uint32_t j : idx) any_obj = any_obj || is_object[j];
+                if (!any_obj || depth >= tp.max_depth || idx.size() < tp.min_subset_size) continue;
+                split.push_back(f);
+                for (uint32_t c = 0; c < M; ++c) {
+                    const double u0 = rng.next(), u1 = rng.next(), u2 = rng.next(), u3 = rng.next(), u4 = rng.next();
+                    int32_t r[8];
+                    scale_and_replace(sw, sh, sc, u0, u1, r);
+                    scale_and_replace(sw, sh, sc, u2, u3, r + 4);
+                    cand_rects.insert(cand_rects.end(), r, r + 8);
+                    cand_thr.push_back(-256.0 + u4 * (256.0 - -256.0));
+                }
+            }
+            std::vector<int> chosen(frontier.size(), -1);  // candidate index per frontier node
+            if (!split.empty()) {
+                std::vector<uint32_t> all_idx;
+                std::vector<uint64_t> node_off(1, 0);
+                for (size_t f : split) {
+                    all_idx.insert(all_idx.end(), frontier[f].second.begin(), frontier[f].second.end());
+                    node_off.push_back(all_idx.size());
+                }
+                std::vector<dh_split_stats> st(split.size() * (size_t)M);
+                train_score_level(*ts, all_idx.data(), node_off.data(), (uint32_t)split.size(), cand_rects.data(), cand_thr.data(), M,
+                                  depth, tp.steepness, st.data());
+                std::vector<size_t> deciding;       // positions in `split` that found a candidate
+                std::vector<int32_t> ch_rects;
+                std::vector<double> ch_thr;
+                for (size_t k = 0; k < split.size(); ++k) {
+                    int best = -1;
+                    for (uint32_t c = 0; c < M; ++c) {
+                        const double v = st[k * M + c].impurity;
+                        if (v != v) continue;                                   // the reference aborts on this candidate
+                        if (best < 0 || v < st[k * M + (size_t)best].impurity) best = (int)c;  // smallest, first of equals
+                    }
+                    if (best < 0) continue;
+                    chosen[split[k]] = best;
+                    deciding.push_back(k);
+                    ch_rects.insert(ch_rects.end(), cand_rects.begin() + (k * M + (size_t)best) * 8, cand_rects.begin() + (k * M + (size_t)best + 1) * 8);
+                    ch_thr.push_back(cand_thr[k * M + (size_t)best]);
+                }
+                if (!deciding.empty()) {
+                    std::vector<uint32_t> sub_idx;
+                    std::vector<uint64_t> sub_off(1, 0);
+                    for (size_t k : deciding) {
+                        const auto& v = frontier[split[k]].second;
+                        sub_idx.insert(sub_idx.end(), v.begin(), v.end());
+                        sub_off.push_back(sub_idx.size());
+                    }
+                    std::vector<uint8_t> bits(sub_idx.size());
+                    train_split_level(*ts, sub_idx.data(), sub_off.data(), (uint32_t)deciding.size(), ch_rects.data(), ch_thr.data(), bits.data());
+                    std::vector<std::pair<uint32_t, std::vector<uint32_t>>> next;
+                    // children are created in frontier order, like the Python mirror (slots numbered as they appear)
+                    size_t d = 0;
+                    std::vector<std::pair<size_t, size_t>> where(frontier.size(), {SIZE_MAX, 0});  // frontier node -> position in deciding
+                    for (size_t q = 0; q < deciding.size(); ++q) where[split[deciding[q]]] = {q, 0};
+                    for (size_t f = 0; f < frontier.size(); ++f) {
+                        if (chosen[f] < 0) { leaf_sets.emplace_back(frontier[f].first, std::move(frontier[f].second)); continue; }
+                        const size_t q = where[f].first;
+                        const uint32_t slot = frontier[f].first;
+                        std::vector<uint32_t> side[2];
+                        const auto& v = frontier[f].second;
+                        for (size_t i = 0; i < v.size(); ++i) side[bits[sub_off[q] + i] ? 1 : 0].push_back(v[i]);
+                        slots[slot].is_node = true;
+                        std::memcpy(slots[slot].rect, &ch_rects[q * 8], sizeof(int32_t) * 8);
+                        slots[slot].thr = ch_thr[q];
+                        for (int b = 0; b < 2; ++b) {
+                            slots[slot].child[b] = (int32_t)slots.size();
+                            next.emplace_back((uint32_t)slots.size(), std::move(side[b]));
+                            slots.emplace_back();
+                        }
+                        (void)d;
+                    }
+                    frontier.swap(next);
+                    continue;
+                }
+            }
+            for (auto& fr : frontier) leaf_sets.emplace_back(fr.first, std::move(fr.second));
+            frontier.clear();
+        }
+        // leaves in creation order; slots that became leaves drop out of the node table
+        for (size_t i = 0; i < leaf_sets.size(); ++i) slots[leaf_sets[i].first].leaf = (int64_t)i;
+        std::vector<int32_t> node_of(slots.size(), -1);
+        int32_t nn = 0;
+        for (size_t s2 = 0; s2 < slots.size(); ++s2)
+            if (slots[s2].is_node) node_of[s2] = nn++;
+        for (size_t s2 = 0; s2 < slots.size(); ++s2) {
+            if (!slots[s2].is_node) continue;
+            raw.rects.insert(raw.rects.end(), slots[s2].rect, slots[s2].rect + 8);
+            raw.threshold.push_back(slots[s2].thr);
+            for (int b = 0; b < 2; ++b) {
+                const int32_t c = slots[s2].child[b];
+                raw.child.push_back(slots[(size_t)c].is_node ? node_of[(size_t)c] : ~(int32_t)slots[(size_t)c].leaf);
+            }
+        }
+        // comp_leaf_data (houghforest.rs:204-225)
+        for (auto& ls : leaf_sets) {
+            uint64_t pos = 0;
+            for (uint32_t j : ls.second)
+                if (is_object[j]) {
+                    ++pos;
+                    raw.offsets.insert(raw.offsets.end(), offsets + (size_t)j * 3, offsets + (size_t)j * 3 + 3);
+                    raw.rotations.insert(raw.rotations.end(), rotations + (size_t)j * 3, rotations + (size_t)j * 3 + 3);
+                }
+            raw.prob.push_back((double)pos / (double)ls.second.size());
+            raw.vote_off.push_back((int64_t)(raw.offsets.size() / 3));
+        }
+        raw.tree_node_off.push_back((int64_t)raw.threshold.size());
+        raw.tree_leaf_off.push_back((int64_t)raw.prob.size());
+    }
+    HostForest* hf = flatten_forest(raw);
+    hf->fn_min_subrect_factor = hf->fn_max_subrect_factor = sc;
+    hf->fn_steepness = tp.steepness;
+    hf->fn_number_of_gen_features = M;
+    hf->fn_max_depth = tp.max_depth;
+    hf->fn_min_subset_size = tp.min_subset_size;
+    return hf;
+}
+
 void trainset_free(TrainSet* t) { delete t; }
 
 }  // namespace dh

@@ -15,7 +15,9 @@ from `rand::thread_rng()`; both are therefore builder-defined here and stated on
     unreachable!()) are skipped; a node is a leaf iff `early_stop` says so or no candidate is left;
     otherwise the candidate with the SMALLEST impurity wins, the first of equals;
   * samples keep their order through a split; `children[bit]` receives the side `binarize` == bit;
-  * one seeded numpy Generator stands in for thread_rng.
+  * a counter-based generator (splitmix64 of seed + k * golden ratio, `CounterRng`) stands in for
+    thread_rng; the C++ trainer behind `dh_train_forest` consumes the same stream in the same
+    order, so both grow identical forests from the same samples and seed.
 The expensive part — `impurity` of every candidate of every node of a level — runs in
 `train_score_kernel` through the C ABI (`dh_train_score_level`), bit-identical to the CPU
 restatement of the callbacks (tests/test_gpu_train.py).
@@ -28,6 +30,37 @@ import numpy as np
 
 from . import capi
 from .api import Context, HoughPrediction, IntrinsicMatrix, default_context
+
+
+class CounterRng:
+    """draw k = splitmix64(seed + k * 0x9E3779B97F4A7C15), k = 1, 2, ..; uniform [0,1) = top 53 bits."""
+    G = np.uint64(0x9E3779B97F4A7C15)
+
+    def __init__(self, seed: int):
+        self.seed = np.uint64(seed & 0xFFFFFFFFFFFFFFFF)
+        self.k = 0
+
+    def random(self, n: int) -> np.ndarray:
+        with np.errstate(over="ignore"):
+            ks = np.arange(self.k + 1, self.k + 1 + n, dtype=np.uint64)
+            z = self.seed + ks * self.G
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+        self.k += n
+        return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+    def permutation(self, n: int) -> np.ndarray:
+        """Fisher-Yates from the back: for i = n-1 .. 1 swap a[i], a[floor(u * (i + 1))]."""
+        a = np.arange(n, dtype=np.int64)
+        if n < 2:
+            return a
+        u = self.random(n - 1)
+        js = (u * np.arange(n, 1, -1, dtype=np.float64)).astype(np.int64)
+        for t, i in enumerate(range(n - 1, 0, -1)):
+            j = js[t]
+            a[i], a[j] = a[j], a[i]
+        return a
 
 
 class TrainSet:
@@ -163,13 +196,14 @@ class HoughLearning:
         self.last_forest = None
 
     # -- HoughTreeFunctions callbacks (host side)
-    def param_set(self, rng: np.random.Generator, n: int):
-        """param_set (houghforest.rs:227-246): n random NodeParams -> rects [n,8], thresholds [n]."""
-        u = rng.random((n, 4))
+    def param_set(self, rng, n: int):
+        """param_set (houghforest.rs:227-246; types.rs:140-160): n random NodeParams -> rects [n,8],
+        thresholds [n].  Five draws per candidate, in the reference's order: four offsets, threshold."""
+        u = rng.random(5 * n).reshape(n, 5)
         a = scale_and_replace(self.sub_w, self.sub_h, self.scale, u[:, 0], u[:, 1])
         b = scale_and_replace(self.sub_w, self.sub_h, self.scale, u[:, 2], u[:, 3])
         rects = np.stack(list(a) + list(b), 1).astype(np.int32)
-        thr = rng.uniform(-256.0, 256.0, n)
+        thr = -256.0 + u[:, 4] * (256.0 - -256.0)
         return rects, thr
 
     def early_stop(self, depth: int, is_object: np.ndarray) -> bool:
@@ -186,7 +220,7 @@ class HoughLearning:
         return float(len(pos)) / float(len(idx)), ts.offsets[pos], ts.rotations[pos]
 
     # -- builder-defined stand-in for stamm's trainer (see the module docstring)
-    def train_tree(self, ts: TrainSet, subset: np.ndarray, rng: np.random.Generator) -> dict:
+    def train_tree(self, ts: TrainSet, subset: np.ndarray, rng) -> dict:
         rects, thr, child, leaves = [], [], [], []
         frontier = [(0, np.asarray(subset, np.uint32))]   # (node slot, samples); slot -1 = the tree is one leaf
         rects.append(None); thr.append(None); child.append([0, 0])
@@ -247,13 +281,10 @@ class HoughLearning:
                     threshold=np.asarray([thr[s] for s in node_slots], np.float64),
                     child=np.asarray(out_child, np.int32).reshape(-1, 2), leaves=[l for _, l in leaves])
 
-    def train_forest(self, ts: TrainSet, rng: np.random.Generator) -> dict:
+    def train_forest(self, ts: TrainSet, rng) -> dict:
         trees = []
         for _ in range(self.n_trees):
-            if ts.n > self.subset:
-                subset = rng.choice(ts.n, self.subset, replace=False)
-            else:
-                subset = rng.permutation(ts.n)
+            subset = rng.permutation(ts.n)[:min(self.subset, ts.n)]   # drawn without replacement, in drawn order
             trees.append(self.train_tree(ts, subset, rng))
         node_off = np.concatenate([[0], np.cumsum([len(t["threshold"]) for t in trees])]).astype(np.int64)
         leaf_off = np.concatenate([[0], np.cumsum([len(t["leaves"]) for t in trees])]).astype(np.int64)
@@ -268,18 +299,38 @@ class HoughLearning:
                     rotations=np.concatenate([l[2] for l in leaves]).astype(np.float64).reshape(-1, 3),
                     sub_w=self.sub_w, sub_h=self.sub_h, max_depth=self.max_depth)
 
-    def learn(self, gaussian_sigma: float, data, seed: int = 0, ctx: Context | None = None) -> HoughPrediction:
+    def train_native(self, gaussian_sigma: float, patches, is_object, offsets, rotations, seed: int,
+                     ctx: Context | None = None) -> HoughPrediction:
+        """The same tree growing in C++ behind the C ABI (dh_train_forest): identical forest for
+        identical samples and seed."""
+        ctx = ctx or default_context()
+        p = capi.dh_train_params()
+        p.stepwidth, p.subimage_width, p.subimage_height = self.stepwidth, self.sub_w, self.sub_h
+        p.max_depth, p.n_trees, p.subset_per_tree = self.max_depth, self.n_trees, self.subset
+        p.subrect_feature_scale, p.features_per_node, p.min_subset_size = self.scale, self.n_features, self.min_subset
+        p.steepness, p.gaussian_sigma, p.seed = self.steepness, float(gaussian_sigma), int(seed) & 0xFFFFFFFFFFFFFFFF
+        px = np.ascontiguousarray(patches, np.uint16)
+        io = np.ascontiguousarray(is_object, np.uint8)
+        of = np.ascontiguousarray(offsets, np.float32)
+        ro = np.ascontiguousarray(rotations, np.float64)
+        h = C.c_void_p()
+        capi.check(capi.load().dh_train_forest(ctx._h, C.byref(p), capi.ptr(px), len(px), capi.ptr(io), capi.ptr(of), capi.ptr(ro),
+                                               C.byref(h)))
+        return HoughPrediction(h)
+
+    def learn(self, gaussian_sigma: float, data, seed: int = 0, ctx: Context | None = None, native: bool = False) -> HoughPrediction:
         """HoughLearning::learn (prediction.rs:145-234).  `data`: iterable of dicts with `depth`
         [h,w] u16, `mask` [h,w] u8, `intrinsic` IntrinsicMatrix, `pos3d` [3], `rot` [3]
-        (db_reader DepthTrue)."""
-        rng = np.random.default_rng(seed)
+        (db_reader DepthTrue).  native=True grows the trees in C++ (dh_train_forest) instead of the
+        Python loop; both give the same forest."""
+        rng = CounterRng(seed)
         patches, is_obj, offs, rots = [], [], [], []
         for truth in data:
             org, flag, o, r = extract_samples(truth["depth"], truth["mask"], truth["intrinsic"], truth["pos3d"], truth["rot"],
                                               self.stepwidth, self.sub_w, self.sub_h)
             neg, pos = np.flatnonzero(flag == 0), np.flatnonzero(flag != 0)
             # rand_perm + take(20), negatives first (prediction.rs:216-226)
-            for part in (rng.permutation(neg)[:20], rng.permutation(pos)[:20]):
+            for part in (neg[rng.permutation(len(neg))][:20], pos[rng.permutation(len(pos))][:20]):
                 for i in part:
                     x0, y0 = org[i]
                     patches.append(np.asarray(truth["depth"])[y0:y0 + self.sub_h, x0:x0 + self.sub_w])   # to_cropped_subimage
@@ -289,9 +340,14 @@ class HoughLearning:
         perm = rng.permutation(len(patches))            # rand_perm(train_ref), prediction.rs:229
         scale = self.scale
         rw, rh = int(np.uint32(float(self.sub_w) * scale)), int(np.uint32(float(self.sub_h) * scale))
-        ts = TrainSet(np.stack(patches)[perm], np.asarray(is_obj)[perm], np.asarray(offs)[perm], np.asarray(rots)[perm], rw, rh, ctx=ctx)
+        self.last_samples = (np.stack(patches)[perm], np.asarray(is_obj, np.uint8)[perm], np.asarray(offs, np.float32)[perm],
+                             np.asarray(rots, np.float64)[perm])
+        if native:
+            self.last_forest = None
+            return self.train_native(gaussian_sigma, *self.last_samples, seed=seed + 1, ctx=ctx)
+        ts = TrainSet(*self.last_samples, rw, rh, ctx=ctx)
         try:
-            self.last_forest = self.train_forest(ts, rng)
+            self.last_forest = self.train_forest(ts, CounterRng(seed + 1))
         finally:
             ts.close()
         return HoughPrediction.from_arrays(self.last_forest, self.stepwidth, gaussian_sigma=gaussian_sigma, meanshift_iterations=20,

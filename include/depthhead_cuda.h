@@ -191,6 +191,28 @@ int dh_train_score_level(dh_ctx* c, const dh_trainset* t, const uint32_t* sample
 int dh_train_split_level(dh_ctx* c, const dh_trainset* t, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
                          const int32_t* rects, const double* thr, uint8_t* bits);
 
+/* HoughLearning::new + learn (prediction.rs:106-143, 145-234) on an already extracted sample set
+ * (the windows the per-image loop of learn collects, in training order): grows n_trees trees with
+ * the callbacks of houghforest.rs:196-311 scored on the GPU and returns the model, ready for
+ * dh_predict* and dh_forest_to_json.  The tree-growing loop and the random numbers are this
+ * library's (stamm 0.2.0 and rand::thread_rng cannot be reproduced);
+ * the same seed and samples always give the same forest. */
+typedef struct dh_train_params {
+    uint32_t stepwidth, subimage_width, subimage_height;   /* HoughLearning::new arguments, in order */
+    uint32_t max_depth, n_trees, subset_per_tree;
+    double subrect_feature_scale;
+    uint32_t features_per_node, min_subset_size;
+    double steepness;
+    float gaussian_sigma;                                  /* learn(gaussian_sigma, ..) */
+    uint32_t _pad;
+    uint64_t seed;
+} dh_train_params;
+int dh_train_forest(dh_ctx* c, const dh_train_params* p, const uint16_t* patches, uint64_t n, const uint8_t* is_object,
+                    const float* offsets, const double* rotations, dh_forest** out);
+/* serde_json::to_string(&HoughPrediction) — what hough_tree_trainer.rs:182 writes.  Copies at most
+ * cap bytes (no terminator) and reports the full length in *needed; call with cap = 0 to size the buffer. */
+int dh_forest_to_json(const dh_forest* f, char* buf, size_t cap, size_t* needed);
+
 /* ------------------------------------------------------------------ measurement */
 /* Per-stage device time (CUDA events on the context's stream) of the LAST dh_predict_batch call,
  * summed over its chunks, in milliseconds.  Order of stages: see DH_STAGE_*. */

@@ -131,3 +131,59 @@ def test_learn_end_to_end(ctx):
     of = oracle.OracleForest.from_json(js)
     tr = of.predict(test_frames[0], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
     assert np.array_equal(a["mid_point"][0], tr.mid_point) and np.array_equal(a["rotation"][0], tr.rotation)
+
+
+def _canonical(arr, t):
+    """tree t as nested tuples from the root, independent of node / leaf numbering"""
+    n0, l0 = int(arr["tree_node_off"][t]), int(arr["tree_leaf_off"][t])
+
+    def leaf(i):
+        v0, v1 = int(arr["vote_off"][l0 + i]), int(arr["vote_off"][l0 + i + 1])
+        return ("leaf", float(arr["prob"][l0 + i]), arr["offsets"][v0:v1].astype(np.float32).tobytes(),
+                arr["rotations"][v0:v1].astype(np.float64).tobytes())
+
+    def node(i):
+        c = arr["child"][n0 + i]
+        kids = tuple(node(int(k)) if k >= 0 else leaf(int(~k)) for k in c)
+        return ("node", tuple(int(x) for x in arr["rects"][n0 + i]), float(arr["threshold"][n0 + i]), kids)
+    if int(arr["tree_node_off"][t + 1]) == n0:
+        return leaf(0)
+    return node(0)
+
+
+def test_native_trainer_matches_the_python_mirror(ctx):
+    """dh_train_forest (C++ tree growing) and train.py (the mirror of HoughLearning) consume the same
+    random stream and the same GPU scores: identical forests; dh_forest_to_json round-trips."""
+    import json
+    n_train = 24
+    frames, centres, rots, masks = synth.make_frames(n_train, seed=55, with_truth=True)
+    data = [dict(depth=frames[i], mask=masks[i], intrinsic=K, pos3d=centres[i], rot=rots[i]) for i in range(n_train)]
+    args = dict(stepwidth=10, subimg_width=80, subimg_height=80, max_depth=6, num_of_trees=3, subset_size_per_tree=600,
+                subrect_feature_scale=0.3, feature_number_per_node=64, min_subset_size_to_stop=20, steepness_weighting=5.0)
+    hl = train.HoughLearning(**args)
+    hp_py = hl.learn(8.0, data, seed=3, ctx=ctx)
+    arr_py = hl.last_forest
+    hp_cc = train.HoughLearning(**args).learn(8.0, data, seed=3, ctx=ctx, native=True)
+    doc = json.loads(hp_cc.to_json())
+    assert (doc["stepwidth"], doc["subimage_width"], doc["subimage_height"], doc["meanshift_iterations"]) == (10, 80, 80, 20)
+    assert doc["gaussian_sigma"] == 8.0
+    fn = doc["forest"]["trees"][0]["functions"]
+    assert fn["number_of_gen_features"] == 64 and fn["max_depth"] == 6 and fn["min_subrect_factor"] == 0.3 and fn["steepness"] == 5.0
+    arr_cc = oracle.forest_arrays_from_doc(doc)
+    assert arr_cc["n_trees"] == 3
+    for t in range(3):
+        assert _canonical(arr_cc, t) == _canonical(arr_py, t), "tree %d differs" % t
+    # the document loads again and predicts like the forest it came from, and like the Python-grown one
+    hp_rt = HoughPrediction.from_json(hp_cc.to_json())
+    test_frames = synth.make_frames(5, seed=77)
+    a, b, c = (h.predict_batch(test_frames, K, ctx=ctx) for h in (hp_cc, hp_rt, hp_py))
+    for other in (b, c):
+        assert np.array_equal(a["mid_point"], other["mid_point"]) and np.array_equal(a["rotation"], other["rotation"])
+    # to_json of a loaded random forest round-trips too (thresholds, f32 offsets, f64 rotations in shortest form)
+    rnd = synth.make_forest(seed=4, n_trees=2, max_depth=4)
+    h1 = HoughPrediction.from_json(synth.forest_to_json(rnd, stepwidth=7))
+    d1 = oracle.forest_arrays_from_doc(json.loads(h1.to_json()))
+    for t in range(2):
+        assert _canonical(d1, t) == _canonical(rnd, t)
+    with pytest.raises(Exception):
+        train.HoughLearning(**{**args, "feature_number_per_node": 64}).train_native(8.0, np.zeros((0, 80, 80), np.uint16), [], np.zeros((0, 3)), np.zeros((0, 3)), 1, ctx=ctx)

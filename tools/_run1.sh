@@ -1,4 +1,3 @@
 set -x
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_all.log
-tail -5 gpurun_out/t_all.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -3 gpurun_out/smoke.log
+timeout 900 python -m pytest tests/test_gpu_train.py -m gpu -x -q > gpurun_out/t_train.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_train.log
+tail -30 gpurun_out/t_train.log

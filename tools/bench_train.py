@@ -45,7 +45,11 @@ def main():
     t0 = time.perf_counter()
     hp = hl.learn(8.0, data, seed=7, ctx=ctx)
     t_learn = time.perf_counter() - t0
-    arr = hl.last_forest
+    # the same trees grown by the C++ loop behind dh_train_forest (samples already extracted)
+    t0 = time.perf_counter()
+    hp_native = hl.train_native(8.0, *hl.last_samples, seed=8, ctx=ctx)
+    t_native = time.perf_counter() - t0
+    assert hp_native.n_nodes == hp.n_nodes
     # CPU restatement on a sample: root-like node, a few candidates
     rng = np.random.default_rng(3)
     P, F, O, R = [], [], [], []
@@ -71,10 +75,11 @@ def main():
         "trees": a.trees, "samples_in_set": int(40 * a.frames), "subset_per_tree": a.subset, "features_per_node": a.features,
         "max_depth": a.depth, "nodes": int(hp.n_nodes), "leaves": int(hp.n_leaves),
         "learn_seconds": t_learn, "seconds_per_tree": t_learn / a.trees, "scorer_seconds": t_score[0],
+        "native_trainer_seconds": t_native, "native_seconds_per_tree": t_native / a.trees,
         "candidate_x_sample_evaluations": cand_samples[0], "gpu_candidate_samples_per_s": cand_samples[0] / t_score[0],
         "cpu_port_candidate_samples_per_s_1_thread": cpu_rate,
         "cpu_port_seconds_per_tree_1_thread_extrapolated": cand_samples[0] / a.trees / cpu_rate,
-        "note": "learn_seconds includes sample extraction, box tables, the host tree-growing loop (Python) and the scorer calls"}))
+        "note": "learn_seconds: Python mirror incl. sample extraction from the frames; native_trainer_seconds: dh_train_forest (C++ loop) on the extracted samples incl. box tables and flattening"}))
 
 
 if __name__ == "__main__":
