@@ -27,6 +27,7 @@
 #include "dh_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -1831,6 +1832,27 @@ constexpr int kTraverseThreads = 512;
 using namespace dev;
 
 // ================================================================ launch wrappers
+// cudaFuncSetAttribute is per device: remember, per device, the largest dynamic shared-memory
+// size each kernel family was configured for (several contexts on several GPUs may live in one
+// process; a context is single-threaded, but two contexts may race here, hence the atomics).
+namespace {
+constexpr int kMaxDevices = 64;
+struct SmemConfig {
+    std::atomic<uint32_t> bytes[kMaxDevices];
+    SmemConfig() { for (auto& b : bytes) b.store(0); }
+    // true if `want` exceeds what the current device was configured for (and records it)
+    bool raise(uint32_t want) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= kMaxDevices) return true;
+        uint32_t cur = bytes[dev].load();
+        while (want > cur)
+            if (bytes[dev].compare_exchange_weak(cur, want)) return true;
+        return false;
+    }
+};
+}  // namespace
+
 int launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s) {
     if (b.band_u && g.w + 1 <= 1024) {
         int launches = 0;
@@ -1838,11 +1860,8 @@ int launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cuda
         const uint32_t n_bands = (g.h + kSatBandRows - 1) / kSatBandRows;
         const uint32_t threads = (g.w + 1 + 31) & ~31u;
         const uint32_t smem = kSatBandRows * ((g.w + 1 + 8) & ~7u) * 4u;
-        static uint32_t configured = 0;
-        if (smem > configured) {
-            cudaFuncSetAttribute(sat_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
+        static SmemConfig configured;
+        if (configured.raise(smem)) cudaFuncSetAttribute(sat_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 gr(n_bands, n_frames);
         sat_band_sums_kernel<<<gr, threads, 0, s>>>(b.depth, b.band_u, g.w, g.h, n_bands);
         sat_band_kernel<<<gr, kSatBandRows * 32, smem, s>>>(b.depth, b.band_u, b.sat, g.w, g.h, g.sat_pitch, n_bands);
@@ -1873,11 +1892,10 @@ int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames
     uint32_t wpc = n_strips <= (uint32_t)kBoxMaxWarps ? n_strips : 2u;  // warps per CTA
     while (wpc > 1u && wpc * per_warp > 100u * 1024u) --wpc;           // tall rectangles: long pixel rings
     const uint32_t smem = wpc * per_warp;
-    static uint32_t configured = 0;
-    if (smem > configured) {
+    static SmemConfig configured;
+    if (configured.raise(smem)) {
         cudaFuncSetAttribute(box_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(box_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
     }
     // bands: a band re-reads the rh - 1 rows above it, so as few as possible, but enough that the
     // warps of one launch fill the GPU once; never shorter than rh rows
@@ -1915,15 +1933,14 @@ int traverse_kernel_attrs(int* regs, int* max_smem) {
 template <int kThreads>
 static void launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
                               const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
-    static int configured_smem = -1;
-    if ((int)tp.smem_bytes > configured_smem) {
+    static SmemConfig configured;
+    if (configured.raise(tp.smem_bytes)) {
         cudaFuncSetAttribute(traverse_kernel<kThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
-        configured_smem = (int)tp.smem_bytes;
     }
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
     if (f.uni && g.rw && f.hot_tex)
@@ -1984,11 +2001,8 @@ int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const Forest
 
 int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t iterations,
                      cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(meanshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes);
-        configured = true;
-    }
+    static SmemConfig configured;
+    if (configured.raise((uint32_t)kMsSmemBytes)) cudaFuncSetAttribute(meanshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes);
     meanshift_kernel<<<2u * n_frames, kMsThreads, kMsSmemBytes, s>>>(b, g, f, iterations);
     return 1;
 }

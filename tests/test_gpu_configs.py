@@ -225,3 +225,29 @@ def test_drifting_mean_shift_rebuilds_the_cube(ctx):
         assert abs(int(res.mid_point[0]) - start) > 14       # the position really left the first cube
         total += ctx.counters()["cube_rebuilds"]
     assert total >= 2
+
+
+def test_two_devices_in_one_process():
+    """one dh_ctx per GPU in ONE process (the forest object is shared): both devices give the
+    oracle's answers; skipped on single-GPU boxes"""
+    try:
+        c1 = Context(1)
+    except Exception:
+        pytest.skip("needs a second GPU")
+    c0 = Context(0)
+    try:
+        arr = synth.make_forest(seed=2, n_trees=5, max_depth=9)
+        hp = HoughPrediction.from_arrays(arr, stepwidth=5)
+        of = oracle.OracleForest(arr, 5, 80, 80, 8.0, 20)
+        frames = synth.make_frames(6, seed=14)
+        a = hp.predict_batch(frames, K, ctx=c1)       # the second device first: nothing was configured there yet
+        b = hp.predict_batch(frames, K, ctx=c0)
+        assert a.tobytes() == b.tobytes()
+        for i in (0, 5):
+            tr = of.predict(frames[i], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+            assert np.array_equal(a["mid_point"][i], tr.mid_point) and np.array_equal(a["rotation"][i], tr.rotation)
+        r1 = hp.predict_parameter_parallel(frames[2], K, ctx=c1)
+        assert np.array_equal(r1.mid_point, a["mid_point"][2])
+    finally:
+        c0.close()
+        c1.close()
