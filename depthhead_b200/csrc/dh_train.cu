@@ -257,6 +257,7 @@ void Context::train_score_level(const TrainSet& ts, const uint32_t* sample_idx, 
                                 const int32_t* cand_rects, const double* cand_thr, uint32_t m, uint64_t depth, double steepness,
                                 dh_split_stats* out) {
     DH_CUDA_T(cudaSetDevice(device_));
+    if (ts.device != device_) throw ModelError(DH_E_ARG, "the training set lives on another GPU than this context");
     if (n_nodes == 0 || m == 0) return;
     const uint64_t total = node_off[n_nodes];
     for (uint32_t k = 0; k < n_nodes; ++k)
@@ -288,6 +289,7 @@ void Context::train_score_level(const TrainSet& ts, const uint32_t* sample_idx, 
 void Context::train_split_level(const TrainSet& ts, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
                                 const int32_t* rects, const double* thr, uint8_t* bits) {
     DH_CUDA_T(cudaSetDevice(device_));
+    if (ts.device != device_) throw ModelError(DH_E_ARG, "the training set lives on another GPU than this context");
     if (n_nodes == 0) return;
     const uint64_t total = node_off[n_nodes];
     if (total == 0) return;
