@@ -293,3 +293,32 @@ def test_full_size_properties(ctx):
     for i in (0, 11, 23):
         tr = of.predict(frames[i], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
         assert np.array_equal(a["mid_point"][i], tr.mid_point) and np.array_equal(a["rotation"][i], tr.rotation)
+
+
+def test_against_committed_golden_vectors(ctx):
+    """the CUDA path against tests/golden/oracle_small.npz directly (no oracle run in this test):
+    leaf ids, gate, both seed grids, seeds and the final pose of every golden case"""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(here, "golden", "oracle_small.npz"))
+    ctx.enable_debug(True)
+    try:
+        for name, fk, step, fseed, n in mg.CASES:
+            arr = synth.make_forest(**fk)
+            hp = HoughPrediction.from_arrays(arr, stepwidth=step)
+            for i, d in enumerate(synth.make_frames(n, seed=fseed)):
+                res = hp.predict_parameter_parallel(d, K, ctx=ctx)
+                p = "%s/%d/" % (name, i)
+                assert np.array_equal(ctx.debug_leaf_indices(), g[p + "leaf"]), (name, i)
+                assert np.array_equal(ctx.debug_patches()[1], g[p + "gate"]), (name, i)
+                gp, gr, sm, sr = ctx.debug_seeds()
+                assert np.array_equal(gp, g[p + "guess_pos"]) and np.array_equal(gr, g[p + "guess_rot"]), (name, i)
+                assert np.array_equal(sm, g[p + "seed_mid"]) and np.array_equal(sr, g[p + "seed_rot"]), (name, i)
+                assert np.array_equal(res.mid_point, g[p + "mid_point"]), (name, i)
+                assert np.array_equal(res.rotation.view(np.uint64), g[p + "rotation"].view(np.uint64)), (name, i)
+    finally:
+        ctx.enable_debug(False)
