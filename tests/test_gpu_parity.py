@@ -239,6 +239,13 @@ def test_device_resident_batch(ctx):
     out = hp.predict_batch(None, K, ctx=ctx, device_ptr=dev.data_ptr(), n=6, w=640, h=480)
     assert np.array_equal(out["mid_point"], host["mid_point"])
     assert np.array_equal(out["rotation"], host["rotation"])
+    # frames that start on an odd 2-byte boundary: no 16-byte pixel loads in the front-end kernels
+    flat = torch.zeros(frames.size + 8, dtype=torch.int16, device="cuda")
+    for off in (1, 3):
+        flat[off:off + frames.size] = torch.from_numpy(frames.view(np.int16).reshape(-1)).cuda()
+        torch.cuda.synchronize()
+        out = hp.predict_batch(None, K, ctx=ctx, device_ptr=flat.data_ptr() + 2 * off, n=6, w=640, h=480)
+        assert np.array_equal(out["mid_point"], host["mid_point"]) and np.array_equal(out["rotation"], host["rotation"])
 
 
 def test_json_and_arrays_loaders_agree(ctx, small_case):
