@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
 // votes go into the two coarse seed grids (prediction.rs:630-636, 661-675) held in shared memory;
 // non-zero cells are then added to the frame's grids in global memory.  Everything that is
 // constant per leaf (valtoadd, spread gates) was precomputed by leaf_gate_kernel.
-constexpr int kGateThreads = 256;
+constexpr int kGateThreads = 512;   // 3 CTAs of 59 KB per SM: 48 warps (256 threads with 48 KB: 32 warps)
 constexpr int kTouchedCap = 1024;
 
 // 2-D projection of one centre vote onto the 20x20 seed grid (prediction.rs:661-675)
@@ -828,11 +828,14 @@ __device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(kGateThreads) gate_coarse_kernel(FrameBuffers b, Geometry g, ForestDev f) {
-    __shared__ uint32_t s_grid[kPosGridCells + kRotGridCells];  // [0,400) centre, [400,8400) rotation
-    __shared__ float4 s_gated[kGateThreads];                     // p3 + patch index of the CTA's gated patches
-    __shared__ uint16_t s_touched[kTouchedCap];                  // rotation cells this CTA made non-zero
-    __shared__ PairSlot s_slots[kGateThreads / 32][32];         // vote spreading, one set per warp
+constexpr int kGateSmemBytes = kGateThreads * 16 + (kGateThreads / 32) * 32 * 32 + (kPosGridCells + kRotGridCells) * 4 + kTouchedCap * 2;
+
+__global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffers b, Geometry g, ForestDev f) {
+    extern __shared__ __align__(16) uint8_t gate_smem[];
+    float4* s_gated = reinterpret_cast<float4*>(gate_smem);                                   // [kGateThreads] p3 + patch index of the CTA's gated patches
+    PairSlot(*s_slots)[32] = reinterpret_cast<PairSlot(*)[32]>(gate_smem + kGateThreads * 16);  // [warps][32] vote spreading, one set per warp
+    uint32_t* s_grid = reinterpret_cast<uint32_t*>(gate_smem + kGateThreads * 16 + (kGateThreads / 32) * 32 * 32);  // [0,400) centre, [400,8400) rotation
+    uint16_t* s_touched = reinterpret_cast<uint16_t*>(s_grid + kPosGridCells + kRotGridCells);  // rotation cells this CTA made non-zero
     __shared__ uint32_t s_ngate, s_base, s_ntouched, s_next;
     const uint32_t frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31u;
     const uint32_t p = blockIdx.x * kGateThreads + tid;
@@ -1982,8 +1985,10 @@ uint32_t vote_box_dim() { return (uint32_t)kBox; }
 // and the queue header must be zero when these run.  Each returns the kernels it launched.
 int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
     if (!g.P) return 0;
+    static SmemConfig configured;
+    if (configured.raise((uint32_t)kGateSmemBytes)) cudaFuncSetAttribute(gate_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateSmemBytes);
     dim3 gr((g.P + kGateThreads - 1) / kGateThreads, n_frames);
-    gate_coarse_kernel<<<gr, kGateThreads, 0, s>>>(b, g, f);
+    gate_coarse_kernel<<<gr, kGateThreads, kGateSmemBytes, s>>>(b, g, f);
     return 1;
 }
 
