@@ -288,40 +288,65 @@ __global__ void __launch_bounds__(kSatBandRows * 32) sat_band_kernel(const uint1
 // 16-byte load per lane per row, fetched eight rows ahead) and sweeps down a band of rows with the
 // rh-row window sums of its columns in registers: acc += row r, acc -= row r - rh + 1, the
 // departing row coming from a lane-private ring of the last rh rows in shared memory (16 bytes
-// per lane per row, no synchronisation).  Per output row the window sums are turned into
-// exclusive prefix sums along x (shuffle scan), staged in a warp-private row of shared memory, and
-// B[y][x] = P[x + rw] - P[x] goes out with 16-byte stores.  No block-level barrier; all arithmetic
-// in u32 (rw*rh*65535 < 2^31 is checked at load; prefix sums may wrap, differences are exact).
+// per lane per row, no synchronisation).  Per output row the window sums become B either through
+// nine shuffles (rectangle width a multiple of the lane's pixel count) or through exclusive
+// prefix sums along x staged in a warp-private row of shared memory, B[y][x] = P[x + rw] - P[x];
+// 16-byte stores.  No block-level barrier; all arithmetic in u32 (rw*rh*65535 < 2^31 is checked
+// at load; prefix sums may wrap, differences are exact).  DH_BOX_PX=4 selects 4 pixels per lane
+// (twice the warps, half the ring each): measured slower (0.47 vs 0.43 ms), kept as a variant.
 constexpr int kBoxMaxWarps = 8;                 // warps per CTA = strips of one (frame, band), when there are at most 8
-constexpr int kBoxStripIn = 256;                // input columns per strip: 8 per lane
-constexpr int kBoxRowPitch = 272;               // P[0..256] + the slack the last active lane may read
 constexpr int kBoxAhead = 8;                    // rows fetched ahead
 
-__device__ __forceinline__ uint4 box_fetch(const uint16_t* __restrict__ row, uint32_t w, uint32_t x, bool vec_ok, bool on) {
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (!on) return q;
-    if (vec_ok) return __ldg(reinterpret_cast<const uint4*>(row + x));
-    uint32_t v[8];
+// kPx pixels per lane: 8 (16-byte loads, strips of 256 columns) or 4 (8-byte loads, strips of 128
+// columns: twice the warps for the same frame, half the ring per warp)
+template <int kPx>
+struct BoxRow {
+    uint32_t q[kPx / 2];  // kPx u16 pixels
+};
+template <int kPx>
+__device__ __forceinline__ BoxRow<kPx> box_fetch(const uint16_t* __restrict__ row, uint32_t w, uint32_t x, bool vec_ok, bool on) {
+    BoxRow<kPx> r;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (x + j < w) ? (uint32_t)__ldg(row + x + j) : 0u;
-    return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+    for (int j = 0; j < kPx / 2; ++j) r.q[j] = 0u;
+    if (!on) return r;
+    if (vec_ok) {
+        if (kPx == 8) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(row + x));
+            r.q[0] = t.x; r.q[1] = t.y; r.q[kPx / 2 - 2] = t.z; r.q[kPx / 2 - 1] = t.w;
+        } else {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(row + x));
+            r.q[0] = t.x; r.q[1] = t.y;
+        }
+        return r;
+    }
+#pragma unroll
+    for (int j = 0; j < kPx / 2; ++j) {
+        const uint32_t lo = (x + 2 * j < w) ? (uint32_t)__ldg(row + x + 2 * j) : 0u;
+        const uint32_t hi = (x + 2 * j + 1 < w) ? (uint32_t)__ldg(row + x + 2 * j + 1) : 0u;
+        r.q[j] = lo | (hi << 16);
+    }
+    return r;
 }
-template <bool kAdd>
-__device__ __forceinline__ void box_apply(uint32_t acc[8], const uint4 q) {
-    const uint32_t v[8] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16, q.z & 0xffffu, q.z >> 16, q.w & 0xffffu, q.w >> 16};
+template <int kPx, bool kAdd>
+__device__ __forceinline__ void box_apply(uint32_t acc[kPx], const BoxRow<kPx>& r) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = kAdd ? acc[j] + v[j] : acc[j] - v[j];
+    for (int j = 0; j < kPx / 2; ++j) {
+        const uint32_t lo = r.q[j] & 0xffffu, hi = r.q[j] >> 16;
+        acc[2 * j] = kAdd ? acc[2 * j] + lo : acc[2 * j] - lo;
+        acc[2 * j + 1] = kAdd ? acc[2 * j + 1] + hi : acc[2 * j + 1] - hi;
+    }
 }
 
-// kWhole: rw is a multiple of 8, i.e. a rectangle row is a suffix of one lane's 8 columns, rw/8 - 1
-// whole lanes and a prefix of one more lane: B comes straight out of shuffles, without the prefix
-// sums over the whole warp and their trip through shared memory.
-template <bool kWhole>
+// kWhole: rw is a multiple of kPx, i.e. a rectangle row is a suffix of one lane's columns,
+// rw/kPx - 1 whole lanes and a prefix of one more lane: B comes straight out of shuffles, without
+// the prefix sums over the whole warp and their trip through shared memory.
+template <int kPx, bool kWhole>
 __global__ void __launch_bounds__(kBoxMaxWarps * 32) box_image_kernel(const uint16_t* __restrict__ depth, uint32_t* __restrict__ box,
                                                                 uint32_t w, uint32_t h, uint32_t rw, uint32_t rh, uint32_t bw,
                                                                 uint32_t bh, uint32_t bpitch, uint32_t strip_out, uint32_t n_strips,
                                                                 uint32_t band_rows, uint32_t n_bands, uint32_t n_units) {
-    extern __shared__ __align__(16) uint32_t s_box[];  // [warps][2][kBoxRowPitch] prefix rows, then [warps][rh][32] uint4 pixel rings
+    constexpr uint32_t kRowPitch = 32 * kPx + 16;      // P[0 .. 32*kPx] + the slack the last active lane may read
+    extern __shared__ __align__(16) uint32_t s_box[];  // [warps][2][kRowPitch] prefix rows (general widths only), then [warps][rh][32] pixel rings
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t n_warps = blockDim.x >> 5;  // the strips of one (frame, band) sit in one CTA: their reads and writes
                                                // of a row are adjacent in memory and happen at about the same time
@@ -330,28 +355,29 @@ __global__ void __launch_bounds__(kBoxMaxWarps * 32) box_image_kernel(const uint
     const uint32_t strip = unit % n_strips;
     unit /= n_strips;
     const uint32_t band = unit % n_bands, frame = unit / n_bands;
-    const uint32_t c0 = strip * strip_out, c1 = min(bw, c0 + strip_out);  // output columns (c0 is a multiple of 8)
+    const uint32_t c0 = strip * strip_out, c1 = min(bw, c0 + strip_out);  // output columns (c0 is a multiple of kPx)
     const uint32_t y0 = band * band_rows, y1 = min(bh, y0 + band_rows);   // output rows
     if (c0 >= c1 || y0 >= y1) return;
     const uint32_t x_end = c1 + rw - 1u;          // one past the last input column (<= w)
     const uint32_t r_end = y1 + rh - 1u;          // one past the last input row (<= h)
     const uint16_t* img = depth + (size_t)frame * h * w;
-    const bool vec_ok = ((w & 7u) == 0u) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0u);
-    const uint32_t my_x = c0 + lane * 8u;
+    const bool vec_ok = ((w & (kPx - 1u)) == 0u) && ((reinterpret_cast<uintptr_t>(img) & (2u * kPx - 1u)) == 0u);
+    const uint32_t my_x = c0 + lane * kPx;
     const bool lane_in = my_x < x_end;            // the lane holds input pixels
     const bool lane_out = my_x < c1;              // the lane holds output columns
     const bool q_vec = (rw & 3u) == 0u;
-    uint32_t* sp0 = s_box + warp * 2u * kBoxRowPitch + lane * 8u;
-    uint4* ring = reinterpret_cast<uint4*>(s_box + n_warps * 2u * kBoxRowPitch) + (size_t)warp * rh * 32u + lane;
+    const uint32_t p_words = kWhole ? 0u : n_warps * 2u * kRowPitch;
+    uint32_t* sp0 = s_box + warp * 2u * kRowPitch + lane * kPx;
+    BoxRow<kPx>* ring = reinterpret_cast<BoxRow<kPx>*>(s_box + p_words) + (size_t)warp * rh * 32u + lane;
     uint32_t* out = box + ((size_t)frame * bh + y0) * bpitch + my_x;
     const uint16_t* row_nxt = img + (size_t)y0 * w;   // next input row to fetch
-    uint32_t acc[8];
+    uint32_t acc[kPx];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0u;
-    uint4 q[kBoxAhead];
+    for (int j = 0; j < kPx; ++j) acc[j] = 0u;
+    BoxRow<kPx> q[kBoxAhead];
 #pragma unroll
     for (int k = 0; k < kBoxAhead; ++k) {
-        q[k] = box_fetch(row_nxt, w, my_x, vec_ok, lane_in && y0 + (uint32_t)k < r_end);
+        q[k] = box_fetch<kPx>(row_nxt, w, my_x, vec_ok, lane_in && y0 + (uint32_t)k < r_end);
         row_nxt += w;
     }
     uint32_t buf = 0, slot = 0;                   // slot = (r - y0) mod rh
@@ -360,35 +386,30 @@ __global__ void __launch_bounds__(kBoxMaxWarps * 32) box_image_kernel(const uint
         for (int k = 0; k < kBoxAhead; ++k) {
             const uint32_t r = r0 + (uint32_t)k;
             if (r >= r_end) break;
-            const uint4 cur = q[k];
-            q[k] = box_fetch(row_nxt, w, my_x, vec_ok, lane_in && r + kBoxAhead < r_end);
+            const BoxRow<kPx> cur = q[k];
+            q[k] = box_fetch<kPx>(row_nxt, w, my_x, vec_ok, lane_in && r + kBoxAhead < r_end);
             row_nxt += w;
             ring[slot * 32u] = cur;               // row r takes the place of row r - rh (left the window last round)
             if (++slot == rh) slot = 0;
-            box_apply<true>(acc, cur);
+            box_apply<kPx, true>(acc, cur);
             if (r + 1u >= y0 + rh) {              // the window [r - rh + 1, r] is complete
-                const uint4 old = ring[slot * 32u];  // row r - rh + 1 leaves the window
-                // exclusive prefix sums of the lane's 8 window sums
-                uint32_t e[8], tot = 0;
+                const BoxRow<kPx> old = ring[slot * 32u];  // row r - rh + 1 leaves the window
+                // exclusive prefix sums of the lane's window sums
+                uint32_t e[kPx], tot = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < kPx; ++j) {
                     e[j] = tot;
                     tot += acc[j];
                 }
+                uint32_t t[kPx];
                 if (kWhole) {
-                    // B[8l + j] = (T_l - e_l[j]) + T_{l+1} + .. + T_{l+k-1} + e_{l+k}[j],  k = rw / 8
-                    const uint32_t k = rw >> 3;
+                    // B[kPx*l + j] = (T_l - e_l[j]) + T_{l+1} + .. + T_{l+k-1} + e_{l+k}[j],  k = rw / kPx
+                    const uint32_t k2 = rw / kPx;
                     uint32_t whole = tot;
-                    for (uint32_t i = 1; i < k; ++i) whole += __shfl_down_sync(0xffffffffu, tot, i);
-                    uint32_t t[8];
+                    for (uint32_t i = 1; i < k2; ++i) whole += __shfl_down_sync(0xffffffffu, tot, i);
                     t[0] = whole;
 #pragma unroll
-                    for (int j = 1; j < 8; ++j) t[j] = whole - e[j] + __shfl_down_sync(0xffffffffu, e[j], k);
-                    if (lane_out) {
-                        // columns at or beyond bw are row padding (never read); beyond the pitch nothing is stored
-                        if (my_x < bpitch) *reinterpret_cast<uint4*>(out) = make_uint4(t[0], t[1], t[2], t[3]);
-                        if (my_x + 4u < bpitch) *reinterpret_cast<uint4*>(out + 4) = make_uint4(t[4], t[5], t[6], t[7]);
-                    }
+                    for (int j = 1; j < kPx; ++j) t[j] = whole - e[j] + __shfl_down_sync(0xffffffffu, e[j], k2);
                 } else {
                     // general width: prefix sums over the whole warp, staged in shared memory
                     uint32_t incl = tot;
@@ -399,28 +420,34 @@ __global__ void __launch_bounds__(kBoxMaxWarps * 32) box_image_kernel(const uint
                     }
                     const uint32_t base = incl - tot;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) e[j] += base;
-                    uint32_t* sp = sp0 + buf * kBoxRowPitch;
-                    *reinterpret_cast<uint4*>(sp) = make_uint4(e[0], e[1], e[2], e[3]);
-                    *reinterpret_cast<uint4*>(sp + 4) = make_uint4(e[4], e[5], e[6], e[7]);
-                    if (lane == 31u) sp[8] = incl;  // P[256]
+                    for (int j = 0; j < kPx; ++j) e[j] += base;
+                    uint32_t* sp = sp0 + buf * kRowPitch;
+#pragma unroll
+                    for (int j = 0; j < kPx; j += 4) *reinterpret_cast<uint4*>(sp + j) = make_uint4(e[j], e[j + 1], e[j + 2], e[j + 3]);
+                    if (lane == 31u) sp[kPx] = incl;  // P[32 * kPx]
                     __syncwarp();
                     if (lane_out) {
-                        uint32_t t[8];
                         if (q_vec) {
-                            const uint4 a = *reinterpret_cast<const uint4*>(sp + rw), b2 = *reinterpret_cast<const uint4*>(sp + rw + 4);
-                            t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b2.x; t[5] = b2.y; t[6] = b2.z; t[7] = b2.w;
+#pragma unroll
+                            for (int j = 0; j < kPx; j += 4) {
+                                const uint4 a = *reinterpret_cast<const uint4*>(sp + rw + j);
+                                t[j] = a.x - e[j]; t[j + 1] = a.y - e[j + 1]; t[j + 2] = a.z - e[j + 2]; t[j + 3] = a.w - e[j + 3];
+                            }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) t[j] = sp[rw + j];
+                            for (int j = 0; j < kPx; ++j) t[j] = sp[rw + j] - e[j];
                         }
-                        if (my_x < bpitch) *reinterpret_cast<uint4*>(out) = make_uint4(t[0] - e[0], t[1] - e[1], t[2] - e[2], t[3] - e[3]);
-                        if (my_x + 4u < bpitch) *reinterpret_cast<uint4*>(out + 4) = make_uint4(t[4] - e[4], t[5] - e[5], t[6] - e[6], t[7] - e[7]);
                     }
+                    buf ^= 1u;
+                }
+                if (lane_out) {
+                    // columns at or beyond bw are row padding (never read); beyond the pitch nothing is stored
+#pragma unroll
+                    for (int j = 0; j < kPx; j += 4)
+                        if (my_x + (uint32_t)j < bpitch) *reinterpret_cast<uint4*>(out + j) = make_uint4(t[j], t[j + 1], t[j + 2], t[j + 3]);
                 }
                 out += bpitch;
-                buf ^= 1u;
-                box_apply<false>(acc, old);
+                box_apply<kPx, false>(acc, old);
             }
         }
     }
@@ -1886,19 +1913,20 @@ bool box_image_supported(uint32_t w, uint32_t h, uint32_t sw, uint32_t sh, uint3
     return ((sw + rw - 1u) / rw) * ((sh + rh - 1u) / rh) <= 64u;
 }
 
-int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, int n_sms, cudaStream_t s) {
-    // strips: a multiple of 8 output columns each, at most 257 - rw (column c reads P[c + rw] <= P[256])
-    const uint32_t max_out = ((uint32_t)kBoxStripIn + 1u - g.rw) & ~7u;
+template <int kPx>
+static int launch_box_image_t(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, int n_sms, bool whole, cudaStream_t s) {
+    // strips: a multiple of kPx output columns each, at most 32*kPx + 1 - rw (column c reads P[c + rw] <= P[32*kPx])
+    const uint32_t max_out = (32u * kPx + 1u - g.rw) & ~(uint32_t)(kPx - 1);
     const uint32_t n_strips = (g.box_w + max_out - 1u) / max_out;
-    const uint32_t strip_out = (((g.box_w + n_strips - 1u) / n_strips) + 7u) & ~7u;
-    const uint32_t per_warp = 2u * kBoxRowPitch * 4u + g.rh * 512u;
+    const uint32_t strip_out = (((g.box_w + n_strips - 1u) / n_strips) + kPx - 1u) & ~(uint32_t)(kPx - 1);
+    const uint32_t per_warp = (whole ? 0u : 2u * (32u * kPx + 16u) * 4u) + g.rh * 64u * kPx;
     uint32_t wpc = n_strips <= (uint32_t)kBoxMaxWarps ? n_strips : 2u;  // warps per CTA
     while (wpc > 1u && wpc * per_warp > 100u * 1024u) --wpc;           // tall rectangles: long pixel rings
     const uint32_t smem = wpc * per_warp;
     static SmemConfig configured;
     if (configured.raise(smem)) {
-        cudaFuncSetAttribute(box_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(box_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(box_image_kernel<kPx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(box_image_kernel<kPx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     // bands: a band re-reads the rh - 1 rows above it, so as few as possible, but enough that the
     // warps of one launch fill the GPU once; never shorter than rh rows
@@ -1909,14 +1937,22 @@ int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames
     const uint32_t band_rows = (g.box_h + n_bands - 1u) / n_bands;
     n_bands = (g.box_h + band_rows - 1u) / band_rows;
     const uint32_t n_units = n_strips * n_bands * n_frames;
-    static const bool allow_whole = !(std::getenv("DH_BOX_WHOLE") && std::atoi(std::getenv("DH_BOX_WHOLE")) == 0);
-    if ((g.rw & 7u) == 0u && allow_whole)
-        box_image_kernel<true><<<(n_units + wpc - 1u) / wpc, wpc * 32u, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h,
-                                                                                  g.box_pitch, strip_out, n_strips, band_rows, n_bands, n_units);
+    const uint32_t blocks = (n_units + wpc - 1u) / wpc;
+    if (whole)
+        box_image_kernel<kPx, true><<<blocks, wpc * 32u, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h, g.box_pitch,
+                                                                   strip_out, n_strips, band_rows, n_bands, n_units);
     else
-        box_image_kernel<false><<<(n_units + wpc - 1u) / wpc, wpc * 32u, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h,
-                                                                                   g.box_pitch, strip_out, n_strips, band_rows, n_bands, n_units);
+        box_image_kernel<kPx, false><<<blocks, wpc * 32u, smem, s>>>(b.depth, b.box, g.w, g.h, g.rw, g.rh, g.box_w, g.box_h, g.box_pitch,
+                                                                    strip_out, n_strips, band_rows, n_bands, n_units);
     return 1;
+}
+
+int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, int n_sms, cudaStream_t s) {
+    static const bool allow_whole = !(std::getenv("DH_BOX_WHOLE") && std::atoi(std::getenv("DH_BOX_WHOLE")) == 0);
+    static const int px = std::getenv("DH_BOX_PX") ? std::atoi(std::getenv("DH_BOX_PX")) : 8;
+    // 4 pixels per lane: only through the shuffle path (rw a multiple of 4, at most 124)
+    if (px == 4 && allow_whole && (g.rw & 3u) == 0u && g.rw <= 124u) return launch_box_image_t<4>(b, g, n_frames, n_sms, true, s);
+    return launch_box_image_t<8>(b, g, n_frames, n_sms, allow_whole && (g.rw & 7u) == 0u, s);
 }
 
 uint32_t traverse_smem_bytes(uint32_t tw, uint32_t th, uint32_t patches_per_tile) {

@@ -42,6 +42,7 @@ VARIANTS = [
     {"DH_SAT_BANDS": "0", "DH_BOX_IMAGE": "0"},     # two-pass summed-area table
     {"DH_BOX_IMAGE": "0"},                          # uniform forest on the summed-area table (box sums made in the tile)
     {"DH_BOX_IMAGE": "0", "DH_UNI_LDG": "1"},
+    {"DH_BOX_PX": "4"},                             # box image with 4 pixels per lane
     {"DH_BOX_WHOLE": "0"},                          # box image through warp-wide prefix sums (the path of widths not divisible by 8)
     {"DH_TRAV_THREADS": "512"},                     # 512-thread traversal tiles
     {"DH_LANES": "1"},
