@@ -120,6 +120,27 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Multi-GPU runs: keep this rank's host threads (and therefore its pinned frame buffers, first
+    touched below) on the CPU cores next to its GPU, so that eight ranks do not pull their
+    host->device copies across the socket interconnect.  Plumbing only; silently skipped when NVML
+    or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:  # noqa: BLE001
+        return None
+    return None
+
+
 def make_workload(rank: int, n_frames: int):
     from depthhead_b200 import synth
     arr = synth.make_forest(seed=1, n_trees=N_TREES, max_depth=MAX_DEPTH)
@@ -226,6 +247,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libdepthhead_cuda has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -392,6 +414,7 @@ def main():
                    "forest": "%d trees, depth %d, %d nodes, %d leaves, %d votes; loaded from %s in %.1f s"
                              % (N_TREES, MAX_DEPTH, hp.n_nodes, hp.n_leaves, hp.n_votes, model_src, t_load),
                    "sharding": "frames by rank, forest replicated, no collective on the data path",
+                   "host_affinity": ("rank bound to the %d cores next to its GPU (NVML)" % numa) if numa else "not bound",
                    "l2": "inputs (%.0f MB per step) and the box-sum scratch exceed the 126 MB L2; no flush" % (frames.nbytes / 1e6)},
         "evals_per_s": counters["evals"] * world / (ms_dev / 1000.0),
         "patch_tree_evals_per_frame": counters["evals"] / max(1, counters["frames"]),
