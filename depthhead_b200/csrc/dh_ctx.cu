@@ -94,6 +94,7 @@ Context::Context(int device) : device_(device) {
     dev_alloc(d_counters_, DH_N_COUNTERS);
     DH_CUDA(cudaHostAlloc((void**)&h_fs_, sizeof(FrameState), cudaHostAllocDefault));
     DH_CUDA(cudaHostAlloc((void**)&h_counters_, sizeof(unsigned long long) * DH_N_COUNTERS, cudaHostAllocDefault));
+    use_graphs_ = env_flag("DH_GRAPH", true);
     chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 0);  // 0 = adaptive (128 for host input, 512 for device input)
     debug_sync_ = env_u32("DH_DEBUG_SYNC", 0) != 0;
     std::memset(stage_ms_, 0, sizeof(stage_ms_));
@@ -103,6 +104,7 @@ Context::Context(int device) : device_(device) {
 Context::~Context() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
+    drop_graph();
     free_scratch();
     free_forest();
     dev_free(d_counters_);
@@ -139,6 +141,7 @@ void Context::synchronize() {
 
 // ------------------------------------------------------------------------------------------------ model upload
 void Context::free_forest() {
+    drop_graph();
     dev_free(df_nodes_);
     dev_free(df_hot_);
     dev_free(df_uni_);
@@ -268,7 +271,14 @@ void Context::free_lane(Lane& L) {
     L.allocated = false;
 }
 
+void Context::drop_graph() {
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    graph_exec_ = nullptr;
+    graph_seen_valid_ = false;
+}
+
 void Context::free_scratch() {
+    drop_graph();
     for (int i = 0; i < 2; ++i) dev_free(d_depth_[i]);
     staging_elems_ = 0;
     for (int i = 0; i < kMaxLanes; ++i) free_lane(lanes_[i]);
@@ -570,14 +580,68 @@ void Context::predict(const HostForest& hf, const uint16_t* depth, uint32_t w, u
         gs.has_guess |= 2u;
         for (int k = 0; k < 3; ++k) gs.rot_guess[k] = rot_guess[k];
     }
-    {
+    if (h_results_cap_ < 1) {
+        DH_CUDA(cudaHostAlloc((void**)&h_results_, sizeof(dh_result), cudaHostAllocDefault));
+        h_results_cap_ = 1;
+    }
+    // everything after the input copy: per-frame state, front end, back end, result and counters to pinned memory
+    auto enqueue = [&] {
         FrameBuffers b = buffers(lanes_[0], d_depth_[0]);
         run_front(lanes_[0], b, 1, &gs);
         run_back(lanes_[0], b, 1, iterations);
+        DH_CUDA(cudaMemcpyAsync(h_results_, lanes_[0].results, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
+    };
+    bool replayed = false;
+    if (use_graphs_ && !timing_ && !debug_ && !debug_sync_) {
+        GraphKey key;
+        key.serial = hf.serial; key.sigma_version = df_sigma_version_;
+        key.w = w; key.h = h; key.stride = geom_.stride; key.iterations = iterations;
+        std::memcpy(key.K, K, sizeof(key.K));
+        key.stream = (void*)stream_; key.depth = d_depth_[0]; key.scratch = lanes_[0].fs;
+        if (graph_exec_ && !(graph_key_ == key)) drop_graph();
+        if (!graph_exec_ && graph_seen_valid_ && graph_seen_ == key) {
+            // second call with this key: capture the sequence (the first, eager call planned the node
+            // table and configured every kernel)
+            cudaGraph_t graph = nullptr;
+            const uint64_t before = launches_;
+            if (cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                use_graphs_ = false;  // e.g. the legacy default stream: eager launches for the rest of this context's life
+            } else {
+                try {
+                    enqueue();
+                } catch (...) {
+                    cudaStreamEndCapture(stream_, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    throw;
+                }
+                cudaError_t e = cudaStreamEndCapture(stream_, &graph);
+                graph_launches_ = launches_ - before;
+                launches_ = before;
+                if (e == cudaSuccess) e = cudaGraphInstantiate(&graph_exec_, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+                if (e != cudaSuccess) {
+                    graph_exec_ = nullptr;
+                    use_graphs_ = false;
+                    cudaGetLastError();
+                } else {
+                    graph_key_ = key;
+                }
+            }
+        }
+        graph_seen_ = key;
+        graph_seen_valid_ = true;
+        if (graph_exec_) {
+            *h_fs_ = gs;  // the graph's copy node reads the caller's seeds from this pinned struct
+            DH_CUDA(cudaGraphLaunch(graph_exec_, stream_));
+            launches_ += graph_launches_;
+            replayed = true;
+        }
     }
-    DH_CUDA(cudaMemcpyAsync(out, lanes_[0].results, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
+    if (!replayed) enqueue();
     mark(-1);
     end_call();
+    *out = *h_results_;
     have_debug_ = debug_;
     debug_iterations_ = iterations;
 }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -177,6 +178,30 @@ private:
     unsigned long long* h_counters_ = nullptr;
     dh_result* h_results_ = nullptr;
     size_t h_results_cap_ = 0;
+
+    // dh_predict as a CUDA graph: the single-frame pipeline is a dozen small launches, i.e. bound
+    // by launch overhead; after one eager call with a given (model, shape, intrinsics, stream) the
+    // same sequence is captured once and replayed.  Kernel arguments are baked into the graph, so
+    // anything they depend on is part of the key.
+    struct GraphKey {
+        uint64_t serial = 0, sigma_version = 0;
+        uint32_t w = 0, h = 0, stride = 0, iterations = 0;
+        float K[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        void* stream = nullptr;
+        const void* depth = nullptr;
+        const void* scratch = nullptr;
+        bool operator==(const GraphKey& o) const {
+            return serial == o.serial && sigma_version == o.sigma_version && w == o.w && h == o.h && stride == o.stride &&
+                   iterations == o.iterations && std::memcmp(K, o.K, sizeof(K)) == 0 && stream == o.stream && depth == o.depth &&
+                   scratch == o.scratch;
+        }
+    };
+    void drop_graph();
+    cudaGraphExec_t graph_exec_ = nullptr;
+    GraphKey graph_key_{}, graph_seen_{};
+    bool graph_seen_valid_ = false;
+    uint64_t graph_launches_ = 0;
+    bool use_graphs_ = true;
 
     // measurement
     bool timing_ = false, debug_ = false, have_debug_ = false, debug_sync_ = false;

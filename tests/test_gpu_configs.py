@@ -252,3 +252,47 @@ def test_two_devices_in_one_process():
     finally:
         c0.close()
         c1.close()
+
+
+def test_single_frame_graph_replay_equals_eager_launches(monkeypatch):
+    """dh_predict replays a captured CUDA graph from its third call with unchanged model / shape /
+    intrinsics; seeds, frames, and every setter that is baked into the graph must still take effect"""
+    arr = synth.make_forest(seed=6, n_trees=4, max_depth=8)
+    frames = synth.make_frames(5, seed=33)
+    K2 = IntrinsicMatrix([[575.816, 0.0, 320.0], [0.0, 575.816, 240.0], [0.0, 0.0, 1.0]])
+
+    def run(flag):
+        monkeypatch.setenv("DH_GRAPH", flag)
+        c = Context(0)
+        hp = HoughPrediction.from_arrays(arr, stepwidth=6)
+        out = []
+        try:
+            res = None
+            for rep in range(3):                       # eager, capture, replay ...
+                for d in frames:
+                    res = hp.predict_parameter_parallel(d, K, None if res is None or rep == 1 else res.mid_point,
+                                                        None if res is None else res.rotation, ctx=c)
+                    out.append((res.mid_point.copy(), res.rotation.copy()))
+            for change in ("stepwidth", "iterations", "sigma", "K", "crop"):
+                if change == "stepwidth":
+                    hp.stepwidth = 9
+                elif change == "iterations":
+                    hp.meanshift_iterations = 3
+                elif change == "sigma":
+                    hp.update_sigma(5.0)
+                kk = K2 if change in ("K", "crop") else K
+                for rep in range(3):
+                    for d in frames[:2]:
+                        dd = d[:400, :600].copy() if change == "crop" else d
+                        res = hp.predict_parameter_parallel(dd, kk, ctx=c)
+                        out.append((res.mid_point.copy(), res.rotation.copy()))
+        finally:
+            c.close()
+        return out
+    a, b = run("1"), run("0")
+    assert len(a) == len(b)
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]), i
+    of = oracle.OracleForest(arr, 6, 80, 80, 8.0, 20)
+    tr = of.predict(frames[0], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+    assert np.array_equal(a[0][0], tr.mid_point) and np.array_equal(a[0][1], tr.rotation)
