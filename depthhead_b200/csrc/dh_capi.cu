@@ -269,6 +269,15 @@ int dh_train_forest(dh_ctx* c, const dh_train_params* p, const uint16_t* patches
         *out = new dh_forest{std::move(hf)};
     });
 }
+int dh_train_learn(dh_ctx* c, const dh_train_params* p, uint32_t n_frames, uint32_t w, uint32_t h, const uint16_t* depth,
+                   const uint8_t* mask, const float* K, const float* pos3d, const float* rot, dh_forest** out) {
+    return guarded([&] {
+        REQUIRE(c && p && out && (n_frames == 0 || (depth && mask && K && pos3d && rot)), "dh_train_learn: NULL argument");
+        *out = nullptr;
+        std::unique_ptr<dh::HostForest> hf(c->cx->train_learn(*p, n_frames, w, h, depth, mask, K, pos3d, rot));
+        *out = new dh_forest{std::move(hf)};
+    });
+}
 int dh_forest_to_json(const dh_forest* f, char* buf, size_t cap, size_t* needed) {
     return guarded([&] {
         REQUIRE(f && needed && (cap == 0 || buf), "dh_forest_to_json: NULL argument");

@@ -82,6 +82,8 @@ public:
                            dh_split_stats* out);
     HostForest* train_forest(const dh_train_params& tp, const uint16_t* patches, uint64_t n, const uint8_t* is_object,
                              const float* offsets, const double* rotations);
+    HostForest* train_learn(const dh_train_params& tp, uint32_t n_frames, uint32_t w, uint32_t h, const uint16_t* depth,
+                            const uint8_t* mask, const float* K, const float* pos3d, const float* rot);
     void train_split_level(const TrainSet& ts, const uint32_t* sample_idx, const uint64_t* node_off, uint32_t n_nodes,
                            const int32_t* rects, const double* thr, uint8_t* bits);
     void predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask);

@@ -504,6 +504,96 @@ HostForest* Context::train_forest(const dh_train_params& tp, const uint16_t* pat
     return hf;
 }
 
+// HoughLearning::learn (prediction.rs:145-234): per annotated frame, every non-background window
+// with its truth; 20 negatives then 20 positives per frame after a random permutation; one more
+// permutation of the whole set; then the trees.  Random numbers: CounterRng(seed) for the sample
+// selection, CounterRng(seed + 1) for the trees (the Python mirror does the same).
+HostForest* Context::train_learn(const dh_train_params& tp, uint32_t n_frames, uint32_t w, uint32_t h, const uint16_t* depth,
+                                 const uint8_t* mask, const float* K, const float* pos3d, const float* rot) {
+    const uint32_t sw = tp.subimage_width, sh = tp.subimage_height, step = tp.stepwidth;
+    if (!sw || !sh || !step) throw ModelError(DH_E_ARG, "dh_train_learn: zero sub-image / stepwidth");
+    if (w < sw || h < sh) throw ModelError(DH_E_SHAPE, "image smaller than the sub-image (the reference underflows u32 at types.rs:371-373)");
+    const uint32_t left_w = sw / 2, left_h = sh / 2, right_w = sw - left_w, right_h = sh - left_h;  // types.rs:365-368
+    CounterRng rng(tp.seed);
+    std::vector<uint16_t> patches;
+    std::vector<uint8_t> is_obj;
+    std::vector<float> offs;
+    std::vector<double> rots;
+    std::vector<uint32_t> nz((size_t)(w + 1) * (h + 1));
+    struct Cand { uint32_t x, y; };
+    for (uint32_t f = 0; f < n_frames; ++f) {
+        const uint16_t* d = depth + (size_t)f * w * h;
+        const uint8_t* m = mask + (size_t)f * w * h;
+        // count of non-zero pixels: average_value_in_rect(whole window) > 0.0 <=> any non-zero pixel (prediction.rs:189-190)
+        std::fill(nz.begin(), nz.begin() + (w + 1), 0u);
+        for (uint32_t y = 0; y < h; ++y) {
+            uint32_t row = 0;
+            nz[(size_t)(y + 1) * (w + 1)] = 0;
+            for (uint32_t x = 0; x < w; ++x) {
+                row += d[(size_t)y * w + x] != 0;
+                nz[(size_t)(y + 1) * (w + 1) + x + 1] = nz[(size_t)y * (w + 1) + x + 1] + row;
+            }
+        }
+        std::vector<Cand> neg, pos;
+        for (uint32_t y = left_h; y < h - right_h; y += step)          // iterate_subimage, types.rs:369-383
+            for (uint32_t x = left_w; x < w - right_w; x += step) {
+                const uint32_t x0 = x - left_w, y0 = y - left_h;
+                const uint32_t cnt = nz[(size_t)(y0 + sh) * (w + 1) + x0 + sw] - nz[(size_t)y0 * (w + 1) + x0 + sw] -
+                                     nz[(size_t)(y0 + sh) * (w + 1) + x0] + nz[(size_t)y0 * (w + 1) + x0];
+                if (!cnt) continue;
+                (m[(size_t)y * w + x] ? pos : neg).push_back(Cand{x, y});   // mask[(x, y)], prediction.rs:191
+            }
+        float inv[9];
+        mat3_inverse_f32(K + (size_t)f * 9, inv);
+        const std::vector<Cand>* parts[2] = {&neg, &pos};                 // negatives first (prediction.rs:222-226)
+        for (int part = 0; part < 2; ++part) {
+            const std::vector<Cand>& v = *parts[part];
+            const std::vector<uint32_t> perm = rng.permutation(v.size());  // rand_perm, prediction.rs:216-217
+            for (size_t k = 0; k < perm.size() && k < 20; ++k) {
+                const Cand c = v[perm[k]];
+                const uint32_t x0 = c.x - left_w, y0 = c.y - left_h;
+                for (uint32_t yy = 0; yy < sh; ++yy)                        // to_cropped_subimage
+                    patches.insert(patches.end(), d + (size_t)(y0 + yy) * w + x0, d + (size_t)(y0 + yy) * w + x0 + sw);
+                is_obj.push_back(part ? 1 : 0);
+                // img_to_space_coord (types.rs:432-445), f32, products and sums unfused; offset = vec3 - mid (prediction.rs:196-198)
+                const float xf = (float)c.x, yf = (float)c.y, z = (float)d[(size_t)c.y * w + c.x];
+                float r[3];
+                for (int j = 0; j < 3; ++j) {
+                    volatile float t = xf * inv[j * 3 + 0];
+                    volatile float u = yf * inv[j * 3 + 1];
+                    t = t + u;
+                    u = 1.0f * inv[j * 3 + 2];
+                    t = t + u;
+                    r[j] = t;
+                }
+                const float cc = z / r[2];
+                for (int j = 0; j < 3; ++j) {
+                    volatile float pj = r[j] * cc;
+                    offs.push_back(pj - pos3d[(size_t)f * 3 + j]);
+                    rots.push_back((double)rot[(size_t)f * 3 + j]);    // rot[k] as f64, prediction.rs:176
+                }
+            }
+        }
+    }
+    const uint64_t n = is_obj.size();
+    if (!n) throw ModelError(DH_E_ARG, "dh_train_learn: no training samples (every window is background)");
+    const std::vector<uint32_t> perm = rng.permutation(n);                // rand_perm(train_ref), prediction.rs:229
+    const size_t px = (size_t)sw * sh;
+    std::vector<uint16_t> p2(patches.size());
+    std::vector<uint8_t> o2(n);
+    std::vector<float> f2(n * 3);
+    std::vector<double> r2(n * 3);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t s2 = perm[i];
+        std::memcpy(&p2[i * px], &patches[(size_t)s2 * px], px * sizeof(uint16_t));
+        o2[i] = is_obj[s2];
+        for (int j = 0; j < 3; ++j) { f2[i * 3 + j] = offs[(size_t)s2 * 3 + j]; r2[i * 3 + j] = rots[(size_t)s2 * 3 + j]; }
+    }
+    dh_train_params t2 = tp;
+    t2.seed = tp.seed + 1;
+    return train_forest(t2, p2.data(), n, o2.data(), f2.data(), r2.data());
+}
+
 void trainset_free(TrainSet* t) { delete t; }
 
 }  // namespace dh

@@ -318,6 +318,31 @@ class HoughLearning:
                                                C.byref(h)))
         return HoughPrediction(h)
 
+    def _params(self, gaussian_sigma: float, seed: int):
+        p = capi.dh_train_params()
+        p.stepwidth, p.subimage_width, p.subimage_height = self.stepwidth, self.sub_w, self.sub_h
+        p.max_depth, p.n_trees, p.subset_per_tree = self.max_depth, self.n_trees, self.subset
+        p.subrect_feature_scale, p.features_per_node, p.min_subset_size = self.scale, self.n_features, self.min_subset
+        p.steepness, p.gaussian_sigma, p.seed = self.steepness, float(gaussian_sigma), int(seed) & 0xFFFFFFFFFFFFFFFF
+        return p
+
+    def learn_native(self, gaussian_sigma: float, data, seed: int = 0, ctx: Context | None = None) -> HoughPrediction:
+        """HoughLearning::learn entirely in C++ behind the C ABI (dh_train_learn): sample extraction and
+        tree growing; the same forest as learn() for the same frames and seed."""
+        ctx = ctx or default_context()
+        data = list(data)
+        depth = np.ascontiguousarray(np.stack([np.asarray(t["depth"], np.uint16) for t in data]))
+        mask = np.ascontiguousarray(np.stack([np.asarray(t["mask"], np.uint8) for t in data]))
+        K = np.ascontiguousarray(np.stack([t["intrinsic"].mat.reshape(9) for t in data]), np.float32)
+        pos = np.ascontiguousarray(np.stack([np.asarray(t["pos3d"], np.float32) for t in data]))
+        rot = np.ascontiguousarray(np.stack([np.asarray(t["rot"], np.float32) for t in data]))
+        n, h, w = depth.shape
+        p = self._params(gaussian_sigma, seed)
+        hnd = C.c_void_p()
+        capi.check(capi.load().dh_train_learn(ctx._h, C.byref(p), n, w, h, capi.ptr(depth), capi.ptr(mask), capi.ptr(K), capi.ptr(pos),
+                                              capi.ptr(rot), C.byref(hnd)))
+        return HoughPrediction(hnd)
+
     def learn(self, gaussian_sigma: float, data, seed: int = 0, ctx: Context | None = None, native: bool = False) -> HoughPrediction:
         """HoughLearning::learn (prediction.rs:145-234).  `data`: iterable of dicts with `depth`
         [h,w] u16, `mask` [h,w] u8, `intrinsic` IntrinsicMatrix, `pos3d` [3], `rot` [3]

@@ -209,6 +209,14 @@ typedef struct dh_train_params {
 } dh_train_params;
 int dh_train_forest(dh_ctx* c, const dh_train_params* p, const uint16_t* patches, uint64_t n, const uint8_t* is_object,
                     const float* offsets, const double* rotations, dh_forest** out);
+/* HoughLearning::learn (prediction.rs:145-234) from annotated frames (db_reader DepthTrue): depth
+ * [n][h][w] u16, head mask [n][h][w] u8 (non-zero = head), per-frame intrinsics K[n][9], head
+ * centre pos3d[n][3] (mm) and rotation rot[n][3].  Extracts the windows exactly as the reference
+ * (sliding window at p->stepwidth, background test, truth from the mask at the window centre,
+ * offset = back-projected centre - pos3d; 20 negatives and 20 positives per frame after a random
+ * permutation), then dh_train_forest with seed + 1. */
+int dh_train_learn(dh_ctx* c, const dh_train_params* p, uint32_t n_frames, uint32_t w, uint32_t h, const uint16_t* depth,
+                   const uint8_t* mask, const float* K, const float* pos3d, const float* rot, dh_forest** out);
 /* serde_json::to_string(&HoughPrediction) — what hough_tree_trainer.rs:182 writes.  Copies at most
  * cap bytes (no terminator) and reports the full length in *needed; call with cap = 0 to size the buffer. */
 int dh_forest_to_json(const dh_forest* f, char* buf, size_t cap, size_t* needed);

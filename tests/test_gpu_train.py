@@ -173,6 +173,11 @@ def test_native_trainer_matches_the_python_mirror(ctx):
     assert arr_cc["n_trees"] == 3
     for t in range(3):
         assert _canonical(arr_cc, t) == _canonical(arr_py, t), "tree %d differs" % t
+    # HoughLearning::learn entirely in C++ (sample extraction included): the same forest again
+    hp_all = train.HoughLearning(**args).learn_native(8.0, data, seed=3, ctx=ctx)
+    arr_all = oracle.forest_arrays_from_doc(json.loads(hp_all.to_json()))
+    for t in range(3):
+        assert _canonical(arr_all, t) == _canonical(arr_py, t), "tree %d differs (dh_train_learn)" % t
     # the document loads again and predicts like the forest it came from, and like the Python-grown one
     hp_rt = HoughPrediction.from_json(hp_cc.to_json())
     test_frames = synth.make_frames(5, seed=77)
