@@ -392,6 +392,8 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes / launches, "launches": launches,
                 "avg_launch_ms": trav_ms / launches,
                 "ncu_pipe_utilisation_pct": pipes,
+                "binding_resource": "L1TEX data pipe (shared-memory tap wavefronts + texture node-fetch wavefronts, one per cycle per SM)",
+                "binding_frac": (pipes or {}).get("l1tex_data_pipe_total", 0.0) / 100.0 if pipes else None,
                 "note": "algorithmic bytes (SURVEY 8d: 56 B per node visit + 16 B per evaluation) are served from "
                         "shared memory (taps) and L1/L2 (node records), not HBM, so the fraction exceeds 1; `traffic` "
                         "is the DRAM traffic of one launch from ncu (profiles/); what binds the kernel is the L1TEX "
