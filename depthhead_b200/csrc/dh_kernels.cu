@@ -1008,8 +1008,8 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
 // ================================================================ K4a: seeds
 // One CTA per frame: arg-max of the two coarse grids -> mean-shift seeds (prediction.rs:694-752,
 // 437-460) and the origin of the frame's two accumulator cubes.
-constexpr int kBox = 48;                      // cells per axis of the dense accumulator cube
-constexpr int kBoxCells = kBox * kBox * kBox; // 110 592 cells = 432 KB
+constexpr int kBox = 40;                      // cells per axis of the dense accumulator cube
+constexpr int kBoxCells = kBox * kBox * kBox; // 64 000 cells = 250 KB
 constexpr int kSeedThreads = 256;
 constexpr int kMsHistory = 64;
 
@@ -1108,7 +1108,7 @@ __global__ void __launch_bounds__(kSeedThreads) seed_kernel(FrameBuffers b, Geom
         for (int k = 0; k < 3; ++k) {
             fs->seed_mid[k] = sm[k];
             fs->seed_rot[k] = sr[k];
-            // cube centred on the seed: 14 cells of margin around the 20^3 window
+            // cube centred on the seed: 10 cells of margin around the 20^3 window = every position one mean-shift step away
             fs->box_org[0][k] = (int32_t)((uint32_t)sm[k] - (uint32_t)(kBox / 2));
             fs->box_org[1][k] = (int32_t)((uint32_t)sr[k] - (uint32_t)(kBox / 2));
         }
@@ -1234,7 +1234,7 @@ __global__ void __launch_bounds__(kBuildThreads) box_build_kernel(FrameBuffers b
 // cells in reference order (ballots + one cross-warp prefix) (x outermost, z innermost, offsets -10..+9: meanshift.rs:340-346),
 // stage the summands in shared memory at that rank and four lanes fold them into the f32
 // accumulators one after the other in exactly that order.  A round moves the position by at most
-// 10 cells and the cube leaves 14 cells of margin around the seed's window; if the window would
+// 10 cells and the cube leaves 10 cells of margin around the seed's window; if the window would
 // leave the cube, the cube is rebuilt around the current position from the frame's gated patches
 // (counted in FrameState::rebuilds), so the results stay exactly those of the unbounded map.
 constexpr int kMsThreads = 512;
