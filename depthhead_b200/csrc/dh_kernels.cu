@@ -1,19 +1,23 @@
 // dh_kernels.cu — hand-written sm_100a kernels for depthhead's Hough-forest prediction path.
 //
 // Pipeline per chunk of frames (reference: src/hough/prediction.rs:421-753):
-//   K1  sat_rows / sat_cols      u16 depth -> u32 summed-area table (wrap-around exact, see below)
-//   K2  traverse_kernel          TMA-staged SAT tile in shared memory; one thread per patch x tree
-//                                walks root->leaf (houghforest.rs:185-193, types.rs:317-339)
-//   K3  gate_coarse_kernel       ordered f64 prob sum, 0.7 gate, back-projection, hit list and the two
+//   K1  box_image_kernel         u16 depth -> u32 box-sum image B[y][x] = sum of the rw x rh rectangle at
+//                                (x, y), for forests whose feature rectangles all have one size (what the
+//                                reference's trainer produces); sat_band_* / sat_rows / sat_cols: the general
+//                                summed-area table for forests with mixed rectangle sizes
+//   K2  traverse_kernel          TMA-staged tile of B (or of the SAT) in shared memory; one thread per
+//                                patch x tree walks root->leaf (houghforest.rs:185-193, types.rs:317-339)
+//   K3  gate_coarse_kernel       ordered f64 prob sum, 0.7 gate, back-projection, gated-patch list and the two
 //                                coarse seed grids (prediction.rs:551-554,582-595,630-636,661-675)
 //   K4a seed_kernel              arg-max seeds (prediction.rs:694-752, 437-460)
 //   K4b box_build_kernel         dense local cubes of the SparseArray3D<u32> accumulators
-//                                (meanshift.rs:14-68, prediction.rs:635,667), one thread per hit
-//   K4c meanshift_warp_kernel    mean-shift in reference accumulation order (meanshift.rs:328-407),
-//                                one warp per accumulator; rebuild_meanshift_kernel is its fallback
-//                                for positions that drift out of the cube
+//                                (meanshift.rs:14-68, prediction.rs:635,667)
+//   K4c meanshift_kernel         mean-shift in reference accumulation order (meanshift.rs:328-407), one CTA
+//                                per accumulator; rebuilds its cube around positions that drift out of it
 //   K5  leaf_gate_kernel         estimate_mean_cov traces + valtoadd per leaf, once per model
 //                                (meancov_estimation.rs:359-378, prediction.rs:594-600,643)
+//   +   mask_kernel, hough_image_kernel (prediction.rs:850-905, 760-841), biwi_decode_kernel
+//       (db_reader/biwi.rs:81-103); training's split scoring lives in dh_train.cu
 //
 // Exactness rules: float->int is truncation (cvt.rzi, saturating, NaN->0 ==
 // Rust `as`); no FMA contraction anywhere a float feeds a truncation or comparison (explicit

@@ -184,7 +184,7 @@ def test_config2_sequence_sharded_by_frame(ctx):
 def _ramp_forest(n_trees=6):
     """Trees without nodes (a single leaf each) whose centre votes pile up exponentially along x:
     cell x of [0, 32) receives about 1.25^x votes per patch.  Mean-shift seeded at the thin end
-    climbs the ramp by several cells per round, far more than the 14 cells of margin around the
+    climbs the ramp by several cells per round, far more than the 10 cells of margin around the
     seed's window."""
     mult = np.maximum(1, np.round(1.25 ** np.arange(32))).astype(np.int64)
     xs = np.repeat(np.arange(32), mult)                      # one entry per vote
