@@ -392,13 +392,13 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes / launches, "launches": launches,
                 "avg_launch_ms": trav_ms / launches,
                 "ncu_pipe_utilisation_pct": pipes,
-                "binding_resource": "latency of the dependent node-fetch -> taps -> compare chain at full occupancy; busiest unit: "
-                                    "L1TEX LSU data pipe (shared-memory taps)",
-                "busiest_unit_frac": (pipes or {}).get("lsu_data_pipe", 0.0) / 100.0 if pipes else None,
+                "binding_resource": "unified L1 / shared-memory data array (shared-memory tap wavefronts + texture node-fetch "
+                                    "wavefronts, one per cycle per SM)",
+                "binding_frac": ((pipes or {}).get("lsu_data_pipe", 0.0) + (pipes or {}).get("tex_data_pipe", 0.0)) / 100.0 if pipes else None,
                 "note": "algorithmic bytes (SURVEY 8d: 56 B per node visit + 16 B per evaluation) are served from "
                         "shared memory (taps) and L1/L2 (node records), not HBM, so the fraction exceeds 1; `traffic` "
-                        "is the DRAM traffic of one launch from ncu (profiles/); the kernel is bound by the latency of "
-                        "its dependent chain at full occupancy (no unit above 55 %), see DESIGN.md"}
+                        "is the DRAM traffic of one launch from ncu (profiles/); what binds the kernel is the SM's "
+                        "unified L1 / shared-memory data array (LSU + TEX data-pipe wavefronts add up to ~1 per cycle), see DESIGN.md"}
     # the HBM-bound kernel of the step: the front end (box-sum image, or summed-area table for
     # forests with mixed rectangle sizes) reads the depth once and writes its table once
     fe_ms = stage.get("sat", 0.0)

@@ -326,7 +326,9 @@ void Context::alloc_lane(Lane& L) {
 TilePlan Context::plan_tiles(const Geometry& g) const {
     // Choose the patch tile that minimises total shared-memory fill traffic per frame, subject to
     // the tile (plus bookkeeping) fitting `limit` bytes so that several CTAs share an SM.
-    const uint32_t big = env_u32("DH_TRAV_THREADS", 1024) >= 1024 ? 1u : 0u;
+    const uint32_t want_threads = env_u32("DH_TRAV_THREADS", 1024);
+    const uint32_t trav_threads = want_threads >= 1024 ? 1024u : (want_threads >= 768 ? 768u : 512u);
+    const uint32_t big = trav_threads >= 768 ? 1u : 0u;  // two CTAs per SM; 512 threads: three
     const uint32_t limits[3] = {big ? 113000u : 75000u, 113000u, smem_optin_ > 2048u ? smem_optin_ - 1024u : smem_optin_};
     for (uint32_t limit : limits) {
         TilePlan best{};
@@ -347,7 +349,7 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
                 const double cost = (double)tiles_x * tiles_y * ((double)tw * th * 4.0 + 8192.0);
                 if (cost < best_cost) {
                     best_cost = cost;
-                    best = TilePlan{tpx, tpy, tiles_x, tiles_y, tw, th, bytes, (big && limit <= 113000u) ? 1024u : 512u};
+                    best = TilePlan{tpx, tpy, tiles_x, tiles_y, tw, th, bytes, (big && limit <= 113000u) ? trav_threads : 512u};
                 }
             }
         if (best.tpx) return best;

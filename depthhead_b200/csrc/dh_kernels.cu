@@ -546,9 +546,10 @@ __device__ __noinline__ bool binarize_ieee(const NodeRec* __restrict__ nodes, in
 // path; 2: uniform rectangles (box-sum tile, UniNode through the texture path); 3: the same with
 // UniNode through the LSU path; 4 and 5: as 2 and 3, but the TMA load brings a window of the
 // box-sum image (box_image_kernel) instead of the summed-area table, so the tile needs no
-// conversion and is (sw - rw + 1)-ish wide instead of (sw + 1)-ish.
+// conversion and is (sw - rw + 1)-ish wide instead of (sw + 1)-ish; 6: as 4 with TWO walks per
+// thread in flight (two independent fetch -> tap -> compare chains hide each other's latency).
 template <int kThreads, int kMode>
-__global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_kernel(const __grid_constant__ CUtensorMap sat_map,
+__global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_kernel(const __grid_constant__ CUtensorMap sat_map,
                                                             cudaTextureObject_t hot_tex,
                                                             const HotNode* __restrict__ hot,
                                                             const UniNode* __restrict__ uni,
@@ -709,6 +710,43 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 1024 ? 2 : 3) traverse_k
     const uint4* hot4 = reinterpret_cast<const uint4*>(hot);
     // it / nlive by multiply-high (exact while it * nlive < 2^32)
     const uint32_t nl_magic = (nlive >= 2u && (unsigned long long)items * nlive < (1ull << 32)) ? (uint32_t)((1ull << 32) / nlive) + 1u : 0u;
+    if (kMode == 6) {
+        // two walks per thread: items it and it + kThreads
+        for (uint32_t it = tid; it < items; it += 2u * kThreads) {
+            const uint32_t itB = it + kThreads;
+            const bool hasB = itB < items;
+            const uint32_t tA = nl_magic ? __umulhi(it, nl_magic) : it / nlive;
+            const uint32_t tB = hasB ? (nl_magic ? __umulhi(itB, nl_magic) : itB / nlive) : 0u;
+            const uint32_t lpA = lds_u32(live_a + 4u * (it - tA * nlive));
+            const uint32_t lpB = hasB ? lds_u32(live_a + 4u * (itB - tB * nlive)) : 0u;
+            const uint32_t oA = org_a + ((lpA & 0xffffu) << 2), oB = org_a + ((lpB & 0xffffu) << 2);
+            int32_t nA = __ldg(roots + tA), nB = hasB ? __ldg(roots + tB) : -1;
+            while ((nA & nB) >= 0) {  // at least one of the two is still inside its tree
+                const bool a = nA >= 0, b2 = nB >= 0;
+                uint4 UA = make_uint4(0u, 0u, 0u, 0u), UB = UA;
+                if (a) UA = tex1Dfetch<uint4>(hot_tex, nA);
+                if (b2) UB = tex1Dfetch<uint4>(hot_tex, nB);
+                if (a) {
+                    const uint32_t s1 = lds_u32(oA + ((UA.x & 0xffffu) << 2)), s2 = lds_u32(oA + ((UA.x >> 16) << 2));
+                    const int32_t d2 = (int32_t)(s1 - s2) << 1, E = (int32_t)UA.w;
+                    int32_t next = d2 > E ? (int)UA.z : (int)UA.y;
+                    if (d2 == E) next = binarize_ieee(nodes, nA, s1, s2) ? (int)UA.z : (int)UA.y;
+                    nA = next;
+                    ++visits;
+                }
+                if (b2) {
+                    const uint32_t s1 = lds_u32(oB + ((UB.x & 0xffffu) << 2)), s2 = lds_u32(oB + ((UB.x >> 16) << 2));
+                    const int32_t d2 = (int32_t)(s1 - s2) << 1, E = (int32_t)UB.w;
+                    int32_t next = d2 > E ? (int)UB.z : (int)UB.y;
+                    if (d2 == E) next = binarize_ieee(nodes, nB, s1, s2) ? (int)UB.z : (int)UB.y;
+                    nB = next;
+                    ++visits;
+                }
+            }
+            leaf_f[(size_t)tA * g.P + (py0 + (lpA >> 24)) * g.npx + (px0 + ((lpA >> 16) & 0xffu))] = ~nA;
+            if (hasB) leaf_f[(size_t)tB * g.P + (py0 + (lpB >> 24)) * g.npx + (px0 + ((lpB >> 16) & 0xffu))] = ~nB;
+        }
+    } else
     for (uint32_t it = tid; it < items; it += kThreads) {
         const uint32_t t = nl_magic ? __umulhi(it, nl_magic) : it / nlive;
         const uint32_t lp = lds_u32(live_a + 4u * (it - t * nlive));
@@ -1984,9 +2022,14 @@ static void launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b,
         cudaFuncSetAttribute(traverse_kernel<kThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kThreads, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
     }
+    static const bool two_walks = std::getenv("DH_TRAV_ILP") && std::atoi(std::getenv("DH_TRAV_ILP")) == 2;
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
-    if (f.uni && g.rw && f.hot_tex)
+    if (f.uni && g.rw && f.hot_tex && two_walks)
+        traverse_kernel<kThreads, 6><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh);
+    else if (f.uni && g.rw && f.hot_tex)
         traverse_kernel<kThreads, 4><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
                                                                        b.fs, g, tp, f.uni_rw, f.uni_rh);
     else if (f.uni && g.rw)
@@ -2009,6 +2052,7 @@ static void launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b,
 void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
     if (tp.threads >= 1024) launch_traverse_t<1024>(sat_map, b, g, tp, f, n_frames, s);
+    else if (tp.threads >= 768) launch_traverse_t<768>(sat_map, b, g, tp, f, n_frames, s);
     else launch_traverse_t<512>(sat_map, b, g, tp, f, n_frames, s);
 }
 
