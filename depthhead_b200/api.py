@@ -96,6 +96,12 @@ class Context:
         return dict(zip(capi.COUNTERS, (int(x) for x in a)))
 
     # ---- debug exports (parity tests)
+    def tile_plan(self) -> dict:
+        v = np.zeros(8, np.uint32)
+        capi.check(capi.load().dh_debug_tile_plan(self._h, capi.ptr(v)))
+        keys = ("patches_x", "patches_y", "tiles_x", "tiles_y", "tile_w", "tile_h", "smem_bytes", "threads")
+        return {k: int(x) for k, x in zip(keys, v)}
+
     def debug_dims(self):
         a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
         capi.check(capi.load().dh_debug_dims(self._h, C.byref(a), C.byref(b), C.byref(c)))

@@ -114,6 +114,7 @@ SIGNATURES = {
     "dh_debug_votes": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(_u64), _vp, C.POINTER(_i32)]),
     "dh_debug_meanshift": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(_u32)]),
     "dh_debug_meanshift_flags": (C.c_int, [_vp, _vp]),
+    "dh_debug_tile_plan": (C.c_int, [_vp, _vp]),
     "dh_debug_leaf_static": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
 }
 

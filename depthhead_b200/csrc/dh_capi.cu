@@ -260,6 +260,14 @@ int dh_train_split_level(dh_ctx* c, const dh_trainset* t, const uint32_t* sample
         c->cx->train_split_level(*t->ts, sample_idx, node_off, n_nodes, rects, thr, bits);
     });
 }
+int dh_debug_tile_plan(dh_ctx* c, uint32_t plan[8]) {
+    return guarded([&] {
+        REQUIRE(c && plan, "dh_debug_tile_plan: NULL argument");
+        const dh::TilePlan& t = c->cx->tile_plan();
+        const uint32_t v[8] = {t.tpx, t.tpy, t.tiles_x, t.tiles_y, t.tw, t.th, t.smem_bytes, t.threads};
+        std::memcpy(plan, v, sizeof(v));
+    });
+}
 int dh_train_forest(dh_ctx* c, const dh_train_params* p, const uint16_t* patches, uint64_t n, const uint8_t* is_object,
                     const float* offsets, const double* rotations, dh_forest** out) {
     return guarded([&] {

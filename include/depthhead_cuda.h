@@ -263,6 +263,9 @@ int dh_debug_votes(dh_ctx* c, int which, int32_t* keys /*[n][3]*/, uint32_t* val
 int dh_debug_meanshift(dh_ctx* c, int which, int32_t* pos /*[n_iter][3]*/, uint32_t* n_iter);
 /* flags of the last mean-shift runs: bit0 = zero-sum break (meanshift.rs:385-388) */
 int dh_debug_meanshift_flags(dh_ctx* c, uint32_t flags[2]);
+/* tile plan of the traversal kernel for the last call's shape: patches per tile x, y; tiles per
+ * frame x, y; tile extent in elements x, y; dynamic shared memory bytes; threads per CTA */
+int dh_debug_tile_plan(dh_ctx* c, uint32_t plan[8]);
 /* per-leaf static quantities computed by the leaf-gate kernel: valtoadd, rot_ok, off_ok */
 int dh_debug_leaf_static(dh_ctx* c, const dh_forest* f, uint32_t* valtoadd, uint8_t* rot_ok, uint8_t* off_ok);
 
