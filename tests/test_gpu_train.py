@@ -192,3 +192,38 @@ def test_native_trainer_matches_the_python_mirror(ctx):
         assert _canonical(d1, t) == _canonical(rnd, t)
     with pytest.raises(Exception):
         train.HoughLearning(**{**args, "feature_number_per_node": 64}).train_native(8.0, np.zeros((0, 80, 80), np.uint16), [], np.zeros((0, 3)), np.zeros((0, 3)), 1, ctx=ctx)
+
+
+def test_trainer_edge_cases(ctx):
+    """degenerate training sets through dh_train_forest: early_stop at the root in all its forms
+    (houghforest.rs:302-311), subsets larger than the set, and the models they give"""
+    patches, is_obj, offs, rots = _samples(3, seed=21)
+    n = len(patches)
+    base = dict(stepwidth=10, subimg_width=80, subimg_height=80, max_depth=5, num_of_trees=2, subset_size_per_tree=10 * n,
+                subrect_feature_scale=0.3, feature_number_per_node=32, min_subset_size_to_stop=20, steepness_weighting=5.0)
+    frames = synth.make_frames(2, seed=3)
+    # only NoObject samples: every tree is one leaf with prob 0 and no votes
+    hp = train.HoughLearning(**base).train_native(8.0, patches, np.zeros(n, np.uint8), offs, rots, seed=1, ctx=ctx)
+    assert (hp.n_trees, hp.n_nodes, hp.n_leaves, hp.n_votes) == (2, 0, 2, 0)
+    out = hp.predict_batch(frames, K, ctx=ctx)
+    of = oracle.OracleForest.from_json(hp.to_json())
+    tr = of.predict(frames[0], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+    assert np.array_equal(out["mid_point"][0], tr.mid_point) and np.array_equal(out["rotation"][0], tr.rotation)
+    # max_depth 0 and a set below min_subset_size: the root is a leaf holding every Object sample in set order
+    for kw in (dict(max_depth=0), dict(min_subset_size_to_stop=n + 1)):
+        hl = train.HoughLearning(**{**base, **kw})
+        hp = hl.train_native(8.0, patches, is_obj, offs, rots, seed=2, ctx=ctx)
+        assert hp.n_nodes == 0 and hp.n_leaves == 2 and hp.n_votes == 2 * int(is_obj.sum())
+        import json
+        arr = oracle.forest_arrays_from_doc(json.loads(hp.to_json()))
+        assert np.allclose(arr["prob"], is_obj.mean())
+    # a normal run on the same set grows real trees, and identical ones for the identical seed
+    a = train.HoughLearning(**base).train_native(8.0, patches, is_obj, offs, rots, seed=5, ctx=ctx)
+    b = train.HoughLearning(**base).train_native(8.0, patches, is_obj, offs, rots, seed=5, ctx=ctx)
+    c = train.HoughLearning(**base).train_native(8.0, patches, is_obj, offs, rots, seed=6, ctx=ctx)
+    assert a.n_nodes > 2 and a.to_json() == b.to_json() and a.to_json() != c.to_json()
+    # parameter errors of HoughLearning::new surface as errors of the call
+    bad = train.HoughLearning(**base)
+    bad.steepness = 0.0
+    with pytest.raises(Exception):
+        bad.train_native(8.0, patches, is_obj, offs, rots, seed=1, ctx=ctx)
