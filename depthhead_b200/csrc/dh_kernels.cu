@@ -1162,11 +1162,16 @@ __global__ void __launch_bounds__(kSeedThreads) seed_kernel(FrameBuffers b, Geom
 // SparseArray3D<u32> (meanshift.rs:14-68) restricted to a dense kBox^3 cube of cells per
 // (frame, accumulator), z fastest: plain u32 atomicAdd per in-cube vote, no hashing; votes outside
 // the cube never touch memory.  One thread (or G lanes) per gated patch x tree pair.
+// 32-bit and exact for every int32 cell and origin: for x >= org the difference fits u32.
 __device__ __forceinline__ bool in_box(int x, int y, int z, const int32_t* org, uint32_t* idx) {
-    const long long rx = (long long)x - org[0], ry = (long long)y - org[1], rz = (long long)z - org[2];
-    if (rx < 0 || rx >= kBox || ry < 0 || ry >= kBox || rz < 0 || rz >= kBox) return false;
-    *idx = ((uint32_t)rx * kBox + (uint32_t)ry) * kBox + (uint32_t)rz;
+    const uint32_t rx = (uint32_t)x - (uint32_t)org[0], ry = (uint32_t)y - (uint32_t)org[1], rz = (uint32_t)z - (uint32_t)org[2];
+    if (x < org[0] || y < org[1] || z < org[2] || rx >= (uint32_t)kBox || ry >= (uint32_t)kBox || rz >= (uint32_t)kBox) return false;
+    *idx = (rx * kBox + ry) * kBox + rz;
     return true;
+}
+// lo..hi (cells an axis of a leaf's votes can reach) misses [org, org + kBox)
+__device__ __forceinline__ bool misses_box(int lo, int hi, int org) {
+    return hi < org || (lo >= org && (uint32_t)lo - (uint32_t)org >= (uint32_t)kBox);
 }
 
 // Adds the votes of one frame that fall into the cube(s).  Warp `first_warp` of `n_warps` takes
@@ -1200,17 +1205,14 @@ __device__ __forceinline__ void accumulate_pairs(const float4* __restrict__ gate
                     const float omax[3] = {__uint_as_float(bb0.w), __uint_as_float(bb1.x), __uint_as_float(bb1.y)};
                     const float pc[3] = {h.x, h.y, h.z};
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const long long lo = (long long)__float2int_rz(__fsub_rn(pc[k], omax[k])) - org_c[k];
-                        const long long hi = (long long)__float2int_rz(__fsub_rn(pc[k], omin[k])) - org_c[k];
-                        if (hi < 0 || lo >= kBox) do_c = false;
-                    }
+                    for (int k = 0; k < 3; ++k)
+                        if (misses_box(__float2int_rz(__fsub_rn(pc[k], omax[k])), __float2int_rz(__fsub_rn(pc[k], omin[k])), org_c[k])) do_c = false;
                 }
                 if (do_r) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const int rmin = (int)((bb1.z >> (8 * k)) & 0xffu), rmax = (int)((bb1.w >> (8 * k)) & 0xffu);
-                        if ((long long)rmax - org_r[k] < 0 || (long long)rmin - org_r[k] >= kBox) do_r = false;
+                        if (misses_box(rmin, rmax, org_r[k])) do_r = false;
                     }
                 }
                 v0 = li.vote_start;
