@@ -504,8 +504,13 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
     stage_check("sat");
     mark(DH_STAGE_TRAVERSE);
     if (g.P) {
-        // leaf ids start at -1 (background); the traversal writes the non-background patches only
-        DH_CUDA(cudaMemsetAsync(L.leaf, 0xFF, sizeof(int32_t) * (size_t)n * g.n_trees * g.P, st));
+        // leaf ids start at -1 (background); the traversal writes the non-background patches only.
+        // Every reader decides "background" on the slice of tree 0, so only that slice is filled
+        // (36 KB instead of 358 KB per frame); debug passes export all of it and fill all of it.
+        if (debug_)
+            DH_CUDA(cudaMemsetAsync(L.leaf, 0xFF, sizeof(int32_t) * (size_t)n * g.n_trees * g.P, st));
+        else
+            DH_CUDA(cudaMemset2DAsync(L.leaf, sizeof(int32_t) * (size_t)g.n_trees * g.P, 0xFF, sizeof(int32_t) * (size_t)g.P, n, st));
         launch_traverse(L.sat_map, b, g, tiles_, fdev_, n, st);
         launches_ += 1;
         stage_check("traverse");

@@ -1646,8 +1646,8 @@ __global__ void __launch_bounds__(256) hough_image_kernel(FrameBuffers b, Geomet
     const uint32_t T = g.n_trees;
     if (idx >= g.P * T) return;
     const uint32_t p = idx % g.P, t = idx / g.P;
+    if (b.leaf[p] < 0) return;  // background patch: decided on the slice of tree 0 (the only one prefilled with -1)
     const int32_t L = b.leaf[(size_t)t * g.P + p];
-    if (L < 0) return;
     const double lp = f.leaf_prob[L];
     if (!(lp >= 0.95)) return;                                             // :805
     const uint32_t v0 = f.leaf_info[L].vote_start, n = f.leaf_info[L].n_votes;
