@@ -46,6 +46,23 @@ extern "C" {
     fn dh_biwi_parse_cal(text: *const c_char, len: usize, k: *mut f32) -> c_int;
     fn dh_biwi_parse_pose(file: *const u8, len: usize, k: *const f32, pos3d: *mut f32, pos2d: *mut f32,
                           rot: *mut f32) -> c_int;
+    // training (src/hough/prediction.rs:106-234, src/hough/houghforest.rs:196-311)
+    fn dh_train_learn(c: *mut DhCtx, p: *const DhTrainParams, n_frames: u32, w: u32, h: u32, depth: *const u16,
+                      mask: *const u8, k: *const f32, pos3d: *const f32, rot: *const f32, out: *mut *mut DhForest) -> c_int;
+    fn dh_train_forest(c: *mut DhCtx, p: *const DhTrainParams, patches: *const u16, n: u64, is_object: *const u8,
+                       offsets: *const f32, rotations: *const f64, out: *mut *mut DhForest) -> c_int;
+    fn dh_forest_to_json(f: *const DhForest, buf: *mut c_char, cap: usize, needed: *mut usize) -> c_int;
+}
+
+/// HoughLearning::new arguments (prediction.rs:106-116), learn's sigma, and a seed (the reference
+/// draws from thread_rng; here the same seed always gives the same forest)
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct DhTrainParams {
+    pub stepwidth: u32, pub subimage_width: u32, pub subimage_height: u32,
+    pub max_depth: u32, pub n_trees: u32, pub subset_per_tree: u32,
+    pub subrect_feature_scale: f64, pub features_per_node: u32, pub min_subset_size: u32,
+    pub steepness: f64, pub gaussian_sigma: f32, _pad: u32, pub seed: u64,
 }
 
 #[derive(Debug)]
@@ -134,6 +151,30 @@ impl HoughPrediction {
 }
 impl Drop for HoughPrediction {
     fn drop(&mut self) { unsafe { dh_ctx_free(self.ctx); dh_forest_free(self.forest); } }
+}
+
+impl HoughPrediction {
+    /// HoughLearning::learn (prediction.rs:145-234) on the GPU: `depth`/`mask` are n frames back to
+    /// back, `k` one row-major 3x3 matrix per frame, `pos3d`/`rot` the annotated head pose per frame.
+    pub fn learn_on(params: &DhTrainParams, n: u32, w: u32, h: u32, depth: &[u16], mask: &[u8], k: &[f32],
+                    pos3d: &[f32], rot: &[f32], device: i32) -> Result<Self, Error> {
+        let (mut f, mut c) = (std::ptr::null_mut(), std::ptr::null_mut());
+        check(unsafe { dh_ctx_create(device, &mut c) })?;
+        if let Err(e) = check(unsafe { dh_train_learn(c, params, n, w, h, depth.as_ptr(), mask.as_ptr(), k.as_ptr(),
+                                                      pos3d.as_ptr(), rot.as_ptr(), &mut f) }) {
+            unsafe { dh_ctx_free(c) };
+            return Err(e);
+        }
+        Ok(HoughPrediction { forest: f, ctx: c })
+    }
+    /// what `tojson(&tree, filename)` writes (examples/hough_tree_trainer.rs:182)
+    pub fn to_json(&self) -> Result<String, Error> {
+        let mut need = 0usize;
+        check(unsafe { dh_forest_to_json(self.forest, std::ptr::null_mut(), 0, &mut need) })?;
+        let mut buf = vec![0u8; need];
+        check(unsafe { dh_forest_to_json(self.forest, buf.as_mut_ptr() as *mut c_char, need, &mut need) })?;
+        Ok(String::from_utf8_lossy(&buf).into_owned())
+    }
 }
 
 /// src/db_reader/biwi.rs: the three file formats on the way to the prediction path.
