@@ -145,8 +145,8 @@ def make_forest(seed: int = 0, n_trees: int = 10, max_depth: int = 15, sub_w: in
         ch = np.asarray(children, np.int64).reshape(-1, 2)
         # rectangles: origin floor(u*(W-rw)), fixed rw x rh  (types.rs:82-91)
         if ragged_rects:
-            ww = rng.integers(0, rw * 2 + 1, (n_nodes, 2))
-            hh = rng.integers(0, rh * 2 + 1, (n_nodes, 2))
+            ww = rng.integers(0, min(rw * 2, sub_w) + 1, (n_nodes, 2))
+            hh = rng.integers(0, min(rh * 2, sub_h) + 1, (n_nodes, 2))
         else:
             ww = np.full((n_nodes, 2), rw)
             hh = np.full((n_nodes, 2), rh)
