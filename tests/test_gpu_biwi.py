@@ -124,3 +124,54 @@ def test_predict_from_compressed_files(ctx):
     with pytest.raises(DhError):
         biwi.predict_files(hp, blob2, off2, 640, 480, K, ctx=ctx)
     assert ctx.counters()["launches"] >= 0
+
+
+def test_decode_mutated_streams_against_the_oracle(ctx):
+    """Seeded mutation fuzzing of the run-length reader: bytes flipped, header fields replaced by
+    extreme values, files cut short or extended.  For every stream the GPU reader either fails
+    where the reference reader fails (biwi.rs:81-103: UnexpectedEof, index out of bounds) or
+    returns the same pixels.  Both sides see the same bytes (the 16-byte padding of pack_files
+    is part of the file the ABI is given)."""
+    rng = np.random.default_rng(20240)
+    lib = capi.load()
+    n_fail = n_ok = 0
+    for case in range(400):
+        h, w = int(rng.integers(1, 49)), int(rng.integers(1, 65))
+        if case % 50 == 0:
+            h, w = 480, 640
+        fill = float(rng.choice([0.02, 0.3, 0.5, 0.9]))
+        frame = np.where(rng.random((h, w)) < fill, rng.integers(1, 65536, (h, w)), 0).astype(np.uint16)
+        data = bytearray(biwi.encode_depth(frame))
+        kind = int(rng.integers(0, 6))
+        body = len(data) - 8
+        if kind == 0 and body > 0:      # flip one byte behind the size header
+            data[8 + int(rng.integers(0, body))] ^= int(rng.integers(1, 256))
+        elif kind == 1 and body >= 4:   # an extreme value in some aligned word (a header field or two pixels)
+            pos = 8 + 2 * int(rng.integers(0, (body - 4) // 2 + 1))
+            data[pos:pos + 4] = struct.pack("<I", int(rng.choice([0, 1, w * h, w * h + 1, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF, 0xFFFFFFFE])))
+        elif kind == 2:                 # cut short
+            data = data[: 8 + int(rng.integers(0, body + 1))]
+        elif kind == 3:                 # trailing garbage
+            data += bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8))
+        elif kind == 4 and body >= 8:   # delete an aligned piece
+            pos = 8 + 2 * int(rng.integers(0, body // 2))
+            del data[pos:pos + 2 * int(rng.integers(1, 5))]
+        # kind 5: unchanged
+        blob, off = biwi.pack_files([bytes(data)])
+        seen = bytes(blob[: int(off[1])])
+        try:
+            want = oracle.biwi_read_depth(seen)
+        except oracle.BiwiError:
+            want = None
+        out = np.full((1, h, w), 0xABCD, np.uint16)
+        rc = lib.dh_biwi_decode_depth(ctx._h, capi.ptr(blob), capi.ptr(off), 1, w, h, capi.ptr(out), capi.DH_DEPTH_HOST)
+        if want is None:
+            assert rc == capi.DH_E_ARG, "case %d kind %d: the reference reader fails, the GPU reader returned %d" % (case, kind, rc)
+            n_fail += 1
+        else:
+            assert rc == capi.DH_OK, "case %d kind %d: %s" % (case, kind, lib.dh_last_error())
+            assert np.array_equal(out[0], want), "case %d kind %d" % (case, kind)
+            n_ok += 1
+    assert n_fail > 50 and n_ok > 50
+    good = biwi.encode_depth(synth.make_frames(1, seed=4)[0])
+    assert np.array_equal(biwi.read_depth(good, ctx=ctx), oracle.biwi_read_depth(good))
