@@ -419,6 +419,15 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
         };
         g.magic_w = magic(w);
         g.magic_h = magic(h);
+        {
+            // prob = sum / n_trees > 0.7 (prediction.rs:582-584) as a comparison of the sum: walk to the
+            // smallest double whose rounded quotient exceeds 0.7
+            const double t = (double)g.n_trees;
+            double smin = 0.7 * t;
+            while (smin / t > 0.7) smin = std::nextafter(smin, -HUGE_VAL);
+            while (!(smin / t > 0.7)) smin = std::nextafter(smin, HUGE_VAL);
+            g.gate_min_sum = smin;
+        }
         if ((uint64_t)g.P * g.n_trees > 0x7fffffffull) throw ModelError(DH_E_SHAPE, "too many patch x tree pairs per frame");
         if (g.P) tiles_ = plan_tiles(g);
         sk_ = k;

@@ -855,7 +855,7 @@ __device__ __forceinline__ uint32_t flat_owner(uint32_t start, uint32_t v) {
 // every pair whose first vote falls into the window sets that bit, and vote j belongs to slot
 // (pairs that began before the window) + popc(bits <= j) - 1.
 struct alignas(16) PairSlot {
-    uint4 a;    // start, first vote of the leaf, weight, unused
+    uint4 a;    // start, first vote of the leaf, weight, caller's tag
     float4 h;   // p3 (prediction.rs:554) + patch index
 };
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane) {
@@ -867,10 +867,10 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane) {
     return x;
 }
 
-// Calls body(vote index, weight, p3) once per vote of the warp's 32 pairs, 32 votes at a time.
+// Calls body(vote index, weight, tag, p3) once per vote of the warp's 32 pairs, 32 votes at a time.
 // n: votes of this lane's pair (0 = none), v0: its first vote.  All 32 lanes must call.
 template <typename Body>
-__device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t wgt, const float4 h, PairSlot* slots,
+__device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t wgt, uint32_t tag, const float4 h, PairSlot* slots,
                                               uint32_t lane, Body&& body) {
     const uint32_t has = __ballot_sync(0xffffffffu, n > 0u);
     if (!has) return;
@@ -879,7 +879,7 @@ __device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t 
     __syncwarp();  // the previous call's readers are done with the slots
     if (n > 0u) {
         PairSlot* mine = slots + __popc(has & ((1u << lane) - 1u));
-        mine->a = make_uint4(start, v0, wgt, 0u);
+        mine->a = make_uint4(start, v0, wgt, tag);
         mine->h = h;
     }
     __syncwarp();
@@ -892,13 +892,16 @@ __device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t 
         if (vb + lane < total) {
             const uint4 a = slots[k].a;
             const float4 c = slots[k].h;
-            body(a.y + (vb + lane - a.x), a.z, c);
+            body(a.y + (vb + lane - a.x), a.z, a.w, c);
         }
     }
 }
 
 constexpr int kGateSmemBytes = kGateThreads * 16 + (kGateThreads / 32) * 32 * 32 + (kPosGridCells + kRotGridCells) * 4 + kTouchedCap * 2;
 
+// kFused: one pass over the votes of every pair feeds both grids (a vote is an offset and a rotation;
+// the pair's tag says which of the two spread gates is open) instead of one pass per grid.
+template <bool kFused>
 __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffers b, Geometry g, ForestDev f) {
     extern __shared__ __align__(16) uint8_t gate_smem[];
     float4* s_gated = reinterpret_cast<float4*>(gate_smem);                                   // [kGateThreads] p3 + patch index of the CTA's gated patches
@@ -939,7 +942,7 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
                 for (int u = 0; u < 4; ++u)
                     if (t0 + u < T) s = __dadd_rn(s, pr[u]);
             }
-            gate = __ddiv_rn(s, (double)T) > 0.7;  // prediction.rs:584
+            gate = s >= g.gate_min_sum;  // sum / T > 0.7 (prediction.rs:584), see Geometry::gate_min_sum
         }
         if (gate) {
             const uint32_t gx = p % g.npx, gy = p / g.npx;
@@ -995,21 +998,30 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
                 if (li.flags & kLeafRotOk) { n_r = li.n_votes; ++cnt_r; nrot += li.n_votes; }
             }
         }
-        // centre votes -> 20x20 grid
-        for_each_vote(n_c, v0, wgt, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, const float4& c) {
+        // centre votes -> 20x20 grid: np = p3 - offset (prediction.rs:647); np.z < 0 is skipped (:650)
+        auto centre_vote = [&](uint32_t vote, uint32_t ow, const float4& c) {
             const float4 o = __ldg(f.offsets + vote);
-            // np = p3 - offset (prediction.rs:647); np.z < 0 is skipped (:650)
             const float nx = __fsub_rn(c.x, o.x), ny = __fsub_rn(c.y, o.y), nz = __fsub_rn(c.z, o.z);
             if (!(nz < 0.0f)) atomicAdd(&s_grid[coarse_pos_cell(g, nx, ny, nz)], ow);
-        });
+        };
         // rotation votes -> 20^3 grid; rough = r * 20 / 120 per axis (prediction.rs:630-636), static per vote
-        for_each_vote(n_r, v0, wgt, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, const float4&) {
+        auto rot_vote = [&](uint32_t vote, uint32_t ow) {
             const uint32_t cell = __ldg(f.rot_coarse + vote);
             if (atomicAdd(&s_grid[kPosGridCells + cell], ow) == 0u) {
                 const uint32_t slot = atomicAdd(&s_ntouched, 1u);
                 if (slot < (uint32_t)kTouchedCap) s_touched[slot] = (uint16_t)cell;
             }
-        });
+        };
+        if (kFused) {
+            const uint32_t tag = (n_c ? 1u : 0u) | (n_r ? 2u : 0u);
+            for_each_vote(n_c | n_r, v0, wgt, tag, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t tg, const float4& c) {
+                if (tg & 1u) centre_vote(vote, ow, c);
+                if (tg & 2u) rot_vote(vote, ow);
+            });
+        } else {
+            for_each_vote(n_c, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4& c) { centre_vote(vote, ow, c); });
+            for_each_vote(n_r, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4&) { rot_vote(vote, ow); });
+        }
     }
     // per-frame counters, one atomic per warp
 #pragma unroll
@@ -2072,9 +2084,14 @@ uint32_t vote_box_dim() { return (uint32_t)kBox; }
 int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
     if (!g.P) return 0;
     static SmemConfig configured;
-    if (configured.raise((uint32_t)kGateSmemBytes)) cudaFuncSetAttribute(gate_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateSmemBytes);
+    if (configured.raise((uint32_t)kGateSmemBytes)) {
+        cudaFuncSetAttribute(gate_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateSmemBytes);
+        cudaFuncSetAttribute(gate_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateSmemBytes);
+    }
+    static const bool fused = !(std::getenv("DH_GATE_FUSED") && std::atoi(std::getenv("DH_GATE_FUSED")) == 0);
     dim3 gr((g.P + kGateThreads - 1) / kGateThreads, n_frames);
-    gate_coarse_kernel<<<gr, kGateThreads, kGateSmemBytes, s>>>(b, g, f);
+    if (fused) gate_coarse_kernel<true><<<gr, kGateThreads, kGateSmemBytes, s>>>(b, g, f);
+    else gate_coarse_kernel<false><<<gr, kGateThreads, kGateSmemBytes, s>>>(b, g, f);
     return 1;
 }
 

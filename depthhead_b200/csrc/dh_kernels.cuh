@@ -47,6 +47,8 @@ struct Geometry {
     uint32_t box_w, box_h;    // w - rw + 1, h - rh + 1
     uint32_t box_pitch;       // elements per row of B (multiple of 4)
     float K[9], Kinv[9];
+    double gate_min_sum;      // smallest f64 s with fl(s / n_trees) > 0.7: the patch gate of prediction.rs:582-584
+                              // without the division (IEEE division by a positive constant is monotone in s)
 };
 
 struct TilePlan {

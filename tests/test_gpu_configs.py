@@ -46,6 +46,7 @@ VARIANTS = [
     {"DH_BOX_WHOLE": "0"},                          # box image through warp-wide prefix sums (the path of widths not divisible by 8)
     {"DH_TRAV_THREADS": "512"},                     # 512-thread traversal tiles
     {"DH_TRAV_ILP": "2", "DH_TRAV_THREADS": "768"}, # two walks in flight per thread, 768-thread tiles
+    {"DH_GATE_FUSED": "0"},                         # seed grids: one pass over the votes per grid instead of one for both
     {"DH_LANES": "1"},
     {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},
 ]
