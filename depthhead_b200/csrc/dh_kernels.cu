@@ -1984,12 +1984,16 @@ static int launch_box_image_t(const FrameBuffers& b, const Geometry& g, uint32_t
         cudaFuncSetAttribute(box_image_kernel<kPx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(box_image_kernel<kPx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    // bands: a band re-reads the rh - 1 rows above it, so as few as possible, but enough that the
-    // warps of one launch fill the GPU once; never shorter than rh rows
+    // bands: a band re-reads the rh - 1 rows above it, so few of them, but enough that the launch has
+    // about two rounds of CTAs (the CTAs of a single round do not divide evenly over the SMs and the
+    // fullest SM sets the time: 512 frames x 1 band = 3.46 CTAs per SM ran 0.428 ms, 4 bands 0.376 ms);
+    // never shorter than rh rows.  DH_BOX_BANDS=n forces the count.
     const uint32_t ctas_per_sm = std::max<uint32_t>(1u, std::min<uint32_t>(16u, (227u * 1024u) / (smem + 1024u)));
     const uint32_t slots = (uint32_t)n_sms * ctas_per_sm * wpc;
     const uint32_t units = n_strips * n_frames;
-    uint32_t n_bands = std::max<uint32_t>(1u, std::min<uint32_t>(slots / units, std::max<uint32_t>(1u, g.box_h / g.rh)));
+    uint32_t n_bands = std::max<uint32_t>(1u, std::min<uint32_t>((2u * slots + units - 1u) / units, std::max<uint32_t>(1u, g.box_h / g.rh)));
+    static const uint32_t bands_env = std::getenv("DH_BOX_BANDS") ? (uint32_t)std::atoi(std::getenv("DH_BOX_BANDS")) : 0u;
+    if (bands_env) n_bands = std::max<uint32_t>(1u, std::min<uint32_t>(bands_env, std::max<uint32_t>(1u, g.box_h / g.rh)));
     const uint32_t band_rows = (g.box_h + n_bands - 1u) / n_bands;
     n_bands = (g.box_h + band_rows - 1u) / band_rows;
     const uint32_t n_units = n_strips * n_bands * n_frames;

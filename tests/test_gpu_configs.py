@@ -43,6 +43,8 @@ VARIANTS = [
     {"DH_BOX_IMAGE": "0"},                          # uniform forest on the summed-area table (box sums made in the tile)
     {"DH_BOX_IMAGE": "0", "DH_UNI_LDG": "1"},
     {"DH_BOX_PX": "4"},                             # box image with 4 pixels per lane
+    {"DH_BOX_BANDS": "1"},                          # box image: one band per frame / five bands instead of the launch heuristic
+    {"DH_BOX_BANDS": "5"},
     {"DH_BOX_WHOLE": "0"},                          # box image through warp-wide prefix sums (the path of widths not divisible by 8)
     {"DH_TRAV_THREADS": "512"},                     # 512-thread traversal tiles
     {"DH_TRAV_ILP": "2", "DH_TRAV_THREADS": "768"}, # two walks in flight per thread, 768-thread tiles
