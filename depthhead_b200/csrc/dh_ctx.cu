@@ -352,7 +352,23 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
                     best = TilePlan{tpx, tpy, tiles_x, tiles_y, tw, th, bytes, (big && limit <= 113000u) ? trav_threads : 512u};
                 }
             }
-        if (best.tpx) return best;
+        if (best.tpx) {
+            if (env_u32("DH_TRAV_BLOCK", 0)) {
+                // a warp walks a block of 8 x 4 neighbouring patches: its lanes stay on the same nodes for
+                // longer.  On one node lane (c, r) reads word stride * (c + r * tw) + const: with
+                // stride * tw = 8 (mod 32) and an odd stride the 32 lanes hit 32 different banks.
+                best.blocked = 1u;
+                for (uint32_t tw2 = best.tw; tw2 < best.tw + 32u && tw2 <= 256u; tw2 += 4u) {
+                    const uint32_t bytes = traverse_smem_bytes(tw2, best.th, best.tpx * best.tpy);
+                    if (((g.stride * tw2) & 31u) == 8u && bytes <= limit) {
+                        best.tw = tw2;
+                        best.smem_bytes = bytes;
+                        break;
+                    }
+                }
+            }
+            return best;
+        }
     }
     throw ModelError(DH_E_SHAPE, "sub-image too large: its summed-area window does not fit in shared memory");
 }

@@ -640,11 +640,22 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
     // ---- background test (prediction.rs:567-571: mean over the whole patch > 0  <=>  sum != 0)
     const uint32_t tw4 = tp.tw * 4u;
     const uint32_t org_a = tile_a + dx * 4u;  // patch (0,0) of the tile
-    for (uint32_t lp = tid; lp < ((npt + 31u) & ~31u); lp += kThreads) {
+    // patches in row order, 32 per warp, or (tp.blocked) in blocks of 8 x 4 patches, one per warp
+    const uint32_t nbx = (tp.tpx + 7u) >> 3;
+    const uint32_t n_lp = tp.blocked ? nbx * ((tp.tpy + 3u) >> 2) * 32u : ((npt + 31u) & ~31u);
+    for (uint32_t lp = tid; lp < n_lp; lp += kThreads) {
         bool ok = false;
         uint32_t packed = 0;
-        if (lp < npt) {
-            const uint32_t lx = lp % tp.tpx, ly = lp / tp.tpx;
+        uint32_t lx, ly;
+        if (tp.blocked) {
+            const uint32_t blk = lp >> 5;
+            lx = (blk % nbx) * 8u + (lp & 7u);
+            ly = (blk / nbx) * 4u + ((lp >> 3) & 3u);
+        } else {
+            lx = lp % tp.tpx;
+            ly = lp / tp.tpx;
+        }
+        if (lx < tp.tpx && ly < tp.tpy) {
             const uint32_t gx = px0 + lx, gy = py0 + ly;
             if (gx < g.npx && gy < g.npy) {
                 const uint32_t o = org_a + ly * g.stride * tw4 + lx * g.stride * 4u;

@@ -58,6 +58,8 @@ struct TilePlan {
                               // table window, or box-sum image window in box-image mode
     uint32_t smem_bytes;
     uint32_t threads;
+    uint32_t blocked;         // 1: the patches of a tile are enumerated in blocks of 8 x 4 (a warp = a compact block)
+                              // instead of row by row (experimental, DH_TRAV_BLOCK=1)
 };
 
 struct ForestDev {

@@ -49,6 +49,8 @@ VARIANTS = [
     {"DH_TRAV_THREADS": "512"},                     # 512-thread traversal tiles
     {"DH_TRAV_ILP": "2", "DH_TRAV_THREADS": "768"}, # two walks in flight per thread, 768-thread tiles
     {"DH_GATE_FUSED": "0"},                         # seed grids: one pass over the votes per grid instead of one for both
+    {"DH_TRAV_BLOCK": "1"},                         # a warp walks a block of 8 x 4 patches instead of a row of 32 (experimental)
+    {"DH_TRAV_BLOCK": "1", "DH_BOX_IMAGE": "0"},
     {"DH_LANES": "1"},
     {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},
 ]
