@@ -312,12 +312,12 @@ def main():
             if with_stages:
                 for k, v in ctx.stage_ms().items():
                     stage[k] = stage.get(k, 0.0) + v
-            for k, v in ctx.counters().items():
-                counters[k] = counters.get(k, 0) + v
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
+        # work counters: read once, after the timed region (every step does the same work)
+        counters = {k: v * steps for k, v in ctx.counters().items()}
         if dist is not None:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -339,6 +339,7 @@ def main():
     sampler.begin_region()
     ms_dev, wall_dev, _, counters, out_dev = timed(step_device, args.steps)
     ms_e2e, wall_e2e, _, _, out_host = timed(step_host, args.steps)
+    xfer = ctx.transfer_info()
     ms_biwi, wall_biwi, _, _, out_biwi = timed(step_biwi, args.steps)
     # per-stage times (and the roofline of the traversal kernel): the same steps again with the
     # pipeline serialised on one stream, CUDA events between the stages
@@ -422,9 +423,13 @@ def main():
         "evals_per_s": counters["evals"] * world / (ms_dev / 1000.0),
         "patch_tree_evals_per_frame": counters["evals"] / max(1, counters["frames"]),
         "mean_visited_depth": counters["node_visits"] / max(1, counters["evals"]),
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(xfer["h2d_bytes"]),
                 "d2h_bytes_per_step": int(out_host.nbytes), "ms_per_step": ms_e2e / args.steps,
-                "wall_ms_per_step": wall_e2e / args.steps},
+                "wall_ms_per_step": wall_e2e / args.steps, "host_frame_bytes_per_step": int(frames.nbytes),
+                "host_threads": int(xfer["encode_threads"]), "chunks_rewritten_per_step": int(xfer["encoded_chunks"]),
+                "note": "dh_predict_batch on pinned host u16 frames: worker threads of the library rewrite every chunk as "
+                        "run-length files (Biwi format, biwi.rs:81-103) in pinned memory, those bytes cross PCIe and the GPU "
+                        "expands them bit for bit (DH_HOST_ENCODE=0: raw copy)"},
         "e2e_biwi": {"value": total_frames / (ms_biwi / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": int(offsets[-1]),
                      "d2h_bytes_per_step": int(out_biwi.nbytes), "ms_per_step": ms_biwi / args.steps,
                      "wall_ms_per_step": wall_biwi / args.steps, "compression": float(frames.nbytes) / float(offsets[-1]),

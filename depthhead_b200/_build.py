@@ -15,8 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdepthhead_cuda.so")
-SOURCES = ["dh_kernels.cu", "dh_ctx.cu", "dh_capi.cu", "dh_forest.cpp", "dh_biwi.cpp", "dh_train.cu"]
-HEADERS = ["dh_kernels.cuh", "dh_ctx.hpp", "dh_forest.hpp", "dh_json.hpp", "dh_types.hpp",
+SOURCES = ["dh_kernels.cu", "dh_ctx.cu", "dh_capi.cu", "dh_forest.cpp", "dh_biwi.cpp", "dh_train.cu", "dh_hostenc.cpp"]
+HEADERS = ["dh_kernels.cuh", "dh_ctx.hpp", "dh_forest.hpp", "dh_json.hpp", "dh_types.hpp", "dh_hostenc.hpp",
            os.path.join("..", "..", "include", "depthhead_cuda.h")]
 
 
@@ -34,13 +34,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def build_id() -> str:
+    """sha256 over the library's sources and headers, first 12 hex digits (dh_build_id())."""
+    import hashlib
+    hsh = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            hsh.update(f.encode() + b"\0" + fh.read() + b"\0")
+    return hsh.hexdigest()[:12]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2",
-           "-shared", "-cudart", "static", "-o", LIB]
+           "-shared", "-cudart", "static", "-Xcompiler", "-pthread", "-DDH_BUILD_ID=\"%s\"" % build_id(), "-o", LIB]
     if host_cxx:
         cmd += ["-ccbin", host_cxx]
     if verbose:

@@ -76,6 +76,15 @@ class Context:
     def set_chunk_frames(self, frames: int):
         capi.check(capi.load().dh_ctx_set_chunk_frames(self._h, int(frames)))
 
+    def set_encode_threads(self, n: int):
+        """worker threads of the compressed host->device path of predict_batch (0 = default)"""
+        capi.check(capi.load().dh_ctx_set_encode_threads(self._h, int(n)))
+
+    def transfer_info(self) -> dict:
+        a = np.zeros(4, np.uint64)
+        capi.check(capi.load().dh_ctx_transfer_info(self._h, capi.ptr(a)))
+        return {"h2d_bytes": int(a[0]), "encoded_chunks": int(a[1]), "encode_threads": int(a[2])}
+
     def synchronize(self):
         capi.check(capi.load().dh_ctx_synchronize(self._h))
 

@@ -47,6 +47,24 @@ def encode_depth(img: np.ndarray) -> bytes:
     return b"".join(parts)
 
 
+def encode_frames(frames: np.ndarray, threads: int = 0) -> tuple:
+    """[n, h, w] uint16 -> (blob, offsets) through the library's own multi-threaded writer
+    (dh_biwi_encode_depth: the encoder dh_predict_batch runs for host frames; runs at a
+    granularity of 16 pixels, so isolated zeros travel as literal zeros).  Host-only."""
+    a = np.ascontiguousarray(frames, dtype=np.uint16)
+    if a.ndim != 3:
+        raise ValueError("frames must be [n, h, w] uint16")
+    n, h, w = a.shape
+    L = capi.load()
+    offsets = np.zeros(n + 1, np.uint64)
+    need = C.c_size_t(0)
+    cap = int(L.dh_biwi_encode_bound(w, h)) * n + 16
+    blob = np.zeros(cap, np.uint8)
+    capi.check(L.dh_biwi_encode_depth(capi.ptr(a) if n else None, n, w, h, int(threads), capi.ptr(blob), cap, capi.ptr(offsets),
+                                      C.byref(need)))
+    return blob[:need.value].copy(), offsets
+
+
 def pack_files(files) -> tuple:
     """Concatenate compressed depth files into the blob + offsets the C ABI takes (every file
     starts at a multiple of 16 bytes)."""

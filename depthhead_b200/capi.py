@@ -87,6 +87,11 @@ SIGNATURES = {
     "dh_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "dh_ctx_set_chunk_frames": (C.c_int, [_vp, _u32]),
     "dh_ctx_synchronize": (C.c_int, [_vp]),
+    "dh_ctx_set_encode_threads": (C.c_int, [_vp, _u32]),
+    "dh_ctx_transfer_info": (C.c_int, [_vp, _vp]),
+    "dh_build_id": (C.c_char_p, []),
+    "dh_biwi_encode_bound": (C.c_size_t, [_u32, _u32]),
+    "dh_biwi_encode_depth": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _vp, C.c_size_t, _vp, C.POINTER(C.c_size_t)]),
     "dh_predict": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, C.POINTER(dh_result)]),
     "dh_predict_batch": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, C.c_int, _vp]),
     "dh_biwi_depth_dims": (C.c_int, [_vp, C.c_size_t, C.POINTER(_u32), C.POINTER(_u32)]),

@@ -4,7 +4,9 @@
 #include <cstring>
 #include <memory>
 #include <new>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "../../include/depthhead_cuda.h"
 #include "dh_ctx.hpp"
@@ -56,6 +58,10 @@ extern "C" {
 
 const char* dh_last_error(void) { return g_last_error.c_str(); }
 int dh_abi_version(void) { return DH_ABI_VERSION; }
+#ifndef DH_BUILD_ID
+#define DH_BUILD_ID "unknown"
+#endif
+const char* dh_build_id(void) { return DH_BUILD_ID; }
 
 int dh_forest_from_json(const char* json, size_t len, dh_forest** out) {
     return guarded([&] {
@@ -171,6 +177,22 @@ int dh_ctx_set_chunk_frames(dh_ctx* c, uint32_t frames) {
         c->cx->set_chunk_frames(frames);
     });
 }
+int dh_ctx_set_encode_threads(dh_ctx* c, uint32_t n) {
+    return guarded([&] {
+        REQUIRE(c, "NULL context");
+        REQUIRE(n <= 256, "dh_ctx_set_encode_threads: more than 256 threads");
+        c->cx->set_encode_threads(n);
+    });
+}
+int dh_ctx_transfer_info(dh_ctx* c, uint64_t info[4]) {
+    return guarded([&] {
+        REQUIRE(c && info, "NULL argument");
+        info[0] = c->cx->last_h2d_bytes();
+        info[1] = c->cx->last_encoded_chunks();
+        info[2] = c->cx->encode_threads();
+        info[3] = 0;
+    });
+}
 int dh_ctx_synchronize(dh_ctx* c) {
     return guarded([&] {
         REQUIRE(c, "NULL ctx");
@@ -212,6 +234,34 @@ int dh_predict_batch_biwi(dh_ctx* c, const dh_forest* f, const uint8_t* blob, co
     return guarded([&] {
         REQUIRE(c && f && K && (n == 0 || (blob && offsets && out)), "dh_predict_batch_biwi: NULL argument");
         c->cx->predict_batch_biwi(*f->hf, blob, offsets, n, w, h, K, out);
+    });
+}
+size_t dh_biwi_encode_bound(uint32_t w, uint32_t h) { return dh::rle_frame_bound(w, h); }
+int dh_biwi_encode_depth(const uint16_t* frames, uint32_t n, uint32_t w, uint32_t h, uint32_t threads, uint8_t* blob, size_t cap,
+                         uint64_t* offsets, size_t* needed) {
+    return guarded([&] {
+        REQUIRE(needed && (n == 0 || frames), "dh_biwi_encode_depth: NULL argument");
+        REQUIRE((uint64_t)w * h <= 0x3fffffffull, "dh_biwi_encode_depth: frame of more than 2^30 pixels");
+        const size_t px = (size_t)w * h, bound = dh::rle_frame_bound(w, h);
+        // pass 1 (parallel): every frame into its own slot of an uninitialised scratch area;
+        // pass 2 (parallel): the files move to their packed places
+        std::unique_ptr<uint8_t[]> scratch(new uint8_t[(size_t)std::max<uint32_t>(n, 1u) * bound]);
+        std::vector<size_t> len(n), start(n + 1, 0);
+        dh::WorkerPool pool(threads ? threads : dh::default_encode_threads());
+        uint8_t* sc = scratch.get();
+        pool.wait(pool.run(n, [&](uint32_t i) { len[i] = dh::rle_encode_frame(frames + (size_t)i * px, w, h, sc + (size_t)i * bound); }));
+        for (uint32_t i = 0; i < n; ++i) start[i + 1] = start[i] + ((len[i] + 15) & ~(size_t)15);
+        if (offsets)
+            for (uint32_t i = 0; i < n; ++i) offsets[i] = start[i];
+        if (blob)
+            pool.wait(pool.run(n, [&](uint32_t i) {
+                if (start[i + 1] > cap) return;
+                std::memcpy(blob + start[i], sc + (size_t)i * bound, len[i]);
+                std::memset(blob + start[i] + len[i], 0, start[i + 1] - start[i] - len[i]);
+            }));
+        const size_t pos = start[n];
+        if (offsets) offsets[n] = pos;
+        *needed = pos + 16;  // the decoder reads whole 4-byte words; a little slack after the last file
     });
 }
 int dh_biwi_parse_cal(const char* text, size_t len, float K[9]) {

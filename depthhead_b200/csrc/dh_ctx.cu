@@ -94,6 +94,9 @@ Context::Context(int device) : device_(device) {
     dev_alloc(d_counters_, DH_N_COUNTERS);
     DH_CUDA(cudaHostAlloc((void**)&h_fs_, sizeof(FrameState), cudaHostAllocDefault));
     DH_CUDA(cudaHostAlloc((void**)&h_counters_, sizeof(unsigned long long) * DH_N_COUNTERS, cudaHostAllocDefault));
+    DH_CUDA(cudaHostAlloc((void**)&h_result1_, sizeof(dh_result), cudaHostAllocDefault));
+    for (int i = 0; i < kEncSlots; ++i) DH_CUDA(cudaEventCreateWithFlags(&ev_enc_copied_[i], cudaEventDisableTiming));
+    if (const char* v = std::getenv("DH_HOST_ENCODE")) host_encode_ = *v ? (int)std::strtol(v, nullptr, 10) : -1;
     use_graphs_ = env_flag("DH_GRAPH", true);
     chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 0);  // 0 = adaptive (128 for host input, 512 for device input)
     debug_sync_ = env_u32("DH_DEBUG_SYNC", 0) != 0;
@@ -118,6 +121,14 @@ Context::~Context() {
     if (h_fs_) cudaFreeHost(h_fs_);
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_results_) cudaFreeHost(h_results_);
+    if (h_result1_) cudaFreeHost(h_result1_);
+    pool_.reset();
+    for (int i = 0; i < kEncSlots; ++i) {
+        if (h_enc_[i]) cudaFreeHost(h_enc_[i]);
+        if (h_enc_meta_[i]) cudaFreeHost(h_enc_meta_[i]);
+        if (ev_enc_copied_[i]) cudaEventDestroy(ev_enc_copied_[i]);
+    }
+    for (int i = 0; i < 2; ++i) dev_free(d_enc_meta_[i]);
     for (auto ev : timing_events_) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
         if (ev_copied_[i]) cudaEventDestroy(ev_copied_[i]);
@@ -134,6 +145,10 @@ Context::~Context() {
 
 void Context::set_stream(void* s) { stream_ = s ? reinterpret_cast<cudaStream_t>(s) : own_stream_; }
 void Context::set_chunk_frames(uint32_t f) { chunk_frames_ = f ? std::min<uint32_t>(f, 32768u) : env_u32("DH_CHUNK_FRAMES", 0); }
+void Context::set_encode_threads(uint32_t n) {
+    if (n != encode_threads_req_) pool_.reset();
+    encode_threads_req_ = n;
+}
 void Context::synchronize() {
     DH_CUDA(cudaSetDevice(device_));
     DH_CUDA(cudaStreamSynchronize(stream_));
@@ -353,6 +368,9 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
                 }
             }
         if (best.tpx) {
+            best.tma_first = env_flag("DH_TRAV_TMA_FIRST", false) ? 1u : 0u;
+            // experiment: extra dynamic shared memory per CTA lowers the CTAs per SM without changing the tile
+            best.smem_bytes += std::min<uint32_t>(env_u32("DH_TRAV_PAD_SMEM", 0), smem_optin_ > best.smem_bytes ? smem_optin_ - best.smem_bytes : 0u);
             if (env_u32("DH_TRAV_BLOCK", 0)) {
                 // a warp walks a block of 8 x 4 neighbouring patches: its lanes stay on the same nodes for
                 // longer.  On one node lane (c, r) reads word stride * (c + r * tw) + const: with
@@ -612,16 +630,12 @@ void Context::predict(const HostForest& hf, const uint16_t* depth, uint32_t w, u
         gs.has_guess |= 2u;
         for (int k = 0; k < 3; ++k) gs.rot_guess[k] = rot_guess[k];
     }
-    if (h_results_cap_ < 1) {
-        DH_CUDA(cudaHostAlloc((void**)&h_results_, sizeof(dh_result), cudaHostAllocDefault));
-        h_results_cap_ = 1;
-    }
     // everything after the input copy: per-frame state, front end, back end, result and counters to pinned memory
     auto enqueue = [&] {
         FrameBuffers b = buffers(lanes_[0], d_depth_[0]);
         run_front(lanes_[0], b, 1, &gs);
         run_back(lanes_[0], b, 1, iterations);
-        DH_CUDA(cudaMemcpyAsync(h_results_, lanes_[0].results, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
+        DH_CUDA(cudaMemcpyAsync(h_result1_, lanes_[0].results, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
     };
     bool replayed = false;
     if (use_graphs_ && !timing_ && !debug_ && !debug_sync_) {
@@ -629,7 +643,7 @@ void Context::predict(const HostForest& hf, const uint16_t* depth, uint32_t w, u
         key.serial = hf.serial; key.sigma_version = df_sigma_version_;
         key.w = w; key.h = h; key.stride = geom_.stride; key.iterations = iterations;
         std::memcpy(key.K, K, sizeof(key.K));
-        key.stream = (void*)stream_; key.depth = d_depth_[0]; key.scratch = lanes_[0].fs;
+        key.stream = (void*)stream_; key.depth = d_depth_[0]; key.scratch = lanes_[0].fs; key.result = h_result1_;
         if (graph_exec_ && !(graph_key_ == key)) drop_graph();
         if (!graph_exec_ && graph_seen_valid_ && graph_seen_ == key) {
             // second call with this key: capture the sequence (the first, eager call planned the node
@@ -673,7 +687,7 @@ void Context::predict(const HostForest& hf, const uint16_t* depth, uint32_t w, u
     if (!replayed) enqueue();
     mark(-1);
     end_call();
-    *out = *h_results_;
+    *out = *h_result1_;
     have_debug_ = debug_;
     debug_iterations_ = iterations;
 }
@@ -757,7 +771,7 @@ void Context::biwi_decode(const uint8_t* blob, const uint64_t* offsets, uint32_t
             uint16_t* dst = out_loc == DH_DEPTH_DEVICE ? d_out + (size_t)f0 * frame_px : d_out;
             DH_CUDA(cudaMemcpyAsync(d_blob_[0], blob + offsets[f0], (size_t)(offsets[f0 + nc] - offsets[f0]), cudaMemcpyHostToDevice, stream_));
             DH_CUDA(cudaMemsetAsync(dst, 0, (size_t)nc * frame_px * sizeof(uint16_t), stream_));
-            launch_biwi_decode(d_blob_[0], d_offsets_ + f0, offsets[f0], nc, w, h, dst, d_status_ + f0, stream_);
+            launch_biwi_decode(d_blob_[0], d_offsets_ + f0, nullptr, offsets[f0], nc, w, h, dst, d_status_ + f0, stream_);
             launches_ += 1;
             DH_CUDA(cudaGetLastError());
             if (out_loc != DH_DEPTH_DEVICE)
@@ -785,6 +799,12 @@ void Context::run_batch(const HostForest& hf, const uint16_t* depth, const uint8
         return;
     }
     ensure_forest(hf);
+    last_encoded_chunks_ = 0;
+    last_h2d_bytes_ = 0;
+    if (!blob && depth_loc != DH_DEPTH_DEVICE && want_encode(n, w, h)) {
+        run_batch_encoded(hf, depth, n, w, h, K, out);
+        return;
+    }
     // Chunks go round-robin over the lanes.  Stage timing needs the kernels of a pass back to
     // back on one stream, so it runs single-lane.
     // Biwi input: the run-length expansion is latency-bound (one thread per frame walks the run
@@ -833,12 +853,15 @@ void Context::run_batch(const HostForest& hf, const uint16_t* depth, const uint8
                 t1 = next_event();
                 DH_CUDA(cudaEventRecord(t0, copy_stream_));
             }
-            if (blob)
+            if (blob) {
                 DH_CUDA(cudaMemcpyAsync(d_blob_[slot], blob + offsets[f0], (size_t)(offsets[f0 + nc] - offsets[f0]), cudaMemcpyHostToDevice,
                                         copy_stream_));
-            else
+                last_h2d_bytes_ += (uint64_t)(offsets[f0 + nc] - offsets[f0]);
+            } else {
                 DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
                                         cudaMemcpyHostToDevice, copy_stream_));
+                last_h2d_bytes_ += (uint64_t)nc * frame_px * sizeof(uint16_t);
+            }
             if (timing_) {
                 DH_CUDA(cudaEventRecord(t1, copy_stream_));
                 copy_marks_.push_back({t0, t1});
@@ -848,7 +871,7 @@ void Context::run_batch(const HostForest& hf, const uint16_t* depth, const uint8
             if (blob) {
                 mark(DH_STAGE_H2D);  // the expansion counts as input transfer
                 DH_CUDA(cudaMemsetAsync(d_depth_[slot], 0, (size_t)nc * frame_px * sizeof(uint16_t), L.stream));
-                launch_biwi_decode(d_blob_[slot], d_offsets_ + f0, offsets[f0], nc, w, h, d_depth_[slot], d_status_ + f0, L.stream);
+                launch_biwi_decode(d_blob_[slot], d_offsets_ + f0, nullptr, offsets[f0], nc, w, h, d_depth_[slot], d_status_ + f0, L.stream);
                 launches_ += 1;
             }
             enqueue_chunk(c, d_depth_[slot]);
@@ -865,6 +888,198 @@ void Context::run_batch(const HostForest& hf, const uint16_t* depth, const uint8
     DH_CUDA(cudaStreamSynchronize(stream_));
     end_call();
     if (blob) check_biwi_status(n);
+    std::memcpy(out, h_results_, sizeof(dh_result) * n);
+}
+
+// ------------------------------------------------------------------------------------------------ compressed host input
+// dh_predict_batch from HOST frames is bound by the PCIe copy of the raw pixels (614 KB per VGA
+// frame, ~53 GB/s).  Depth frames are mostly background (0 = invalid), so worker threads rewrite
+// every chunk as Biwi run-length files (biwi.rs:81-103: the format biwi_decode_kernel expands)
+// straight into pinned memory; only those bytes cross PCIe and the frames are rebuilt on the GPU,
+// bit for bit.  Chunks whose sampled density says the rewrite would not pay are copied raw.
+bool Context::want_encode(uint32_t n, uint32_t w, uint32_t h) const {
+    if (host_encode_ == 0) return false;
+    const size_t px = (size_t)w * h;
+    return px >= 16384 && px <= 0x3fffffffull && (size_t)n * px >= (size_t)8 * 640 * 480;
+}
+
+void Context::ensure_encode(uint32_t n, uint32_t F) {
+    if (!pool_) pool_.reset(new WorkerPool(encode_threads_req_ ? encode_threads_req_ : default_encode_threads()));
+    const size_t bound = rle_frame_bound(sk_.w, sk_.h);
+    const uint32_t groups = (F + kEncGroup - 1) / kEncGroup;
+    const size_t slot = (size_t)groups * kEncGroup * bound;
+    if (slot > enc_slot_bytes_ || F > enc_frames_ || bound != enc_frame_bound_) {
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        DH_CUDA(cudaStreamSynchronize(copy_stream_));
+        for (int i = 0; i < kEncSlots; ++i) {
+            if (h_enc_[i]) cudaFreeHost(h_enc_[i]);
+            if (h_enc_meta_[i]) cudaFreeHost(h_enc_meta_[i]);
+            h_enc_[i] = nullptr;
+            h_enc_meta_[i] = nullptr;
+        }
+        for (int i = 0; i < 2; ++i) dev_free(d_enc_meta_[i]);
+        enc_slot_bytes_ = std::max(slot, enc_slot_bytes_);
+        enc_frames_ = std::max(F, enc_frames_);
+        enc_frame_bound_ = bound;
+        for (int i = 0; i < kEncSlots; ++i) {
+            DH_CUDA(cudaHostAlloc((void**)&h_enc_[i], enc_slot_bytes_, cudaHostAllocDefault));
+            DH_CUDA(cudaHostAlloc((void**)&h_enc_meta_[i], sizeof(unsigned long long) * 2 * enc_frames_, cudaHostAllocDefault));
+        }
+        for (int i = 0; i < 2; ++i) dev_alloc(d_enc_meta_[i], (size_t)2 * enc_frames_);
+    }
+    if (enc_slot_bytes_ + 64 > blob_cap_) {
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        DH_CUDA(cudaStreamSynchronize(copy_stream_));
+        for (int i = 0; i < 2; ++i) dev_free(d_blob_[i]);
+        blob_cap_ = enc_slot_bytes_ + 64;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!d_blob_[i]) dev_alloc(d_blob_[i], blob_cap_);
+    if ((size_t)n + 1 > biwi_frames_cap_) {
+        DH_CUDA(cudaStreamSynchronize(stream_));
+        dev_free(d_offsets_);
+        dev_free(d_status_);
+        if (h_status_) cudaFreeHost(h_status_);
+        h_status_ = nullptr;
+        biwi_frames_cap_ = (size_t)n + 1;
+        dev_alloc(d_offsets_, biwi_frames_cap_);
+        dev_alloc(d_status_, biwi_frames_cap_);
+        DH_CUDA(cudaHostAlloc((void**)&h_status_, sizeof(uint32_t) * biwi_frames_cap_, cudaHostAllocDefault));
+    }
+}
+
+void Context::run_batch_encoded(const HostForest& hf, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h, const float K[9],
+                                dh_result* out) {
+    const uint32_t want_chunk = pick_chunk(n, DH_DEPTH_HOST);
+    const int n_lanes = timing_ ? 1 : (int)std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>((uint32_t)max_lanes_, 2u), (n + want_chunk - 1) / want_chunk));
+    ensure_scratch(hf, w, h, want_chunk, K, n_lanes);
+    const uint32_t iterations = hf.meanshift_iterations.load();
+    const uint32_t F = call_chunk_;
+    const uint32_t n_chunks = (n + F - 1) / F;
+    const size_t frame_px = (size_t)w * h;
+    if (h_results_cap_ < n) {
+        if (h_results_) cudaFreeHost(h_results_);
+        h_results_ = nullptr;
+        DH_CUDA(cudaHostAlloc((void**)&h_results_, sizeof(dh_result) * n, cudaHostAllocDefault));
+        h_results_cap_ = n;
+    }
+    ensure_staging(2);
+    ensure_encode(n, F);
+    const size_t bound = enc_frame_bound_;
+    const uint32_t M = enc_frames_;  // stride between the begin and end halves of a meta array
+    DH_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(uint32_t) * n, stream_));
+    DH_CUDA(cudaEventRecord(ev_fork_, stream_));
+    for (int i = 1; i < n_lanes; ++i) DH_CUDA(cudaStreamWaitEvent(lanes_[i].stream, ev_fork_, 0));
+
+    std::vector<uint64_t> tickets(n_chunks, 0);
+    std::vector<uint8_t> encoded(n_chunks, 0);
+    uint32_t submitted = 0;
+    // hands chunk c to the workers (or decides to copy it raw)
+    auto submit = [&](uint32_t c) {
+        const int pslot = (int)(c % (uint32_t)kEncSlots);
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+        bool enc = true;
+        if (host_encode_ < 0) {
+            // sampled share of 16-pixel groups that would have to travel: above ~60 % the rewrite
+            // costs more host time than the copy saves
+            const double d = 0.5 * (rle_sample_density(depth + (size_t)f0 * frame_px, frame_px, 61) +
+                                    rle_sample_density(depth + (size_t)(f0 + nc - 1) * frame_px, frame_px, 61));
+            enc = d < 0.6;
+        }
+        encoded[c] = enc ? 1 : 0;
+        submitted = c + 1;
+        if (!enc) return;
+        if (c >= (uint32_t)kEncSlots) DH_CUDA(cudaEventSynchronize(ev_enc_copied_[pslot]));  // the slot's previous chunk left the host
+        uint8_t* base = h_enc_[pslot];
+        unsigned long long* meta = h_enc_meta_[pslot];
+        const uint16_t* src = depth + (size_t)f0 * frame_px;
+        const uint32_t G = kEncGroup;
+        tickets[c] = pool_->run((nc + G - 1) / G, [=](uint32_t gi) {
+            size_t pos = (size_t)gi * G * bound;
+            for (uint32_t k = gi * G; k < std::min(nc, (gi + 1) * G); ++k) {
+                meta[k] = pos;
+                pos += rle_encode_frame(src + (size_t)k * frame_px, w, h, base + pos);
+                meta[M + k] = pos;
+            }
+        });
+    };
+    auto drain = [&] {
+        for (uint32_t c = 0; c < submitted; ++c)
+            if (encoded[c] && tickets[c]) pool_->wait(tickets[c]);
+    };
+    try {
+        for (uint32_t c = 0; c < std::min<uint32_t>(2u, n_chunks); ++c) submit(c);
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const int slot = (int)(c & 1u), pslot = (int)(c % (uint32_t)kEncSlots);
+            Lane& L = lanes_[c % (uint32_t)n_lanes];
+            const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+            if (encoded[c]) pool_->wait(tickets[c]);
+            // the device slot (compressed bytes, frame table, expanded frames) was last used by chunk c - 2
+            DH_CUDA(cudaStreamWaitEvent(copy_stream_, c >= 2 ? ev_consumed_[slot] : ev_fork_, 0));
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (timing_) {
+                t0 = next_event();
+                t1 = next_event();
+                DH_CUDA(cudaEventRecord(t0, copy_stream_));
+            }
+            if (encoded[c]) {
+                const unsigned long long* meta = h_enc_meta_[pslot];
+                for (uint32_t k0 = 0; k0 < nc; k0 += kEncGroup) {  // one copy per group: the groups are not adjacent
+                    const uint32_t k1 = std::min(nc, k0 + kEncGroup) - 1u;
+                    const size_t b0 = (size_t)meta[k0], b1 = (size_t)meta[M + k1];
+                    DH_CUDA(cudaMemcpyAsync(d_blob_[slot] + b0, h_enc_[pslot] + b0, b1 - b0, cudaMemcpyHostToDevice, copy_stream_));
+                    last_h2d_bytes_ += b1 - b0;
+                }
+                DH_CUDA(cudaMemcpyAsync(d_enc_meta_[slot], meta, sizeof(unsigned long long) * 2 * M, cudaMemcpyHostToDevice, copy_stream_));
+                last_h2d_bytes_ += sizeof(unsigned long long) * 2 * M;
+                DH_CUDA(cudaEventRecord(ev_enc_copied_[pslot], copy_stream_));
+                ++last_encoded_chunks_;
+            } else {
+                DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
+                                        cudaMemcpyHostToDevice, copy_stream_));
+                last_h2d_bytes_ += (uint64_t)nc * frame_px * sizeof(uint16_t);
+            }
+            if (timing_) {
+                DH_CUDA(cudaEventRecord(t1, copy_stream_));
+                copy_marks_.push_back({t0, t1});
+            }
+            DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
+            DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
+            if (encoded[c]) {
+                mark(DH_STAGE_H2D);  // the expansion counts as input transfer
+                DH_CUDA(cudaMemsetAsync(d_depth_[slot], 0, (size_t)nc * frame_px * sizeof(uint16_t), L.stream));
+                launch_biwi_decode(d_blob_[slot], d_enc_meta_[slot], d_enc_meta_[slot] + M, 0ull, nc, w, h, d_depth_[slot], d_status_ + f0,
+                                   L.stream);
+                launches_ += 1;
+            }
+            FrameBuffers b = buffers(L, d_depth_[slot]);
+            run_front(L, b, nc, nullptr);
+            run_back(L, b, nc, iterations);
+            DH_CUDA(cudaMemcpyAsync(h_results_ + f0, L.results, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, L.stream));
+            DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
+            if (c + 2 < n_chunks) submit(c + 2);
+        }
+    } catch (...) {
+        drain();  // no worker may still read the caller's frames once this call has returned
+        cudaStreamSynchronize(copy_stream_);
+        for (int i = 0; i < n_lanes; ++i) cudaStreamSynchronize(lanes_[i].stream);
+        throw;
+    }
+    if (n_lanes > 1) {
+        for (int i = 1; i < n_lanes; ++i) {
+            DH_CUDA(cudaEventRecord(lanes_[i].done, lanes_[i].stream));
+            DH_CUDA(cudaStreamWaitEvent(stream_, lanes_[i].done, 0));
+        }
+    }
+    mark(-1);
+    DH_CUDA(cudaStreamSynchronize(stream_));
+    end_call();
+    if (last_encoded_chunks_) {
+        // the library wrote these files itself: a decode failure is a bug, never the caller's input
+        DH_CUDA(cudaMemcpy(h_status_, d_status_, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < n; ++i)
+            if (h_status_[i]) throw ModelError(DH_E_STATE, "internal error: frame " + std::to_string(i) + " did not survive the compressed host->device path");
+    }
     std::memcpy(out, h_results_, sizeof(dh_result) * n);
 }
 

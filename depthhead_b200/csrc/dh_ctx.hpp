@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "dh_forest.hpp"
+#include "dh_hostenc.hpp"
 #include "dh_kernels.cuh"
 
 namespace dh {
@@ -60,6 +61,10 @@ public:
 
     void set_stream(void* s);
     void set_chunk_frames(uint32_t f);
+    void set_encode_threads(uint32_t n);   // 0 = default (default_encode_threads()); see run_batch_encoded
+    uint32_t encode_threads() const { return pool_ ? pool_->size() : 0u; }
+    uint32_t last_encoded_chunks() const { return last_encoded_chunks_; }
+    uint64_t last_h2d_bytes() const { return last_h2d_bytes_; }
     void synchronize();
     void enable_timing(bool on) { timing_ = on; }
     void enable_debug(bool on) { debug_ = on; if (!on) have_debug_ = false; }
@@ -112,6 +117,9 @@ private:
     void run_batch(const HostForest& hf, const uint16_t* depth, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w,
                    uint32_t h, const float K[9], int depth_loc, dh_result* out);
     uint32_t pick_chunk(uint32_t n_frames, int depth_loc) const;
+    bool want_encode(uint32_t n, uint32_t w, uint32_t h) const;
+    void ensure_encode(uint32_t n, uint32_t F);
+    void run_batch_encoded(const HostForest& hf, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h, const float K[9], dh_result* out);
     void free_scratch();
     TilePlan plan_tiles(const Geometry& g) const;
     FrameBuffers buffers(const Lane& L, const uint16_t* depth) const;
@@ -175,11 +183,30 @@ private:
     uint8_t* d_aux8_ = nullptr;
     size_t aux32_cap_ = 0, aux8_cap_ = 0;
 
+    // Compressed host->device path (run_batch_encoded): worker threads write the frames of a chunk
+    // as Biwi run-length files into a pinned slot, in groups of kEncGroup frames; a group owns a
+    // fixed region of the slot, so its bytes are known only to the worker that wrote them and the
+    // groups are copied one cudaMemcpyAsync each.
+    static constexpr int kEncSlots = 3;       // pinned slots: one being copied, two being written
+    static constexpr uint32_t kEncGroup = 8;  // frames per worker task / per copy
+    std::unique_ptr<WorkerPool> pool_;
+    uint32_t encode_threads_req_ = 0;
+    int host_encode_ = -1;                    // DH_HOST_ENCODE: 0 never, 1 whenever possible, -1 by sampled density
+    uint8_t* h_enc_[kEncSlots] = {nullptr, nullptr, nullptr};
+    unsigned long long* h_enc_meta_[kEncSlots] = {nullptr, nullptr, nullptr};  // [2][F]: begin, end of every frame inside the slot
+    unsigned long long* d_enc_meta_[2] = {nullptr, nullptr};
+    cudaEvent_t ev_enc_copied_[kEncSlots] = {nullptr, nullptr, nullptr};
+    size_t enc_slot_bytes_ = 0, enc_frame_bound_ = 0;
+    uint32_t enc_frames_ = 0;
+    uint32_t last_encoded_chunks_ = 0;
+    uint64_t last_h2d_bytes_ = 0;
+
     // pinned host staging
     FrameState* h_fs_ = nullptr;
     unsigned long long* h_counters_ = nullptr;
-    dh_result* h_results_ = nullptr;
+    dh_result* h_results_ = nullptr;      // batch results (grows with the batch; never referenced by a captured graph)
     size_t h_results_cap_ = 0;
+    dh_result* h_result1_ = nullptr;      // dh_predict's own fixed slot: the D2H copy node of its CUDA graph targets it
 
     // dh_predict as a CUDA graph: the single-frame pipeline is a dozen small launches, i.e. bound
     // by launch overhead; after one eager call with a given (model, shape, intrinsics, stream) the
@@ -192,10 +219,11 @@ private:
         void* stream = nullptr;
         const void* depth = nullptr;
         const void* scratch = nullptr;
+        const void* result = nullptr;
         bool operator==(const GraphKey& o) const {
             return serial == o.serial && sigma_version == o.sigma_version && w == o.w && h == o.h && stride == o.stride &&
                    iterations == o.iterations && std::memcmp(K, o.K, sizeof(K)) == 0 && stream == o.stream && depth == o.depth &&
-                   scratch == o.scratch;
+                   scratch == o.scratch && result == o.result;
         }
     };
     void drop_graph();

@@ -583,6 +583,15 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1u) : "memory");
         fence_mbar_init();
         s_nlive = 0;
+        if (tp.tma_first) {
+            // the load is issued before the tile's background check and lands while warp 0 tests
+            // the window (one global round trip less in front of every non-empty tile)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(tile_bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(tile_a),
+                "l"(&sat_map), "r"((int)ax0), "r"((int)y0), "r"((int)frame), "r"(bar_a)
+                : "memory");
+        }
     }
     if (tid < 32u) {
         // window of the tile's patches: [x0, x1) x [y0, y1); every patch of the tile is background
@@ -612,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
         }
         if (tid == 0) {
             s_empty = !any;
-            if (any) {
+            if (any && !tp.tma_first) {
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(tile_bytes) : "memory");
                 asm volatile(
                     "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(tile_a),
@@ -622,7 +631,9 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
         }
     }
     __syncthreads();
-    if (s_empty) return;  // prediction.rs:567-571 fails for every patch of the tile: their leaf ids stay -1
+    // an empty tile whose load is already in flight (tma_first) still waits for it: the CTA must not
+    // leave while the async proxy writes its shared memory
+    if (s_empty && !tp.tma_first) return;  // prediction.rs:567-571 fails for every patch of the tile: their leaf ids stay -1
     {
         asm volatile(
             "{\n"
@@ -636,6 +647,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
             "r"(0u)
             : "memory");
     }
+    if (s_empty) return;
 
     // ---- background test (prediction.rs:567-571: mean over the whole patch > 0  <=>  sum != 0)
     const uint32_t tw4 = tp.tw * 4u;
@@ -1723,6 +1735,7 @@ __device__ __forceinline__ uint32_t rle_u32(const uint16_t* p16, uint32_t i) { r
 
 __global__ void __launch_bounds__(kRleThreads) biwi_decode_kernel(const uint8_t* __restrict__ blob,
                                                                   const unsigned long long* __restrict__ offsets,
+                                                                  const unsigned long long* __restrict__ ends,
                                                                   unsigned long long blob_base, uint32_t w, uint32_t h,
                                                                   uint16_t* __restrict__ out, uint32_t* __restrict__ status) {
     __shared__ __align__(16) uint32_t s_piece[kRlePieceWords + 2];
@@ -1732,7 +1745,8 @@ __global__ void __launch_bounds__(kRleThreads) biwi_decode_kernel(const uint8_t*
     __shared__ uint32_t s_long[kRleLongCap];
     __shared__ uint32_t s_nrun, s_pos, s_p, s_nlong, s_err, s_done, s_end_run, s_bad_run;
     const uint32_t frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const unsigned long long o0 = offsets[frame] - blob_base, o1 = offsets[frame + 1] - blob_base;
+    // frame i occupies [offsets[i], offsets[i+1]), or [offsets[i], ends[i]) when the files do not follow one another
+    const unsigned long long o0 = offsets[frame] - blob_base, o1 = (ends ? ends[frame] : offsets[frame + 1]) - blob_base;
     const uint8_t* file = blob + o0;                  // 4-byte aligned (checked on the host)
     const uint32_t len = (uint32_t)(o1 - o0);
     const uint32_t npx = w * h, cap = npx + 1u;       // npx <= 2^30 (checked on the host): sums of two capped values fit u32
@@ -2155,9 +2169,9 @@ void launch_counters(const FrameBuffers& b, const Geometry& g, uint32_t n_frames
     counters_kernel<<<blocks, 256, 0, s>>>(b.fs, n_frames, out, g.P, g.n_trees);
 }
 
-void launch_biwi_decode(const uint8_t* blob, const unsigned long long* offsets, unsigned long long blob_base, uint32_t n, uint32_t w,
-                        uint32_t h, uint16_t* out, uint32_t* status, cudaStream_t s) {
-    if (n) biwi_decode_kernel<<<n, kRleThreads, 0, s>>>(blob, offsets, blob_base, w, h, out, status);
+void launch_biwi_decode(const uint8_t* blob, const unsigned long long* offsets, const unsigned long long* ends,
+                        unsigned long long blob_base, uint32_t n, uint32_t w, uint32_t h, uint16_t* out, uint32_t* status, cudaStream_t s) {
+    if (n) biwi_decode_kernel<<<n, kRleThreads, 0, s>>>(blob, offsets, ends, blob_base, w, h, out, status);
 }
 
 void launch_box_dump(const FrameBuffers& b, uint32_t frame, int which, int32_t* keys, uint32_t* vals,

@@ -60,6 +60,7 @@ struct TilePlan {
     uint32_t threads;
     uint32_t blocked;         // 1: the patches of a tile are enumerated in blocks of 8 x 4 (a warp = a compact block)
                               // instead of row by row (experimental, DH_TRAV_BLOCK=1)
+    uint32_t tma_first;       // 1: the tile's TMA load is issued before its background check (DH_TRAV_TMA_FIRST)
 };
 
 struct ForestDev {
@@ -119,9 +120,10 @@ void launch_hough_image(const FrameBuffers& b, const Geometry& g, const ForestDe
                         uint16_t* out16, cudaStream_t s);
 void launch_counters(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, unsigned long long* out,
                      cudaStream_t s);
-// Biwi run-length decode: frame i = blob[offsets[i] - blob_base, offsets[i+1] - blob_base); out [n][h][w] must be zero
-void launch_biwi_decode(const uint8_t* blob, const unsigned long long* offsets, unsigned long long blob_base, uint32_t n, uint32_t w,
-                        uint32_t h, uint16_t* out, uint32_t* status, cudaStream_t s);
+// Biwi run-length decode: frame i = blob[offsets[i] - blob_base, offsets[i+1] - blob_base), or up to ends[i] - blob_base
+// when `ends` is given (files with gaps between them); out [n][h][w] must be zero
+void launch_biwi_decode(const uint8_t* blob, const unsigned long long* offsets, const unsigned long long* ends,
+                        unsigned long long blob_base, uint32_t n, uint32_t w, uint32_t h, uint16_t* out, uint32_t* status, cudaStream_t s);
 void launch_box_dump(const FrameBuffers& b, uint32_t frame, int which, int32_t* keys, uint32_t* vals,
                      unsigned long long* count, cudaStream_t s);
 

@@ -58,6 +58,9 @@ typedef struct dh_result {
 /* Thread-local description of the last failure in this thread (never NULL). */
 const char* dh_last_error(void);
 int dh_abi_version(void);
+/* Identifies the build: a hash of the library's sources, fixed at compile time (profiles recorded
+ * under profiles/ carry it, so a number is only ever quoted for the build it was measured on). */
+const char* dh_build_id(void);
 
 /* ------------------------------------------------------------------ model (HoughPrediction) */
 /* serde_json::from_str::<HoughPrediction>(json)  (Readme.md:82-86, prediction.rs:239-256).
@@ -109,6 +112,17 @@ int dh_ctx_set_stream(dh_ctx* c, void* cuda_stream);
 /* Frames processed per pipeline pass (scratch is sized for this many); 0 = default. */
 int dh_ctx_set_chunk_frames(dh_ctx* c, uint32_t frames);
 int dh_ctx_synchronize(dh_ctx* c);
+/* dh_predict_batch with HOST frames: the frames are mostly background (0), so worker threads of the
+ * context rewrite every chunk as run-length files (the Biwi format, see dh_biwi_encode_depth) in
+ * pinned memory, only those bytes cross PCIe, and the GPU expands them again bit for bit; chunks
+ * that are too dense to gain are copied raw.  n = number of worker threads (0 = default: the cores
+ * this process may run on, at most 16; DH_ENCODE_THREADS overrides).  DH_HOST_ENCODE=0 turns the
+ * rewrite off, =1 forces it for every chunk. */
+int dh_ctx_set_encode_threads(dh_ctx* c, uint32_t n);
+/* Host->device traffic of the LAST dh_predict_batch / dh_predict_batch_biwi call:
+ * [0] bytes copied host->device, [1] chunks that went through the run-length rewrite,
+ * [2] worker threads of the context (0 = none started yet), [3] reserved. */
+int dh_ctx_transfer_info(dh_ctx* c, uint64_t info[4]);
 
 /* ------------------------------------------------------------------ prediction */
 #define DH_DEPTH_HOST 0   /* depth points to host memory (pinned preferred) */
@@ -150,6 +164,17 @@ int dh_biwi_decode_depth(dh_ctx* c, const uint8_t* blob, const uint64_t* offsets
  * examples/db_evaluate.rs:296 does per file, with the decode on the GPU. */
 int dh_predict_batch_biwi(dh_ctx* c, const dh_forest* f, const uint8_t* blob, const uint64_t* offsets, uint32_t n,
                           uint32_t w, uint32_t h, const float K[9], dh_result* out);
+/* The writer for that format (the reference only reads it): n raw frames [n][h][w] u16 become n
+ * files in ONE blob, file i at [offsets[i], offsets[i+1]) (offsets: n+1 entries, multiples of 16).
+ * Runs are found at a granularity of 16 pixels: a group of 16 pixels with any non-zero pixel is
+ * stored verbatim (isolated zeros inside it travel as literal zeros, which the format allows), so
+ * read_depth gives back exactly the input.  This is the encoder dh_predict_batch runs on its own
+ * worker threads for host frames (see dh_ctx_set_encode_threads).  Host-only, `threads` workers
+ * (0 = the default).  Copies at most cap bytes and reports the full length in *needed (call with
+ * cap = 0 to size the buffer; dh_biwi_encode_bound(w, h) * n + 16 always suffices). */
+size_t dh_biwi_encode_bound(uint32_t w, uint32_t h);
+int dh_biwi_encode_depth(const uint16_t* frames, uint32_t n, uint32_t w, uint32_t h, uint32_t threads, uint8_t* blob, size_t cap,
+                         uint64_t* offsets, size_t* needed);
 /* read_cal (biwi.rs:27-60): the first three lines of depth.cal, three numbers each (tokens
  * matching \d+[\.\d+]* exactly as the reference's regex, so a sign is not part of a number), to
  * a row-major 3x3 matrix.  Host-only. */

@@ -132,3 +132,56 @@ def test_read_gt_matches_oracle():
 def test_depth_dims_errors():
     with pytest.raises(DhError):
         biwi.depth_dims(b"\x01\x00\x00")
+
+
+# ---- the library's own writer (dh_biwi_encode_depth): what dh_predict_batch runs on its worker
+#      threads for host frames; checked against the oracle's restatement of the reference reader
+def _edge_frames(h, w, seed):
+    rng = np.random.default_rng(seed)
+    fr = []
+    fr.append(np.zeros((h, w), np.uint16))                                   # all background
+    fr.append(rng.integers(1, 65536, (h, w)).astype(np.uint16))              # no background at all
+    a = np.zeros((h, w), np.uint16); a.flat[0] = 7; fr.append(a)             # first pixel only
+    a = np.zeros((h, w), np.uint16); a.flat[-1] = 9; fr.append(a)            # last pixel only (inside the partial tail group)
+    a = rng.integers(1, 4000, (h, w)).astype(np.uint16); a[rng.random((h, w)) < 0.5] = 0; fr.append(a)   # salt and pepper
+    a = np.zeros((h, w), np.uint16); a.flat[::16] = 1; fr.append(a)          # one pixel in every 16-pixel group
+    a = np.zeros((h, w), np.uint16); a.flat[15::32] = 1; fr.append(a)        # every other group
+    a = rng.integers(1, 4000, (h, w)).astype(np.uint16); a.flat[: (h * w) // 2] = 0; fr.append(a)        # one long run each
+    return np.stack(fr)
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (7, 13), (1, 1), (33, 250), (1, 16), (3, 16), (2, 17), (5, 31)])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_library_encoder_round_trips_through_the_reference_reader(shape, threads):
+    h, w = shape
+    frames = _edge_frames(h, w, seed=h * 1000 + w)
+    if shape == (480, 640):
+        frames = np.concatenate([frames, synth.make_frames(3, seed=5)])
+    blob, offsets = biwi.encode_frames(frames, threads=threads)
+    assert len(offsets) == len(frames) + 1 and all(int(o) % 16 == 0 for o in offsets)
+    L = __import__("depthhead_b200").capi.load()
+    bound = int(L.dh_biwi_encode_bound(w, h))
+    for i, f in enumerate(frames):
+        data = blob[int(offsets[i]):int(offsets[i + 1])].tobytes()
+        assert len(data) <= ((bound + 15) & ~15)
+        assert biwi.depth_dims(data) == (w, h)
+        assert np.array_equal(oracle.biwi_read_depth(data), f), (shape, i)
+    # mostly-background frames shrink
+    if shape == (480, 640):
+        assert int(offsets[1]) - int(offsets[0]) < 64                       # all background: header + one run
+        syn = int(offsets[len(frames)]) - int(offsets[len(frames) - 3])
+        assert syn < 3 * h * w * 2 / 3
+
+
+def test_library_encoder_empty_batch_and_sizing():
+    blob, offsets = biwi.encode_frames(np.zeros((0, 4, 4), np.uint16))
+    assert len(offsets) == 1 and offsets[0] == 0
+    # a too-small buffer reports the size it needs and writes nothing past cap
+    import ctypes as C
+    from depthhead_b200 import capi
+    fr = np.ones((2, 8, 8), np.uint16)
+    need = C.c_size_t(0)
+    off = np.zeros(3, np.uint64)
+    small = np.full(32, 0xEE, np.uint8)
+    capi.check(capi.load().dh_biwi_encode_depth(capi.ptr(fr), 2, 8, 8, 1, capi.ptr(small), 16, capi.ptr(off), C.byref(need)))
+    assert need.value >= 2 * (8 + 8 + 128) and np.all(small[16:] == 0xEE)

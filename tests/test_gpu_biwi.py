@@ -175,3 +175,52 @@ def test_decode_mutated_streams_against_the_oracle(ctx):
     assert n_fail > 50 and n_ok > 50
     good = biwi.encode_depth(synth.make_frames(1, seed=4)[0])
     assert np.array_equal(biwi.read_depth(good, ctx=ctx), oracle.biwi_read_depth(good))
+
+
+# ---- the compressed host->device path of dh_predict_batch (worker threads rewrite host frames as
+#      run-length files, the GPU expands them): results must equal the raw copy and the device-resident pass
+@pytest.mark.parametrize("env", [{"DH_HOST_ENCODE": "1"}, {"DH_HOST_ENCODE": "1", "DH_LANES": "1"},
+                                 {"DH_HOST_ENCODE": "1", "DH_ENCODE_THREADS": "1"}, {}])
+def test_predict_batch_host_frames_through_the_run_length_rewrite(monkeypatch, env):
+    import torch
+    arr = synth.make_forest(seed=4, n_trees=3, max_depth=7)
+    frames = synth.make_frames(44, seed=77)
+    rng = np.random.default_rng(5)
+    frames[3] = 0                                                       # all background
+    frames[9] = rng.integers(1, 4000, frames[9].shape).astype(np.uint16)  # no background: the file is LARGER than the frame
+    frames[17, ::2, ::3] = 0                                            # salt and pepper
+    frames[40:] = rng.integers(0, 3, frames[40:].shape).astype(np.uint16) * 900   # a dense last chunk
+    hp = HoughPrediction.from_arrays(arr, stepwidth=8)
+
+    def run(e):
+        for k in ("DH_HOST_ENCODE", "DH_LANES", "DH_ENCODE_THREADS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in e.items():
+            monkeypatch.setenv(k, v)
+        c = Context(0)
+        c.set_chunk_frames(10)
+        try:
+            out = hp.predict_batch(frames, K, ctx=c).copy()
+            info = c.transfer_info()
+            out2 = hp.predict_batch(frames[:25], K, ctx=c).copy()       # same context again, other batch size
+        finally:
+            c.close()
+        return out, out2, info
+    ref, ref2, info0 = run({"DH_HOST_ENCODE": "0"})
+    assert info0["encoded_chunks"] == 0 and info0["h2d_bytes"] == frames.nbytes
+    got, got2, info = run(env)
+    for a, b in ((ref, got), (ref2, got2)):
+        assert np.array_equal(a["mid_point"], b["mid_point"]) and np.array_equal(a["rotation"], b["rotation"])
+    if env.get("DH_HOST_ENCODE") == "1":
+        assert info["encoded_chunks"] == 5
+    else:
+        assert 1 <= info["encoded_chunks"] <= 4                         # the dense chunk goes raw
+    assert info["h2d_bytes"] < frames.nbytes
+    # and the device-resident pass
+    c = Context(0)
+    try:
+        dev = torch.from_numpy(frames.view(np.int16)).cuda()
+        out = hp.predict_batch(None, K, ctx=c, device_ptr=dev.data_ptr(), n=len(frames), w=640, h=480)
+    finally:
+        c.close()
+    assert np.array_equal(out["mid_point"], ref["mid_point"]) and np.array_equal(out["rotation"], ref["rotation"])

@@ -51,6 +51,9 @@ VARIANTS = [
     {"DH_GATE_FUSED": "0"},                         # seed grids: one pass over the votes per grid instead of one for both
     {"DH_TRAV_BLOCK": "1"},                         # a warp walks a block of 8 x 4 patches instead of a row of 32 (experimental)
     {"DH_TRAV_BLOCK": "1", "DH_BOX_IMAGE": "0"},
+    {"DH_TRAV_TMA_FIRST": "1"},                     # the tile's TMA load is issued before its background check
+    {"DH_TRAV_TMA_FIRST": "1", "DH_BOX_IMAGE": "0"},
+    {"DH_TRAV_TMA_FIRST": "1", "DH_TRAV_BLOCK": "1"},
     {"DH_LANES": "1"},
     {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},
 ]
@@ -302,3 +305,42 @@ def test_single_frame_graph_replay_equals_eager_launches(monkeypatch):
     of = oracle.OracleForest(arr, 6, 80, 80, 8.0, 20)
     tr = of.predict(frames[0], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
     assert np.array_equal(a[0][0], tr.mid_point) and np.array_equal(a[0][1], tr.rotation)
+
+
+def test_graph_replay_survives_a_growing_batch_between_single_calls(monkeypatch):
+    """dh_predict's captured graph must not point at anything dh_predict_batch reallocates: single
+    calls, a batch, more single calls (graph captured), a LARGER batch (the batch's pinned result
+    buffer grows), single calls again — equal to the same sequence with eager launches."""
+    arr = synth.make_forest(seed=8, n_trees=3, max_depth=7)
+    frames = synth.make_frames(40, seed=51)
+
+    def run(flag):
+        monkeypatch.setenv("DH_GRAPH", flag)
+        c = Context(0)
+        c.set_chunk_frames(16)
+        hp = HoughPrediction.from_arrays(arr, stepwidth=8)
+        out = []
+        try:
+            out.append(hp.predict_batch(frames[:20], K, ctx=c).copy())
+            for d in frames[:3]:
+                r = hp.predict_parameter_parallel(d, K, ctx=c)
+                out.append((r.mid_point.copy(), r.rotation.copy()))
+            out.append(hp.predict_batch(frames[:40], K, ctx=c).copy())   # grows the batch result staging
+            for d in frames[3:7]:
+                r = hp.predict_parameter_parallel(d, K, ctx=c)
+                out.append((r.mid_point.copy(), r.rotation.copy()))
+            out.append(hp.predict_batch(frames[:5], K, ctx=c).copy())
+            r = hp.predict_parameter_parallel(frames[9], K, ctx=c)
+            out.append((r.mid_point.copy(), r.rotation.copy()))
+        finally:
+            c.close()
+        return out
+    a, b = run("1"), run("0")
+    for i, (x, y) in enumerate(zip(a, b)):
+        if isinstance(x, tuple):
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]), i
+        else:
+            assert np.array_equal(x["mid_point"], y["mid_point"]) and np.array_equal(x["rotation"], y["rotation"]), i
+    # single call 3 + k equals row 3 + k of the 40-frame batch
+    for k in range(4):
+        assert np.array_equal(a[5 + k][0], a[4]["mid_point"][3 + k]) and np.array_equal(a[5 + k][1], a[4]["rotation"][3 + k])
