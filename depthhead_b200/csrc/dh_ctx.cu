@@ -98,6 +98,7 @@ Context::Context(int device) : device_(device) {
     for (int i = 0; i < kEncSlots; ++i) DH_CUDA(cudaEventCreateWithFlags(&ev_enc_copied_[i], cudaEventDisableTiming));
     if (const char* v = std::getenv("DH_HOST_ENCODE")) host_encode_ = *v ? (int)std::strtol(v, nullptr, 10) : -1;
     use_graphs_ = env_flag("DH_GRAPH", true);
+    cube_clear_fused_ = env_flag("DH_CUBE_CLEAR_FUSED", true);
     chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 0);  // 0 = adaptive (128 for host input, 512 for device input)
     debug_sync_ = env_u32("DH_DEBUG_SYNC", 0) != 0;
     std::memset(stage_ms_, 0, sizeof(stage_ms_));
@@ -164,6 +165,11 @@ void Context::free_forest() {
     hot_tex_ = 0;
     hot_tw_ = 0;
     dev_free(df_roots_);
+    dev_free(df_pair_recs_);
+    dev_free(df_pair_topo_);
+    dev_free(df_pair_roots_);
+    dev_free(df_pair_perm_);
+    df_n_pairs_ = 0;
     dev_free(df_leaf_prob_);
     dev_free(df_leaf_info_);
     dev_free(df_offsets_);
@@ -173,6 +179,72 @@ void Context::free_forest() {
     dev_free(df_leaf_box_);
     dev_free(df_kernel_);
     df_serial_ = 0;
+}
+
+// PairRec topology (dh_types.hpp): every internal node at an even depth below its root becomes a
+// record together with its two children; records in breadth-first order, so the (up to four)
+// grandchild records of a record are consecutive; the leaves under a record get consecutive
+// device leaf numbers, mapped back to global leaf ids by the permutation table.
+void Context::build_pair_tables(const HostForest& hf) {
+    if (hf.n_leaves() >= (1u << 26) || hf.max_depth >= 63) return;  // the permutation entry packs leaf id (26 bits) and depth (6 bits)
+    std::vector<PairTopo> topo;
+    std::vector<uint32_t> depth;  // of the record's node X below its root
+    std::vector<int32_t> perm, roots((size_t)hf.n_trees);
+    topo.reserve(hf.n_nodes());
+    perm.reserve(hf.n_leaves() + hf.n_leaves() / 2);
+    for (int32_t t = 0; t < hf.n_trees; ++t) {
+        const int32_t root = hf.roots[(size_t)t];
+        if (root < 0) {  // a tree that is its single leaf
+            roots[(size_t)t] = ~(int32_t)perm.size();
+            perm.push_back(~root);  // depth 0: no node visit
+            continue;
+        }
+        roots[(size_t)t] = (int32_t)topo.size();
+        topo.push_back(PairTopo{root, -1, -1, 0u, 0u});
+        depth.push_back(0u);
+        for (size_t r = (size_t)roots[(size_t)t]; r < topo.size(); ++r) {
+            const NodeRec& X = hf.nodes[(size_t)topo[r].x];
+            int32_t c[2], slot[4];
+            for (int b = 0; b < 2; ++b) {
+                const int32_t C = X.child[b];
+                if (C >= 0) {
+                    c[b] = C;
+                    slot[2 * b] = hf.nodes[(size_t)C].child[0];
+                    slot[2 * b + 1] = hf.nodes[(size_t)C].child[1];
+                } else {
+                    c[b] = -1;
+                    slot[2 * b] = slot[2 * b + 1] = C;  // the dummy test always answers 0; slot 2b+1 is never taken
+                }
+            }
+            const uint32_t first = (uint32_t)topo.size(), first_leaf = (uint32_t)perm.size();
+            uint32_t mask = 0;
+            for (int k = 0; k < 4; ++k) {
+                if (slot[k] < 0) {
+                    // node visits of a walk that ends here: X and, unless the child itself is the leaf, the child
+                    const uint32_t visits = depth[r] + (c[k >> 1] < 0 ? 1u : 2u);
+                    mask |= 1u << k;
+                    perm.push_back((int32_t)((uint32_t)~slot[k] | (visits << 26)));
+                } else {
+                    topo.push_back(PairTopo{slot[k], -1, -1, 0u, 0u});
+                    depth.push_back(depth[r] + 2u);
+                }
+            }
+            if (first_leaf >= (1u << 26) || topo.size() >= (1ull << 31)) return;  // too large for the packed fields: the plain tables serve
+            topo[r].c0 = c[0];
+            topo[r].c1 = c[1];
+            topo[r].first = first;
+            topo[r].tail = (first_leaf << 6) | ((c[1] < 0 ? 1u : 0u) << 5) | ((c[0] < 0 ? 1u : 0u) << 4) | mask;
+        }
+    }
+    df_n_pairs_ = topo.size();
+    dev_alloc(df_pair_recs_, topo.size());
+    dev_alloc(df_pair_topo_, topo.size());
+    dev_alloc(df_pair_roots_, roots.size());
+    dev_alloc(df_pair_perm_, perm.size());
+    if (!topo.empty()) DH_CUDA(cudaMemcpyAsync(df_pair_topo_, topo.data(), topo.size() * sizeof(PairTopo), cudaMemcpyHostToDevice, stream_));
+    DH_CUDA(cudaMemcpyAsync(df_pair_roots_, roots.data(), roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    if (!perm.empty()) DH_CUDA(cudaMemcpyAsync(df_pair_perm_, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    DH_CUDA(cudaStreamSynchronize(stream_));  // the host vectors go away
 }
 
 void Context::ensure_forest(const HostForest& hf) {
@@ -203,6 +275,7 @@ void Context::ensure_forest(const HostForest& hf) {
             td.readMode = cudaReadModeElementType;
             DH_CUDA(cudaCreateTextureObject(&hot_tex_, &rd, &td, nullptr));
         }
+        if (df_uni_ && hot_tex_ && env_flag("DH_TRAV_PAIR", false)) build_pair_tables(hf);
         dev_alloc(df_roots_, (size_t)hf.n_trees);
         dev_alloc(df_leaf_prob_, NL);
         dev_alloc(df_leaf_info_, NL);
@@ -259,6 +332,10 @@ void Context::ensure_forest(const HostForest& hf) {
     fdev_.uni_rw = uni_rw_;
     fdev_.uni_rh = uni_rh_;
     fdev_.roots = df_roots_;
+    fdev_.pair_recs = df_pair_recs_;
+    fdev_.pair_topo = df_pair_topo_;
+    fdev_.pair_roots = df_pair_roots_;
+    fdev_.pair_leaf_perm = df_pair_perm_;
     fdev_.leaf_prob = df_leaf_prob_;
     fdev_.leaf_info = df_leaf_info_;
     fdev_.offsets = df_offsets_;
@@ -284,6 +361,7 @@ void Context::free_lane(Lane& L) {
     dev_free(L.results);
     dev_free(L.ms_trace);
     L.allocated = false;
+    L.cubes_clean = false;
 }
 
 void Context::drop_graph() {
@@ -317,6 +395,8 @@ void Context::alloc_lane(Lane& L) {
     dev_alloc(L.gate, F * P);
     dev_alloc(L.gated, F * P);
     dev_alloc(L.cubes, F * 2 * (size_t)vote_box_cells());
+    DH_CUDA(cudaMemsetAsync(L.cubes, 0, sizeof(uint32_t) * F * 2 * (size_t)vote_box_cells(), stream_));
+    L.cubes_clean = true;
     dev_alloc(L.grids, F * (size_t)(kPosGridCells + kRotGridCells));
     dev_alloc(L.fs, F);
     dev_alloc(L.results, F);
@@ -501,6 +581,7 @@ FrameBuffers Context::buffers(const Lane& L, const uint16_t* depth) const {
     b.ms_trace = L.ms_trace;
     b.ms_trace_cap = sk_.trace_iters;
     b.debug = debug_ ? 1u : 0u;
+    b.clear_cubes = (!debug_ && cube_clear_fused_) ? 1u : 0u;  // debug passes export the cubes after the call
     return b;
 }
 
@@ -539,6 +620,7 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
     }
     if (g.P && hot_tw_ != tiles_.tw) {  // node table for this tile plan (once per forest x plan)
         launch_plan_nodes(df_nodes_, df_hot_, df_uni_, df_n_nodes_, tiles_.tw, stream_);
+        if (df_pair_recs_) launch_plan_pairs(df_pair_topo_, df_uni_, df_pair_recs_, df_n_pairs_, stream_);
         DH_CUDA(cudaStreamSynchronize(stream_));
         hot_tw_ = tiles_.tw;
     }
@@ -567,12 +649,15 @@ void Context::run_back(Lane& L, const FrameBuffers& b, uint32_t n, uint32_t iter
     launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, st);
     stage_check("gate + coarse grids");
     mark(DH_STAGE_VOTE);
-    // the accumulator cubes of this pass start empty
-    if (iterations) DH_CUDA(cudaMemsetAsync(L.cubes, 0, sizeof(uint32_t) * 2 * (size_t)vote_box_cells() * n, st));
+    // the accumulator cubes of this pass start empty: either the previous pass's mean-shift CTAs
+    // cleared them behind themselves, or they are cleared here
+    if (iterations && !L.cubes_clean) DH_CUDA(cudaMemsetAsync(L.cubes, 0, sizeof(uint32_t) * 2 * (size_t)vote_box_cells() * n, st));
+    if (iterations) L.cubes_clean = false;
     launches_ += (uint64_t)launch_seed_and_cubes(b, g, fdev_, n, iterations, st);
     stage_check("seeds + accumulator cubes");
     mark(DH_STAGE_MEANSHIFT);
     launches_ += (uint64_t)launch_meanshift(b, g, fdev_, n, iterations, st);
+    if (b.clear_cubes) L.cubes_clean = true;
     stage_check("mean-shift");
     mark(DH_STAGE_D2H);
     launch_counters(b, g, n, d_counters_, st);
@@ -638,7 +723,8 @@ void Context::predict(const HostForest& hf, const uint16_t* depth, uint32_t w, u
         DH_CUDA(cudaMemcpyAsync(h_result1_, lanes_[0].results, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
     };
     bool replayed = false;
-    if (use_graphs_ && !timing_ && !debug_ && !debug_sync_) {
+    // (a pass that left the cubes dirty — a debug pass — must be followed by an eager pass, which clears them)
+    if (use_graphs_ && !timing_ && !debug_ && !debug_sync_ && lanes_[0].cubes_clean) {
         GraphKey key;
         key.serial = hf.serial; key.sigma_version = df_sigma_version_;
         key.w = w; key.h = h; key.stride = geom_.stride; key.iterations = iterations;
@@ -971,29 +1057,39 @@ void Context::run_batch_encoded(const HostForest& hf, const uint16_t* depth, uin
     DH_CUDA(cudaEventRecord(ev_fork_, stream_));
     for (int i = 1; i < n_lanes; ++i) DH_CUDA(cudaStreamWaitEvent(lanes_[i].stream, ev_fork_, 0));
 
+    // Chunks are handed out from both ends of the batch: the workers rewrite chunks from the
+    // front (two in flight), and whenever the copy engine has nothing to do while they are still
+    // writing, the next chunk from the BACK goes over raw (hybrid: PCIe and the host cores work on
+    // different chunks at the same time; DH_HOST_HYBRID=0: every chunk waits for its rewrite).
+    // The k-th chunk handed to the GPU uses device slot k % 2 and lane k % n_lanes.
     std::vector<uint64_t> tickets(n_chunks, 0);
-    std::vector<uint8_t> encoded(n_chunks, 0);
-    uint32_t submitted = 0;
-    // hands chunk c to the workers (or decides to copy it raw)
-    auto submit = [&](uint32_t c) {
-        const int pslot = (int)(c % (uint32_t)kEncSlots);
+    std::vector<uint8_t> state(n_chunks, 0);  // 0 unassigned, 1 being rewritten, 2 rewritten and sent, 3 sent raw
+    std::vector<uint32_t> pslot_of(n_chunks, 0);
+    uint32_t front = 0, back = n_chunks, enq = 0, n_submitted = 0;
+    std::vector<uint32_t> encq;               // chunks at the workers, oldest first
+    cudaEvent_t pslot_busy[kEncSlots] = {nullptr, nullptr, nullptr};  // H2D of the slot's previous chunk
+    const bool hybrid = env_flag("DH_HOST_HYBRID", true) && !timing_;
+    bool copy_tail_valid = false;
+    auto dense = [&](uint32_t c) {
+        if (host_encode_ >= 0) return false;
         const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
-        bool enc = true;
-        if (host_encode_ < 0) {
-            // sampled share of 16-pixel groups that would have to travel: above ~60 % the rewrite
-            // costs more host time than the copy saves
-            const double d = 0.5 * (rle_sample_density(depth + (size_t)f0 * frame_px, frame_px, 61) +
-                                    rle_sample_density(depth + (size_t)(f0 + nc - 1) * frame_px, frame_px, 61));
-            enc = d < 0.6;
-        }
-        encoded[c] = enc ? 1 : 0;
-        submitted = c + 1;
-        if (!enc) return;
-        if (c >= (uint32_t)kEncSlots) DH_CUDA(cudaEventSynchronize(ev_enc_copied_[pslot]));  // the slot's previous chunk left the host
+        // sampled share of 16-pixel groups that would have to travel: above ~60 % the rewrite
+        // costs more host time than the copy saves
+        const double d = 0.5 * (rle_sample_density(depth + (size_t)f0 * frame_px, frame_px, 61) +
+                                rle_sample_density(depth + (size_t)(f0 + nc - 1) * frame_px, frame_px, 61));
+        return d >= 0.6;
+    };
+    auto submit = [&](uint32_t c) {
+        const int pslot = (int)(n_submitted % (uint32_t)kEncSlots);
+        ++n_submitted;
+        pslot_of[c] = (uint32_t)pslot;
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+        if (pslot_busy[pslot]) DH_CUDA(cudaEventSynchronize(pslot_busy[pslot]));  // the slot's previous chunk left the host
         uint8_t* base = h_enc_[pslot];
         unsigned long long* meta = h_enc_meta_[pslot];
         const uint16_t* src = depth + (size_t)f0 * frame_px;
         const uint32_t G = kEncGroup;
+        state[c] = 1;
         tickets[c] = pool_->run((nc + G - 1) / G, [=](uint32_t gi) {
             size_t pos = (size_t)gi * G * bound;
             for (uint32_t k = gi * G; k < std::min(nc, (gi + 1) * G); ++k) {
@@ -1002,62 +1098,97 @@ void Context::run_batch_encoded(const HostForest& hf, const uint16_t* depth, uin
                 meta[M + k] = pos;
             }
         });
+        encq.push_back(c);
     };
     auto drain = [&] {
-        for (uint32_t c = 0; c < submitted; ++c)
-            if (encoded[c] && tickets[c]) pool_->wait(tickets[c]);
+        for (uint32_t c : encq) pool_->wait(tickets[c]);
+    };
+    // hands chunk c (rewritten or raw) to the copy engine and its lane
+    auto send = [&](uint32_t c, bool enc) {
+        const int slot = (int)(enq & 1u);
+        Lane& L = lanes_[enq % (uint32_t)n_lanes];
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+        // the device slot (compressed bytes, frame table, expanded frames) was last used two chunks ago
+        DH_CUDA(cudaStreamWaitEvent(copy_stream_, enq >= 2 ? ev_consumed_[slot] : ev_fork_, 0));
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (timing_) {
+            t0 = next_event();
+            t1 = next_event();
+            DH_CUDA(cudaEventRecord(t0, copy_stream_));
+        }
+        if (enc) {
+            const int pslot = (int)pslot_of[c];
+            const unsigned long long* meta = h_enc_meta_[pslot];
+            for (uint32_t k0 = 0; k0 < nc; k0 += kEncGroup) {  // one copy per group: the groups are not adjacent
+                const uint32_t k1 = std::min(nc, k0 + kEncGroup) - 1u;
+                const size_t b0 = (size_t)meta[k0], b1 = (size_t)meta[M + k1];
+                DH_CUDA(cudaMemcpyAsync(d_blob_[slot] + b0, h_enc_[pslot] + b0, b1 - b0, cudaMemcpyHostToDevice, copy_stream_));
+                last_h2d_bytes_ += b1 - b0;
+            }
+            DH_CUDA(cudaMemcpyAsync(d_enc_meta_[slot], meta, sizeof(unsigned long long) * 2 * M, cudaMemcpyHostToDevice, copy_stream_));
+            last_h2d_bytes_ += sizeof(unsigned long long) * 2 * M;
+            DH_CUDA(cudaEventRecord(ev_enc_copied_[pslot], copy_stream_));
+            pslot_busy[pslot] = ev_enc_copied_[pslot];
+            ++last_encoded_chunks_;
+        } else {
+            DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
+                                    cudaMemcpyHostToDevice, copy_stream_));
+            last_h2d_bytes_ += (uint64_t)nc * frame_px * sizeof(uint16_t);
+        }
+        if (timing_) {
+            DH_CUDA(cudaEventRecord(t1, copy_stream_));
+            copy_marks_.push_back({t0, t1});
+        }
+        DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
+        copy_tail_valid = true;
+        DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
+        if (enc) {
+            mark(DH_STAGE_H2D);  // the expansion counts as input transfer
+            DH_CUDA(cudaMemsetAsync(d_depth_[slot], 0, (size_t)nc * frame_px * sizeof(uint16_t), L.stream));
+            launch_biwi_decode(d_blob_[slot], d_enc_meta_[slot], d_enc_meta_[slot] + M, 0ull, nc, w, h, d_depth_[slot], d_status_ + f0,
+                               L.stream);
+            launches_ += 1;
+        }
+        FrameBuffers b = buffers(L, d_depth_[slot]);
+        run_front(L, b, nc, nullptr);
+        run_back(L, b, nc, iterations);
+        DH_CUDA(cudaMemcpyAsync(h_results_ + f0, L.results, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, L.stream));
+        DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
+        state[c] = enc ? 2 : 3;
+        ++enq;
+    };
+    // the copy engine has finished everything handed to it so far
+    auto copy_idle = [&] {
+        if (!copy_tail_valid) return true;
+        return cudaEventQuery(ev_copied_[(enq + 1u) & 1u]) != cudaErrorNotReady;  // the slot of the last chunk sent
+    };
+    auto refill = [&] {
+        while (encq.size() < 2 && front < back) {
+            const uint32_t c = front++;
+            if (dense(c)) send(c, false);
+            else submit(c);
+        }
     };
     try {
-        for (uint32_t c = 0; c < std::min<uint32_t>(2u, n_chunks); ++c) submit(c);
-        for (uint32_t c = 0; c < n_chunks; ++c) {
-            const int slot = (int)(c & 1u), pslot = (int)(c % (uint32_t)kEncSlots);
-            Lane& L = lanes_[c % (uint32_t)n_lanes];
-            const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
-            if (encoded[c]) pool_->wait(tickets[c]);
-            // the device slot (compressed bytes, frame table, expanded frames) was last used by chunk c - 2
-            DH_CUDA(cudaStreamWaitEvent(copy_stream_, c >= 2 ? ev_consumed_[slot] : ev_fork_, 0));
-            cudaEvent_t t0 = nullptr, t1 = nullptr;
-            if (timing_) {
-                t0 = next_event();
-                t1 = next_event();
-                DH_CUDA(cudaEventRecord(t0, copy_stream_));
+        refill();
+        while (enq < n_chunks) {
+            if (!encq.empty() && pool_->done(tickets[encq.front()])) {
+                const uint32_t c = encq.front();
+                encq.erase(encq.begin());
+                send(c, true);
+                refill();
+                continue;
             }
-            if (encoded[c]) {
-                const unsigned long long* meta = h_enc_meta_[pslot];
-                for (uint32_t k0 = 0; k0 < nc; k0 += kEncGroup) {  // one copy per group: the groups are not adjacent
-                    const uint32_t k1 = std::min(nc, k0 + kEncGroup) - 1u;
-                    const size_t b0 = (size_t)meta[k0], b1 = (size_t)meta[M + k1];
-                    DH_CUDA(cudaMemcpyAsync(d_blob_[slot] + b0, h_enc_[pslot] + b0, b1 - b0, cudaMemcpyHostToDevice, copy_stream_));
-                    last_h2d_bytes_ += b1 - b0;
-                }
-                DH_CUDA(cudaMemcpyAsync(d_enc_meta_[slot], meta, sizeof(unsigned long long) * 2 * M, cudaMemcpyHostToDevice, copy_stream_));
-                last_h2d_bytes_ += sizeof(unsigned long long) * 2 * M;
-                DH_CUDA(cudaEventRecord(ev_enc_copied_[pslot], copy_stream_));
-                ++last_encoded_chunks_;
-            } else {
-                DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
-                                        cudaMemcpyHostToDevice, copy_stream_));
-                last_h2d_bytes_ += (uint64_t)nc * frame_px * sizeof(uint16_t);
+            if (hybrid && back > front && copy_idle()) {
+                send(--back, false);
+                continue;
             }
-            if (timing_) {
-                DH_CUDA(cudaEventRecord(t1, copy_stream_));
-                copy_marks_.push_back({t0, t1});
+            if (!encq.empty()) {
+                pool_->wait_for(tickets[encq.front()], hybrid && back > front ? 50u : 1000000u);
+                continue;
             }
-            DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
-            DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
-            if (encoded[c]) {
-                mark(DH_STAGE_H2D);  // the expansion counts as input transfer
-                DH_CUDA(cudaMemsetAsync(d_depth_[slot], 0, (size_t)nc * frame_px * sizeof(uint16_t), L.stream));
-                launch_biwi_decode(d_blob_[slot], d_enc_meta_[slot], d_enc_meta_[slot] + M, 0ull, nc, w, h, d_depth_[slot], d_status_ + f0,
-                                   L.stream);
-                launches_ += 1;
-            }
-            FrameBuffers b = buffers(L, d_depth_[slot]);
-            run_front(L, b, nc, nullptr);
-            run_back(L, b, nc, iterations);
-            DH_CUDA(cudaMemcpyAsync(h_results_ + f0, L.results, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, L.stream));
-            DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
-            if (c + 2 < n_chunks) submit(c + 2);
+            refill();  // nothing at the workers: everything left is dense (or already sent)
+            if (encq.empty() && front >= back) break;
         }
     } catch (...) {
         drain();  // no worker may still read the caller's frames once this call has returned

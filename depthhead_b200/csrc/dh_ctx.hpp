@@ -37,6 +37,7 @@ struct Lane {
     uint32_t* cubes = nullptr;      // [F][2][kBox^3]
     CUtensorMap sat_map{};
     bool allocated = false;
+    bool cubes_clean = false;       // every cube is zero (meanshift_kernel cleared behind itself)
 };
 constexpr int kMaxLanes = 4;
 
@@ -108,6 +109,7 @@ public:
 private:
     void ensure_forest(const HostForest& hf);
     void free_forest();
+    void build_pair_tables(const HostForest& hf);
     void ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint32_t n_frames_hint, const float K[9], int n_lanes = 1);
     void alloc_lane(Lane& L);
     void free_lane(Lane& L);
@@ -148,6 +150,12 @@ private:
     UniNode* df_uni_ = nullptr;            // uniform-rectangle forests: box-sum nodes for tile width hot_tw_
     uint32_t uni_rw_ = 0, uni_rh_ = 0;
     size_t df_n_nodes_ = 0;
+    // two-levels-per-record tables for the box-sum traversal (PairRec, dh_types.hpp; DH_TRAV_PAIR)
+    PairRec* df_pair_recs_ = nullptr;
+    PairTopo* df_pair_topo_ = nullptr;
+    int32_t* df_pair_roots_ = nullptr;
+    int32_t* df_pair_perm_ = nullptr;
+    size_t df_n_pairs_ = 0;
     int32_t* df_roots_ = nullptr;
     double* df_leaf_prob_ = nullptr;
     LeafInfo* df_leaf_info_ = nullptr;
@@ -232,6 +240,7 @@ private:
     bool graph_seen_valid_ = false;
     uint64_t graph_launches_ = 0;
     bool use_graphs_ = true;
+    bool cube_clear_fused_ = true;   // DH_CUBE_CLEAR_FUSED=0: one memset of all cubes per pass instead
 
     // measurement
     bool timing_ = false, debug_ = false, have_debug_ = false, debug_sync_ = false;

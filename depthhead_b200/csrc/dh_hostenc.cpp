@@ -154,6 +154,18 @@ void WorkerPool::wait(uint64_t ticket) {
     });
 }
 
+bool WorkerPool::done(uint64_t ticket) {
+    std::lock_guard<std::mutex> lk(mu_);
+    return ticket <= finished_upto_ || std::find(finished_.begin(), finished_.end(), ticket) != finished_.end();
+}
+
+bool WorkerPool::wait_for(uint64_t ticket, unsigned micros) {
+    std::unique_lock<std::mutex> lk(mu_);
+    return cv_done_.wait_for(lk, std::chrono::microseconds(micros), [&] {
+        return ticket <= finished_upto_ || std::find(finished_.begin(), finished_.end(), ticket) != finished_.end();
+    });
+}
+
 void WorkerPool::worker() {
     std::unique_lock<std::mutex> lk(mu_);
     for (;;) {

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstddef>
 #include <cstdint>
@@ -41,6 +42,8 @@ public:
     unsigned size() const { return (unsigned)threads_.size(); }
     uint64_t run(uint32_t n, std::function<void(uint32_t)> fn);
     void wait(uint64_t ticket);
+    bool done(uint64_t ticket);                          // non-blocking
+    bool wait_for(uint64_t ticket, unsigned micros);     // true if the job finished within the time
 
 private:
     struct Job {

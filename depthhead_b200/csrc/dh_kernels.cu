@@ -507,6 +507,35 @@ __global__ void __launch_bounds__(256) plan_nodes_kernel(const NodeRec* __restri
     }
 }
 
+// PairRec (two tree levels per 32-byte record) for the current tile plan: tests copied from the
+// UniNode table plan_nodes_kernel has just written, topology from the host.
+__global__ void __launch_bounds__(256) plan_pairs_kernel(const PairTopo* __restrict__ topo, const UniNode* __restrict__ uni,
+                                                         PairRec* __restrict__ recs, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PairTopo t = topo[i];
+    PairRec r;
+    const UniNode x = uni[t.x];
+    r.taps_x = x.taps;
+    r.e2_x = x.e2;
+    // a child that is a leaf: a test that is never greater and never equal (2*(s1 - s2) is even)
+    r.taps_c0 = 0u; r.e2_c0 = 0x7fffffff;
+    r.taps_c1 = 0u; r.e2_c1 = 0x7fffffff;
+    if (t.c0 >= 0) { const UniNode c = uni[t.c0]; r.taps_c0 = c.taps; r.e2_c0 = c.e2; }
+    if (t.c1 >= 0) { const UniNode c = uni[t.c1]; r.taps_c1 = c.taps; r.e2_c1 = c.e2; }
+    r.first = t.first;
+    r.tail = t.tail;
+    recs[i] = r;
+}
+
+__device__ __forceinline__ PairRec ldg_pair(const PairRec* p) {
+    PairRec r;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.taps_x), "=r"(r.e2_x), "=r"(r.taps_c0), "=r"(r.e2_c0), "=r"(r.taps_c1), "=r"(r.e2_c1), "=r"(r.first), "=r"(r.tail)
+                 : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -557,7 +586,8 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
                                                             const int32_t* __restrict__ roots, int32_t* __restrict__ leaf,
                                                             const uint32_t* __restrict__ sat,
                                                             FrameState* __restrict__ fs, Geometry g, TilePlan tp,
-                                                            uint32_t uni_rw, uint32_t uni_rh) {
+                                                            uint32_t uni_rw, uint32_t uni_rh, const PairRec* __restrict__ pair_recs,
+                                                            const int32_t* __restrict__ pair_roots, const int32_t* __restrict__ pair_perm) {
     extern __shared__ uint8_t smem_raw[];
     // 128-byte aligned tile (TMA destination), then the barrier, then the compacted patch list;
     // everything is addressed through 32-bit shared-window addresses
@@ -768,6 +798,55 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
             }
             leaf_f[(size_t)tA * g.P + (py0 + (lpA >> 24)) * g.npx + (px0 + ((lpA >> 16) & 0xffu))] = ~nA;
             if (hasB) leaf_f[(size_t)tB * g.P + (py0 + (lpB >> 24)) * g.npx + (px0 + ((lpB >> 16) & 0xffu))] = ~nB;
+        }
+    } else if (kMode == 7) {
+        // two levels per fetch: PairRec (dh_types.hpp).  The loop carries only the record index and
+        // the patch origin; the leaf's depth (= node visits of the walk) rides in the top bits of
+        // the leaf permutation entry.  An exact tie (possible for even e2 only) abandons the fast
+        // walk: that evaluation is redone by the one-level walk below, which owns the IEEE path.
+        for (uint32_t it = tid; it < items; it += kThreads) {
+            const uint32_t t = nl_magic ? __umulhi(it, nl_magic) : it / nlive;
+            const uint32_t o = org_a + ((lds_u32(live_a + 4u * (it - t * nlive)) & 0xffffu) << 2);
+            int32_t rec = __ldg(pair_roots + t);
+            bool tie = false;
+            while (rec >= 0) {
+                const PairRec R = ldg_pair(pair_recs + rec);
+                const uint32_t s1 = lds_u32(o + ((R.taps_x & 0xffffu) << 2)), s2 = lds_u32(o + ((R.taps_x >> 16) << 2));
+                const int32_t d1 = (int32_t)(s1 - s2) << 1;
+                const bool b1 = d1 > R.e2_x;
+                const uint32_t taps2 = b1 ? R.taps_c1 : R.taps_c0;
+                const int32_t e2 = b1 ? R.e2_c1 : R.e2_c0;
+                const uint32_t s3 = lds_u32(o + ((taps2 & 0xffffu) << 2)), s4 = lds_u32(o + ((taps2 >> 16) << 2));
+                const int32_t d2 = (int32_t)(s3 - s4) << 1;
+                if (d1 == R.e2_x || d2 == e2) {
+                    tie = true;
+                    break;
+                }
+                const uint32_t slot = (b1 ? 2u : 0u) + (d2 > e2 ? 1u : 0u);
+                const uint32_t mask = R.tail & 15u, below = (uint32_t)__popc(mask & ((1u << slot) - 1u));
+                rec = ((mask >> slot) & 1u) ? ~(int32_t)((R.tail >> 6) + below) : (int32_t)(R.first + slot - below);
+            }
+            int32_t leaf_id;
+            if (!tie) {
+                const uint32_t v = (uint32_t)__ldg(pair_perm + ~rec);  // global leaf id | depth << 26
+                leaf_id = (int32_t)(v & 0x3ffffffu);
+                visits += v >> 26;
+            } else {
+                int32_t node = __ldg(roots + t);
+                while (node >= 0) {
+                    const uint4 U = tex1Dfetch<uint4>(hot_tex, node);
+                    const uint32_t s1 = lds_u32(o + ((U.x & 0xffffu) << 2)), s2 = lds_u32(o + ((U.x >> 16) << 2));
+                    const int32_t d2 = (int32_t)(s1 - s2) << 1, E = (int32_t)U.w;
+                    int32_t next = d2 > E ? (int)U.z : (int)U.y;
+                    if (d2 == E) next = binarize_ieee(nodes, node, s1, s2) ? (int)U.z : (int)U.y;
+                    node = next;
+                    ++visits;
+                }
+                leaf_id = ~node;
+            }
+            const uint32_t lp = lds_u32(live_a + 4u * (it - t * nlive));
+            const uint32_t gp = (py0 + (lp >> 24)) * g.npx + (px0 + ((lp >> 16) & 0xffu));
+            leaf_f[(size_t)t * g.P + gp] = leaf_id;
         }
     } else
     for (uint32_t it = tid; it < items; it += kThreads) {
@@ -1538,6 +1617,12 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
         }
     }
     __syncthreads();
+    if (b.clear_cubes) {
+        // leave the cube empty for the next pass over this scratch: 250 KB of stores that overlap the
+        // other CTAs' rounds instead of one memset of every cube in front of the vote stage
+        uint4* bz = reinterpret_cast<uint4*>(box);
+        for (int i = tid; i < kBoxCells / 4; i += kMsThreads) __stcg(bz + i, make_uint4(0u, 0u, 0u, 0u));
+    }
     if (tid == 0) {
         fs->ms_iters[which] = it;
         fs->ms_flags[which] = s_flags;
@@ -2066,30 +2151,34 @@ static void launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b,
         cudaFuncSetAttribute(traverse_kernel<kThreads, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
         cudaFuncSetAttribute(traverse_kernel<kThreads, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
+        cudaFuncSetAttribute(traverse_kernel<kThreads, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
     }
     static const bool two_walks = std::getenv("DH_TRAV_ILP") && std::atoi(std::getenv("DH_TRAV_ILP")) == 2;
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
-    if (f.uni && g.rw && f.hot_tex && two_walks)
+    if (f.uni && g.rw && f.pair_recs)
+        traverse_kernel<kThreads, 7><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
+    else if (f.uni && g.rw && f.hot_tex && two_walks)
         traverse_kernel<kThreads, 6><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.uni && g.rw && f.hot_tex)
         traverse_kernel<kThreads, 4><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.uni && g.rw)
         traverse_kernel<kThreads, 5><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box, b.fs, g,
-                                                                       tp, f.uni_rw, f.uni_rh);
+                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.uni && f.hot_tex)
         traverse_kernel<kThreads, 2><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.uni)
         traverse_kernel<kThreads, 3><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat, b.fs, g,
-                                                                       tp, f.uni_rw, f.uni_rh);
+                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.hot_tex)
         traverse_kernel<kThreads, 1><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat,
-                                                                       b.fs, g, tp, 0u, 0u);
+                                                                       b.fs, g, tp, 0u, 0u, nullptr, nullptr, nullptr);
     else
         traverse_kernel<kThreads, 0><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat, b.fs, g,
-                                                                       tp, 0u, 0u);
+                                                                       tp, 0u, 0u, nullptr, nullptr, nullptr);
 }
 
 void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
@@ -2102,6 +2191,11 @@ void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Ge
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width, cudaStream_t s) {
     if (n_nodes == 0) return;
     plan_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(nodes, hot, uni, n_nodes, tile_width);
+}
+
+void launch_plan_pairs(const PairTopo* topo, const UniNode* uni, PairRec* recs, size_t n_recs, cudaStream_t s) {
+    if (n_recs == 0) return;
+    plan_pairs_kernel<<<(unsigned)((n_recs + 255) / 256), 256, 0, s>>>(topo, uni, recs, n_recs);
 }
 
 uint32_t sat_band_rows() { return (uint32_t)kSatBandRows; }

@@ -70,6 +70,11 @@ struct ForestDev {
     const UniNode* uni;        // uniform-rectangle forests: 16-byte nodes for the box-sum traversal (or nullptr)
     uint32_t uni_rw, uni_rh;   // the common rectangle size
     const int32_t* roots;
+    // two-levels-per-record tables (PairRec, dh_types.hpp) for the box-sum traversal, or nullptr
+    const PairRec* pair_recs;
+    const PairTopo* pair_topo;
+    const int32_t* pair_roots;      // per tree: >= 0 record index, < 0 ~(device leaf number)
+    const int32_t* pair_leaf_perm;  // device leaf number -> global leaf id
     const double* leaf_prob;
     const LeafInfo* leaf_info;
     const float4* offsets;     // per vote: x, y, z (mm), w unused — one 16-byte load
@@ -96,6 +101,8 @@ struct FrameBuffers {
     int32_t* ms_trace;      // [F][2][iters][3] or nullptr
     uint32_t ms_trace_cap;  // iterations per trace
     uint32_t debug;         // 1: compute the seed grids even when the caller supplied seeds
+    uint32_t clear_cubes;   // 1: meanshift_kernel zeroes its accumulator cube when it is done with it (the next
+                            // pass finds the cubes empty without a memset of all of them)
 };
 
 int launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s);
@@ -104,6 +111,7 @@ bool box_image_supported(uint32_t w, uint32_t h, uint32_t sw, uint32_t sh, uint3
 void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
                      const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width, cudaStream_t s);
+void launch_plan_pairs(const PairTopo* topo, const UniNode* uni, PairRec* recs, size_t n_recs, cudaStream_t s);
 int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
                           uint32_t iterations, cudaStream_t s);

@@ -179,8 +179,8 @@ def test_decode_mutated_streams_against_the_oracle(ctx):
 
 # ---- the compressed host->device path of dh_predict_batch (worker threads rewrite host frames as
 #      run-length files, the GPU expands them): results must equal the raw copy and the device-resident pass
-@pytest.mark.parametrize("env", [{"DH_HOST_ENCODE": "1"}, {"DH_HOST_ENCODE": "1", "DH_LANES": "1"},
-                                 {"DH_HOST_ENCODE": "1", "DH_ENCODE_THREADS": "1"}, {}])
+@pytest.mark.parametrize("env", [{"DH_HOST_ENCODE": "1", "DH_HOST_HYBRID": "0"}, {"DH_HOST_ENCODE": "1", "DH_LANES": "1"},
+                                 {"DH_HOST_ENCODE": "1", "DH_ENCODE_THREADS": "1"}, {"DH_HOST_HYBRID": "0"}, {}])
 def test_predict_batch_host_frames_through_the_run_length_rewrite(monkeypatch, env):
     import torch
     arr = synth.make_forest(seed=4, n_trees=3, max_depth=7)
@@ -193,7 +193,7 @@ def test_predict_batch_host_frames_through_the_run_length_rewrite(monkeypatch, e
     hp = HoughPrediction.from_arrays(arr, stepwidth=8)
 
     def run(e):
-        for k in ("DH_HOST_ENCODE", "DH_LANES", "DH_ENCODE_THREADS"):
+        for k in ("DH_HOST_ENCODE", "DH_LANES", "DH_ENCODE_THREADS", "DH_HOST_HYBRID"):
             monkeypatch.delenv(k, raising=False)
         for k, v in e.items():
             monkeypatch.setenv(k, v)
@@ -211,10 +211,12 @@ def test_predict_batch_host_frames_through_the_run_length_rewrite(monkeypatch, e
     got, got2, info = run(env)
     for a, b in ((ref, got), (ref2, got2)):
         assert np.array_equal(a["mid_point"], b["mid_point"]) and np.array_equal(a["rotation"], b["rotation"])
-    if env.get("DH_HOST_ENCODE") == "1":
-        assert info["encoded_chunks"] == 5
+    if env.get("DH_HOST_HYBRID") == "0" and env.get("DH_HOST_ENCODE") == "1":
+        assert info["encoded_chunks"] == 5                              # every chunk waits for its rewrite
+    elif env.get("DH_HOST_HYBRID") == "0":
+        assert info["encoded_chunks"] == 4                              # the dense chunk goes raw
     else:
-        assert 1 <= info["encoded_chunks"] <= 4                         # the dense chunk goes raw
+        assert 1 <= info["encoded_chunks"] <= 5                         # idle copy engine: chunks from the back go raw
     assert info["h2d_bytes"] < frames.nbytes
     # and the device-resident pass
     c = Context(0)

@@ -54,6 +54,9 @@ VARIANTS = [
     {"DH_TRAV_TMA_FIRST": "1"},                     # the tile's TMA load is issued before its background check
     {"DH_TRAV_TMA_FIRST": "1", "DH_BOX_IMAGE": "0"},
     {"DH_TRAV_TMA_FIRST": "1", "DH_TRAV_BLOCK": "1"},
+    {"DH_TRAV_PAIR": "1"},                          # two tree levels per 32-byte record
+    {"DH_TRAV_PAIR": "1", "DH_TRAV_THREADS": "768", "DH_TRAV_TMA_FIRST": "1"},
+    {"DH_CUBE_CLEAR_FUSED": "0"},                   # one memset of all accumulator cubes per pass instead of the clear behind mean-shift
     {"DH_LANES": "1"},
     {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},
 ]
@@ -344,3 +347,64 @@ def test_graph_replay_survives_a_growing_batch_between_single_calls(monkeypatch)
     # single call 3 + k equals row 3 + k of the 40-frame batch
     for k in range(4):
         assert np.array_equal(a[5 + k][0], a[4]["mid_point"][3 + k]) and np.array_equal(a[5 + k][1], a[4]["rotation"][3 + k])
+
+
+@pytest.mark.parametrize("threads", ["1024", "768"])
+def test_two_levels_per_record_traversal(monkeypatch, threads):
+    """PairRec walk (DH_TRAV_PAIR=1): full trees of odd and even depth, sparse trees (leaves at every
+    depth, children that are leaves), trees that are a single leaf, shuffled node order, exact ties
+    (the fast walk hands them to the one-level walk), and the work counter node_visits, which the
+    fast walk reads off the leaf's depth."""
+    monkeypatch.setenv("DH_TRAV_PAIR", "1")
+    monkeypatch.setenv("DH_TRAV_THREADS", threads)
+    c = Context(0)
+    try:
+        frames = synth.make_frames(3, seed=61)
+        cases = [dict(seed=31, n_trees=3, max_depth=7), dict(seed=32, n_trees=3, max_depth=8),
+                 dict(seed=33, n_trees=6, max_depth=11, stop_prob=0.3, shuffle_nodes=True),
+                 dict(seed=34, n_trees=5, max_depth=1), dict(seed=35, n_trees=4, max_depth=2, stop_prob=0.5),
+                 dict(seed=36, n_trees=8, max_depth=10, tie_thresholds=True)]
+        for kw in cases:
+            arr = synth.make_forest(**kw)
+            js = synth.forest_to_json(arr, stepwidth=6)
+            hp = HoughPrediction.from_json(js)
+            of = oracle.OracleForest.from_json(js)
+            for d in frames[:2]:
+                _compare_frame(c, hp, of, d)
+            if kw.get("tie_thresholds"):
+                stairs = (1000 + (np.arange(640)[None, :] // 24) + 0 * np.arange(480)[:, None]).astype(np.uint16)
+                _compare_frame(c, hp, of, stairs)
+                _compare_frame(c, hp, of, np.full((480, 640), 1000, np.uint16))
+            # node visits = sum over evaluations of the depth of the leaf reached
+            out = hp.predict_batch(frames, K, ctx=c)
+            cnt = c.counters()
+            depth_of_leaf = _leaf_depths(arr)
+            want = 0
+            for d in frames:
+                tr = of.predict(d, synth.KINECT_K, mode=oracle.MODE_SAT, keep=True)
+                valid = tr.leaf[:, 0] >= 0
+                want += int(depth_of_leaf[tr.leaf[valid]].sum())
+            assert cnt["node_visits"] == want, kw
+    finally:
+        c.close()
+
+
+def _leaf_depths(arr):
+    """depth (number of node visits of a walk that ends there) of every global leaf id"""
+    n_leaves = int(arr["tree_leaf_off"][-1])
+    out = np.zeros(n_leaves, np.int64)
+    for t in range(int(arr["n_trees"])):
+        n0, l0 = int(arr["tree_node_off"][t]), int(arr["tree_leaf_off"][t])
+        n_nodes = int(arr["tree_node_off"][t + 1]) - n0
+        if n_nodes == 0:
+            continue
+        stack = [(0, 1)]
+        while stack:
+            i, d = stack.pop()
+            for b in range(2):
+                ch = int(arr["child"][n0 + i, b]) if arr["child"].ndim == 2 else int(arr["child"][2 * (n0 + i) + b])
+                if ch >= 0:
+                    stack.append((ch, d + 1))
+                else:
+                    out[l0 + (~ch)] = d
+    return out

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 2) gather_kernel(Args a) {
 #pragma unroll
     for (int k = 0; k < kIlp; ++k) {
         tree[k] = (warp + 3u * (uint32_t)k + blockIdx.x) % kTrees;
-        node[k] = tree[k] * kNodesPerTree;
+        node[k] = tree[k] * (kNode == kLdg32 ? kRecsPerTree : kNodesPerTree);
         level[k] = 0;
         state[k] = mix(tid * 977u + blockIdx.x * 131071u + (uint32_t)k);
     }
@@ -181,6 +181,58 @@ __global__ void __launch_bounds__(kThreads, 2) gather_kernel(Args a) {
         atomicAdd(&a.wavefronts[0], wf);
         atomicAdd(&a.wavefronts[1], nld);
     }
+}
+
+// ---- data-stage peaks: pointer chases with (almost) no other instructions.
+// kLds: two independent chases through the shared-memory tile (tile[i] = a random index into the
+// tile: every warp-wide load hits random banks, ~3.5 wavefronts).  kTex: a chase through a node
+// table small enough to stay in L1 (8 KB, random 16-byte fetches: texture wavefronts without
+// misses).  Both together show whether the two pipes share the data stage.
+template <bool kLds, bool kTex>
+__global__ void __launch_bounds__(kThreads, 2) chase_kernel(Args a, uint32_t small_nodes) {
+    extern __shared__ __align__(16) uint32_t tile[];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < kTileWords; i += kThreads) tile[i] = (mix(i * 2654435761u + blockIdx.x) % kTileWords) << 2;  // byte offsets
+    __syncthreads();
+    const uint32_t tile_a = (uint32_t)__cvta_generic_to_shared(tile);
+    uint32_t p0 = (mix(tid * 31u + blockIdx.x) % kTileWords) << 2, p1 = (mix(tid * 57u + 7u) % kTileWords) << 2;
+    uint32_t q0 = mix(tid * 3u + blockIdx.x) % small_nodes, q1 = mix(tid * 5u + 11u) % small_nodes;
+    const long long t0 = clock64();
+    for (uint32_t s = 0; s < a.steps; ++s) {
+        if (kLds) {
+            p0 = lds(tile_a + p0);
+            p1 = lds(tile_a + p1);
+        }
+        if (kTex) {
+            q0 = tex1Dfetch<uint4>(a.tex16, (int)q0).y;
+            q1 = tex1Dfetch<uint4>(a.tex16, (int)q1).y;
+        }
+    }
+    const long long t1 = clock64();
+    if ((p0 ^ p1 ^ q0 ^ q1) == 0xdeadbeefu) a.sink[0] = p0;
+    if (tid == 0) a.cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
+template <bool kLds, bool kTex>
+static void run_chase(const char* name, Args a, int n_sms, uint32_t steps, uint32_t small_nodes) {
+    const size_t smem = (size_t)kTileWords * 4;
+    CK(cudaFuncSetAttribute(chase_kernel<kLds, kTex>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = n_sms * 2;
+    a.steps = steps;
+    std::vector<unsigned long long> cyc(grid);
+    unsigned long long best = ~0ull;
+    for (int rep = 0; rep < 3; ++rep) {
+        chase_kernel<kLds, kTex><<<grid, kThreads, smem>>>(a, small_nodes);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(cyc.data(), a.cycles, sizeof(unsigned long long) * grid, cudaMemcpyDeviceToHost));
+        const unsigned long long mx = *std::max_element(cyc.begin(), cyc.end());
+        if (rep && mx < best) best = mx;
+    }
+    const double per_sm = 2.0 * kThreads * 2.0 * steps;  // loads of each kind per SM
+    printf("{\"variant\": \"%s\", \"pattern\": \"chase\", \"steps\": %u, \"cycles\": %llu, \"lds_thread_loads_per_cycle_per_sm\": %.3f, "
+           "\"tex_thread_fetches_per_cycle_per_sm\": %.3f}\n",
+           name, steps, best, kLds ? per_sm / (double)best : 0.0, kTex ? per_sm / (double)best : 0.0);
+    fflush(stdout);
 }
 
 struct Variant {
@@ -306,6 +358,17 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&a.cycles, sizeof(unsigned long long) * n_sms * 2));
     CK(cudaMalloc(&a.wavefronts, 16));
     CK(cudaMalloc(&a.sink, 4));
+    {
+        // the small table: nodes 0..511 (8 KB) linked among themselves at random
+        std::vector<uint4> small(512);
+        for (uint32_t i = 0; i < 512; ++i) small[i] = make_uint4(next(), next() % 512u, next() % 512u, next());
+        CK(cudaMemcpy(d16, small.data(), sizeof(uint4) * 512, cudaMemcpyHostToDevice));
+        run_chase<true, false>("chase_lds", a, n_sms, steps, 512);
+        run_chase<false, true>("chase_tex16_l1", a, n_sms, steps, 512);
+        run_chase<true, true>("chase_lds_tex16_l1", a, n_sms, steps, 512);
+        CK(cudaMemcpy(d16, h16.data(), sizeof(uint4) * kNodes, cudaMemcpyHostToDevice));
+    }
+    if (argc > 4 && atoi(argv[4]) == 0) return 0;  // chases only
     for (int random = 0; random < 2; ++random) {
         const bool r = random != 0;
         // (a) divergent shared-memory taps alone
