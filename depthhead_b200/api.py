@@ -350,6 +350,25 @@ class HoughPrediction:
         capi.check(capi.load().dh_hough_image_raw(ctx._h, self._h, capi.ptr(depth), w, h, intrinsic._ptr(), capi.ptr(out)))
         return out
 
+    def build_hough_image(self, img, intrinsic: IntrinsicMatrix, ctx: Context | None = None) -> np.ndarray:
+        """prediction.rs:760-845: the 2-D vote image after its gaussian blur (sigma = the model's)."""
+        ctx = ctx or default_context()
+        depth = _as_depth(img)
+        h, w = depth.shape
+        out = np.zeros((h, w), np.uint16)
+        capi.check(capi.load().dh_build_hough_image(ctx._h, self._h, capi.ptr(depth), w, h, intrinsic._ptr(), capi.ptr(out)))
+        return out
+
+    def predict_parameter_from2dhough(self, img, intrinsic: IntrinsicMatrix, ctx: Context | None = None) -> PredictionResult:
+        """prediction.rs:343-367: arg-max of the blurred vote image mapped to 3-D; rotation is always 0."""
+        ctx = ctx or default_context()
+        depth = _as_depth(img)
+        h, w = depth.shape
+        res = capi.dh_result()
+        capi.check(capi.load().dh_predict_from2dhough(ctx._h, self._h, capi.ptr(depth), w, h, intrinsic._ptr(), C.byref(res)))
+        return PredictionResult(np.array(res.mid_point[:], np.float32), np.array(res.rotation[:], np.float64),
+                                tuple(res.bounding_box[:]))
+
     def debug_leaf_static(self, ctx: Context | None = None):
         ctx = ctx or default_context()
         n = self.n_leaves

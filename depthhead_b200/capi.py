@@ -108,6 +108,8 @@ SIGNATURES = {
     "dh_forest_to_json": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dh_predict_mask": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "dh_hough_image_raw": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "dh_build_hough_image": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "dh_predict_from2dhough": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, C.POINTER(dh_result)]),
     "dh_ctx_enable_stage_timing": (C.c_int, [_vp, C.c_int]),
     "dh_ctx_stage_ms": (C.c_int, [_vp, _vp]),
     "dh_ctx_counters": (C.c_int, [_vp, _vp]),

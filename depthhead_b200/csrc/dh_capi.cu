@@ -358,6 +358,21 @@ int dh_hough_image_raw(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uin
     });
 }
 
+int dh_build_hough_image(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+                         uint16_t* hough) {
+    return guarded([&] {
+        REQUIRE(c && f && depth && K && hough, "dh_build_hough_image: NULL argument");
+        c->cx->hough_image(*f->hf, depth, w, h, K, hough, true, nullptr);
+    });
+}
+int dh_predict_from2dhough(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+                           dh_result* out) {
+    return guarded([&] {
+        REQUIRE(c && f && depth && K && out, "dh_predict_from2dhough: NULL argument");
+        c->cx->hough_image(*f->hf, depth, w, h, K, nullptr, true, out);
+    });
+}
+
 int dh_ctx_enable_stage_timing(dh_ctx* c, int on) {
     return guarded([&] {
         REQUIRE(c, "NULL ctx");

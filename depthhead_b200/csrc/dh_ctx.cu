@@ -448,10 +448,8 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
                 }
             }
         if (best.tpx) {
-            best.tma_first = env_flag("DH_TRAV_TMA_FIRST", false) ? 1u : 0u;
-            // experiment: extra dynamic shared memory per CTA lowers the CTAs per SM without changing the tile
-            best.smem_bytes += std::min<uint32_t>(env_u32("DH_TRAV_PAD_SMEM", 0), smem_optin_ > best.smem_bytes ? smem_optin_ - best.smem_bytes : 0u);
-            if (env_u32("DH_TRAV_BLOCK", 0)) {
+            best.tma_first = env_flag("DH_TRAV_TMA_FIRST", true) ? 1u : 0u;  // measured: 1.110 -> 1.052 ms per 1024 frames
+            if (env_flag("DH_TRAV_BLOCK", true)) {  // measured with the early load: 1.052 -> 1.037 ms
                 // a warp walks a block of 8 x 4 neighbouring patches: its lanes stay on the same nodes for
                 // longer.  On one node lane (c, r) reads word stride * (c + r * tw) + const: with
                 // stride * tw = 8 (mod 32) and an odd stride the 32 lanes hit 32 different banks.
@@ -465,6 +463,8 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
                     }
                 }
             }
+            // experiment: extra dynamic shared memory per CTA lowers the CTAs per SM without changing the tile
+            best.smem_bytes += std::min<uint32_t>(env_u32("DH_TRAV_PAD_SMEM", 0), smem_optin_ > best.smem_bytes ? smem_optin_ - best.smem_bytes : 0u);
             return best;
         }
     }
@@ -1242,11 +1242,20 @@ void Context::predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t
 
 void Context::hough_image_raw(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
                               uint16_t* votes) {
+    hough_image(hf, depth, w, h, K, votes, false, nullptr);
+}
+
+// build_hough_image (prediction.rs:760-845): vote image (+ gaussian blur with the model's sigma) to
+// `votes` (host, may be NULL); from2d != NULL: predict_parameter_from2dhough (prediction.rs:343-367).
+void Context::hough_image(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9], uint16_t* votes,
+                          bool blur, dh_result* from2d) {
     begin_call();
     have_debug_ = false;
     ensure_forest(hf);
     ensure_scratch(hf, w, h, 1, K);
     ensure_staging(1);
+    std::vector<float> kern;
+    if (blur) kern = build_gaussian_blur_kernel(hf.gaussian_sigma);
     DH_CUDA(cudaMemcpyAsync(d_depth_[0], depth, (size_t)w * h * sizeof(uint16_t), cudaMemcpyHostToDevice, stream_));
     FrameBuffers b = buffers(lanes_[0], d_depth_[0]);
     run_front(lanes_[0], b, 1, nullptr);
@@ -1254,7 +1263,7 @@ void Context::hough_image_raw(const HostForest& hf, const uint16_t* depth, uint3
     if (aux32_cap_ < px) {
         dev_free(d_aux32_);
         dev_free(d_aux16_);
-        dev_alloc(d_aux32_, px);
+        dev_alloc(d_aux32_, px);          // u32 vote sums; reused as two u16 planes by the blur
         dev_alloc(d_aux16_, px);
         aux32_cap_ = px;
     }
@@ -1262,13 +1271,38 @@ void Context::hough_image_raw(const HostForest& hf, const uint16_t* depth, uint3
     if (geom_.P) {
         launch_hough_image(b, geom_, fdev_, d_aux32_, d_aux16_, stream_);
         launches_ += 2;
-        DH_CUDA(cudaGetLastError());
-        DH_CUDA(cudaMemcpyAsync(votes, d_aux16_, px * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream_));
     } else {
-        std::memset(votes, 0, px * sizeof(uint16_t));
+        DH_CUDA(cudaMemsetAsync(d_aux16_, 0, px * sizeof(uint16_t), stream_));
     }
+    const uint16_t* result = d_aux16_;
+    if (blur) {
+        float* d_k = nullptr;
+        dev_alloc(d_k, kern.size());
+        try {
+            DH_CUDA(cudaMemcpyAsync(d_k, kern.data(), kern.size() * sizeof(float), cudaMemcpyHostToDevice, stream_));
+            uint16_t* tmp = reinterpret_cast<uint16_t*>(d_aux32_);  // the u32 sums have been narrowed into d_aux16_
+            launches_ += (uint64_t)launch_gaussian_blur(d_aux16_, tmp, tmp + px, w, h, d_k, (int)(kern.size() / 2), stream_);
+            result = tmp + px;
+            DH_CUDA(cudaGetLastError());
+            DH_CUDA(cudaStreamSynchronize(stream_));  // kern / d_k go away
+        } catch (...) {
+            cudaStreamSynchronize(stream_);
+            dev_free(d_k);
+            throw;
+        }
+        dev_free(d_k);
+    }
+    if (from2d) {
+        if (px == 0) throw ModelError(DH_E_SHAPE, "predict_parameter_from2dhough on an empty image (the reference unwraps None)");
+        launch_hough2d_argmax(result, d_depth_[0], w, h, geom_, lanes_[0].results, stream_);
+        launches_ += 1;
+        DH_CUDA(cudaMemcpyAsync(h_result1_, lanes_[0].results, sizeof(dh_result), cudaMemcpyDeviceToHost, stream_));
+    }
+    DH_CUDA(cudaGetLastError());
+    if (votes) DH_CUDA(cudaMemcpyAsync(votes, result, px * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream_));
     mark(-1);
     end_call();
+    if (from2d) *from2d = *h_result1_;
 }
 
 // ------------------------------------------------------------------------------------------------ debug exports

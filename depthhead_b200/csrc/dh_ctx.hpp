@@ -95,6 +95,8 @@ public:
     void predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask);
     void hough_image_raw(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
                          uint16_t* votes);
+    void hough_image(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9], uint16_t* votes,
+                     bool blur, dh_result* from2d);
 
     void debug_dims(uint32_t* npx, uint32_t* npy, uint32_t* n_trees) const;
     void debug_leaf(int32_t* leaf);

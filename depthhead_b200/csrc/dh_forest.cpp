@@ -388,6 +388,27 @@ void build_meanshift_kernel(float sigma, float* out) {
     }
 }
 
+// imageproc 0.12 gaussian_kernel_f32 (the blur of build_hough_image, prediction.rs:844; external
+// crate, restated from its published source: unpinned): radius ceil(2 sigma), taps
+// (sqrt(2 pi) * sigma).recip() * exp(-i^2 / (2 sigma^2)) in f32, not normalised.
+std::vector<float> build_gaussian_blur_kernel(float sigma) {
+    if (!(sigma > 0.0f)) throw ModelError(DH_E_ARG, "gaussian blur: sigma must be > 0.0 (imageproc asserts it)");
+    const float r2 = std::ceil(2.0f * sigma);
+    if (!(r2 <= 1024.0f)) throw ModelError(DH_E_SHAPE, "gaussian blur: sigma above 512 is not supported");
+    const size_t radius = (size_t)r2;
+    std::vector<float> k(2 * radius + 1, 0.0f);
+    const float two_pi = 2.0f * 3.14159265358979323846264338327950288f;
+    const float norm = 1.0f / (std::sqrt(two_pi) * sigma);
+    const float s2 = sigma * sigma;
+    for (size_t i = 0; i <= radius; ++i) {
+        const float x = (float)i, x2 = x * x;
+        const float v = norm * std::exp(-x2 / (2.0f * s2));
+        k[radius + i] = v;
+        k[radius - i] = v;
+    }
+    return k;
+}
+
 }  // namespace dh
 
 // ------------------------------------------------------------------------------------------------ writer

@@ -86,6 +86,8 @@ std::string forest_to_json(const HostForest& hf);
 void mat3_inverse_f32(const float k[9], float inv[9]);
 // FullArray3D::build_kernel(20, sigma) (meanshift.rs:228-252): 8000 f32, index z*400+y*20+x.
 void build_meanshift_kernel(float sigma, float* out8000);
+// imageproc's gaussian_kernel_f32(sigma): 2 * ceil(2 sigma) + 1 taps (build_hough_image's blur, prediction.rs:844)
+std::vector<float> build_gaussian_blur_kernel(float sigma);
 
 // Biwi side files (dh_biwi.cpp; src/db_reader/biwi.rs:27-86)
 void biwi_depth_dims(const uint8_t* file, size_t len, uint32_t* w, uint32_t* h);

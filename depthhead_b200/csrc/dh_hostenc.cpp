@@ -105,6 +105,7 @@ unsigned default_encode_threads() {
 #endif
     if (n == 0) n = std::thread::hardware_concurrency();
     if (n == 0) n = 4;
+    if (n > 4) n -= 1;  // the calling thread keeps a core: it feeds the copy engine while the workers write
     return std::min(n, 16u);
 }
 

@@ -799,6 +799,58 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
             leaf_f[(size_t)tA * g.P + (py0 + (lpA >> 24)) * g.npx + (px0 + ((lpA >> 16) & 0xffu))] = ~nA;
             if (hasB) leaf_f[(size_t)tB * g.P + (py0 + (lpB >> 24)) * g.npx + (px0 + ((lpB >> 16) & 0xffu))] = ~nB;
         }
+    } else if (kMode == 4) {
+        // the default walk (uniform rectangles, box-sum tile, nodes through the texture path), in two
+        // passes.  The fast pass contains no call: an exact tie (2*(s1 - s2) == E, possible for even E
+        // only) abandons the walk and marks the evaluation's leaf slot; the second pass, entered only
+        // by threads that saw a tie, redoes the marked evaluations with the IEEE-division path.  The
+        // call and everything it keeps alive stay out of the hot loop (no spills around it).
+        constexpr int32_t kTieMark = (int32_t)0x80000000;
+        bool any_tie = false;
+        for (uint32_t it = tid; it < items; it += kThreads) {
+            const uint32_t t = nl_magic ? __umulhi(it, nl_magic) : it / nlive;
+            const uint32_t lp = lds_u32(live_a + 4u * (it - t * nlive));
+            const uint32_t o = org_a + ((lp & 0xffffu) << 2);
+            int32_t node = __ldg(roots + t);
+            uint32_t nv = 0;
+            bool tie = false;
+            while (node >= 0) {
+                const uint4 U = tex1Dfetch<uint4>(hot_tex, node);
+                const uint32_t s1 = lds_u32(o + ((U.x & 0xffffu) << 2)), s2 = lds_u32(o + ((U.x >> 16) << 2));
+                const int32_t d2 = (int32_t)(s1 - s2) << 1, E = (int32_t)U.w;
+                if (d2 == E) {
+                    tie = true;
+                    break;
+                }
+                node = d2 > E ? (int)U.z : (int)U.y;
+                ++nv;
+            }
+            any_tie |= tie;
+            visits += tie ? 0u : nv;
+            const uint32_t gp = (py0 + (lp >> 24)) * g.npx + (px0 + ((lp >> 16) & 0xffu));
+            leaf_f[(size_t)t * g.P + gp] = tie ? kTieMark : ~node;
+        }
+        if (any_tie) {
+            for (uint32_t it = tid; it < items; it += kThreads) {
+                const uint32_t t = nl_magic ? __umulhi(it, nl_magic) : it / nlive;
+                const uint32_t lp = lds_u32(live_a + 4u * (it - t * nlive));
+                const uint32_t gp = (py0 + (lp >> 24)) * g.npx + (px0 + ((lp >> 16) & 0xffu));
+                int32_t* slot = leaf_f + (size_t)t * g.P + gp;
+                if (*slot != kTieMark) continue;  // written by this very thread in the first pass
+                const uint32_t o = org_a + ((lp & 0xffffu) << 2);
+                int32_t node = __ldg(roots + t);
+                while (node >= 0) {
+                    const uint4 U = tex1Dfetch<uint4>(hot_tex, node);
+                    const uint32_t s1 = lds_u32(o + ((U.x & 0xffffu) << 2)), s2 = lds_u32(o + ((U.x >> 16) << 2));
+                    const int32_t d2 = (int32_t)(s1 - s2) << 1, E = (int32_t)U.w;
+                    int32_t next = d2 > E ? (int)U.z : (int)U.y;
+                    if (d2 == E) next = binarize_ieee(nodes, node, s1, s2) ? (int)U.z : (int)U.y;
+                    node = next;
+                    ++visits;
+                }
+                *slot = ~node;
+            }
+        }
     } else if (kMode == 7) {
         // two levels per fetch: PairRec (dh_types.hpp).  The loop carries only the record index and
         // the patch origin; the leaf's depth (= node visits of the walk) rides in the top bits of
@@ -1794,6 +1846,85 @@ __global__ void narrow_u16_kernel(const uint32_t* __restrict__ in, uint16_t* __r
     if (i < n) out[i] = (uint16_t)(in[i] & 0xffffu);
 }
 
+// ---- the blur of build_hough_image (prediction.rs:844 gaussian_blur_f32, imageproc 0.12: restated, unpinned)
+// Separable: a horizontal pass over the u16 vote image, then a vertical pass over its u16 result.
+// Per output pixel acc = 0; for the taps in order acc = acc + (float)pixel * k[i] (no FMA); the
+// coordinate is clamped to the image; the result is stored as u16 by truncation with saturation
+// (Clamp<f32> for u16).  One thread per output pixel; the pixels a block's outputs need are staged
+// in shared memory (a row segment of 128 + 2r pixels, or a column segment of 32 + 2r rows x 32 columns).
+__device__ __forceinline__ uint16_t clamp_f32_u16(float x) {
+    if (x < 65535.0f) return x > 0.0f ? (uint16_t)__float2uint_rz(x) : (uint16_t)0;
+    return 65535;
+}
+constexpr int kBlurHx = 128, kBlurHy = 4;   // horizontal pass: outputs per block
+constexpr int kBlurVx = 32, kBlurVy = 32;   // vertical pass
+__global__ void __launch_bounds__(kBlurHx * kBlurHy) blur_h_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t w,
+                                                                    uint32_t h, const float* __restrict__ k, int radius) {
+    extern __shared__ uint16_t s_px[];  // [kBlurHy][kBlurHx + 2 radius]
+    const int span = kBlurHx + 2 * radius;
+    const int x0 = (int)blockIdx.x * kBlurHx, y = (int)(blockIdx.y * kBlurHy + threadIdx.y);
+    uint16_t* row = s_px + threadIdx.y * span;
+    if (y < (int)h)
+        for (int i = threadIdx.x; i < span; i += kBlurHx) {
+            const int xs = min(max(x0 + i - radius, 0), (int)w - 1);
+            row[i] = in[(size_t)y * w + xs];
+        }
+    __syncthreads();
+    const int x = x0 + (int)threadIdx.x;
+    if (y >= (int)h || x >= (int)w) return;
+    float acc = 0.0f;
+    for (int i = 0; i <= 2 * radius; ++i) acc = __fadd_rn(acc, __fmul_rn((float)row[threadIdx.x + i], __ldg(k + i)));
+    out[(size_t)y * w + x] = clamp_f32_u16(acc);
+}
+__global__ void __launch_bounds__(kBlurVx * kBlurVy) blur_v_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t w,
+                                                                    uint32_t h, const float* __restrict__ k, int radius) {
+    extern __shared__ uint16_t s_px[];  // [kBlurVy + 2 radius][kBlurVx]
+    const int span = kBlurVy + 2 * radius;
+    const int x = (int)(blockIdx.x * kBlurVx + threadIdx.x), y0 = (int)blockIdx.y * kBlurVy;
+    if (x < (int)w)
+        for (int i = threadIdx.y; i < span; i += kBlurVy) {
+            const int ys = min(max(y0 + i - radius, 0), (int)h - 1);
+            s_px[i * kBlurVx + threadIdx.x] = in[(size_t)ys * w + x];
+        }
+    __syncthreads();
+    const int y = y0 + (int)threadIdx.y;
+    if (y >= (int)h || x >= (int)w) return;
+    float acc = 0.0f;
+    for (int i = 0; i <= 2 * radius; ++i) acc = __fadd_rn(acc, __fmul_rn((float)s_px[(threadIdx.y + i) * kBlurVx + threadIdx.x], __ldg(k + i)));
+    out[(size_t)y * w + x] = clamp_f32_u16(acc);
+}
+// predict_parameter_from2dhough (prediction.rs:343-367): Iterator::max_by_key over the pixels in
+// index order — the LAST of equal maxima wins — then z = the depth at that pixel and the
+// back-projection of (x, y, z); rotation 0, bounding box 0.
+__global__ void __launch_bounds__(1024) hough2d_argmax_kernel(const uint16_t* __restrict__ hough, const uint16_t* __restrict__ depth,
+                                                              uint32_t w, uint32_t h, Geometry g, dh_result* __restrict__ out) {
+    __shared__ uint32_t s_val[32], s_idx[32];
+    const uint32_t n = w * h, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t bv = 0, bi = 0;  // every pixel compares >= against pixel 0, as the fold does
+    for (uint32_t i = tid; i < n; i += 1024u) {
+        const uint32_t v = hough[i];
+        if (v > bv || (v == bv && i > bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint32_t ov = __shfl_xor_sync(0xffffffffu, bv, d), oi = __shfl_xor_sync(0xffffffffu, bi, d);
+        if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 32; ++i)
+            if (s_val[i] > bv || (s_val[i] == bv && s_idx[i] > bi)) { bv = s_val[i]; bi = s_idx[i]; }
+        const uint32_t x = bi % w, y = bi / w;
+        float p[3];
+        img_to_space(g.Kinv, (float)x, (float)y, (float)depth[(size_t)y * w + x], p);
+        out->mid_point[0] = p[0]; out->mid_point[1] = p[1]; out->mid_point[2] = p[2];
+        out->_pad = 0;
+        out->rotation[0] = out->rotation[1] = out->rotation[2] = 0.0;
+        out->bounding_box[0] = out->bounding_box[1] = out->bounding_box[2] = out->bounding_box[3] = 0;
+    }
+}
+
 // ================================================================ Biwi run-length decode
 // read_depth (biwi.rs:81-103): [u32 w][u32 h] then, until w*h pixels are covered,
 // [u32 n_empty][u32 n_full][n_full x u16].  The position of a run header depends on every header
@@ -2255,6 +2386,21 @@ void launch_hough_image(const FrameBuffers& b, const Geometry& g, const ForestDe
     hough_image_kernel<<<(n + 255) / 256, 256, 0, s>>>(b, g, f, acc32);
     const uint32_t px = g.w * g.h;
     narrow_u16_kernel<<<(px + 255) / 256, 256, 0, s>>>(acc32, out16, px);
+}
+
+// gaussian blur of a w x h u16 image: in -> tmp (horizontal) -> out (vertical); k: 2 * radius + 1 taps on the device
+int launch_gaussian_blur(const uint16_t* in, uint16_t* tmp, uint16_t* out, uint32_t w, uint32_t h, const float* k, int radius, cudaStream_t s) {
+    const uint32_t smem_h = (uint32_t)(kBlurHy * (kBlurHx + 2 * radius)) * 2u, smem_v = (uint32_t)((kBlurVy + 2 * radius) * kBlurVx) * 2u;
+    static SmemConfig ch, cv;
+    if (ch.raise(smem_h)) cudaFuncSetAttribute(blur_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
+    if (cv.raise(smem_v)) cudaFuncSetAttribute(blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
+    blur_h_kernel<<<dim3((w + kBlurHx - 1) / kBlurHx, (h + kBlurHy - 1) / kBlurHy), dim3(kBlurHx, kBlurHy), smem_h, s>>>(in, tmp, w, h, k, radius);
+    blur_v_kernel<<<dim3((w + kBlurVx - 1) / kBlurVx, (h + kBlurVy - 1) / kBlurVy), dim3(kBlurVx, kBlurVy), smem_v, s>>>(tmp, out, w, h, k, radius);
+    return 2;
+}
+void launch_hough2d_argmax(const uint16_t* hough, const uint16_t* depth, uint32_t w, uint32_t h, const Geometry& g, dh_result* out,
+                           cudaStream_t s) {
+    hough2d_argmax_kernel<<<1, 1024, 0, s>>>(hough, depth, w, h, g, out);
 }
 
 void launch_counters(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, unsigned long long* out,

@@ -15,6 +15,8 @@
  *   src/hough/prediction.rs:259-267   struct PredictionResult                  -> dh_result
  *   src/hough/prediction.rs:850-905   predict_mask                             -> dh_predict_mask
  *   src/hough/prediction.rs:760-841   build_hough_image (votes, before blur)   -> dh_hough_image_raw
+ *   src/hough/prediction.rs:760-845   build_hough_image (with its blur)        -> dh_build_hough_image
+ *   src/hough/prediction.rs:343-367   predict_parameter_from2dhough            -> dh_predict_from2dhough
  *   src/db_reader/biwi.rs:81-103      read_depth (run-length coded depth file)  -> dh_biwi_depth_dims,
  *                                                                                 dh_biwi_decode_depth, dh_predict_batch_biwi
  *   src/db_reader/biwi.rs:27-60       read_cal (depth.cal -> IntrinsicMatrix)   -> dh_biwi_parse_cal
@@ -144,6 +146,18 @@ int dh_predict_mask(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32
 /* build_hough_image before its gaussian blur (prediction.rs:760-841): votes[h][w] u16 to host. */
 int dh_hough_image_raw(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h,
                        const float K[9], uint16_t* votes);
+
+/* build_hough_image (prediction.rs:760-845): the vote image blurred with the model's gaussian_sigma
+ * (imageproc::gaussian_blur_f32, an external crate: its kernel — radius ceil(2 sigma), unnormalised
+ * pdf taps —, edge-clamped borders and u16 truncation after each of the two passes are restated
+ * from its published source): hough[h][w] u16 to host. */
+int dh_build_hough_image(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+                         uint16_t* hough);
+/* predict_parameter_from2dhough (prediction.rs:343-367): arg-max of that image (the LAST of equal
+ * maxima, as Iterator::max_by_key), z = depth at the pixel, mid_point = back-projection; rotation and
+ * bounding box are 0. */
+int dh_predict_from2dhough(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
+                           dh_result* out);
 
 /* ------------------------------------------------------------------ Biwi Kinect Head Pose wire formats */
 /* read_depth (biwi.rs:81-103): u32 width, u32 height, then until width*height pixels are covered

@@ -101,6 +101,14 @@ def lib():
     L.orc_train_impurity_from_stats.argtypes = [vp, u64, f64, vp]
     L.orc_train_early_stop.restype = C.c_int
     L.orc_train_early_stop.argtypes = [vp, vp, u64, u64, u64, u64]
+    L.orc_gaussian_kernel_f32.restype = C.c_int
+    L.orc_gaussian_kernel_f32.argtypes = [C.c_float, vp, u32]
+    L.orc_gaussian_blur_u16.restype = None
+    L.orc_gaussian_blur_u16.argtypes = [vp, u32, u32, C.c_float, vp]
+    L.orc_build_hough_image.restype = C.c_int
+    L.orc_build_hough_image.argtypes = [vp, u32, u32, u32, C.c_float, vp, u32, u32, vp, C.c_int, vp]
+    L.orc_predict_from2dhough.restype = C.c_int
+    L.orc_predict_from2dhough.argtypes = [vp, u32, u32, u32, C.c_float, vp, u32, u32, vp, C.c_int, vp, vp]
     L.orc_biwi_read_depth.restype = C.c_int
     L.orc_biwi_read_depth.argtypes = [vp, u64, vp, u64, vp, vp]
     L.orc_biwi_read_gt.restype = C.c_int
@@ -316,10 +324,51 @@ class OracleForest:
             raise RuntimeError("oracle hough_image_raw rc=%d" % rc)
         return out
 
+    def build_hough_image(self, depth: np.ndarray, K, mode=MODE_SAT) -> np.ndarray:
+        """build_hough_image (prediction.rs:760-845) including its gaussian blur (imageproc: unpinned)"""
+        depth = np.ascontiguousarray(depth, np.uint16)
+        h, w = depth.shape
+        K = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
+        out = np.zeros((h, w), np.uint16)
+        rc = lib().orc_build_hough_image(self._h, self.stepwidth, self.subimage_width, self.subimage_height,
+                                         self.gaussian_sigma, _p(depth), w, h, _p(K), int(mode), _p(out))
+        if rc != 0:
+            raise RuntimeError("oracle build_hough_image rc=%d" % rc)
+        return out
+
+    def predict_parameter_from2dhough(self, depth: np.ndarray, K, mode=MODE_SAT):
+        """prediction.rs:343-367 -> (mid_point[3] f32, (x, y) of the winning pixel)"""
+        depth = np.ascontiguousarray(depth, np.uint16)
+        h, w = depth.shape
+        K = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
+        mid = np.zeros(3, np.float32)
+        xy = np.zeros(2, np.uint32)
+        rc = lib().orc_predict_from2dhough(self._h, self.stepwidth, self.subimage_width, self.subimage_height,
+                                           self.gaussian_sigma, _p(depth), w, h, _p(K), int(mode), _p(mid), _p(xy))
+        if rc != 0:
+            raise RuntimeError("oracle predict_parameter_from2dhough rc=%d" % rc)
+        return mid, (int(xy[0]), int(xy[1]))
+
     def leaf_static(self, leaf: int):
         v, tr, to = C.c_uint32(), C.c_double(), C.c_float()
         lib().orc_leaf_static(self._h, int(leaf), C.addressof(v), C.addressof(tr), C.addressof(to))
         return v.value, tr.value, to.value
+
+
+def gaussian_kernel_f32(sigma: float) -> np.ndarray:
+    """imageproc's gaussian_kernel_f32 as restated in the oracle (unpinned, see depthhead_oracle.cpp)"""
+    n = lib().orc_gaussian_kernel_f32(float(sigma), None, 0)
+    out = np.zeros(n, np.float32)
+    lib().orc_gaussian_kernel_f32(float(sigma), _p(out), n)
+    return out
+
+
+def gaussian_blur_u16(img: np.ndarray, sigma: float) -> np.ndarray:
+    a = np.ascontiguousarray(img, np.uint16)
+    h, w = a.shape
+    out = np.zeros((h, w), np.uint16)
+    lib().orc_gaussian_blur_u16(_p(a), w, h, float(sigma), _p(out))
+    return out
 
 
 def num_threads() -> int:

@@ -996,6 +996,105 @@ int orc_hough_image_raw(const orc_forest* forest, uint32_t stepwidth, uint32_t s
     return hough_image_raw(forest->f, prm, img, intr, mode, out);
 }
 
+// ---- build_hough_image's blur and predict_parameter_from2dhough (prediction.rs:343-367, 841-845)
+// PARITY UNPINNED: gaussian_blur_f32 lives in the external crate imageproc 0.12 (Cargo.toml:26), whose
+// source is not under /root/reference.  Restated here from its published implementation
+// (imageproc/src/filter.rs: gaussian_blur_f32 -> gaussian_kernel_f32 -> separable_filter_equal ->
+// horizontal_filter, vertical_filter; definitions.rs: Clamp<f32> for u16):
+//   * kernel: radius = ceil(2 * sigma) taps on either side, k[r +- i] = gaussian(i as f32, sigma) with
+//     gaussian(x, r) = (sqrt(2 pi) * r).recip() * exp(-x^2 / (2 r^2)), all f32, NOT normalised;
+//   * horizontal pass over the u16 image, then vertical pass over ITS u16 result; per output pixel
+//     acc = 0.0f32; for the taps in order: acc = acc + (pixel as f32) * k[i] (never fused);
+//   * border rule: the coordinate is clamped to the image (edge pixels repeat);
+//   * every pass stores Clamp<f32>::clamp(acc) as u16: >= 65535 -> 65535, <= 0 -> 0, else truncation.
+static inline float gaussian_pdf_f32(float x, float r) {
+    const float two_pi = 2.0f * 3.14159265358979323846264338327950288f;  // 2.0 * f32::consts::PI
+    const float norm = 1.0f / (std::sqrt(two_pi) * r);                      // .recip()
+    const float r2 = r * r, x2 = x * x;                                     // powi(2)
+    return norm * std::exp(-x2 / (2.0f * r2));
+}
+static std::vector<float> gaussian_kernel_f32(float sigma) {
+    const size_t radius = (size_t)std::ceil(2.0f * sigma);
+    std::vector<float> k(2 * radius + 1, 0.0f);
+    for (size_t i = 0; i <= radius; ++i) {
+        const float v = gaussian_pdf_f32((float)i, sigma);
+        k[radius + i] = v;
+        k[radius - i] = v;
+    }
+    return k;
+}
+static inline uint16_t clamp_f32_to_u16(float x) {
+    if (x < 65535.0f) return x > 0.0f ? (uint16_t)x : (uint16_t)0;
+    return 65535;  // also NaN, as the comparison chain of the crate does
+}
+static void gaussian_blur_u16(const uint16_t* in, uint32_t w, uint32_t h, float sigma, uint16_t* out) {
+    const std::vector<float> k = gaussian_kernel_f32(sigma);
+    const int kw = (int)k.size(), half = kw / 2;
+    std::vector<uint16_t> tmp((size_t)w * h);
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            float acc = 0.0f;
+            for (int i = 0; i < kw; ++i) {
+                const int xu = (int)x + i - half;
+                const uint32_t xp = (uint32_t)std::min<int>(std::max(xu, 0), (int)w - 1);
+                acc = acc + (float)in[(size_t)y * w + xp] * k[(size_t)i];
+            }
+            tmp[(size_t)y * w + x] = clamp_f32_to_u16(acc);
+        }
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            float acc = 0.0f;
+            for (int i = 0; i < kw; ++i) {
+                const int yu = (int)y + i - half;
+                const uint32_t yp = (uint32_t)std::min<int>(std::max(yu, 0), (int)h - 1);
+                acc = acc + (float)tmp[(size_t)yp * w + x] * k[(size_t)i];
+            }
+            out[(size_t)y * w + x] = clamp_f32_to_u16(acc);
+        }
+}
+int orc_gaussian_kernel_f32(float sigma, float* out, uint32_t cap) {
+    const std::vector<float> k = gaussian_kernel_f32(sigma);
+    if (out && cap >= k.size()) std::memcpy(out, k.data(), k.size() * sizeof(float));
+    return (int)k.size();
+}
+void orc_gaussian_blur_u16(const uint16_t* in, uint32_t w, uint32_t h, float sigma, uint16_t* out) {
+    gaussian_blur_u16(in, w, h, sigma, out);
+}
+// build_hough_image (prediction.rs:760-845): the vote image, then the blur with gaussian_sigma
+int orc_build_hough_image(const orc_forest* forest, uint32_t stepwidth, uint32_t sub_w, uint32_t sub_h, float sigma,
+                          const uint16_t* depth, uint32_t w, uint32_t h, const float* K, int mode, uint16_t* out) {
+    std::vector<uint16_t> raw((size_t)w * h);
+    const int rc = orc_hough_image_raw(forest, stepwidth, sub_w, sub_h, depth, w, h, K, mode, raw.data());
+    if (rc) return rc;
+    if (!(sigma > 0.0f)) return 7;  // the crate asserts sigma > 0.0
+    gaussian_blur_u16(raw.data(), w, h, sigma, out);
+    return 0;
+}
+// predict_parameter_from2dhough (prediction.rs:343-367): arg-max of the blurred vote image with
+// Iterator::max_by_key (the LAST of equal maxima wins), z = the depth at that pixel,
+// mid_point = img_to_space_coord([x, y], z), rotation 0
+int orc_predict_from2dhough(const orc_forest* forest, uint32_t stepwidth, uint32_t sub_w, uint32_t sub_h, float sigma,
+                            const uint16_t* depth, uint32_t w, uint32_t h, const float* K, int mode, float* mid_point,
+                            uint32_t* best_xy) {
+    if ((uint64_t)w * h == 0) return 8;  // max_by_key on an empty range: unwrap of None
+    std::vector<uint16_t> img((size_t)w * h);
+    const int rc = orc_build_hough_image(forest, stepwidth, sub_w, sub_h, sigma, depth, w, h, K, mode, img.data());
+    if (rc) return rc;
+    size_t best = 0;
+    for (size_t i = 1; i < img.size(); ++i)
+        if (img[i] >= img[best]) best = i;
+    const uint32_t x = (uint32_t)(best % w), y = (uint32_t)(best / w);
+    Intrinsic m;
+    std::memcpy(m.k, K, sizeof(float) * 9);
+    const float xy[2] = {(float)x, (float)y};
+    img_to_space_coord(m, xy, (float)depth[(size_t)y * w + x], mid_point);
+    if (best_xy) {
+        best_xy[0] = x;
+        best_xy[1] = y;
+    }
+    return 0;
+}
+
 // ---- small pieces exposed for the known-answer tests (reference unit tests)
 void orc_rect_scale_and_replace(const uint32_t* xywh, double scale, double rx, double ry, uint32_t* out_xywh) {
     Rect r = rect_new(xywh[0], xywh[1], xywh[2], xywh[3]);

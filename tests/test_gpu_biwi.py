@@ -187,7 +187,7 @@ def test_predict_batch_host_frames_through_the_run_length_rewrite(monkeypatch, e
     frames = synth.make_frames(44, seed=77)
     rng = np.random.default_rng(5)
     frames[3] = 0                                                       # all background
-    frames[9] = rng.integers(1, 4000, frames[9].shape).astype(np.uint16)  # no background: the file is LARGER than the frame
+    frames[8] = rng.integers(1, 4000, frames[8].shape).astype(np.uint16)  # no background: the file is LARGER than the frame
     frames[17, ::2, ::3] = 0                                            # salt and pepper
     frames[40:] = rng.integers(0, 3, frames[40:].shape).astype(np.uint16) * 900   # a dense last chunk
     hp = HoughPrediction.from_arrays(arr, stepwidth=8)

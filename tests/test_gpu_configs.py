@@ -49,13 +49,13 @@ VARIANTS = [
     {"DH_TRAV_THREADS": "512"},                     # 512-thread traversal tiles
     {"DH_TRAV_ILP": "2", "DH_TRAV_THREADS": "768"}, # two walks in flight per thread, 768-thread tiles
     {"DH_GATE_FUSED": "0"},                         # seed grids: one pass over the votes per grid instead of one for both
-    {"DH_TRAV_BLOCK": "1"},                         # a warp walks a block of 8 x 4 patches instead of a row of 32 (experimental)
-    {"DH_TRAV_BLOCK": "1", "DH_BOX_IMAGE": "0"},
-    {"DH_TRAV_TMA_FIRST": "1"},                     # the tile's TMA load is issued before its background check
-    {"DH_TRAV_TMA_FIRST": "1", "DH_BOX_IMAGE": "0"},
-    {"DH_TRAV_TMA_FIRST": "1", "DH_TRAV_BLOCK": "1"},
+    {"DH_TRAV_BLOCK": "0"},                         # a warp walks a row of 32 patches instead of a block of 8 x 4
+    {"DH_TRAV_BLOCK": "0", "DH_BOX_IMAGE": "0"},
+    {"DH_TRAV_TMA_FIRST": "0"},                     # the tile's TMA load is issued after its background check
+    {"DH_TRAV_TMA_FIRST": "0", "DH_BOX_IMAGE": "0"},
+    {"DH_TRAV_TMA_FIRST": "0", "DH_TRAV_BLOCK": "0"},
     {"DH_TRAV_PAIR": "1"},                          # two tree levels per 32-byte record
-    {"DH_TRAV_PAIR": "1", "DH_TRAV_THREADS": "768", "DH_TRAV_TMA_FIRST": "1"},
+    {"DH_TRAV_PAIR": "1", "DH_TRAV_THREADS": "768", "DH_TRAV_TMA_FIRST": "0"},
     {"DH_CUBE_CLEAR_FUSED": "0"},                   # one memset of all accumulator cubes per pass instead of the clear behind mean-shift
     {"DH_LANES": "1"},
     {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},

@@ -269,6 +269,46 @@ def test_predict_mask_and_hough_image(ctx, small_case):
     assert np.array_equal(hp.predict_mask(frames[2], ctx=ctx), of.predict_mask(frames[2]))
 
 
+def test_build_hough_image_and_from2dhough(ctx, small_case):
+    """build_hough_image with its gaussian blur and predict_parameter_from2dhough
+    (prediction.rs:343-367, 760-845) against the oracle, on the image shapes of the box-image test;
+    the blur alone on images that exercise the clamped borders, saturation and the arg-max tie rule"""
+    arr, js, frames = small_case
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    for d in frames[:2]:
+        got = hp.build_hough_image(d, K, ctx=ctx)
+        assert np.array_equal(got, of.build_hough_image(d, synth.KINECT_K))
+        res = hp.predict_parameter_from2dhough(d, K, ctx=ctx)
+        mid, xy = of.predict_parameter_from2dhough(d, synth.KINECT_K)
+        assert np.array_equal(res.mid_point.view(np.uint32), mid.view(np.uint32)) and np.all(res.rotation == 0.0)
+        assert res.bounding_box == (0, 0, 0, 0)
+    # an empty frame: the vote image is all zero, max_by_key returns the LAST pixel
+    z = np.zeros((480, 640), np.uint16)
+    res = hp.predict_parameter_from2dhough(z, K, ctx=ctx)
+    mid, xy = of.predict_parameter_from2dhough(z, synth.KINECT_K)
+    assert xy == (639, 479) and np.array_equal(res.mid_point, mid)
+    # other sigmas (kernel radius ceil(2 sigma)) and other shapes
+    for sigma, (sub, scale, stride, hw) in zip((1.5, 3.0, 0.4, 11.0, 8.0), [((80, 80), 0.3, 5, (480, 640)), ((80, 80), 0.3, 7, (203, 331)),
+                                                                              ((64, 48), 0.5, 4, (150, 296)), ((40, 56), 0.13, 3, (97, 120)),
+                                                                              ((96, 96), 0.9, 9, (200, 264))]):
+        a2 = synth.make_forest(seed=17, n_trees=3, max_depth=6, sub_w=sub[0], sub_h=sub[1], rect_scale=scale)
+        js2 = synth.forest_to_json(a2, stepwidth=stride)
+        hp2 = HoughPrediction.from_json(js2)
+        of2 = oracle.OracleForest.from_json(js2)
+        hp2.update_sigma(sigma)
+        of2.update_sigma(sigma)
+        full = synth.make_frames(2, seed=5)
+        y0, x0 = (480 - hw[0]) // 2, (640 - hw[1]) // 2
+        for d in np.ascontiguousarray(full[:, y0:y0 + hw[0], x0:x0 + hw[1]]):
+            got = hp2.build_hough_image(d, K, ctx=ctx)
+            want = of2.build_hough_image(d, synth.KINECT_K)
+            assert np.array_equal(got, want), (sigma, hw, int(np.sum(got != want)))
+            res = hp2.predict_parameter_from2dhough(d, K, ctx=ctx)
+            mid, _ = of2.predict_parameter_from2dhough(d, synth.KINECT_K)
+            assert np.array_equal(res.mid_point.view(np.uint32), mid.view(np.uint32))
+
+
 def test_shape_errors(ctx, small_case):
     arr, js, frames = small_case
     hp = HoughPrediction.from_json(js)

@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(kThreads, 2) gather_kernel(Args a) {
 // tile: every warp-wide load hits random banks, ~3.5 wavefronts).  kTex: a chase through a node
 // table small enough to stay in L1 (8 KB, random 16-byte fetches: texture wavefronts without
 // misses).  Both together show whether the two pipes share the data stage.
-template <bool kLds, bool kTex>
+// kSplit: even warps run only the shared-memory chases, odd warps only the texture chases, so each
+// pipe gets its own independent instruction streams (in the combined variant above one loop
+// iteration issues both and the slower pipe paces the other).
+template <bool kLds, bool kTex, bool kSplit = false>
 __global__ void __launch_bounds__(kThreads, 2) chase_kernel(Args a, uint32_t small_nodes) {
     extern __shared__ __align__(16) uint32_t tile[];
     const uint32_t tid = threadIdx.x;
@@ -198,6 +201,19 @@ __global__ void __launch_bounds__(kThreads, 2) chase_kernel(Args a, uint32_t sma
     uint32_t p0 = (mix(tid * 31u + blockIdx.x) % kTileWords) << 2, p1 = (mix(tid * 57u + 7u) % kTileWords) << 2;
     uint32_t q0 = mix(tid * 3u + blockIdx.x) % small_nodes, q1 = mix(tid * 5u + 11u) % small_nodes;
     const long long t0 = clock64();
+    if (kSplit) {
+        if ((tid >> 5) & 1u) {
+            for (uint32_t s = 0; s < a.steps; ++s) {
+                q0 = tex1Dfetch<uint4>(a.tex16, (int)q0).y;
+                q1 = tex1Dfetch<uint4>(a.tex16, (int)q1).y;
+            }
+        } else {
+            for (uint32_t s = 0; s < a.steps * 4u; ++s) {  // the shared-memory chase is ~4x faster per step: keep both halves busy to the end
+                p0 = lds(tile_a + p0);
+                p1 = lds(tile_a + p1);
+            }
+        }
+    } else
     for (uint32_t s = 0; s < a.steps; ++s) {
         if (kLds) {
             p0 = lds(tile_a + p0);
@@ -213,25 +229,25 @@ __global__ void __launch_bounds__(kThreads, 2) chase_kernel(Args a, uint32_t sma
     if (tid == 0) a.cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
 }
 
-template <bool kLds, bool kTex>
+template <bool kLds, bool kTex, bool kSplit = false>
 static void run_chase(const char* name, Args a, int n_sms, uint32_t steps, uint32_t small_nodes) {
     const size_t smem = (size_t)kTileWords * 4;
-    CK(cudaFuncSetAttribute(chase_kernel<kLds, kTex>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(chase_kernel<kLds, kTex, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = n_sms * 2;
     a.steps = steps;
     std::vector<unsigned long long> cyc(grid);
     unsigned long long best = ~0ull;
     for (int rep = 0; rep < 3; ++rep) {
-        chase_kernel<kLds, kTex><<<grid, kThreads, smem>>>(a, small_nodes);
+        chase_kernel<kLds, kTex, kSplit><<<grid, kThreads, smem>>>(a, small_nodes);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(cyc.data(), a.cycles, sizeof(unsigned long long) * grid, cudaMemcpyDeviceToHost));
         const unsigned long long mx = *std::max_element(cyc.begin(), cyc.end());
         if (rep && mx < best) best = mx;
     }
-    const double per_sm = 2.0 * kThreads * 2.0 * steps;  // loads of each kind per SM
+    const double per_sm = 2.0 * kThreads * 2.0 * steps * (kSplit ? 0.5 : 1.0);  // loads of each kind per SM (split: half the warps each; LDS x4 below)
     printf("{\"variant\": \"%s\", \"pattern\": \"chase\", \"steps\": %u, \"cycles\": %llu, \"lds_thread_loads_per_cycle_per_sm\": %.3f, "
            "\"tex_thread_fetches_per_cycle_per_sm\": %.3f}\n",
-           name, steps, best, kLds ? per_sm / (double)best : 0.0, kTex ? per_sm / (double)best : 0.0);
+           name, steps, best, kLds ? per_sm * (kSplit ? 4.0 : 1.0) / (double)best : 0.0, kTex ? per_sm / (double)best : 0.0);
     fflush(stdout);
 }
 
@@ -366,6 +382,7 @@ int main(int argc, char** argv) {
         run_chase<true, false>("chase_lds", a, n_sms, steps, 512);
         run_chase<false, true>("chase_tex16_l1", a, n_sms, steps, 512);
         run_chase<true, true>("chase_lds_tex16_l1", a, n_sms, steps, 512);
+        run_chase<true, true, true>("chase_split_lds_tex16_l1", a, n_sms, steps, 512);
         CK(cudaMemcpy(d16, h16.data(), sizeof(uint4) * kNodes, cudaMemcpyHostToDevice));
     }
     if (argc > 4 && atoi(argv[4]) == 0) return 0;  // chases only
