@@ -499,7 +499,6 @@ def main():
                   "host_generation_seconds": t_seq, "results_sha1": sha,
                   "note": "device-resident frames, CUDA events on the launching stream, barrier on both sides, max over ranks; "
                           "results_sha1 covers all %d poses in frame order and is the same for every N" % args.seq_frames}
-        del seq_dev
 
     # the reference's live use (examples/live_prediction.rs:76,86): ONE frame per call, host buffer in,
     # result out, previous result as the next seed — wall-clock latency of dh_predict
@@ -569,6 +568,29 @@ def main():
             del arr_g
         except Exception as e:  # noqa: BLE001
             extra["general_rect_forest"] = {"error": repr(e)[:300]}
+
+    # ---- seeded sequences (the reference's live use, batched): 24 sequences x 625 frames, every frame
+    #      seeded with the pose of the frame before it (examples/live_prediction.rs:75-88)
+    if world == 1 and seq is not None and len(seq) >= 24 * 625:
+        try:
+            sq = seq_dev[:24 * 625]
+            hp.predict_sequences(None, K, 500.0, ctx=ctx, device_ptr=sq.data_ptr(), n_seq=24, frames_per_seq=625, w=W, h=H)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            o_seq = hp.predict_sequences(None, K, 500.0, ctx=ctx, device_ptr=sq.data_ptr(), n_seq=24, frames_per_seq=625, w=W, h=H)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms_sq = e0.elapsed_time(e1)
+            extra["seeded_sequences"] = {
+                "workload": "the 15 000-frame Biwi-shaped sequence as 24 sessions x 625 frames: frame t of every session in one pass, "
+                            "seeded on the device with the pose of frame t - 1 (centre seed if z > 500 mm), device-resident",
+                "value": 24 * 625 / (ms_sq / 1000.0), "unit": "frames/s", "ms": ms_sq, "passes": 625, "frames_per_pass": 24,
+                "launches": int(ctx.counters()["launches"]),
+                "seeded_equals_unseeded_share": float(np.mean(np.all(o_seq.reshape(-1)["mid_point"] == out_seq[:24 * 625]["mid_point"], axis=1)))
+                if strong is not None and world == 1 else None}
+        except Exception as e:  # noqa: BLE001
+            extra["seeded_sequences"] = {"error": repr(e)[:300]}
 
     total_frames = n * world * args.steps
     value = total_frames / (ms_dev / 1000.0)

@@ -332,6 +332,28 @@ class HoughPrediction:
                                                 capi.ptr(out)))
         return out
 
+    def predict_sequences(self, frames, intrinsic: IntrinsicMatrix, min_seed_z: float = 500.0, ctx: Context | None = None,
+                          device_ptr: int | None = None, n_seq: int | None = None, frames_per_seq: int | None = None,
+                          w: int | None = None, h: int | None = None) -> np.ndarray:
+        """n_seq independent sequences, every frame seeded with the pose of the frame before it as
+        examples/live_prediction.rs:75-88 does (centre seed only if the previous z > min_seed_z).
+        `frames`: [n_seq, frames_per_seq, h, w] uint16 on the host, or device_ptr + the four sizes.
+        Returns capi.RESULT_DTYPE[n_seq, frames_per_seq]."""
+        ctx = ctx or default_context()
+        if device_ptr is None:
+            a = np.asarray(frames)
+            if a.dtype != np.uint16 or a.ndim != 4:
+                raise ValueError("frames must be [n_seq, frames_per_seq, h, w] uint16")
+            a = np.ascontiguousarray(a)
+            n_seq, frames_per_seq, h, w = a.shape
+            p, loc = capi.ptr(a), capi.DH_DEPTH_HOST
+        else:
+            p, loc = C.c_void_p(int(device_ptr)), capi.DH_DEPTH_DEVICE
+        out = np.zeros((int(n_seq), int(frames_per_seq)), capi.RESULT_DTYPE)
+        capi.check(capi.load().dh_predict_sequences(ctx._h, self._h, p, int(n_seq), int(frames_per_seq), int(w), int(h),
+                                                    intrinsic._ptr(), loc, float(min_seed_z), capi.ptr(out)))
+        return out
+
     def predict_mask(self, img, ctx: Context | None = None) -> np.ndarray:
         """prediction.rs:850-905."""
         ctx = ctx or default_context()

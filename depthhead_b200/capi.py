@@ -107,6 +107,7 @@ SIGNATURES = {
     "dh_train_learn": (C.c_int, [_vp, C.POINTER(dh_train_params), _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "dh_forest_to_json": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dh_predict_mask": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp]),
+    "dh_predict_sequences": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _vp, C.c_int, _f32, _vp]),
     "dh_hough_image_raw": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "dh_build_hough_image": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "dh_predict_from2dhough": (C.c_int, [_vp, _vp, _vp, _u32, _u32, _vp, C.POINTER(dh_result)]),

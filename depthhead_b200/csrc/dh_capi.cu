@@ -358,6 +358,14 @@ int dh_hough_image_raw(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uin
     });
 }
 
+int dh_predict_sequences(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t n_seq, uint32_t frames_per_seq,
+                         uint32_t w, uint32_t h, const float K[9], int depth_loc, float min_seed_z, dh_result* out) {
+    return guarded([&] {
+        REQUIRE(c && f && K && ((uint64_t)n_seq * frames_per_seq == 0 || (depth && out)), "dh_predict_sequences: NULL argument");
+        REQUIRE(depth_loc == DH_DEPTH_HOST || depth_loc == DH_DEPTH_DEVICE, "dh_predict_sequences: bad depth_loc");
+        c->cx->predict_sequences(*f->hf, depth, n_seq, frames_per_seq, w, h, K, depth_loc, min_seed_z, out);
+    });
+}
 int dh_build_hough_image(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, const float K[9],
                          uint16_t* hough) {
     return guarded([&] {

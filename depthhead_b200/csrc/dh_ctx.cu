@@ -609,7 +609,8 @@ void Context::mark(int stage_begin_of) {
 
 // ------------------------------------------------------------------------------------------------ one pass
 // Front end shared by every entry point: SAT + traversal (+ zeroed per-frame state).
-void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameState* guess_state) {
+void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameState* guess_state, const dh_result* prev_results,
+                        float min_seed_z) {
     const Geometry& g = geom_;
     cudaStream_t st = L.stream;
     DH_CUDA(cudaMemsetAsync(L.fs, 0, sizeof(FrameState) * n, st));
@@ -617,6 +618,10 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
     if (guess_state) {
         *h_fs_ = *guess_state;
         DH_CUDA(cudaMemcpyAsync(L.fs, h_fs_, sizeof(FrameState), cudaMemcpyHostToDevice, st));
+    }
+    if (prev_results) {  // seeded sequences: the seeds of this pass are the poses of the previous one, on the device
+        launch_seq_guess(L.fs, prev_results, n, min_seed_z, st);
+        launches_ += 1;
     }
     if (g.P && hot_tw_ != tiles_.tw) {  // node table for this tile plan (once per forest x plan)
         launch_plan_nodes(df_nodes_, df_hot_, df_uni_, df_n_nodes_, tiles_.tw, stream_);
@@ -1212,6 +1217,73 @@ void Context::run_batch_encoded(const HostForest& hf, const uint16_t* depth, uin
             if (h_status_[i]) throw ModelError(DH_E_STATE, "internal error: frame " + std::to_string(i) + " did not survive the compressed host->device path");
     }
     std::memcpy(out, h_results_, sizeof(dh_result) * n);
+}
+
+// ------------------------------------------------------------------------------------------------ seeded sequences
+// The reference's real use (examples/live_prediction.rs:75-88) predicts a SEQUENCE: every frame is
+// seeded with the pose of the frame before it, which makes a sequence sequential — but separate
+// sequences stay independent.  Frame t of all n_seq sequences goes through the pipeline as one
+// pass of n_seq frames (gathered out of the sequence-major input by one strided copy), the seeds
+// of pass t are written on the device from the results of pass t - 1, and nothing returns to the
+// host before the last pass.  Results in the input's order: out[s * frames_per_seq + t].
+void Context::predict_sequences(const HostForest& hf, const uint16_t* depth, uint32_t n_seq, uint32_t frames_per_seq, uint32_t w, uint32_t h,
+                                const float K[9], int depth_loc, float min_seed_z, dh_result* out) {
+    begin_call();
+    have_debug_ = false;
+    last_encoded_chunks_ = 0;
+    last_h2d_bytes_ = 0;
+    const size_t total = (size_t)n_seq * frames_per_seq;
+    if (total == 0) {
+        end_call();
+        return;
+    }
+    if (total > 0x7fffffffull) throw ModelError(DH_E_ARG, "dh_predict_sequences: more than 2^31 frames");
+    ensure_forest(hf);
+    const uint32_t want = chunk_frames_ ? std::min(chunk_frames_, n_seq) : std::min<uint32_t>(n_seq, 512u);
+    ensure_scratch(hf, w, h, want, K, 1);
+    ensure_staging(2);
+    const uint32_t iterations = hf.meanshift_iterations.load();
+    const uint32_t F = call_chunk_;  // sequences per group
+    const size_t px = (size_t)w * h;
+    const cudaMemcpyKind kind = depth_loc == DH_DEPTH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    dh_result* d_all = nullptr;  // [frames_per_seq][group] poses of the current group, pass-major
+    dev_alloc(d_all, (size_t)frames_per_seq * F);
+    std::vector<dh_result> host_all((size_t)frames_per_seq * F);
+    Lane& L = lanes_[0];
+    try {
+        DH_CUDA(cudaEventRecord(ev_fork_, stream_));
+        DH_CUDA(cudaStreamWaitEvent(copy_stream_, ev_fork_, 0));
+        for (uint32_t g0 = 0; g0 < n_seq; g0 += F) {
+            const uint32_t ns = std::min<uint32_t>(F, n_seq - g0);
+            for (uint32_t t = 0; t < frames_per_seq; ++t) {
+                const int slot = (int)(t & 1u);
+                // frame t of sequences g0 .. g0 + ns - 1: rows of one strided copy (row = a frame, pitch = a sequence)
+                if (t >= 2 || g0) DH_CUDA(cudaStreamWaitEvent(copy_stream_, ev_consumed_[slot], 0));
+                DH_CUDA(cudaMemcpy2DAsync(d_depth_[slot], px * sizeof(uint16_t), depth + ((size_t)g0 * frames_per_seq + t) * px,
+                                          (size_t)frames_per_seq * px * sizeof(uint16_t), px * sizeof(uint16_t), ns, kind, copy_stream_));
+                if (depth_loc != DH_DEPTH_DEVICE) last_h2d_bytes_ += (uint64_t)ns * px * sizeof(uint16_t);
+                DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
+                DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
+                FrameBuffers b = buffers(L, d_depth_[slot]);
+                run_front(L, b, ns, nullptr, t ? L.results : nullptr, min_seed_z);
+                run_back(L, b, ns, iterations);
+                DH_CUDA(cudaMemcpyAsync(d_all + (size_t)t * F, L.results, sizeof(dh_result) * ns, cudaMemcpyDeviceToDevice, L.stream));
+                DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
+            }
+            DH_CUDA(cudaMemcpyAsync(host_all.data(), d_all, sizeof(dh_result) * (size_t)frames_per_seq * F, cudaMemcpyDeviceToHost, L.stream));
+            DH_CUDA(cudaStreamSynchronize(L.stream));
+            for (uint32_t s2 = 0; s2 < ns; ++s2)
+                for (uint32_t t = 0; t < frames_per_seq; ++t) out[((size_t)g0 + s2) * frames_per_seq + t] = host_all[(size_t)t * F + s2];
+        }
+    } catch (...) {
+        cudaStreamSynchronize(copy_stream_);
+        cudaStreamSynchronize(stream_);
+        dev_free(d_all);
+        throw;
+    }
+    dev_free(d_all);
+    mark(-1);
+    end_call();
 }
 
 void Context::predict_mask(const HostForest& hf, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask) {

@@ -76,6 +76,10 @@ public:
                  const float* midp_guess, const double* rot_guess, dh_result* out);
     void predict_batch(const HostForest& hf, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h,
                        const float K[9], int depth_loc, dh_result* out);
+    // n_seq independent sequences of frames_per_seq frames (sequence-major): frame t of every sequence in one pass,
+    // seeded with the pose of frame t - 1 (examples/live_prediction.rs:75-88)
+    void predict_sequences(const HostForest& hf, const uint16_t* depth, uint32_t n_seq, uint32_t frames_per_seq, uint32_t w, uint32_t h,
+                           const float K[9], int depth_loc, float min_seed_z, dh_result* out);
     // Biwi run-length coded frames (biwi.rs:81-103): blob/offsets in host memory, see depthhead_cuda.h
     void biwi_decode(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w, uint32_t h, uint16_t* out, int out_loc);
     void predict_batch_biwi(const HostForest& hf, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t w, uint32_t h,
@@ -127,7 +131,8 @@ private:
     void free_scratch();
     TilePlan plan_tiles(const Geometry& g) const;
     FrameBuffers buffers(const Lane& L, const uint16_t* depth) const;
-    void run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameState* guess_state);
+    void run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameState* guess_state, const dh_result* prev_results = nullptr,
+                   float min_seed_z = 0.0f);
     void run_back(Lane& L, const FrameBuffers& b, uint32_t n, uint32_t iterations);
     void begin_call();
     void end_call();

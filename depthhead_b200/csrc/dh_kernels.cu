@@ -2125,6 +2125,29 @@ __global__ void box_dump_kernel(FrameBuffers b, uint32_t frame, int which, int32
     }
 }
 
+// ================================================================ seeded sequences
+// examples/live_prediction.rs:75-88: frame t of a sequence is predicted with the pose of frame
+// t - 1 as its seeds — the centre only if its z exceeds a threshold (500 mm there; latest_midp starts
+// at 0, so the first frame has no centre seed), the rotation whenever there was a previous frame.
+// One thread per sequence copies the previous pass's result into the frame state the seed kernel reads.
+__global__ void __launch_bounds__(128) seq_guess_kernel(FrameState* __restrict__ fs, const dh_result* __restrict__ prev, uint32_t n,
+                                                        float min_seed_z) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const dh_result r = prev[i];
+    uint32_t g = 2u;
+    if (r.mid_point[2] > min_seed_z) {
+        g |= 1u;
+        fs[i].midp_guess[0] = r.mid_point[0];
+        fs[i].midp_guess[1] = r.mid_point[1];
+        fs[i].midp_guess[2] = r.mid_point[2];
+    }
+    fs[i].rot_guess[0] = r.rotation[0];
+    fs[i].rot_guess[1] = r.rotation[1];
+    fs[i].rot_guess[2] = r.rotation[2];
+    fs[i].has_guess = g;
+}
+
 // ================================================================ work counters of a pass
 __global__ void __launch_bounds__(256) counters_kernel(const FrameState* __restrict__ fs, uint32_t n_frames,
                                                        unsigned long long* __restrict__ out, uint32_t P, uint32_t T) {
@@ -2401,6 +2424,10 @@ int launch_gaussian_blur(const uint16_t* in, uint16_t* tmp, uint16_t* out, uint3
 void launch_hough2d_argmax(const uint16_t* hough, const uint16_t* depth, uint32_t w, uint32_t h, const Geometry& g, dh_result* out,
                            cudaStream_t s) {
     hough2d_argmax_kernel<<<1, 1024, 0, s>>>(hough, depth, w, h, g, out);
+}
+
+void launch_seq_guess(FrameState* fs, const dh_result* prev, uint32_t n, float min_seed_z, cudaStream_t s) {
+    if (n) seq_guess_kernel<<<(n + 127) / 128, 128, 0, s>>>(fs, prev, n, min_seed_z);
 }
 
 void launch_counters(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, unsigned long long* out,

@@ -129,6 +129,7 @@ void launch_hough_image(const FrameBuffers& b, const Geometry& g, const ForestDe
 int launch_gaussian_blur(const uint16_t* in, uint16_t* tmp, uint16_t* out, uint32_t w, uint32_t h, const float* k, int radius, cudaStream_t s);
 void launch_hough2d_argmax(const uint16_t* hough, const uint16_t* depth, uint32_t w, uint32_t h, const Geometry& g, dh_result* out,
                            cudaStream_t s);
+void launch_seq_guess(FrameState* fs, const dh_result* prev, uint32_t n, float min_seed_z, cudaStream_t s);
 void launch_counters(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, unsigned long long* out,
                      cudaStream_t s);
 // Biwi run-length decode: frame i = blob[offsets[i] - blob_base, offsets[i+1] - blob_base), or up to ends[i] - blob_base

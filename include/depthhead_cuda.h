@@ -13,6 +13,7 @@
  *   src/types.rs:405-446              IntrinsicMatrix                          -> `const float K[9]`
  *   src/hough/prediction.rs:376-409   predict_parameter{,_parallel}            -> dh_predict, dh_predict_batch
  *   src/hough/prediction.rs:259-267   struct PredictionResult                  -> dh_result
+ *   examples/live_prediction.rs:75-88 frame-to-frame seeding of a sequence     -> dh_predict_sequences
  *   src/hough/prediction.rs:850-905   predict_mask                             -> dh_predict_mask
  *   src/hough/prediction.rs:760-841   build_hough_image (votes, before blur)   -> dh_hough_image_raw
  *   src/hough/prediction.rs:760-845   build_hough_image (with its blur)        -> dh_build_hough_image
@@ -140,6 +141,17 @@ int dh_predict(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w,
  * where `depth` lives.  Synchronous. */
 int dh_predict_batch(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h,
                      const float K[9], int depth_loc, dh_result* out);
+
+/* The reference's real use predicts SEQUENCES (examples/live_prediction.rs:75-88): frame t is seeded
+ * with the pose of frame t - 1 — midp_guess = the previous mid_point if its z exceeds min_seed_z
+ * (500.0 there; the first frame has none), rot_guess = the previous rotation (none for the first
+ * frame).  That makes one sequence sequential, but separate sequences are independent: depth holds
+ * n_seq sequences of frames_per_seq frames, sequence-major ([n_seq][frames_per_seq][h][w]); frame t
+ * of every sequence runs as one pass on the GPU, seeded on the device from pass t - 1.  Results in
+ * input order: out[s * frames_per_seq + t], equal to calling dh_predict frame by frame with those
+ * seeds.  Synchronous. */
+int dh_predict_sequences(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t n_seq, uint32_t frames_per_seq,
+                         uint32_t w, uint32_t h, const float K[9], int depth_loc, float min_seed_z, dh_result* out);
 
 /* predict_mask (prediction.rs:850-905): mask[h][w] u8 to host memory. */
 int dh_predict_mask(dh_ctx* c, const dh_forest* f, const uint16_t* depth, uint32_t w, uint32_t h, uint8_t* mask);

@@ -408,3 +408,45 @@ def _leaf_depths(arr):
                 else:
                     out[l0 + (~ch)] = d
     return out
+
+
+def test_seeded_sequences_equal_frame_by_frame_prediction(ctx):
+    """dh_predict_sequences: frame t of every sequence in one pass, seeded on the device with the
+    pose of frame t - 1 (examples/live_prediction.rs:75-88) == dh_predict frame by frame with those
+    seeds == the oracle with those seeds; host and device input, groups smaller than the batch."""
+    import torch
+    arr = synth.make_forest(seed=12, n_trees=4, max_depth=8)
+    js = synth.forest_to_json(arr, stepwidth=8)
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    n_seq, T = 5, 6
+    frames = np.stack([synth.make_frames(T, seed=400 + s, sequence=True, start_index=625 * s) for s in range(n_seq)])
+    frames[3, 2] = 0            # an empty frame in the middle of a sequence: pose (0, 0, 0) -> z <= 500 -> no centre seed for the next frame
+    got = hp.predict_sequences(frames, K, min_seed_z=500.0, ctx=ctx)
+    assert got.shape == (n_seq, T)
+    for s in range(n_seq):
+        mid, rot = None, None
+        for t in range(T):
+            mg = mid if (mid is not None and mid[2] > np.float32(500.0)) else None
+            res = hp.predict_parameter_parallel(frames[s, t], K, mg, rot, ctx=ctx)
+            assert np.array_equal(got[s, t]["mid_point"], res.mid_point) and np.array_equal(got[s, t]["rotation"], res.rotation), (s, t)
+            if s < 2:
+                tr = of.predict(frames[s, t], synth.KINECT_K, mg, rot, mode=oracle.MODE_SAT, keep=False)
+                assert np.array_equal(res.mid_point, tr.mid_point) and np.array_equal(res.rotation, tr.rotation)
+            mid, rot = res.mid_point, res.rotation
+    # device-resident input, and groups of 2 sequences per pass
+    dev = torch.from_numpy(frames.view(np.int16)).cuda()
+    c2 = Context(0)
+    try:
+        c2.set_chunk_frames(2)
+        got2 = hp.predict_sequences(None, K, 500.0, ctx=c2, device_ptr=dev.data_ptr(), n_seq=n_seq, frames_per_seq=T, w=640, h=480)
+    finally:
+        c2.close()
+    assert np.array_equal(got2["mid_point"], got["mid_point"]) and np.array_equal(got2["rotation"], got["rotation"])
+    # min_seed_z = -inf: always seeded with the previous centre; differs from the 500 mm rule only after the empty frame
+    got3 = hp.predict_sequences(frames, K, min_seed_z=float("-inf"), ctx=ctx)
+    assert np.array_equal(got3[:3]["mid_point"], got[:3]["mid_point"])
+    # one frame per sequence == the unseeded batch
+    one = hp.predict_sequences(frames[:, :1], K, ctx=ctx)
+    bat = hp.predict_batch(np.ascontiguousarray(frames[:, 0]), K, ctx=ctx)
+    assert np.array_equal(one[:, 0]["mid_point"], bat["mid_point"]) and np.array_equal(one[:, 0]["rotation"], bat["rotation"])
