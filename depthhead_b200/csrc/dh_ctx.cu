@@ -4,10 +4,13 @@
 #include "dh_ctx.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace dh {
 
@@ -96,6 +99,7 @@ Context::Context(int device) : device_(device) {
     DH_CUDA(cudaHostAlloc((void**)&h_counters_, sizeof(unsigned long long) * DH_N_COUNTERS, cudaHostAllocDefault));
     DH_CUDA(cudaHostAlloc((void**)&h_result1_, sizeof(dh_result), cudaHostAllocDefault));
     for (int i = 0; i < kEncSlots; ++i) DH_CUDA(cudaEventCreateWithFlags(&ev_enc_copied_[i], cudaEventDisableTiming));
+    DH_CUDA(cudaEventCreateWithFlags(&ev_copy_tail_, cudaEventDisableTiming));
     if (const char* v = std::getenv("DH_HOST_ENCODE")) host_encode_ = *v ? (int)std::strtol(v, nullptr, 10) : -1;
     use_graphs_ = env_flag("DH_GRAPH", true);
     cube_clear_fused_ = env_flag("DH_CUBE_CLEAR_FUSED", true);
@@ -129,6 +133,7 @@ Context::~Context() {
         if (h_enc_meta_[i]) cudaFreeHost(h_enc_meta_[i]);
         if (ev_enc_copied_[i]) cudaEventDestroy(ev_enc_copied_[i]);
     }
+    if (ev_copy_tail_) cudaEventDestroy(ev_copy_tail_);
     for (int i = 0; i < 2; ++i) dev_free(d_enc_meta_[i]);
     for (auto ev : timing_events_) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
@@ -175,7 +180,7 @@ void Context::free_forest() {
     dev_free(df_offsets_);
     dev_free(df_offsets3_);
     dev_free(df_rot_bins_);
-    dev_free(df_rot_coarse_);
+    dev_free(df_rot_cells_);
     dev_free(df_leaf_box_);
     dev_free(df_kernel_);
     df_serial_ = 0;
@@ -282,7 +287,7 @@ void Context::ensure_forest(const HostForest& hf) {
         dev_alloc(df_offsets_, NV);       // float4 per vote
         dev_alloc(df_offsets3_, NV * 3);  // packed copy, only for the leaf-gate kernel below
         dev_alloc(df_rot_bins_, NV);
-        dev_alloc(df_rot_coarse_, NV);
+        dev_alloc(df_rot_cells_, NV);
         dev_alloc(df_leaf_box_, NL);
         dev_alloc(df_kernel_, (size_t)kKernelCells);
         if (NN) DH_CUDA(cudaMemcpyAsync(df_nodes_, hf.nodes.data(), NN * sizeof(NodeRec), cudaMemcpyHostToDevice, stream_));
@@ -304,7 +309,7 @@ void Context::ensure_forest(const HostForest& hf) {
         DH_CUDA(cudaMemcpyAsync(d_vs, hf.leaf_vote_start.data(), NL * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
         DH_CUDA(cudaMemcpyAsync(d_nv, hf.leaf_n_votes.data(), NL * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
         if (NV) DH_CUDA(cudaMemcpyAsync(d_rot, hf.rotations.data(), NV * 3 * sizeof(double), cudaMemcpyHostToDevice, stream_));
-        launch_leaf_gates(df_leaf_prob_, d_vs, d_nv, df_offsets3_, d_rot, df_rot_bins_, df_leaf_info_, df_leaf_box_, df_rot_coarse_,
+        launch_leaf_gates(df_leaf_prob_, d_vs, d_nv, df_offsets3_, d_rot, df_rot_bins_, df_leaf_info_, df_leaf_box_, df_rot_cells_,
                           (uint32_t)NL, stream_);
         DH_CUDA(cudaGetLastError());
         DH_CUDA(cudaStreamSynchronize(stream_));
@@ -340,7 +345,7 @@ void Context::ensure_forest(const HostForest& hf) {
     fdev_.leaf_info = df_leaf_info_;
     fdev_.offsets = df_offsets_;
     fdev_.rot_bins = df_rot_bins_;
-    fdev_.rot_coarse = df_rot_coarse_;
+    fdev_.rot_cells = df_rot_cells_;
     fdev_.leaf_box = df_leaf_box_;
     fdev_.ms_kernel = df_kernel_;
     fdev_.n_trees = hf.n_trees;
@@ -1058,149 +1063,179 @@ void Context::run_batch_encoded(const HostForest& hf, const uint16_t* depth, uin
     ensure_encode(n, F);
     const size_t bound = enc_frame_bound_;
     const uint32_t M = enc_frames_;  // stride between the begin and end halves of a meta array
+    const uint32_t G = kEncGroup;
     DH_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(uint32_t) * n, stream_));
     DH_CUDA(cudaEventRecord(ev_fork_, stream_));
     for (int i = 1; i < n_lanes; ++i) DH_CUDA(cudaStreamWaitEvent(lanes_[i].stream, ev_fork_, 0));
+    DH_CUDA(cudaStreamWaitEvent(copy_stream_, ev_fork_, 0));
 
-    // Chunks are handed out from both ends of the batch: the workers rewrite chunks from the
-    // front (two in flight), and whenever the copy engine has nothing to do while they are still
-    // writing, the next chunk from the BACK goes over raw (hybrid: PCIe and the host cores work on
-    // different chunks at the same time; DH_HOST_HYBRID=0: every chunk waits for its rewrite).
-    // The k-th chunk handed to the GPU uses device slot k % 2 and lane k % n_lanes.
-    std::vector<uint64_t> tickets(n_chunks, 0);
-    std::vector<uint8_t> state(n_chunks, 0);  // 0 unassigned, 1 being rewritten, 2 rewritten and sent, 3 sent raw
-    std::vector<uint32_t> pslot_of(n_chunks, 0);
-    uint32_t front = 0, back = n_chunks, enq = 0, n_submitted = 0;
-    std::vector<uint32_t> encq;               // chunks at the workers, oldest first
-    cudaEvent_t pslot_busy[kEncSlots] = {nullptr, nullptr, nullptr};  // H2D of the slot's previous chunk
+    // Every chunk is cut into groups of G frames.  The workers take a chunk's groups from the FRONT
+    // and rewrite them as run-length files into the chunk's pinned slot; while they do, this thread
+    // takes groups from the BACK of the same chunk whenever the copy engine has nothing to do and
+    // sends them raw, straight into the chunk's device frames (hybrid: the host cores and PCIe work
+    // on the same chunk at once and meet somewhere in the middle; DH_HOST_HYBRID=0: the workers
+    // rewrite everything).  A chunk goes to its lane as soon as all its groups are settled.
+    struct ChunkState {
+        std::atomic<uint64_t> fb{0};        // front | back << 32: groups [front, back) are unclaimed
+        std::atomic<uint32_t> enc_done{0};  // groups the workers have finished writing
+    };
+    std::unique_ptr<ChunkState[]> cs(new ChunkState[n_chunks]);
     const bool hybrid = env_flag("DH_HOST_HYBRID", true) && !timing_;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0), ng = (nc + G - 1) / G;
+        bool dense = false;
+        if (host_encode_ < 0) {
+            // sampled share of 16-pixel groups that would have to travel: above ~60 % the rewrite
+            // costs more host time than the copy saves, the whole chunk goes raw
+            const double d = 0.5 * (rle_sample_density(depth + (size_t)f0 * frame_px, frame_px, 61) +
+                                    rle_sample_density(depth + (size_t)(f0 + nc - 1) * frame_px, frame_px, 61));
+            dense = d >= 0.6;
+        }
+        cs[c].fb.store(dense ? 0ull : ((uint64_t)ng << 32));
+    }
+    std::atomic<uint32_t> released{(uint32_t)kEncSlots};  // chunk c may be written into its pinned slot once c < released
+    std::atomic<bool> abort{false};
+    ChunkState* csp = cs.get();
+    auto worker = [=, &released, &abort](uint32_t) {
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+            if ((uint32_t)csp[c].fb.load() >= (uint32_t)(csp[c].fb.load() >> 32)) continue;  // nothing (left) to rewrite here
+            while (c >= released.load(std::memory_order_acquire)) {  // the slot still holds an earlier chunk on its way to the GPU
+                if (abort.load()) return;
+                std::this_thread::sleep_for(std::chrono::microseconds(20));
+            }
+            uint8_t* base = h_enc_[c % (uint32_t)kEncSlots];
+            unsigned long long* meta = h_enc_meta_[c % (uint32_t)kEncSlots];
+            for (;;) {
+                uint64_t v = csp[c].fb.load();
+                uint32_t fr = (uint32_t)v, bk = (uint32_t)(v >> 32);
+                bool got = false;
+                while (fr < bk) {
+                    if (csp[c].fb.compare_exchange_weak(v, ((uint64_t)bk << 32) | (fr + 1u))) {
+                        got = true;
+                        break;
+                    }
+                    fr = (uint32_t)v;
+                    bk = (uint32_t)(v >> 32);
+                }
+                if (!got || abort.load()) break;
+                size_t pos = (size_t)fr * G * bound;
+                for (uint32_t k = fr * G; k < std::min(nc, (fr + 1u) * G); ++k) {
+                    meta[k] = pos;
+                    pos += rle_encode_frame(depth + (size_t)(f0 + k) * frame_px, w, h, base + pos);
+                    meta[M + k] = pos;
+                }
+                csp[c].enc_done.fetch_add(1u, std::memory_order_release);
+            }
+        }
+    };
+    const uint64_t ticket = pool_->run(pool_->size(), worker);
     bool copy_tail_valid = false;
-    auto dense = [&](uint32_t c) {
-        if (host_encode_ >= 0) return false;
-        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
-        // sampled share of 16-pixel groups that would have to travel: above ~60 % the rewrite
-        // costs more host time than the copy saves
-        const double d = 0.5 * (rle_sample_density(depth + (size_t)f0 * frame_px, frame_px, 61) +
-                                rle_sample_density(depth + (size_t)(f0 + nc - 1) * frame_px, frame_px, 61));
-        return d >= 0.6;
-    };
-    auto submit = [&](uint32_t c) {
-        const int pslot = (int)(n_submitted % (uint32_t)kEncSlots);
-        ++n_submitted;
-        pslot_of[c] = (uint32_t)pslot;
-        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
-        if (pslot_busy[pslot]) DH_CUDA(cudaEventSynchronize(pslot_busy[pslot]));  // the slot's previous chunk left the host
-        uint8_t* base = h_enc_[pslot];
-        unsigned long long* meta = h_enc_meta_[pslot];
-        const uint16_t* src = depth + (size_t)f0 * frame_px;
-        const uint32_t G = kEncGroup;
-        state[c] = 1;
-        tickets[c] = pool_->run((nc + G - 1) / G, [=](uint32_t gi) {
-            size_t pos = (size_t)gi * G * bound;
-            for (uint32_t k = gi * G; k < std::min(nc, (gi + 1) * G); ++k) {
-                meta[k] = pos;
-                pos += rle_encode_frame(src + (size_t)k * frame_px, w, h, base + pos);
-                meta[M + k] = pos;
-            }
-        });
-        encq.push_back(c);
-    };
-    auto drain = [&] {
-        for (uint32_t c : encq) pool_->wait(tickets[c]);
-    };
-    // hands chunk c (rewritten or raw) to the copy engine and its lane
-    auto send = [&](uint32_t c, bool enc) {
-        const int slot = (int)(enq & 1u);
-        Lane& L = lanes_[enq % (uint32_t)n_lanes];
-        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
-        // the device slot (compressed bytes, frame table, expanded frames) was last used two chunks ago
-        DH_CUDA(cudaStreamWaitEvent(copy_stream_, enq >= 2 ? ev_consumed_[slot] : ev_fork_, 0));
-        cudaEvent_t t0 = nullptr, t1 = nullptr;
-        if (timing_) {
-            t0 = next_event();
-            t1 = next_event();
-            DH_CUDA(cudaEventRecord(t0, copy_stream_));
-        }
-        if (enc) {
-            const int pslot = (int)pslot_of[c];
-            const unsigned long long* meta = h_enc_meta_[pslot];
-            for (uint32_t k0 = 0; k0 < nc; k0 += kEncGroup) {  // one copy per group: the groups are not adjacent
-                const uint32_t k1 = std::min(nc, k0 + kEncGroup) - 1u;
-                const size_t b0 = (size_t)meta[k0], b1 = (size_t)meta[M + k1];
-                DH_CUDA(cudaMemcpyAsync(d_blob_[slot] + b0, h_enc_[pslot] + b0, b1 - b0, cudaMemcpyHostToDevice, copy_stream_));
-                last_h2d_bytes_ += b1 - b0;
-            }
-            DH_CUDA(cudaMemcpyAsync(d_enc_meta_[slot], meta, sizeof(unsigned long long) * 2 * M, cudaMemcpyHostToDevice, copy_stream_));
-            last_h2d_bytes_ += sizeof(unsigned long long) * 2 * M;
-            DH_CUDA(cudaEventRecord(ev_enc_copied_[pslot], copy_stream_));
-            pslot_busy[pslot] = ev_enc_copied_[pslot];
-            ++last_encoded_chunks_;
-        } else {
-            DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
-                                    cudaMemcpyHostToDevice, copy_stream_));
-            last_h2d_bytes_ += (uint64_t)nc * frame_px * sizeof(uint16_t);
-        }
-        if (timing_) {
-            DH_CUDA(cudaEventRecord(t1, copy_stream_));
-            copy_marks_.push_back({t0, t1});
-        }
-        DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
-        copy_tail_valid = true;
-        DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
-        if (enc) {
-            mark(DH_STAGE_H2D);  // the expansion counts as input transfer
-            DH_CUDA(cudaMemsetAsync(d_depth_[slot], 0, (size_t)nc * frame_px * sizeof(uint16_t), L.stream));
-            launch_biwi_decode(d_blob_[slot], d_enc_meta_[slot], d_enc_meta_[slot] + M, 0ull, nc, w, h, d_depth_[slot], d_status_ + f0,
-                               L.stream);
-            launches_ += 1;
-        }
-        FrameBuffers b = buffers(L, d_depth_[slot]);
-        run_front(L, b, nc, nullptr);
-        run_back(L, b, nc, iterations);
-        DH_CUDA(cudaMemcpyAsync(h_results_ + f0, L.results, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, L.stream));
-        DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
-        state[c] = enc ? 2 : 3;
-        ++enq;
-    };
-    // the copy engine has finished everything handed to it so far
-    auto copy_idle = [&] {
-        if (!copy_tail_valid) return true;
-        return cudaEventQuery(ev_copied_[(enq + 1u) & 1u]) != cudaErrorNotReady;  // the slot of the last chunk sent
-    };
-    auto refill = [&] {
-        while (encq.size() < 2 && front < back) {
-            const uint32_t c = front++;
-            if (dense(c)) send(c, false);
-            else submit(c);
+    std::vector<uint8_t> chunk_has_enc(n_chunks, 0);
+    uint32_t sent = 0;  // chunks handed to the GPU so far (their pinned slots are released in order as their copies finish)
+    auto try_release = [&] {
+        // chunk r = released - kEncSlots is the oldest whose slot is still reserved; it can be reused once that chunk has been
+        // sent and its encoded bytes have left the host
+        for (;;) {
+            const uint32_t r = released.load() - (uint32_t)kEncSlots;
+            if (r >= sent) return;
+            if (chunk_has_enc[r] && cudaEventQuery(ev_enc_copied_[r % (uint32_t)kEncSlots]) == cudaErrorNotReady) return;
+            released.fetch_add(1u, std::memory_order_release);
         }
     };
+    auto copy_idle = [&] { return !copy_tail_valid || cudaEventQuery(ev_copy_tail_) != cudaErrorNotReady; };
     try {
-        refill();
-        while (enq < n_chunks) {
-            if (!encq.empty() && pool_->done(tickets[encq.front()])) {
-                const uint32_t c = encq.front();
-                encq.erase(encq.begin());
-                send(c, true);
-                refill();
-                continue;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const int slot = (int)(c & 1u), pslot = (int)(c % (uint32_t)kEncSlots);
+            Lane& L = lanes_[c % (uint32_t)n_lanes];
+            const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0), ng = (nc + G - 1) / G;
+            // the device slot (compressed bytes, frame table, frames) was last used by chunk c - 2; the frames start out zero
+            DH_CUDA(cudaStreamWaitEvent(copy_stream_, c >= 2 ? ev_consumed_[slot] : ev_fork_, 0));
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (timing_) {
+                t0 = next_event();
+                t1 = next_event();
+                DH_CUDA(cudaEventRecord(t0, copy_stream_));
             }
-            if (hybrid && back > front && copy_idle()) {
-                send(--back, false);
-                continue;
+            const bool all_raw = (cs[c].fb.load() >> 32) == 0;
+            if (all_raw) {
+                DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
+                                        cudaMemcpyHostToDevice, copy_stream_));
+                last_h2d_bytes_ += (uint64_t)nc * frame_px * sizeof(uint16_t);
+            } else {
+                DH_CUDA(cudaMemsetAsync(d_depth_[slot], 0, (size_t)nc * frame_px * sizeof(uint16_t), copy_stream_));
+                // ---- raw groups from the back while the workers write from the front
+                uint32_t split;
+                for (;;) {
+                    try_release();
+                    uint64_t v = cs[c].fb.load();
+                    uint32_t fr = (uint32_t)v, bk = (uint32_t)(v >> 32);
+                    if (fr >= bk) {
+                        if (cs[c].enc_done.load(std::memory_order_acquire) == fr) {
+                            split = fr;
+                            break;
+                        }
+                    } else if (hybrid && copy_idle()) {
+                        if (cs[c].fb.compare_exchange_strong(v, ((uint64_t)(bk - 1u) << 32) | fr)) {
+                            const uint32_t g = bk - 1u, k0 = g * G, kn = std::min(nc, k0 + G) - k0;
+                            DH_CUDA(cudaMemcpyAsync(d_depth_[slot] + (size_t)k0 * frame_px, depth + (size_t)(f0 + k0) * frame_px,
+                                                    (size_t)kn * frame_px * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream_));
+                            DH_CUDA(cudaEventRecord(ev_copy_tail_, copy_stream_));
+                            copy_tail_valid = true;
+                            last_h2d_bytes_ += (uint64_t)kn * frame_px * sizeof(uint16_t);
+                        }
+                        continue;
+                    }
+                    std::this_thread::sleep_for(std::chrono::microseconds(15));
+                }
+                // ---- the rewritten groups [0, split): one copy each (the groups are not adjacent in the slot), then the frame table
+                unsigned long long* meta = h_enc_meta_[pslot];
+                for (uint32_t k = split * G; k < nc; ++k) meta[k] = ~0ull;  // sent raw: nothing to expand
+                for (uint32_t g = 0; g < split; ++g) {
+                    const uint32_t k1 = std::min(nc, (g + 1u) * G) - 1u;
+                    const size_t b0 = (size_t)meta[g * G], b1 = (size_t)meta[M + k1];
+                    DH_CUDA(cudaMemcpyAsync(d_blob_[slot] + b0, h_enc_[pslot] + b0, b1 - b0, cudaMemcpyHostToDevice, copy_stream_));
+                    last_h2d_bytes_ += b1 - b0;
+                }
+                if (split) {
+                    DH_CUDA(cudaMemcpyAsync(d_enc_meta_[slot], meta, sizeof(unsigned long long) * 2 * M, cudaMemcpyHostToDevice, copy_stream_));
+                    last_h2d_bytes_ += sizeof(unsigned long long) * 2 * M;
+                    DH_CUDA(cudaEventRecord(ev_enc_copied_[pslot], copy_stream_));
+                    chunk_has_enc[c] = 1;
+                    ++last_encoded_chunks_;
+                }
+                DH_CUDA(cudaEventRecord(ev_copy_tail_, copy_stream_));
+                copy_tail_valid = true;
+                (void)ng;
             }
-            if (!encq.empty()) {
-                pool_->wait_for(tickets[encq.front()], hybrid && back > front ? 50u : 1000000u);
-                continue;
+            if (timing_) {
+                DH_CUDA(cudaEventRecord(t1, copy_stream_));
+                copy_marks_.push_back({t0, t1});
             }
-            refill();  // nothing at the workers: everything left is dense (or already sent)
-            if (encq.empty() && front >= back) break;
+            DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
+            DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
+            if (chunk_has_enc[c]) {
+                mark(DH_STAGE_H2D);  // the expansion counts as input transfer
+                launch_biwi_decode(d_blob_[slot], d_enc_meta_[slot], d_enc_meta_[slot] + M, 0ull, nc, w, h, d_depth_[slot], d_status_ + f0,
+                                   L.stream);
+                launches_ += 1;
+            }
+            FrameBuffers b = buffers(L, d_depth_[slot]);
+            run_front(L, b, nc, nullptr);
+            run_back(L, b, nc, iterations);
+            DH_CUDA(cudaMemcpyAsync(h_results_ + f0, L.results, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, L.stream));
+            DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
+            sent = c + 1;
+            try_release();
         }
     } catch (...) {
-        drain();  // no worker may still read the caller's frames once this call has returned
+        abort.store(true);
+        pool_->wait(ticket);  // no worker may still read the caller's frames once this call has returned
         cudaStreamSynchronize(copy_stream_);
         for (int i = 0; i < n_lanes; ++i) cudaStreamSynchronize(lanes_[i].stream);
         throw;
     }
+    pool_->wait(ticket);
     if (n_lanes > 1) {
         for (int i = 1; i < n_lanes; ++i) {
             DH_CUDA(cudaEventRecord(lanes_[i].done, lanes_[i].stream));

@@ -169,7 +169,7 @@ private:
     float4* df_offsets_ = nullptr;
     float* df_offsets3_ = nullptr;
     uint32_t* df_rot_bins_ = nullptr;
-    uint16_t* df_rot_coarse_ = nullptr;
+    uint32_t* df_rot_cells_ = nullptr;
     LeafBox* df_leaf_box_ = nullptr;
     float* df_kernel_ = nullptr;
     ForestDev fdev_{};
@@ -203,7 +203,7 @@ private:
     // fixed region of the slot, so its bytes are known only to the worker that wrote them and the
     // groups are copied one cudaMemcpyAsync each.
     static constexpr int kEncSlots = 3;       // pinned slots: one being copied, two being written
-    static constexpr uint32_t kEncGroup = 8;  // frames per worker task / per copy
+    static constexpr uint32_t kEncGroup = 4;  // frames per group: the unit a worker rewrites, or that goes over raw
     std::unique_ptr<WorkerPool> pool_;
     uint32_t encode_threads_req_ = 0;
     int host_encode_ = -1;                    // DH_HOST_ENCODE: 0 never, 1 whenever possible, -1 by sampled density
@@ -211,6 +211,7 @@ private:
     unsigned long long* h_enc_meta_[kEncSlots] = {nullptr, nullptr, nullptr};  // [2][F]: begin, end of every frame inside the slot
     unsigned long long* d_enc_meta_[2] = {nullptr, nullptr};
     cudaEvent_t ev_enc_copied_[kEncSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copy_tail_ = nullptr;      // after the last copy handed to the copy stream (is the copy engine idle?)
     size_t enc_slot_bytes_ = 0, enc_frame_bound_ = 0;
     uint32_t enc_frames_ = 0;
     uint32_t last_encoded_chunks_ = 0;

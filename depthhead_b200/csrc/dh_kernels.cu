@@ -1021,7 +1021,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, uint32_t lane) {
     return x;
 }
 
-// Calls body(vote index, weight, tag, p3) once per vote of the warp's 32 pairs, 32 votes at a time.
+// Calls body(vote index, weight, tag, p3, number of the vote within its pair) once per vote of the warp's 32 pairs, 32 votes at a time.
 // n: votes of this lane's pair (0 = none), v0: its first vote.  All 32 lanes must call.
 template <typename Body>
 __device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t wgt, uint32_t tag, const float4 h, PairSlot* slots,
@@ -1046,7 +1046,7 @@ __device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t 
         if (vb + lane < total) {
             const uint4 a = slots[k].a;
             const float4 c = slots[k].h;
-            body(a.y + (vb + lane - a.x), a.z, a.w, c);
+            body(a.y + (vb + lane - a.x), a.z, a.w, c, vb + lane - a.x);
         }
     }
 }
@@ -1149,7 +1149,8 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
                 v0 = li.vote_start;
                 wgt = li.valtoadd;
                 if (li.flags & kLeafOffOk) { n_c = li.n_votes; ++cnt_c; nmid += li.n_votes; }
-                if (li.flags & kLeafRotOk) { n_r = li.n_votes; ++cnt_r; nrot += li.n_votes; }
+                // rotation votes: the leaf's distinct seed-grid cells with their multiplicities (leaf_gate_kernel)
+                if (li.flags & kLeafRotOk) { n_r = li.flags >> kLeafRotCellsShift; ++cnt_r; nrot += li.n_votes; }
             }
         }
         // centre votes -> 20x20 grid: np = p3 - offset (prediction.rs:647); np.z < 0 is skipped (:650)
@@ -1159,22 +1160,24 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
             if (!(nz < 0.0f)) atomicAdd(&s_grid[coarse_pos_cell(g, nx, ny, nz)], ow);
         };
         // rotation votes -> 20^3 grid; rough = r * 20 / 120 per axis (prediction.rs:630-636), static per vote
-        auto rot_vote = [&](uint32_t vote, uint32_t ow) {
-            const uint32_t cell = __ldg(f.rot_coarse + vote);
-            if (atomicAdd(&s_grid[kPosGridCells + cell], ow) == 0u) {
+        auto rot_vote = [&](uint32_t entry, uint32_t ow) {
+            const uint32_t e = __ldg(f.rot_cells + entry), cell = e & ((1u << kRotCellBits) - 1u);
+            if (atomicAdd(&s_grid[kPosGridCells + cell], ow * (e >> kRotCellBits)) == 0u) {
                 const uint32_t slot = atomicAdd(&s_ntouched, 1u);
                 if (slot < (uint32_t)kTouchedCap) s_touched[slot] = (uint16_t)cell;
             }
         };
         if (kFused) {
-            const uint32_t tag = (n_c ? 1u : 0u) | (n_r ? 2u : 0u);
-            for_each_vote(n_c | n_r, v0, wgt, tag, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t tg, const float4& c) {
-                if (tg & 1u) centre_vote(vote, ow, c);
-                if (tg & 2u) rot_vote(vote, ow);
-            });
+            // one pass: item j of a pair is its centre vote j (j < n_c) and its rotation cell j (j < n_r <= n_votes)
+            const uint32_t tag = (n_c ? 1u : 0u) | (n_r << 1);
+            for_each_vote(max(n_c, n_r), v0, wgt, tag, h, s_slots[tid >> 5], lane,
+                          [&](uint32_t vote, uint32_t ow, uint32_t tg, const float4& c, uint32_t j) {
+                              if (tg & 1u) centre_vote(vote, ow, c);
+                              if (j < (tg >> 1)) rot_vote(vote, ow);
+                          });
         } else {
-            for_each_vote(n_c, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4& c) { centre_vote(vote, ow, c); });
-            for_each_vote(n_r, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4&) { rot_vote(vote, ow); });
+            for_each_vote(n_c, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4& c, uint32_t) { centre_vote(vote, ow, c); });
+            for_each_vote(n_r, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4&, uint32_t) { rot_vote(vote, ow); });
         }
     }
     // per-frame counters, one atomic per warp
@@ -1695,7 +1698,7 @@ __global__ void __launch_bounds__(128) leaf_gate_kernel(const double* __restrict
                                                         const double* __restrict__ rotations,
                                                         const uint32_t* __restrict__ rot_bins,
                                                         LeafInfo* __restrict__ out, LeafBox* __restrict__ box_out,
-                                                        uint16_t* __restrict__ rot_coarse, uint32_t n_leaves) {
+                                                        uint32_t* __restrict__ rot_cells, uint32_t n_leaves) {
     const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_leaves) return;
     const uint32_t v0 = vote_start[l], n = n_votes[l];
@@ -1762,6 +1765,7 @@ __global__ void __launch_bounds__(128) leaf_gate_kernel(const double* __restrict
         if (k < 3) bx.omin[k] = bx.omax[k] = 0.0f;
         bx.rmin[k] = bx.rmax[k] = 0;
     }
+    uint32_t n_cells = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t bins = rot_bins[v0 + i];
         uint32_t q[3];
@@ -1778,9 +1782,18 @@ __global__ void __launch_bounds__(128) leaf_gate_kernel(const double* __restrict
             if (i == 0 || r > bx.rmax[k]) bx.rmax[k] = r;
             q[k] = (uint32_t)r * kGuessGridParts / kRotGridParts;
         }
-        rot_coarse[v0 + i] = (uint16_t)(q[2] * 400u + q[1] * 20u + q[0]);
+        // compact list of the leaf's cells: (cell | votes in it << 13) in the first n_cells slots of its
+        // range.  Short lists are searched linearly; a leaf with very many votes keeps one entry per vote.
+        const uint32_t cell = q[2] * 400u + q[1] * 20u + q[0];
+        uint32_t j = n_cells;
+        if (n <= 1024u)
+            for (j = 0; j < n_cells; ++j)
+                if ((rot_cells[v0 + j] & ((1u << kRotCellBits) - 1u)) == cell && (rot_cells[v0 + j] >> kRotCellBits) < kRotCellMaxCount) break;
+        if (j < n_cells) rot_cells[v0 + j] += 1u << kRotCellBits;
+        else rot_cells[v0 + n_cells++] = cell | (1u << kRotCellBits);
     }
     box_out[l] = bx;
+    out[l].flags = li.flags | (n_cells << kLeafRotCellsShift);
 }
 
 // ================================================================ next-row back-ends on the same front-end
@@ -1961,6 +1974,7 @@ __global__ void __launch_bounds__(kRleThreads) biwi_decode_kernel(const uint8_t*
     __shared__ uint32_t s_long[kRleLongCap];
     __shared__ uint32_t s_nrun, s_pos, s_p, s_nlong, s_err, s_done, s_end_run, s_bad_run;
     const uint32_t frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (offsets[frame] == ~0ull) return;  // no file for this frame: its pixels arrived another way
     // frame i occupies [offsets[i], offsets[i+1]), or [offsets[i], ends[i]) when the files do not follow one another
     const unsigned long long o0 = offsets[frame] - blob_base, o1 = (ends ? ends[frame] : offsets[frame + 1]) - blob_base;
     const uint8_t* file = blob + o0;                  // 4-byte aligned (checked on the host)
@@ -2394,9 +2408,9 @@ int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& 
 
 void launch_leaf_gates(const double* leaf_prob, const uint32_t* vote_start, const uint32_t* n_votes,
                        const float* offsets, const double* rotations, const uint32_t* rot_bins, LeafInfo* out,
-                       LeafBox* box_out, uint16_t* rot_coarse, uint32_t n_leaves, cudaStream_t s) {
+                       LeafBox* box_out, uint32_t* rot_cells, uint32_t n_leaves, cudaStream_t s) {
     leaf_gate_kernel<<<(n_leaves + 127) / 128, 128, 0, s>>>(leaf_prob, vote_start, n_votes, offsets, rotations, rot_bins, out,
-                                                           box_out, rot_coarse, n_leaves);
+                                                           box_out, rot_cells, n_leaves);
 }
 
 void launch_mask(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint8_t* mask, cudaStream_t s) {

@@ -79,7 +79,7 @@ struct ForestDev {
     const LeafInfo* leaf_info;
     const float4* offsets;     // per vote: x, y, z (mm), w unused — one 16-byte load
     const uint32_t* rot_bins;  // per vote
-    const uint16_t* rot_coarse; // per vote: cell of the 20^3 rotation seed grid
+    const uint32_t* rot_cells;  // per leaf, at its vote_start: compact list of (cell of the 20^3 rotation seed grid | votes in it << 13)
     const LeafBox* leaf_box;   // per leaf: bounding boxes of its votes
     const float* ms_kernel;    // 8000
     int32_t n_trees;
@@ -122,7 +122,7 @@ uint32_t vote_box_cells();
 uint32_t vote_box_dim();
 void launch_leaf_gates(const double* leaf_prob, const uint32_t* vote_start, const uint32_t* n_votes,
                        const float* offsets, const double* rotations, const uint32_t* rot_bins, LeafInfo* out,
-                       LeafBox* box_out, uint16_t* rot_coarse, uint32_t n_leaves, cudaStream_t s);
+                       LeafBox* box_out, uint32_t* rot_cells, uint32_t n_leaves, cudaStream_t s);
 void launch_mask(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint8_t* mask, cudaStream_t s);
 void launch_hough_image(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t* acc32,
                         uint16_t* out16, cudaStream_t s);

@@ -102,5 +102,11 @@ struct alignas(32) LeafBox {
 };
 static_assert(sizeof(LeafBox) == 32, "LeafBox must be one 32-byte sector");
 constexpr uint32_t kLeafRotOk = 1u, kLeafOffOk = 2u, kLeafVotes = 4u;
+// LeafInfo::flags bits 8..31: number of entries of the leaf's compact rotation seed-grid list
+// (ForestDev::rot_cells): distinct cells of the 20^3 grid its rotation votes fall into, with their
+// multiplicities (the contribution of a leaf to that grid is static, prediction.rs:630-636)
+constexpr uint32_t kLeafRotCellsShift = 8u;
+constexpr uint32_t kRotCellBits = 13u;                    // 8000 cells
+constexpr uint32_t kRotCellMaxCount = (1u << (32u - kRotCellBits)) - 1u;
 
 }  // namespace dh

@@ -37,7 +37,8 @@ WANT = {
     "dram_pct": ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 1),
     "regs": ("launch__registers_per_thread", 1),
 }
-UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9}
+UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9,
+              "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}
 
 
 def load(report):
