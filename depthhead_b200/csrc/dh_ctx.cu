@@ -90,7 +90,8 @@ Context::Context(int device) : device_(device) {
         DH_CUDA(cudaEventCreateWithFlags(&lanes_[i].done, cudaEventDisableTiming));
         if (i > 0) DH_CUDA(cudaStreamCreateWithFlags(&lanes_[i].own, cudaStreamNonBlocking));
     }
-    for (int i = 0; i < 2; ++i) {
+    DH_CUDA(cudaStreamCreateWithFlags(&copy_stream2_, cudaStreamNonBlocking));
+    for (int i = 0; i < kStageSlots; ++i) {
         DH_CUDA(cudaEventCreateWithFlags(&ev_copied_[i], cudaEventDisableTiming));
         DH_CUDA(cudaEventCreateWithFlags(&ev_consumed_[i], cudaEventDisableTiming));
     }
@@ -136,7 +137,8 @@ Context::~Context() {
     if (ev_copy_tail_) cudaEventDestroy(ev_copy_tail_);
     for (int i = 0; i < 2; ++i) dev_free(d_enc_meta_[i]);
     for (auto ev : timing_events_) cudaEventDestroy(ev);
-    for (int i = 0; i < 2; ++i) {
+    if (copy_stream2_) cudaStreamDestroy(copy_stream2_);
+    for (int i = 0; i < kStageSlots; ++i) {
         if (ev_copied_[i]) cudaEventDestroy(ev_copied_[i]);
         if (ev_consumed_[i]) cudaEventDestroy(ev_consumed_[i]);
     }
@@ -377,7 +379,7 @@ void Context::drop_graph() {
 
 void Context::free_scratch() {
     drop_graph();
-    for (int i = 0; i < 2; ++i) dev_free(d_depth_[i]);
+    for (int i = 0; i < kStageSlots; ++i) dev_free(d_depth_[i]);
     staging_elems_ = 0;
     for (int i = 0; i < kMaxLanes; ++i) free_lane(lanes_[i]);
     sk_ = ScratchKey();
@@ -562,10 +564,11 @@ void Context::ensure_staging(int slots) {
     if (n > staging_elems_) {
         DH_CUDA(cudaStreamSynchronize(stream_));
         DH_CUDA(cudaStreamSynchronize(copy_stream_));
-        for (int i = 0; i < 2; ++i) dev_free(d_depth_[i]);
+        DH_CUDA(cudaStreamSynchronize(copy_stream2_));
+        for (int i = 0; i < kStageSlots; ++i) dev_free(d_depth_[i]);
         staging_elems_ = n;
     }
-    for (int i = 0; i < slots && i < 2; ++i)
+    for (int i = 0; i < slots && i < kStageSlots; ++i)
         if (!d_depth_[i]) dev_alloc(d_depth_[i], staging_elems_);
 }
 
@@ -1003,7 +1006,7 @@ void Context::ensure_encode(uint32_t n, uint32_t F) {
     if (!pool_) pool_.reset(new WorkerPool(encode_threads_req_ ? encode_threads_req_ : default_encode_threads()));
     const size_t bound = rle_frame_bound(sk_.w, sk_.h);
     const uint32_t groups = (F + kEncGroup - 1) / kEncGroup;
-    const size_t slot = (size_t)groups * kEncGroup * bound;
+    const size_t slot = (size_t)(groups + 1) * kEncGroup * bound;  // tasks of up to kEncGroup frames at a fixed stride: room for a ragged last task
     if (slot > enc_slot_bytes_ || F > enc_frames_ || bound != enc_frame_bound_) {
         DH_CUDA(cudaStreamSynchronize(stream_));
         DH_CUDA(cudaStreamSynchronize(copy_stream_));
@@ -1046,8 +1049,17 @@ void Context::ensure_encode(uint32_t n, uint32_t F) {
 
 void Context::run_batch_encoded(const HostForest& hf, const uint16_t* depth, uint32_t n, uint32_t w, uint32_t h, const float K[9],
                                 dh_result* out) {
+    // Two streams of chunks meet inside the batch.  FRONT: the workers rewrite chunks 0, 1, 2, .. as
+    // run-length files (two chunks in flight, pinned slots 0..2); a finished chunk's bytes go over
+    // the first copy stream into device slots 0 / 1 and are expanded and predicted on lane 0.
+    // BACK (hybrid, DH_HOST_HYBRID=0 turns it off): chunks n-1, n-2, .. go over RAW on a second copy
+    // stream into device slots 2 / 3 and are predicted on lane 1, one after the other as fast as
+    // PCIe takes them.  Whoever reaches a chunk first takes it; the call ends where they meet.
+    // The host cores and the copy engines therefore work all the time, on different chunks, and
+    // the split adapts to how dense the frames are and how many cores the caller gave the workers.
+    const bool hybrid = env_flag("DH_HOST_HYBRID", true) && !timing_ && max_lanes_ >= 2;
     const uint32_t want_chunk = pick_chunk(n, DH_DEPTH_HOST);
-    const int n_lanes = timing_ ? 1 : (int)std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>((uint32_t)max_lanes_, 2u), (n + want_chunk - 1) / want_chunk));
+    const int n_lanes = hybrid ? 2 : 1;
     ensure_scratch(hf, w, h, want_chunk, K, n_lanes);
     const uint32_t iterations = hf.meanshift_iterations.load();
     const uint32_t F = call_chunk_;
@@ -1059,183 +1071,178 @@ void Context::run_batch_encoded(const HostForest& hf, const uint16_t* depth, uin
         DH_CUDA(cudaHostAlloc((void**)&h_results_, sizeof(dh_result) * n, cudaHostAllocDefault));
         h_results_cap_ = n;
     }
-    ensure_staging(2);
+    ensure_staging(hybrid ? 4 : 2);
     ensure_encode(n, F);
     const size_t bound = enc_frame_bound_;
     const uint32_t M = enc_frames_;  // stride between the begin and end halves of a meta array
-    const uint32_t G = kEncGroup;
+    // frames per worker task (and per copy): about two tasks per worker and chunk
+    const uint32_t G = std::max<uint32_t>(1u, std::min<uint32_t>(kEncGroup, F / std::max<uint32_t>(1u, 2u * pool_->size())));
     DH_CUDA(cudaMemsetAsync(d_status_, 0, sizeof(uint32_t) * n, stream_));
     DH_CUDA(cudaEventRecord(ev_fork_, stream_));
     for (int i = 1; i < n_lanes; ++i) DH_CUDA(cudaStreamWaitEvent(lanes_[i].stream, ev_fork_, 0));
     DH_CUDA(cudaStreamWaitEvent(copy_stream_, ev_fork_, 0));
+    DH_CUDA(cudaStreamWaitEvent(copy_stream2_, ev_fork_, 0));
 
-    // Every chunk is cut into groups of G frames.  The workers take a chunk's groups from the FRONT
-    // and rewrite them as run-length files into the chunk's pinned slot; while they do, this thread
-    // takes groups from the BACK of the same chunk whenever the copy engine has nothing to do and
-    // sends them raw, straight into the chunk's device frames (hybrid: the host cores and PCIe work
-    // on the same chunk at once and meet somewhere in the middle; DH_HOST_HYBRID=0: the workers
-    // rewrite everything).  A chunk goes to its lane as soon as all its groups are settled.
-    struct ChunkState {
-        std::atomic<uint64_t> fb{0};        // front | back << 32: groups [front, back) are unclaimed
-        std::atomic<uint32_t> enc_done{0};  // groups the workers have finished writing
+    std::vector<uint64_t> tickets(n_chunks, 0);
+    std::vector<uint32_t> pslot_of(n_chunks, 0);
+    std::vector<uint32_t> encq;               // chunks at the workers, oldest first
+    uint32_t front = 0, back = n_chunks;      // chunks [front, back) belong to nobody yet
+    uint32_t n_submitted = 0, n_front_sent = 0, n_back_sent = 0, done_chunks = 0;
+    cudaEvent_t pslot_busy[kEncSlots] = {nullptr, nullptr, nullptr};  // H2D of the slot's previous chunk
+    cudaEvent_t last_front_copy = nullptr;                            // after the last copy handed to the front stream
+    auto dense = [&](uint32_t c) {
+        if (host_encode_ >= 0) return false;
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+        // sampled share of 16-pixel groups that would have to travel: above ~60 % the rewrite
+        // costs more host time than the copy saves
+        const double d = 0.5 * (rle_sample_density(depth + (size_t)f0 * frame_px, frame_px, 61) +
+                                rle_sample_density(depth + (size_t)(f0 + nc - 1) * frame_px, frame_px, 61));
+        return d >= 0.6;
     };
-    std::unique_ptr<ChunkState[]> cs(new ChunkState[n_chunks]);
-    const bool hybrid = env_flag("DH_HOST_HYBRID", true) && !timing_;
-    for (uint32_t c = 0; c < n_chunks; ++c) {
-        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0), ng = (nc + G - 1) / G;
-        bool dense = false;
-        if (host_encode_ < 0) {
-            // sampled share of 16-pixel groups that would have to travel: above ~60 % the rewrite
-            // costs more host time than the copy saves, the whole chunk goes raw
-            const double d = 0.5 * (rle_sample_density(depth + (size_t)f0 * frame_px, frame_px, 61) +
-                                    rle_sample_density(depth + (size_t)(f0 + nc - 1) * frame_px, frame_px, 61));
-            dense = d >= 0.6;
-        }
-        cs[c].fb.store(dense ? 0ull : ((uint64_t)ng << 32));
-    }
-    std::atomic<uint32_t> released{(uint32_t)kEncSlots};  // chunk c may be written into its pinned slot once c < released
-    std::atomic<bool> abort{false};
-    ChunkState* csp = cs.get();
-    auto worker = [=, &released, &abort](uint32_t) {
-        for (uint32_t c = 0; c < n_chunks; ++c) {
-            const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
-            if ((uint32_t)csp[c].fb.load() >= (uint32_t)(csp[c].fb.load() >> 32)) continue;  // nothing (left) to rewrite here
-            while (c >= released.load(std::memory_order_acquire)) {  // the slot still holds an earlier chunk on its way to the GPU
-                if (abort.load()) return;
-                std::this_thread::sleep_for(std::chrono::microseconds(20));
+    auto submit = [&](uint32_t c) {
+        const int pslot = (int)(n_submitted % (uint32_t)kEncSlots);
+        ++n_submitted;
+        pslot_of[c] = (uint32_t)pslot;
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+        if (pslot_busy[pslot]) DH_CUDA(cudaEventSynchronize(pslot_busy[pslot]));  // the slot's previous chunk has left the host
+        uint8_t* base = h_enc_[pslot];
+        unsigned long long* meta = h_enc_meta_[pslot];
+        const uint16_t* src = depth + (size_t)f0 * frame_px;
+        tickets[c] = pool_->run((nc + G - 1) / G, [=](uint32_t gi) {
+            size_t pos = (size_t)gi * G * bound;
+            for (uint32_t k = gi * G; k < std::min(nc, (gi + 1) * G); ++k) {
+                meta[k] = pos;
+                pos += rle_encode_frame(src + (size_t)k * frame_px, w, h, base + pos);
+                meta[M + k] = pos;
             }
-            uint8_t* base = h_enc_[c % (uint32_t)kEncSlots];
-            unsigned long long* meta = h_enc_meta_[c % (uint32_t)kEncSlots];
-            for (;;) {
-                uint64_t v = csp[c].fb.load();
-                uint32_t fr = (uint32_t)v, bk = (uint32_t)(v >> 32);
-                bool got = false;
-                while (fr < bk) {
-                    if (csp[c].fb.compare_exchange_weak(v, ((uint64_t)bk << 32) | (fr + 1u))) {
-                        got = true;
-                        break;
-                    }
-                    fr = (uint32_t)v;
-                    bk = (uint32_t)(v >> 32);
-                }
-                if (!got || abort.load()) break;
-                size_t pos = (size_t)fr * G * bound;
-                for (uint32_t k = fr * G; k < std::min(nc, (fr + 1u) * G); ++k) {
-                    meta[k] = pos;
-                    pos += rle_encode_frame(depth + (size_t)(f0 + k) * frame_px, w, h, base + pos);
-                    meta[M + k] = pos;
-                }
-                csp[c].enc_done.fetch_add(1u, std::memory_order_release);
-            }
+        });
+        encq.push_back(c);
+    };
+    // the pipeline of one chunk whose frames are (about to be) in device slot `slot`
+    auto run_chunk = [&](Lane& L, int slot, uint32_t c) {
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+        FrameBuffers b = buffers(L, d_depth_[slot]);
+        run_front(L, b, nc, nullptr);
+        run_back(L, b, nc, iterations);
+        DH_CUDA(cudaMemcpyAsync(h_results_ + f0, L.results, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, L.stream));
+        DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
+        ++done_chunks;
+    };
+    auto send_encoded = [&](uint32_t c) {
+        const int slot = (int)(n_front_sent & 1u), pslot = (int)pslot_of[c];
+        Lane& L = lanes_[0];
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+        DH_CUDA(cudaStreamWaitEvent(copy_stream_, n_front_sent >= 2 ? ev_consumed_[slot] : ev_fork_, 0));
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (timing_) {
+            t0 = next_event();
+            t1 = next_event();
+            DH_CUDA(cudaEventRecord(t0, copy_stream_));
+        }
+        const unsigned long long* meta = h_enc_meta_[pslot];
+        for (uint32_t k0 = 0; k0 < nc; k0 += G) {  // one copy per task: the tasks' bytes are not adjacent
+            const uint32_t k1 = std::min(nc, k0 + G) - 1u;
+            const size_t b0 = (size_t)meta[k0], b1 = (size_t)meta[M + k1];
+            DH_CUDA(cudaMemcpyAsync(d_blob_[slot] + b0, h_enc_[pslot] + b0, b1 - b0, cudaMemcpyHostToDevice, copy_stream_));
+            last_h2d_bytes_ += b1 - b0;
+        }
+        DH_CUDA(cudaMemcpyAsync(d_enc_meta_[slot], meta, sizeof(unsigned long long) * 2 * M, cudaMemcpyHostToDevice, copy_stream_));
+        last_h2d_bytes_ += sizeof(unsigned long long) * 2 * M;
+        DH_CUDA(cudaEventRecord(ev_enc_copied_[pslot], copy_stream_));
+        pslot_busy[pslot] = ev_enc_copied_[pslot];
+        ++last_encoded_chunks_;
+        if (timing_) {
+            DH_CUDA(cudaEventRecord(t1, copy_stream_));
+            copy_marks_.push_back({t0, t1});
+        }
+        DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
+        last_front_copy = ev_copied_[slot];
+        DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
+        mark(DH_STAGE_H2D);  // the expansion counts as input transfer
+        DH_CUDA(cudaMemsetAsync(d_depth_[slot], 0, (size_t)nc * frame_px * sizeof(uint16_t), L.stream));
+        launch_biwi_decode(d_blob_[slot], d_enc_meta_[slot], d_enc_meta_[slot] + M, 0ull, nc, w, h, d_depth_[slot], d_status_ + f0, L.stream);
+        launches_ += 1;
+        run_chunk(L, slot, c);
+        ++n_front_sent;
+    };
+    // raw chunk: front stream (a dense chunk met on the way: slots 0 / 1, lane 0) or back stream (slots 2 / 3, lane 1)
+    auto send_raw = [&](uint32_t c, bool back_stream) {
+        const uint32_t k = back_stream ? n_back_sent : n_front_sent;
+        const int slot = (back_stream ? 2 : 0) + (int)(k & 1u);
+        cudaStream_t cs = back_stream ? copy_stream2_ : copy_stream_;
+        Lane& L = lanes_[back_stream ? 1 : 0];
+        const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0);
+        DH_CUDA(cudaStreamWaitEvent(cs, k >= 2 ? ev_consumed_[slot] : ev_fork_, 0));
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (timing_) {
+            t0 = next_event();
+            t1 = next_event();
+            DH_CUDA(cudaEventRecord(t0, cs));
+        }
+        DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t), cudaMemcpyHostToDevice, cs));
+        last_h2d_bytes_ += (uint64_t)nc * frame_px * sizeof(uint16_t);
+        if (timing_) {
+            DH_CUDA(cudaEventRecord(t1, cs));
+            copy_marks_.push_back({t0, t1});
+        }
+        DH_CUDA(cudaEventRecord(ev_copied_[slot], cs));
+        if (!back_stream) last_front_copy = ev_copied_[slot];
+        DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
+        run_chunk(L, slot, c);
+        if (back_stream) ++n_back_sent; else ++n_front_sent;
+    };
+    // The back stream takes another chunk only while NO copy is in flight on either copy stream.
+    // Raw and rewritten bytes compete for the same host memory bandwidth (a rewritten frame costs the
+    // host ~870 KB of DRAM traffic, a raw one 614 KB, and this host sustains ~95 GB/s): measured on
+    // the 16-core box, a raw stream that is always busy slows the workers by more than it adds
+    // (107 k frames/s at 44 % raw against 124 k with no raw chunk at all), while raw chunks that
+    // only fill the copy engines' idle time add to the total (134-137 k at ~25 % raw).
+    auto back_ready = [&] {
+        if (last_front_copy && cudaEventQuery(last_front_copy) == cudaErrorNotReady) return false;
+        if (n_back_sent && cudaEventQuery(ev_copied_[2 + (int)((n_back_sent - 1u) & 1u)]) == cudaErrorNotReady) return false;
+        return true;
+    };
+    auto refill = [&] {
+        while (encq.size() < 2 && front < back) {
+            const uint32_t c = front++;
+            if (dense(c)) send_raw(c, false);
+            else submit(c);
         }
     };
-    const uint64_t ticket = pool_->run(pool_->size(), worker);
-    bool copy_tail_valid = false;
-    std::vector<uint8_t> chunk_has_enc(n_chunks, 0);
-    uint32_t sent = 0;  // chunks handed to the GPU so far (their pinned slots are released in order as their copies finish)
-    auto try_release = [&] {
-        // chunk r = released - kEncSlots is the oldest whose slot is still reserved; it can be reused once that chunk has been
-        // sent and its encoded bytes have left the host
-        for (;;) {
-            const uint32_t r = released.load() - (uint32_t)kEncSlots;
-            if (r >= sent) return;
-            if (chunk_has_enc[r] && cudaEventQuery(ev_enc_copied_[r % (uint32_t)kEncSlots]) == cudaErrorNotReady) return;
-            released.fetch_add(1u, std::memory_order_release);
-        }
+    auto drain = [&] {
+        for (uint32_t c : encq) pool_->wait(tickets[c]);
     };
-    auto copy_idle = [&] { return !copy_tail_valid || cudaEventQuery(ev_copy_tail_) != cudaErrorNotReady; };
     try {
-        for (uint32_t c = 0; c < n_chunks; ++c) {
-            const int slot = (int)(c & 1u), pslot = (int)(c % (uint32_t)kEncSlots);
-            Lane& L = lanes_[c % (uint32_t)n_lanes];
-            const uint32_t f0 = c * F, nc = std::min<uint32_t>(F, n - f0), ng = (nc + G - 1) / G;
-            // the device slot (compressed bytes, frame table, frames) was last used by chunk c - 2; the frames start out zero
-            DH_CUDA(cudaStreamWaitEvent(copy_stream_, c >= 2 ? ev_consumed_[slot] : ev_fork_, 0));
-            cudaEvent_t t0 = nullptr, t1 = nullptr;
-            if (timing_) {
-                t0 = next_event();
-                t1 = next_event();
-                DH_CUDA(cudaEventRecord(t0, copy_stream_));
+        refill();
+        while (done_chunks < n_chunks) {
+            bool progressed = false;
+            if (!encq.empty() && pool_->done(tickets[encq.front()])) {
+                const uint32_t c = encq.front();
+                encq.erase(encq.begin());
+                send_encoded(c);
+                refill();
+                progressed = true;
             }
-            const bool all_raw = (cs[c].fb.load() >> 32) == 0;
-            if (all_raw) {
-                DH_CUDA(cudaMemcpyAsync(d_depth_[slot], depth + (size_t)f0 * frame_px, (size_t)nc * frame_px * sizeof(uint16_t),
-                                        cudaMemcpyHostToDevice, copy_stream_));
-                last_h2d_bytes_ += (uint64_t)nc * frame_px * sizeof(uint16_t);
+            if (hybrid && back > front && back_ready()) {
+                send_raw(--back, true);
+                progressed = true;
+            }
+            if (progressed) continue;
+            if (!encq.empty()) {
+                pool_->wait_for(tickets[encq.front()], hybrid && back > front ? 30u : 1000000u);
+            } else if (front < back) {
+                refill();  // nothing at the workers (dense chunks only so far)
             } else {
-                DH_CUDA(cudaMemsetAsync(d_depth_[slot], 0, (size_t)nc * frame_px * sizeof(uint16_t), copy_stream_));
-                // ---- raw groups from the back while the workers write from the front
-                uint32_t split;
-                for (;;) {
-                    try_release();
-                    uint64_t v = cs[c].fb.load();
-                    uint32_t fr = (uint32_t)v, bk = (uint32_t)(v >> 32);
-                    if (fr >= bk) {
-                        if (cs[c].enc_done.load(std::memory_order_acquire) == fr) {
-                            split = fr;
-                            break;
-                        }
-                    } else if (hybrid && copy_idle()) {
-                        if (cs[c].fb.compare_exchange_strong(v, ((uint64_t)(bk - 1u) << 32) | fr)) {
-                            const uint32_t g = bk - 1u, k0 = g * G, kn = std::min(nc, k0 + G) - k0;
-                            DH_CUDA(cudaMemcpyAsync(d_depth_[slot] + (size_t)k0 * frame_px, depth + (size_t)(f0 + k0) * frame_px,
-                                                    (size_t)kn * frame_px * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream_));
-                            DH_CUDA(cudaEventRecord(ev_copy_tail_, copy_stream_));
-                            copy_tail_valid = true;
-                            last_h2d_bytes_ += (uint64_t)kn * frame_px * sizeof(uint16_t);
-                        }
-                        continue;
-                    }
-                    std::this_thread::sleep_for(std::chrono::microseconds(15));
-                }
-                // ---- the rewritten groups [0, split): one copy each (the groups are not adjacent in the slot), then the frame table
-                unsigned long long* meta = h_enc_meta_[pslot];
-                for (uint32_t k = split * G; k < nc; ++k) meta[k] = ~0ull;  // sent raw: nothing to expand
-                for (uint32_t g = 0; g < split; ++g) {
-                    const uint32_t k1 = std::min(nc, (g + 1u) * G) - 1u;
-                    const size_t b0 = (size_t)meta[g * G], b1 = (size_t)meta[M + k1];
-                    DH_CUDA(cudaMemcpyAsync(d_blob_[slot] + b0, h_enc_[pslot] + b0, b1 - b0, cudaMemcpyHostToDevice, copy_stream_));
-                    last_h2d_bytes_ += b1 - b0;
-                }
-                if (split) {
-                    DH_CUDA(cudaMemcpyAsync(d_enc_meta_[slot], meta, sizeof(unsigned long long) * 2 * M, cudaMemcpyHostToDevice, copy_stream_));
-                    last_h2d_bytes_ += sizeof(unsigned long long) * 2 * M;
-                    DH_CUDA(cudaEventRecord(ev_enc_copied_[pslot], copy_stream_));
-                    chunk_has_enc[c] = 1;
-                    ++last_encoded_chunks_;
-                }
-                DH_CUDA(cudaEventRecord(ev_copy_tail_, copy_stream_));
-                copy_tail_valid = true;
-                (void)ng;
+                break;  // everything has been handed out
             }
-            if (timing_) {
-                DH_CUDA(cudaEventRecord(t1, copy_stream_));
-                copy_marks_.push_back({t0, t1});
-            }
-            DH_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
-            DH_CUDA(cudaStreamWaitEvent(L.stream, ev_copied_[slot], 0));
-            if (chunk_has_enc[c]) {
-                mark(DH_STAGE_H2D);  // the expansion counts as input transfer
-                launch_biwi_decode(d_blob_[slot], d_enc_meta_[slot], d_enc_meta_[slot] + M, 0ull, nc, w, h, d_depth_[slot], d_status_ + f0,
-                                   L.stream);
-                launches_ += 1;
-            }
-            FrameBuffers b = buffers(L, d_depth_[slot]);
-            run_front(L, b, nc, nullptr);
-            run_back(L, b, nc, iterations);
-            DH_CUDA(cudaMemcpyAsync(h_results_ + f0, L.results, sizeof(dh_result) * nc, cudaMemcpyDeviceToHost, L.stream));
-            DH_CUDA(cudaEventRecord(ev_consumed_[slot], L.stream));
-            sent = c + 1;
-            try_release();
         }
     } catch (...) {
-        abort.store(true);
-        pool_->wait(ticket);  // no worker may still read the caller's frames once this call has returned
+        drain();  // no worker may still read the caller's frames once this call has returned
         cudaStreamSynchronize(copy_stream_);
+        cudaStreamSynchronize(copy_stream2_);
         for (int i = 0; i < n_lanes; ++i) cudaStreamSynchronize(lanes_[i].stream);
         throw;
     }
-    pool_->wait(ticket);
     if (n_lanes > 1) {
         for (int i = 1; i < n_lanes; ++i) {
             DH_CUDA(cudaEventRecord(lanes_[i].done, lanes_[i].stream));

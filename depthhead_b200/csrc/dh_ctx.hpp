@@ -145,7 +145,9 @@ private:
     int n_sms_ = 148;
     uint32_t smem_optin_ = 0;
     cudaStream_t own_stream_ = nullptr, copy_stream_ = nullptr, stream_ = nullptr;
-    cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_consumed_[2] = {nullptr, nullptr};
+    static constexpr int kStageSlots = 4;   // device staging slots for host frames: 0, 1 everywhere; 2, 3 the raw stream of the hybrid host path
+    cudaEvent_t ev_copied_[kStageSlots] = {nullptr, nullptr, nullptr, nullptr}, ev_consumed_[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream2_ = nullptr;   // raw chunks of the hybrid host path (their own copy stream beside the rewritten chunks')
 
     // device copy of the model
     uint64_t df_serial_ = 0, df_sigma_version_ = 0;
@@ -183,7 +185,7 @@ private:
     cudaEvent_t ev_fork_ = nullptr;
     uint32_t chunk_frames_ = 0;   // 0 = adaptive
     uint32_t call_chunk_ = 1;
-    uint16_t* d_depth_[2] = {nullptr, nullptr};
+    uint16_t* d_depth_[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
     size_t staging_elems_ = 0;
     unsigned long long* d_counters_ = nullptr;
     // Biwi input: compressed bytes of a chunk (two slots), file offsets, per-frame decode status
@@ -203,7 +205,7 @@ private:
     // fixed region of the slot, so its bytes are known only to the worker that wrote them and the
     // groups are copied one cudaMemcpyAsync each.
     static constexpr int kEncSlots = 3;       // pinned slots: one being copied, two being written
-    static constexpr uint32_t kEncGroup = 4;  // frames per group: the unit a worker rewrites, or that goes over raw
+    static constexpr uint32_t kEncGroup = 4;  // most frames per worker task (and per copy of rewritten bytes)
     std::unique_ptr<WorkerPool> pool_;
     uint32_t encode_threads_req_ = 0;
     int host_encode_ = -1;                    // DH_HOST_ENCODE: 0 never, 1 whenever possible, -1 by sampled density
