@@ -104,6 +104,7 @@ Context::Context(int device) : device_(device) {
     if (const char* v = std::getenv("DH_HOST_ENCODE")) host_encode_ = *v ? (int)std::strtol(v, nullptr, 10) : -1;
     use_graphs_ = env_flag("DH_GRAPH", true);
     cube_clear_fused_ = env_flag("DH_CUBE_CLEAR_FUSED", true);
+    gate_split_ = env_flag("DH_GATE_SPLIT", true);
     chunk_frames_ = env_u32("DH_CHUNK_FRAMES", 0);  // 0 = adaptive (128 for host input, 512 for device input)
     debug_sync_ = env_u32("DH_DEBUG_SYNC", 0) != 0;
     std::memset(stage_ms_, 0, sizeof(stage_ms_));
@@ -192,7 +193,7 @@ void Context::free_forest() {
 // record together with its two children; records in breadth-first order, so the (up to four)
 // grandchild records of a record are consecutive; the leaves under a record get consecutive
 // device leaf numbers, mapped back to global leaf ids by the permutation table.
-void Context::build_pair_tables(const HostForest& hf) {
+void Context::build_pair_tables(const HostForest& hf, const std::vector<int32_t>& dev_index) {
     if (hf.n_leaves() >= (1u << 26) || hf.max_depth >= 63) return;  // the permutation entry packs leaf id (26 bits) and depth (6 bits)
     std::vector<PairTopo> topo;
     std::vector<uint32_t> depth;  // of the record's node X below its root
@@ -243,6 +244,12 @@ void Context::build_pair_tables(const HostForest& hf) {
             topo[r].tail = (first_leaf << 6) | ((c[1] < 0 ? 1u : 0u) << 5) | ((c[0] < 0 ? 1u : 0u) << 4) | mask;
         }
     }
+    if (!dev_index.empty())  // the device node table is laid out differently from the host's (ensure_forest)
+        for (PairTopo& pt : topo) {
+            pt.x = dev_index[(size_t)pt.x];
+            if (pt.c0 >= 0) pt.c0 = dev_index[(size_t)pt.c0];
+            if (pt.c1 >= 0) pt.c1 = dev_index[(size_t)pt.c1];
+        }
     df_n_pairs_ = topo.size();
     dev_alloc(df_pair_recs_, topo.size());
     dev_alloc(df_pair_topo_, topo.size());
@@ -258,16 +265,65 @@ void Context::ensure_forest(const HostForest& hf) {
     if (df_serial_ != hf.serial) {
         DH_CUDA(cudaStreamSynchronize(stream_));
         free_forest();
-        const size_t NN = hf.n_nodes(), NL = hf.n_leaves(), NV = hf.n_votes();
-        dev_alloc(df_nodes_, NN);
-        dev_alloc(df_hot_, NN);
-        df_n_nodes_ = NN;
+        const size_t NL = hf.n_leaves(), NV = hf.n_votes();
+        size_t NN = hf.n_nodes();
         // Node fetches go through the texture path when the table fits a 1-D texture (2^27
         // texels); forests whose rectangles all have one size get the 16-byte box-sum nodes.
         uni_rw_ = uni_rh_ = 0;
         const bool use_tex = env_flag("DH_TEX", true);
         const bool uni_ldg = env_flag("DH_UNI_LDG", false);
-        if (NN && env_flag("DH_UNIFORM", true) && hf.uniform_rw && (uni_ldg || (use_tex && NN < (1ull << 27)))) {
+        const bool want_uni = NN && env_flag("DH_UNIFORM", true) && hf.uniform_rw && (uni_ldg || (use_tex && NN < (1ull << 26)));
+        // Device order of the node table.  The host keeps every tree in breadth-first order, so the
+        // internal children of a node are neighbours; with 16-byte nodes a 32-byte sector holds two
+        // of them, and a pad record in front of a pair that would straddle two sectors makes the
+        // lanes of a warp that part ways at a node fetch ONE sector for both sides (DH_NODE_ALIGN=0:
+        // host order; pads are never visited).
+        std::vector<int32_t> dev_index;
+        std::vector<NodeRec> dev_nodes;
+        std::vector<int32_t> dev_roots(hf.roots);
+        if (want_uni && env_flag("DH_NODE_ALIGN", true)) {
+            dev_index.assign(NN, -1);
+            int32_t d = 0;
+            bool ok = true;
+            for (int32_t t = 0; t < hf.n_trees && ok; ++t) {
+                const int64_t n0 = hf.tree_node_off[(size_t)t], n1 = hf.tree_node_off[(size_t)t + 1];
+                if (n1 == n0) continue;
+                dev_index[(size_t)n0] = d++;
+                int64_t next = n0 + 1;  // breadth-first: the next node without a place is the next child met
+                for (int64_t h = n0; h < n1 && ok; ++h) {
+                    const NodeRec& r = hf.nodes[(size_t)h];
+                    const int kids = (r.child[0] >= 0 ? 1 : 0) + (r.child[1] >= 0 ? 1 : 0);
+                    if (kids == 2 && (d & 1)) ++d;  // the pad
+                    for (int b = 0; b < 2; ++b)
+                        if (r.child[b] >= 0) {
+                            if (r.child[b] != (int32_t)next || next >= n1) { ok = false; break; }
+                            dev_index[(size_t)next++] = d++;
+                        }
+                }
+                if (next != n1) ok = false;
+            }
+            if (ok && (size_t)d < (1ull << 27)) {
+                NodeRec pad;
+                std::memset(&pad, 0, sizeof(pad));
+                pad.child[0] = pad.child[1] = -1;
+                dev_nodes.assign((size_t)d, pad);
+                for (size_t h = 0; h < NN; ++h) {
+                    NodeRec r = hf.nodes[h];
+                    for (int b = 0; b < 2; ++b)
+                        if (r.child[b] >= 0) r.child[b] = dev_index[(size_t)r.child[b]];
+                    dev_nodes[(size_t)dev_index[h]] = r;
+                }
+                for (int32_t& r : dev_roots)
+                    if (r >= 0) r = dev_index[(size_t)r];
+                NN = (size_t)d;
+            } else {
+                dev_index.clear();
+            }
+        }
+        dev_alloc(df_nodes_, NN);
+        dev_alloc(df_hot_, NN);
+        df_n_nodes_ = NN;
+        if (want_uni) {
             dev_alloc(df_uni_, NN);
             uni_rw_ = hf.uniform_rw;
             uni_rh_ = hf.uniform_rh;
@@ -282,7 +338,7 @@ void Context::ensure_forest(const HostForest& hf) {
             td.readMode = cudaReadModeElementType;
             DH_CUDA(cudaCreateTextureObject(&hot_tex_, &rd, &td, nullptr));
         }
-        if (df_uni_ && hot_tex_ && env_flag("DH_TRAV_PAIR", false)) build_pair_tables(hf);
+        if (df_uni_ && hot_tex_ && env_flag("DH_TRAV_PAIR", false)) build_pair_tables(hf, dev_index);
         dev_alloc(df_roots_, (size_t)hf.n_trees);
         dev_alloc(df_leaf_prob_, NL);
         dev_alloc(df_leaf_info_, NL);
@@ -292,8 +348,10 @@ void Context::ensure_forest(const HostForest& hf) {
         dev_alloc(df_rot_cells_, NV);
         dev_alloc(df_leaf_box_, NL);
         dev_alloc(df_kernel_, (size_t)kKernelCells);
-        if (NN) DH_CUDA(cudaMemcpyAsync(df_nodes_, hf.nodes.data(), NN * sizeof(NodeRec), cudaMemcpyHostToDevice, stream_));
-        DH_CUDA(cudaMemcpyAsync(df_roots_, hf.roots.data(), hf.roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        if (NN)
+            DH_CUDA(cudaMemcpyAsync(df_nodes_, dev_nodes.empty() ? hf.nodes.data() : dev_nodes.data(), NN * sizeof(NodeRec),
+                                    cudaMemcpyHostToDevice, stream_));
+        DH_CUDA(cudaMemcpyAsync(df_roots_, dev_roots.data(), dev_roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
         DH_CUDA(cudaMemcpyAsync(df_leaf_prob_, hf.leaf_prob.data(), NL * sizeof(double), cudaMemcpyHostToDevice, stream_));
         std::vector<float4> off4(NV);
         for (size_t v = 0; v < NV; ++v) off4[v] = make_float4(hf.offsets[v * 3], hf.offsets[v * 3 + 1], hf.offsets[v * 3 + 2], 0.0f);
@@ -319,6 +377,11 @@ void Context::ensure_forest(const HostForest& hf) {
         dev_free(d_nv);
         dev_free(d_rot);
         dev_free(df_offsets3_);
+        // probability codes in the node table (plan_nodes_kernel, GateTail): 23 bits of leaf id, prob in [0, 1]
+        prob_codes_ok_ = NL < (size_t)kLeafIdMask;
+        for (size_t l = 0; l < NL && prob_codes_ok_; ++l)
+            if (!(hf.leaf_prob[l] >= 0.0 && hf.leaf_prob[l] <= 1.0)) prob_codes_ok_ = false;
+        if (!env_flag("DH_PROB_CODES", true)) prob_codes_ok_ = false;
         df_serial_ = hf.serial;
         df_sigma_version_ = 0;
         df_n_leaves_ = NL;
@@ -362,6 +425,8 @@ void Context::free_lane(Lane& L) {
     dev_free(L.p3);
     dev_free(L.gate);
     dev_free(L.gated);
+    dev_free(L.cand);
+    dev_free(L.tile_cnt);
     dev_free(L.cubes);
     dev_free(L.grids);
     dev_free(L.fs);
@@ -401,6 +466,10 @@ void Context::alloc_lane(Lane& L) {
     dev_alloc(L.p3, F * P * 3);
     dev_alloc(L.gate, F * P);
     dev_alloc(L.gated, F * P);
+    if (g.P) {
+        dev_alloc(L.cand, F * (size_t)tiles_.tiles_x * tiles_.tiles_y * tiles_.tpx * tiles_.tpy);
+        dev_alloc(L.tile_cnt, F * (size_t)tiles_.tiles_x * tiles_.tiles_y);
+    }
     dev_alloc(L.cubes, F * 2 * (size_t)vote_box_cells());
     DH_CUDA(cudaMemsetAsync(L.cubes, 0, sizeof(uint32_t) * F * 2 * (size_t)vote_box_cells(), stream_));
     L.cubes_clean = true;
@@ -579,8 +648,8 @@ FrameBuffers Context::buffers(const Lane& L, const uint16_t* depth) const {
     b.band_u = L.band_u;
     b.box = L.box;
     b.leaf = L.leaf;
-    b.p3 = L.p3;
-    b.gate = L.gate;
+    b.p3 = debug_ ? L.p3 : nullptr;      // per-patch exports of debug passes only
+    b.gate = debug_ ? L.gate : nullptr;
     b.gated = L.gated;
     b.grids = L.grids;
     b.fs = L.fs;
@@ -632,7 +701,7 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
         launches_ += 1;
     }
     if (g.P && hot_tw_ != tiles_.tw) {  // node table for this tile plan (once per forest x plan)
-        launch_plan_nodes(df_nodes_, df_hot_, df_uni_, df_n_nodes_, tiles_.tw, stream_);
+        launch_plan_nodes(df_nodes_, df_hot_, df_uni_, df_n_nodes_, tiles_.tw, prob_codes_ok_ ? df_leaf_prob_ : nullptr, stream_);
         if (df_pair_recs_) launch_plan_pairs(df_pair_topo_, df_uni_, df_pair_recs_, df_n_pairs_, stream_);
         DH_CUDA(cudaStreamSynchronize(stream_));
         hot_tw_ = tiles_.tw;
@@ -649,7 +718,23 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
             DH_CUDA(cudaMemsetAsync(L.leaf, 0xFF, sizeof(int32_t) * (size_t)n * g.n_trees * g.P, st));
         else
             DH_CUDA(cudaMemset2DAsync(L.leaf, sizeof(int32_t) * (size_t)g.n_trees * g.P, 0xFF, sizeof(int32_t) * (size_t)g.P, n, st));
-        launch_traverse(L.sat_map, b, g, tiles_, fdev_, n, st);
+        // the default walk also applies the patch gate (prediction.rs:582-584) to the patches it has just
+        // walked and writes the frame's gated-patch list: see GateTail
+        GateTail gt{};
+        gt.leaf_mask = prob_codes_ok_ ? kLeafIdMask : 0x7fffffffu;
+        if (gate_split_ && prob_codes_ok_ && g.n_trees <= 4096u) {
+            gt.cand = L.cand;
+            gt.tile_cnt = L.tile_cnt;
+            gt.cand_pitch = tiles_.tiles_x * tiles_.tiles_y * tiles_.tpx * tiles_.tpy;
+            // the f64 fold of T probabilities differs from their real sum by less than T^2 * 2^-52
+            const double T = (double)g.n_trees, slack = T * T * std::ldexp(1.0, -50);
+            gt.pass_min = (uint32_t)std::ceil((g.gate_min_sum + slack) * 256.0);
+            gt.fail_max = (uint32_t)std::max(0.0, std::ceil((g.gate_min_sum - slack) * 256.0) - 1.0);
+            DH_CUDA(cudaMemsetAsync(L.tile_cnt, 0, sizeof(uint32_t) * (size_t)n * tiles_.tiles_x * tiles_.tiles_y, st));
+            if (debug_) DH_CUDA(cudaMemsetAsync(L.gate, 0, (size_t)n * g.P, st));  // gate_compact_kernel marks the passing patches only
+        }
+        L.have_list = launch_traverse(L.sat_map, b, g, tiles_, fdev_, gt, n, st);
+        L.tail = gt;
         launches_ += 1;
         stage_check("traverse");
     }
@@ -659,7 +744,7 @@ void Context::run_back(Lane& L, const FrameBuffers& b, uint32_t n, uint32_t iter
     const Geometry& g = geom_;
     cudaStream_t st = L.stream;
     mark(DH_STAGE_GATE);
-    launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, st);
+    launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, gate_split_, L.have_list ? &L.tail : nullptr, tiles_, n_sms_, st);
     stage_check("gate + coarse grids");
     mark(DH_STAGE_VOTE);
     // the accumulator cubes of this pass start empty: either the previous pass's mean-shift CTAs

@@ -459,8 +459,12 @@ __global__ void __launch_bounds__(kBoxMaxWarps * 32) box_image_kernel(const uint
 
 // ================================================================ K2: forest traversal
 // Node table prepared for one tile plan: see HotNode (dh_types.hpp).
+// prob_codes != nullptr: a leaf child of a UniNode carries the leaf's probability code in bits 23..30
+// of the complemented word, ~(leaf | code << 23) with code = min(floor(prob * 256), 255), so that a walk
+// knows prob to within 1/256 without another fetch (kLeafIdMask recovers the id; GateTail).
 __global__ void __launch_bounds__(256) plan_nodes_kernel(const NodeRec* __restrict__ nodes, HotNode* __restrict__ hot,
-                                                         UniNode* __restrict__ uni, size_t n, uint32_t tw) {
+                                                         UniNode* __restrict__ uni, size_t n, uint32_t tw,
+                                                         const double* __restrict__ prob_codes) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const NodeRec r = nodes[i];
@@ -483,8 +487,17 @@ __global__ void __launch_bounds__(256) plan_nodes_kernel(const NodeRec* __restri
     if (uni) {  // all rectangles have one size: c[0] == c[1] == the common pixel count
         UniNode u;
         u.taps = (h.r1 & 0xffffu) | (h.r2 << 16);
-        u.child[0] = r.child[0];
-        u.child[1] = r.child[1];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            int32_t c = r.child[k];
+            if (c < 0 && prob_codes) {
+                const uint32_t leaf = (uint32_t)~c;
+                const double pr = prob_codes[leaf];  // in [0, 1], checked on the host
+                const uint32_t code = min((uint32_t)__double2uint_rd(__dmul_rn(pr, 256.0)), 255u);
+                c = ~(int32_t)(leaf | (code << kProbCodeShift));
+            }
+            u.child[k] = c;
+        }
         // Decision value E for d2 = 2*(s1 - s2), |s1 - s2| < 2^30 (rw*rh <= 16383 is checked at
         // load).  The reference compares fl(fl(s1/c) - fl(s2/c)) > thr; its three roundings move
         // the left side by < 2.2e-11 (|s/c| <= 65535, eps = 2^-53), so whenever the real numbers
@@ -549,6 +562,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void atomicAdd_smem(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
 }
@@ -587,7 +603,8 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
                                                             const uint32_t* __restrict__ sat,
                                                             FrameState* __restrict__ fs, Geometry g, TilePlan tp,
                                                             uint32_t uni_rw, uint32_t uni_rh, const PairRec* __restrict__ pair_recs,
-                                                            const int32_t* __restrict__ pair_roots, const int32_t* __restrict__ pair_perm) {
+                                                            const int32_t* __restrict__ pair_roots, const int32_t* __restrict__ pair_perm,
+                                                            const GateTail gt) {
     extern __shared__ uint8_t smem_raw[];
     // 128-byte aligned tile (TMA destination), then the barrier, then the compacted patch list;
     // everything is addressed through 32-bit shared-window addresses
@@ -595,13 +612,14 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
     const uint32_t tile_bytes = tp.tw * tp.th * 4u;
     const uint32_t bar_a = tile_a + ((tile_bytes + 15u) & ~15u);
     const uint32_t live_a = bar_a + 16u;
-    __shared__ uint32_t s_nlive, s_empty;
+    __shared__ uint32_t s_nlive, s_empty, s_ncand;
 
     const uint32_t frame = blockIdx.y;
     const uint32_t tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
     const uint32_t px0 = tile_x * tp.tpx, py0 = tile_y * tp.tpy;  // first patch of the tile
     const uint32_t tid = threadIdx.x;
     const uint32_t npt = tp.tpx * tp.tpy;
+    const uint32_t sum_a = live_a + ((npt + 31u) & ~31u) * 4u;  // per live patch: sum of its leaves' probability codes (GateTail)
     const int T = (int)g.n_trees;
     int32_t* leaf_f = leaf + (size_t)frame * T * g.P;
 
@@ -613,6 +631,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1u) : "memory");
         fence_mbar_init();
         s_nlive = 0;
+        s_ncand = 0;
         if (tp.tma_first) {
             // the load is issued before the tile's background check and lands while warp 0 tests
             // the window (one global round trip less in front of every non-empty tile)
@@ -685,6 +704,8 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
     // patches in row order, 32 per warp, or (tp.blocked) in blocks of 8 x 4 patches, one per warp
     const uint32_t nbx = (tp.tpx + 7u) >> 3;
     const uint32_t n_lp = tp.blocked ? nbx * ((tp.tpy + 3u) >> 2) * 32u : ((npt + 31u) & ~31u);
+    if (kMode == 4 && gt.cand)
+        for (uint32_t i = tid; i < npt; i += kThreads) sts_u32(sum_a + 4u * i, 0u);
     for (uint32_t lp = tid; lp < n_lp; lp += kThreads) {
         bool ok = false;
         uint32_t packed = 0;
@@ -796,8 +817,8 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
                     ++visits;
                 }
             }
-            leaf_f[(size_t)tA * g.P + (py0 + (lpA >> 24)) * g.npx + (px0 + ((lpA >> 16) & 0xffu))] = ~nA;
-            if (hasB) leaf_f[(size_t)tB * g.P + (py0 + (lpB >> 24)) * g.npx + (px0 + ((lpB >> 16) & 0xffu))] = ~nB;
+            leaf_f[(size_t)tA * g.P + (py0 + (lpA >> 24)) * g.npx + (px0 + ((lpA >> 16) & 0xffu))] = (int32_t)((uint32_t)~nA & gt.leaf_mask);
+            if (hasB) leaf_f[(size_t)tB * g.P + (py0 + (lpB >> 24)) * g.npx + (px0 + ((lpB >> 16) & 0xffu))] = (int32_t)((uint32_t)~nB & gt.leaf_mask);
         }
     } else if (kMode == 4) {
         // the default walk (uniform rectangles, box-sum tile, nodes through the texture path), in two
@@ -828,7 +849,9 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
             any_tie |= tie;
             visits += tie ? 0u : nv;
             const uint32_t gp = (py0 + (lp >> 24)) * g.npx + (px0 + ((lp >> 16) & 0xffu));
-            leaf_f[(size_t)t * g.P + gp] = tie ? kTieMark : ~node;
+            const uint32_t lw = (uint32_t)~node;  // leaf | probability code << 23 (plan_nodes_kernel)
+            leaf_f[(size_t)t * g.P + gp] = tie ? kTieMark : (int32_t)(lw & gt.leaf_mask);
+            if (gt.cand && !tie) atomicAdd_smem(sum_a + 4u * (it - t * nlive), lw >> kProbCodeShift);
         }
         if (any_tie) {
             for (uint32_t it = tid; it < items; it += kThreads) {
@@ -848,7 +871,9 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
                     node = next;
                     ++visits;
                 }
-                *slot = ~node;
+                const uint32_t lw = (uint32_t)~node;
+                *slot = (int32_t)(lw & gt.leaf_mask);
+                if (gt.cand) atomicAdd_smem(sum_a + 4u * (it - t * nlive), lw >> kProbCodeShift);
             }
         }
     } else if (kMode == 7) {
@@ -894,7 +919,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
                     node = next;
                     ++visits;
                 }
-                leaf_id = ~node;
+                leaf_id = (int32_t)((uint32_t)~node & gt.leaf_mask);
             }
             const uint32_t lp = lds_u32(live_a + 4u * (it - t * nlive));
             const uint32_t gp = (py0 + (lp >> 24)) * g.npx + (px0 + ((lp >> 16) & 0xffu));
@@ -953,7 +978,40 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
             ++visits;
         }
         const uint32_t gp = (py0 + ly) * g.npx + (px0 + lx);
-        leaf_f[(size_t)t * g.P + gp] = ~node;
+        leaf_f[(size_t)t * g.P + gp] = kMode >= 2 ? (int32_t)((uint32_t)~node & gt.leaf_mask) : ~node;
+    }
+
+    // ---- patch gate (prediction.rs:582-584) of the tile's live patches, decided from the sums of the
+    //      probability codes the walks brought along: prob_t lies in [code_t / 256, (code_t + 1) / 256],
+    //      so the f64 fold of the reference lies within [S, S + T] / 256 (up to its own rounding, which
+    //      gt.pass_min / gt.fail_max leave room for).  A patch that passes for certain, or whose sum
+    //      lies inside that band (flagged: a few percent), goes to the tile's candidate list; nothing
+    //      here waits for global memory.  gate_compact_kernel settles the flagged ones with the exact
+    //      fold and turns the candidates into the frame's gated-patch list.
+    if (kMode == 4 && gt.cand && nlive) {
+        __syncthreads();            // every walk of the tile has added its code
+        uint32_t* cand = gt.cand + (size_t)frame * gt.cand_pitch + (size_t)blockIdx.x * npt;
+        for (uint32_t i0 = tid & ~31u; i0 < nlive; i0 += kThreads) {  // warp-uniform trip count
+            const uint32_t i = i0 + (tid & 31u);
+            uint32_t word = 0;
+            bool keep = false;
+            if (i < nlive) {
+                const uint32_t lp = lds_u32(live_a + 4u * i);
+                const uint32_t S = lds_u32(sum_a + 4u * i);
+                const bool pass = S >= gt.pass_min;
+                keep = pass || S + (uint32_t)T > gt.fail_max;
+                word = ((py0 + (lp >> 24)) * g.npx + (px0 + ((lp >> 16) & 0xffu))) | (pass ? 0u : 0x80000000u);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (!m) continue;
+            uint32_t base = 0;
+            if ((tid & 31u) == 0) {
+                base = atomicAdd(&s_ncand, (uint32_t)__popc(m));                                          // rank inside the tile
+                atomicAdd(gt.tile_cnt + (size_t)frame * gridDim.x + blockIdx.x, (uint32_t)__popc(m));  // nobody waits for this one
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) cand[base + __popc(m & ((1u << (tid & 31u)) - 1u))] = word;
+        }
     }
 
     // ---- per-frame counters (measured mean depth feeds the roofline arithmetic)
@@ -1053,31 +1111,18 @@ __device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t 
 
 constexpr int kGateSmemBytes = kGateThreads * 16 + (kGateThreads / 32) * 32 * 32 + (kPosGridCells + kRotGridCells) * 4 + kTouchedCap * 2;
 
-// kFused: one pass over the votes of every pair feeds both grids (a vote is an offset and a rotation;
-// the pair's tag says which of the two spread gates is open) instead of one pass per grid.
-template <bool kFused>
-__global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffers b, Geometry g, ForestDev f) {
-    extern __shared__ __align__(16) uint8_t gate_smem[];
-    float4* s_gated = reinterpret_cast<float4*>(gate_smem);                                   // [kGateThreads] p3 + patch index of the CTA's gated patches
-    PairSlot(*s_slots)[32] = reinterpret_cast<PairSlot(*)[32]>(gate_smem + kGateThreads * 16);  // [warps][32] vote spreading, one set per warp
-    uint32_t* s_grid = reinterpret_cast<uint32_t*>(gate_smem + kGateThreads * 16 + (kGateThreads / 32) * 32 * 32);  // [0,400) centre, [400,8400) rotation
-    uint16_t* s_touched = reinterpret_cast<uint16_t*>(s_grid + kPosGridCells + kRotGridCells);  // rotation cells this CTA made non-zero
-    __shared__ uint32_t s_ngate, s_base, s_ntouched, s_next;
-    const uint32_t frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31u;
-    const uint32_t p = blockIdx.x * kGateThreads + tid;
+// The patch gate on its own (phase A of gate_coarse_kernel), one thread per patch: the passing patches
+// are appended to the frame's gated-patch list, one reservation per warp.  gate_coarse_kernel<., true>
+// then reads slices of that list.  Runs when the traversal variant of the pass has no gate tail
+// (GateTail): it re-reads every leaf id and gathers every leaf's probability (0.19 ms per 1024
+// frames of configs[1], bound by the L1 miss path), which the tail avoids.
+constexpr int kPatchGateThreads = 256;
+__global__ void __launch_bounds__(kPatchGateThreads) patch_gate_kernel(FrameBuffers b, Geometry g, ForestDev f) {
+    const uint32_t frame = blockIdx.y, lane = threadIdx.x & 31u;
+    const uint32_t p = blockIdx.x * kPatchGateThreads + threadIdx.x;
     const uint32_t T = g.n_trees;
     const int32_t* leaf_f = b.leaf + (size_t)frame * T * g.P;
-    FrameState* fs = b.fs + frame;
-    if (tid == 0) {
-        s_ngate = 0;
-        s_ntouched = 0;
-        s_next = 0;
-    }
-    __syncthreads();
-
-    // ---- phase A
     bool gate = false;
-    float p3[3] = {0.f, 0.f, 0.f};
     if (p < g.P) {
         if (leaf_f[p] >= 0) {
             // prob = sum(leaf.prob) / len: f64 fold from 0.0 in tree order (prediction.rs:582);
@@ -1098,87 +1143,226 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
             }
             gate = s >= g.gate_min_sum;  // sum / T > 0.7 (prediction.rs:584), see Geometry::gate_min_sum
         }
+        if (b.gate) b.gate[(size_t)frame * g.P + p] = gate ? 1 : 0;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, gate);
+    if (!m) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&b.fs[frame].n_gate, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (gate) {
+        const uint32_t gx = p % g.npx, gy = p / g.npx;
+        const uint32_t x = g.left_w + gx * g.stride, y = g.left_h + gy * g.stride;
+        const uint16_t z = b.depth[((size_t)frame * g.h + y) * g.w + x];  // prediction.rs:551
+        float p3[3];
+        img_to_space(g.Kinv, (float)x, (float)y, (float)z, p3);           // prediction.rs:554
+        b.gated[(size_t)frame * g.P + base + __popc(m & ((1u << lane) - 1u))] = make_float4(p3[0], p3[1], p3[2], __uint_as_float(p));
+        if (b.p3) {
+            float* o = b.p3 + ((size_t)frame * g.P + p) * 3;
+            o[0] = p3[0]; o[1] = p3[1]; o[2] = p3[2];
+        }
+    }
+}
+
+// Candidates of the traversal's gate tail (GateTail) -> the frame's gated-patch list.  One warp per
+// tile, a lane per candidate: a flagged candidate (its code sum could not decide) gets the exact fold
+// of patch_gate_kernel; a patch that passes is back-projected and appended, one reservation per warp.
+__global__ void __launch_bounds__(kPatchGateThreads) gate_compact_kernel(FrameBuffers b, Geometry g, ForestDev f, GateTail gt,
+                                                                         uint32_t npt, uint32_t n_tiles) {
+    const uint32_t frame = blockIdx.y, lane = threadIdx.x & 31u;
+    const uint32_t tile = blockIdx.x * (kPatchGateThreads / 32) + (threadIdx.x >> 5);  // a warp per tile
+    if (tile >= n_tiles) return;
+    const uint32_t T = g.n_trees;
+    const uint32_t n = gt.tile_cnt[(size_t)frame * n_tiles + tile];
+    const uint32_t* cand = gt.cand + (size_t)frame * gt.cand_pitch + (size_t)tile * npt;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
+        bool gate = false;
+        uint32_t p = 0;
+        if (i0 + lane < n) {
+            const uint32_t w = cand[i0 + lane];
+            p = w & 0x7fffffffu;
+            gate = true;
+            if (w >> 31) {
+                const int32_t* leaf_f = b.leaf + (size_t)frame * T * g.P;
+                double s = 0.0;  // prob = sum(leaf.prob) / len: f64 fold from 0.0 in tree order (prediction.rs:582)
+                for (uint32_t t = 0; t < T; ++t) s = __dadd_rn(s, __ldg(f.leaf_prob + leaf_f[(size_t)t * g.P + p]));
+                gate = s >= g.gate_min_sum;
+            }
+            if (b.gate && gate) b.gate[(size_t)frame * g.P + p] = 1;  // zeroed by the caller
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, gate);
+        if (!m) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&b.fs[frame].n_gate, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
         if (gate) {
             const uint32_t gx = p % g.npx, gy = p / g.npx;
             const uint32_t x = g.left_w + gx * g.stride, y = g.left_h + gy * g.stride;
             const uint16_t z = b.depth[((size_t)frame * g.h + y) * g.w + x];  // prediction.rs:551
+            float p3[3];
             img_to_space(g.Kinv, (float)x, (float)y, (float)z, p3);           // prediction.rs:554
+            b.gated[(size_t)frame * g.P + base + __popc(m & ((1u << lane) - 1u))] = make_float4(p3[0], p3[1], p3[2], __uint_as_float(p));
             if (b.p3) {
                 float* o = b.p3 + ((size_t)frame * g.P + p) * 3;
                 o[0] = p3[0]; o[1] = p3[1]; o[2] = p3[2];
             }
         }
-        if (b.gate) b.gate[(size_t)frame * g.P + p] = gate ? 1 : 0;
     }
-    {
-        const uint32_t m = __ballot_sync(0xffffffffu, gate);
-        uint32_t base = 0;
-        if (lane == 0 && m) base = atomicAdd(&s_ngate, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (gate) s_gated[base + __popc(m & ((1u << lane) - 1u))] = make_float4(p3[0], p3[1], p3[2], __uint_as_float(p));
-    }
-    __syncthreads();
-    const uint32_t ngate = s_ngate;
-    if (ngate == 0u) return;
-    if (tid == 0) s_base = atomicAdd(&fs->n_gate, ngate);
-    for (int i = tid; i < kPosGridCells + kRotGridCells; i += kGateThreads) s_grid[i] = 0;
-    __syncthreads();
-    if (tid < ngate) b.gated[(size_t)frame * g.P + s_base + tid] = s_gated[tid];
+}
 
-    // ---- phase B: pair = (tree, gated patch), neighbouring lanes = neighbouring gated patches.
-    // A warp takes 32 pairs at a time and spreads their votes evenly over its lanes (for_each_vote),
-    // so leaves with few, many or no votes cost the same per vote.
+// kFused: one pass over the votes of every pair feeds both grids (a vote is an offset and a rotation;
+// the pair's tag says which of the two spread gates is open) instead of one pass per grid.
+// kFromList: the patch gate has already been applied (traversal tail or patch_gate_kernel): the CTA
+// takes slices of kGateThreads entries of the frame's gated-patch list (blockIdx.x, + gridDim.x, ...)
+// instead of gating the kGateThreads patches of its own index range, so that every CTA that runs
+// has a full slice behind the fixed costs of its seed grids (clearing and flushing 8400 cells);
+// CTAs beyond the end of the list leave at once.
+template <bool kFused, bool kFromList>
+__global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffers b, Geometry g, ForestDev f) {
+    extern __shared__ __align__(16) uint8_t gate_smem[];
+    float4* s_gated = reinterpret_cast<float4*>(gate_smem);                                   // [kGateThreads] p3 + patch index of the CTA's gated patches
+    PairSlot(*s_slots)[32] = reinterpret_cast<PairSlot(*)[32]>(gate_smem + kGateThreads * 16);  // [warps][32] vote spreading, one set per warp
+    uint32_t* s_grid = reinterpret_cast<uint32_t*>(gate_smem + kGateThreads * 16 + (kGateThreads / 32) * 32 * 32);  // [0,400) centre, [400,8400) rotation
+    uint16_t* s_touched = reinterpret_cast<uint16_t*>(s_grid + kPosGridCells + kRotGridCells);  // rotation cells this CTA made non-zero
+    __shared__ uint32_t s_ngate, s_base, s_ntouched, s_next;
+    const uint32_t frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t p = blockIdx.x * kGateThreads + tid;
+    const uint32_t T = g.n_trees;
+    const int32_t* leaf_f = b.leaf + (size_t)frame * T * g.P;
+    FrameState* fs = b.fs + frame;
+    uint32_t slice0 = blockIdx.x * kGateThreads, n_list = 0;
+    if (kFromList) {
+        n_list = fs->n_gate;  // complete: written by the traversal's tail or by patch_gate_kernel
+        if (slice0 >= n_list) return;
+    }
+    if (tid == 0) {
+        s_ngate = 0;
+        s_ntouched = 0;
+        s_next = 0;
+    }
+    if (kFromList)
+        for (int i = tid; i < kPosGridCells + kRotGridCells; i += kGateThreads) s_grid[i] = 0;
+    __syncthreads();
+
+    uint32_t ngate;
+    if (!kFromList) {
+        // ---- phase A
+        bool gate = false;
+        float p3[3] = {0.f, 0.f, 0.f};
+        if (p < g.P) {
+            if (leaf_f[p] >= 0) {
+                // prob = sum(leaf.prob) / len: f64 fold from 0.0 in tree order (prediction.rs:582);
+                // four independent gathers in flight, the additions stay in tree order
+                double s = 0.0;
+                for (uint32_t t0 = 0; t0 < T; t0 += 4) {
+                    int32_t L[4];
+                    double pr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (t0 + u < T) L[u] = leaf_f[(size_t)(t0 + u) * g.P + p];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (t0 + u < T) pr[u] = __ldg(f.leaf_prob + L[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (t0 + u < T) s = __dadd_rn(s, pr[u]);
+                }
+                gate = s >= g.gate_min_sum;  // sum / T > 0.7 (prediction.rs:584), see Geometry::gate_min_sum
+            }
+            if (gate) {
+                const uint32_t gx = p % g.npx, gy = p / g.npx;
+                const uint32_t x = g.left_w + gx * g.stride, y = g.left_h + gy * g.stride;
+                const uint16_t z = b.depth[((size_t)frame * g.h + y) * g.w + x];  // prediction.rs:551
+                img_to_space(g.Kinv, (float)x, (float)y, (float)z, p3);           // prediction.rs:554
+                if (b.p3) {
+                    float* o = b.p3 + ((size_t)frame * g.P + p) * 3;
+                    o[0] = p3[0]; o[1] = p3[1]; o[2] = p3[2];
+                }
+            }
+            if (b.gate) b.gate[(size_t)frame * g.P + p] = gate ? 1 : 0;
+        }
+        {
+            const uint32_t m = __ballot_sync(0xffffffffu, gate);
+            uint32_t base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_ngate, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (gate) s_gated[base + __popc(m & ((1u << lane) - 1u))] = make_float4(p3[0], p3[1], p3[2], __uint_as_float(p));
+        }
+        __syncthreads();
+        ngate = s_ngate;
+        if (ngate == 0u) return;
+        if (tid == 0) s_base = atomicAdd(&fs->n_gate, ngate);
+        for (int i = tid; i < kPosGridCells + kRotGridCells; i += kGateThreads) s_grid[i] = 0;
+        __syncthreads();
+        if (tid < ngate) b.gated[(size_t)frame * g.P + s_base + tid] = s_gated[tid];
+    }
+
     uint32_t cnt_c = 0, cnt_r = 0;
     unsigned long long nmid = 0, nrot = 0;
-    const uint32_t npairs = ngate * T;
-    // batches of 32 pairs are handed out through a shared counter: their vote counts differ a lot
-    for (;;) {
-        uint32_t blk = 0;
-        if (lane == 0) blk = atomicAdd(&s_next, 32u);
-        blk = __shfl_sync(0xffffffffu, blk, 0);
-        if (blk >= npairs) break;
-        const uint32_t i = blk + lane;
-        uint32_t n_c = 0, n_r = 0, v0 = 0, wgt = 0;
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < npairs) {
-            const uint32_t t = i / ngate;
-            h = s_gated[i - t * ngate];
-            const int32_t L = leaf_f[(size_t)t * g.P + __float_as_uint(h.w)];
-            const LeafInfo li = f.leaf_info[L];
-            if (li.flags & kLeafVotes) {  // prob > 0 (prediction.rs:590), weight != 0, a spread gate open
-                v0 = li.vote_start;
-                wgt = li.valtoadd;
-                if (li.flags & kLeafOffOk) { n_c = li.n_votes; ++cnt_c; nmid += li.n_votes; }
-                // rotation votes: the leaf's distinct seed-grid cells with their multiplicities (leaf_gate_kernel)
-                if (li.flags & kLeafRotOk) { n_r = li.flags >> kLeafRotCellsShift; ++cnt_r; nrot += li.n_votes; }
+    for (;;) {  // kFromList: one round per slice of the list; else one round
+        if (kFromList) {
+            ngate = min((uint32_t)kGateThreads, n_list - slice0);
+            if (tid < ngate) s_gated[tid] = __ldcg(b.gated + (size_t)frame * g.P + slice0 + tid);
+            __syncthreads();
+        }
+        // ---- phase B: pair = (tree, gated patch), neighbouring lanes = neighbouring gated patches.
+        // A warp takes 32 pairs at a time and spreads their votes evenly over its lanes (for_each_vote),
+        // so leaves with few, many or no votes cost the same per vote.
+        const uint32_t npairs = ngate * T;
+        // batches of 32 pairs are handed out through a shared counter: their vote counts differ a lot
+        for (;;) {
+            uint32_t blk = 0;
+            if (lane == 0) blk = atomicAdd(&s_next, 32u);
+            blk = __shfl_sync(0xffffffffu, blk, 0);
+            if (blk >= npairs) break;
+            const uint32_t i = blk + lane;
+            uint32_t n_c = 0, n_r = 0, v0 = 0, wgt = 0;
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < npairs) {
+                const uint32_t t = i / ngate;
+                h = s_gated[i - t * ngate];
+                const int32_t L = leaf_f[(size_t)t * g.P + __float_as_uint(h.w)];
+                const LeafInfo li = f.leaf_info[L];
+                if (li.flags & kLeafVotes) {  // prob > 0 (prediction.rs:590), weight != 0, a spread gate open
+                    v0 = li.vote_start;
+                    wgt = li.valtoadd;
+                    if (li.flags & kLeafOffOk) { n_c = li.n_votes; ++cnt_c; nmid += li.n_votes; }
+                    // rotation votes: the leaf's distinct seed-grid cells with their multiplicities (leaf_gate_kernel)
+                    if (li.flags & kLeafRotOk) { n_r = li.flags >> kLeafRotCellsShift; ++cnt_r; nrot += li.n_votes; }
+                }
+            }
+            // centre votes -> 20x20 grid: np = p3 - offset (prediction.rs:647); np.z < 0 is skipped (:650)
+            auto centre_vote = [&](uint32_t vote, uint32_t ow, const float4& c) {
+                const float4 o = __ldg(f.offsets + vote);
+                const float nx = __fsub_rn(c.x, o.x), ny = __fsub_rn(c.y, o.y), nz = __fsub_rn(c.z, o.z);
+                if (!(nz < 0.0f)) atomicAdd(&s_grid[coarse_pos_cell(g, nx, ny, nz)], ow);
+            };
+            // rotation votes -> 20^3 grid; rough = r * 20 / 120 per axis (prediction.rs:630-636), static per vote
+            auto rot_vote = [&](uint32_t entry, uint32_t ow) {
+                const uint32_t e = __ldg(f.rot_cells + entry), cell = e & ((1u << kRotCellBits) - 1u);
+                if (atomicAdd(&s_grid[kPosGridCells + cell], ow * (e >> kRotCellBits)) == 0u) {
+                    const uint32_t slot = atomicAdd(&s_ntouched, 1u);
+                    if (slot < (uint32_t)kTouchedCap) s_touched[slot] = (uint16_t)cell;
+                }
+            };
+            if (kFused) {
+                // one pass: item j of a pair is its centre vote j (j < n_c) and its rotation cell j (j < n_r <= n_votes)
+                const uint32_t tag = (n_c ? 1u : 0u) | (n_r << 1);
+                for_each_vote(max(n_c, n_r), v0, wgt, tag, h, s_slots[tid >> 5], lane,
+                              [&](uint32_t vote, uint32_t ow, uint32_t tg, const float4& c, uint32_t j) {
+                                  if (tg & 1u) centre_vote(vote, ow, c);
+                                  if (j < (tg >> 1)) rot_vote(vote, ow);
+                              });
+            } else {
+                for_each_vote(n_c, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4& c, uint32_t) { centre_vote(vote, ow, c); });
+                for_each_vote(n_r, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4&, uint32_t) { rot_vote(vote, ow); });
             }
         }
-        // centre votes -> 20x20 grid: np = p3 - offset (prediction.rs:647); np.z < 0 is skipped (:650)
-        auto centre_vote = [&](uint32_t vote, uint32_t ow, const float4& c) {
-            const float4 o = __ldg(f.offsets + vote);
-            const float nx = __fsub_rn(c.x, o.x), ny = __fsub_rn(c.y, o.y), nz = __fsub_rn(c.z, o.z);
-            if (!(nz < 0.0f)) atomicAdd(&s_grid[coarse_pos_cell(g, nx, ny, nz)], ow);
-        };
-        // rotation votes -> 20^3 grid; rough = r * 20 / 120 per axis (prediction.rs:630-636), static per vote
-        auto rot_vote = [&](uint32_t entry, uint32_t ow) {
-            const uint32_t e = __ldg(f.rot_cells + entry), cell = e & ((1u << kRotCellBits) - 1u);
-            if (atomicAdd(&s_grid[kPosGridCells + cell], ow * (e >> kRotCellBits)) == 0u) {
-                const uint32_t slot = atomicAdd(&s_ntouched, 1u);
-                if (slot < (uint32_t)kTouchedCap) s_touched[slot] = (uint16_t)cell;
-            }
-        };
-        if (kFused) {
-            // one pass: item j of a pair is its centre vote j (j < n_c) and its rotation cell j (j < n_r <= n_votes)
-            const uint32_t tag = (n_c ? 1u : 0u) | (n_r << 1);
-            for_each_vote(max(n_c, n_r), v0, wgt, tag, h, s_slots[tid >> 5], lane,
-                          [&](uint32_t vote, uint32_t ow, uint32_t tg, const float4& c, uint32_t j) {
-                              if (tg & 1u) centre_vote(vote, ow, c);
-                              if (j < (tg >> 1)) rot_vote(vote, ow);
-                          });
-        } else {
-            for_each_vote(n_c, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4& c, uint32_t) { centre_vote(vote, ow, c); });
-            for_each_vote(n_r, v0, wgt, 0u, h, s_slots[tid >> 5], lane, [&](uint32_t vote, uint32_t ow, uint32_t, const float4&, uint32_t) { rot_vote(vote, ow); });
-        }
+        if (!kFromList) break;
+        slice0 += gridDim.x * kGateThreads;
+        if (slice0 >= n_list) break;
+        __syncthreads();  // every warp is done with this slice's patches and has left the batch loop
+        if (tid == 0) s_next = 0;
     }
     // per-frame counters, one atomic per warp
 #pragma unroll
@@ -1455,7 +1639,9 @@ constexpr int kMsWarps = kMsThreads / 32;
 constexpr int kMsSegment = 1024;  // non-zero window cells summed per pass
 constexpr uint32_t kMsChunks = kKernelCells / 32;  // 250 steps of 32 cells
 constexpr int kMsLoads = (kKernelCells + kMsThreads - 1) / kMsThreads;  // 16 window cells per thread
-constexpr int kMsSmemBytes = kKernelCells * 4 + 4 * kMsSegment * 4;
+constexpr int kMsSmemBytes = kKernelCells * 4 + 4 * kMsSegment * 4;   // window + summands
+constexpr int kMsSmemBytesCompact = kMsSegment * 8 + 4 * kMsSegment * 4 + (kMsLoads / 2) * kMsThreads * 4;  // list of non-zero cells + summands + cell offsets
+constexpr uint32_t kMsNoCell = 0xffffu;  // packed cell offset of a thread's load slot beyond the window
 
 __device__ __forceinline__ void store_result(dh_result* r, uint32_t which, const int32_t* pos) {
     if (which == 0) {  // prediction.rs:486-488
@@ -1492,11 +1678,18 @@ __device__ __noinline__ void rebuild_cube(const float4* __restrict__ gated, uint
     __syncthreads();
 }
 
+// kCompact: the window never goes to shared memory.  A thread keeps its 16 cells in registers from the
+// gather to the ranking, the non-zero ones are written as (cell, value) at their rank, and the summands
+// are then computed densely, one thread per non-zero cell (the kCompact = false form walks all 250
+// chunks of 32 cells with only the non-zero lanes working: 53 % of the kernel's instructions, measured).
+template <bool kCompact>
 __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b, Geometry g, ForestDev f, uint32_t iterations) {
     extern __shared__ __align__(16) uint8_t ms_smem[];
-    uint32_t* s_win = reinterpret_cast<uint32_t*>(ms_smem);  // [8000] window cells in reference order
-    float(*s_terms)[kMsSegment] = reinterpret_cast<float(*)[kMsSegment]>(ms_smem + kKernelCells * 4);  // [4][kMsSegment]
+    uint32_t* s_win = reinterpret_cast<uint32_t*>(ms_smem);  // [8000] window cells in reference order (!kCompact)
+    uint2* s_list = reinterpret_cast<uint2*>(ms_smem);       // [kMsSegment] (ord, value) of the non-zero cells by rank (kCompact)
+    float(*s_terms)[kMsSegment] = reinterpret_cast<float(*)[kMsSegment]>(ms_smem + (kCompact ? kMsSegment * 8 : kKernelCells * 4));  // [4][kMsSegment]
                                                        // summands (num x,y,z, den) in reference order
+    uint32_t* s_offp = reinterpret_cast<uint32_t*>(ms_smem + kMsSegment * 8 + 4 * kMsSegment * 4);  // [kMsLoads / 2][kMsThreads] (kCompact)
     __shared__ uint32_t s_mask[kMsChunks];             // non-zero window cells, bit j of word c = ord c*32+j
     __shared__ uint32_t s_off[kMsChunks + 1];          // rank of the first non-zero cell of every chunk
     __shared__ int32_t s_hist[kMsHistory + 1][3];      // positions P_0 (seed), P_1, ... for cycle detection
@@ -1513,6 +1706,21 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
         for (int k = 0; k < 3; ++k) {
             s_pos[k] = s_hist[0][k] = seed[k];
             s_org[k] = fs->box_org[which][k];
+        }
+    }
+    // kCompact: cube offsets of this thread's window cells ord = j * kMsThreads + tid, two per word,
+    // computed once and parked in shared memory (eight registers less across the rounds)
+    if (kCompact) {
+#pragma unroll
+        for (int j = 0; j < kMsLoads; j += 2) {
+            uint32_t pk = 0;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t ord = (uint32_t)(j + u) * kMsThreads + tid;
+                const uint32_t xo = ord / 400u, yo = (ord / 20u) % 20u, zo = ord % 20u;
+                pk |= (ord < (uint32_t)kKernelCells ? (xo * kBox + yo) * kBox + zo : kMsNoCell) << (16 * u);
+            }
+            s_offp[(j >> 1) * kMsThreads + tid] = pk;
         }
     }
     uint32_t rebuilds = 0;
@@ -1536,12 +1744,27 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
             rebuild_cube(b.gated + (size_t)frame * g.P, fs->n_gate, g.n_trees, b.leaf + (size_t)frame * g.n_trees * g.P, g.P,
                          f.leaf_info, f.leaf_box, f.offsets, f.rot_bins, which, org[0], org[1], org[2], box);
         }
-        // gather the 20^3 window into shared memory, all loads of a thread in flight at once.
-        // ord enumerates the cells in the reference loop order (x outermost, z innermost).
-        {
-            const uint32_t base = ((uint32_t)((long long)pos[0] - 10 - org[0]) * kBox + (uint32_t)((long long)pos[1] - 10 - org[1])) * kBox +
-                                  (uint32_t)((long long)pos[2] - 10 - org[2]);
-            uint32_t v[kMsLoads];
+        const uint32_t base = ((uint32_t)((long long)pos[0] - 10 - org[0]) * kBox + (uint32_t)((long long)pos[1] - 10 - org[1])) * kBox +
+                              (uint32_t)((long long)pos[2] - 10 - org[2]);
+        // gather the 20^3 window, all loads of a thread in flight at once.  ord enumerates the cells in
+        // the reference loop order (x outermost, z innermost); a warp's load j is chunk j * kMsWarps + warp.
+        uint32_t v[kMsLoads];
+        if (kCompact) {
+#pragma unroll
+            for (int j = 0; j < kMsLoads; j += 2) {
+                const uint32_t pk = s_offp[(j >> 1) * kMsThreads + tid];
+                const uint32_t o0 = pk & 0xffffu, o1 = pk >> 16;
+                v[j] = o0 != kMsNoCell ? __ldcg(box + base + o0) : 0u;
+                v[j + 1] = o1 != kMsNoCell ? __ldcg(box + base + o1) : 0u;
+            }
+            // non-zero mask of every 32-cell chunk straight from the registers
+#pragma unroll
+            for (int j = 0; j < kMsLoads; ++j) {
+                const uint32_t m = __ballot_sync(0xffffffffu, v[j] != 0u);
+                const uint32_t c = (uint32_t)j * kMsWarps + warp;
+                if (lane == 0 && c < kMsChunks) s_mask[c] = m;
+            }
+        } else {
 #pragma unroll
             for (int j = 0; j < kMsLoads; ++j) {
                 const uint32_t ord = (uint32_t)j * kMsThreads + tid;
@@ -1556,14 +1779,15 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
                 const uint32_t ord = (uint32_t)j * kMsThreads + tid;
                 if (ord < (uint32_t)kKernelCells) s_win[ord] = v[j];
             }
+            __syncthreads();
+            // non-zero mask of every 32-cell chunk
+            for (uint32_t c = warp; c < kMsChunks; c += kMsWarps) {
+                const uint32_t m = __ballot_sync(0xffffffffu, s_win[c * 32u + lane] != 0u);
+                if (lane == 0) s_mask[c] = m;
+            }
         }
         __syncthreads();
-        // non-zero mask of every 32-cell chunk, then (warp 0) the exclusive prefix of their populations
-        for (uint32_t c = warp; c < kMsChunks; c += kMsWarps) {
-            const uint32_t m = __ballot_sync(0xffffffffu, s_win[c * 32u + lane] != 0u);
-            if (lane == 0) s_mask[c] = m;
-        }
-        __syncthreads();
+        // (warp 0) the exclusive prefix of the chunks' populations = rank of their first non-zero cell
         if (warp == 0) {
             uint32_t run = 0;
             for (uint32_t c0 = 0; c0 < kMsChunks; c0 += 32) {
@@ -1584,22 +1808,46 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
         const uint32_t nnz = s_off[kMsChunks];
         float acc = 0.0f;
         for (uint32_t seg = 0; seg < nnz; seg += kMsSegment) {
-            // every non-zero cell stages its four summands at its rank in reference order
-            for (uint32_t c = warp; c < kMsChunks; c += kMsWarps) {
-                if (s_off[c + 1] <= seg || s_off[c] >= seg + kMsSegment) continue;  // warp-uniform
-                const uint32_t m = s_mask[c];
-                if (!((m >> lane) & 1u)) continue;
-                const uint32_t r = s_off[c] + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                if (r < seg || r >= seg + kMsSegment) continue;
-                const uint32_t ord = c * 32u + lane;
-                const uint32_t xo = ord / 400u, yo = (ord / 20u) % 20u, zo = ord % 20u;
-                // influence * factor with kernel[(x+10, y+10, z+10)], dense index z*400 + y*20 + x
-                // (meanshift.rs:370-377, 78-88); then abs_pos * that
-                const float wgt = __fmul_rn(__ldg(f.ms_kernel + zo * 400u + yo * 20u + xo), (float)s_win[ord]);
-                s_terms[0][r - seg] = __fmul_rn((float)(int)((uint32_t)pos[0] + xo - 10u), wgt);
-                s_terms[1][r - seg] = __fmul_rn((float)(int)((uint32_t)pos[1] + yo - 10u), wgt);
-                s_terms[2][r - seg] = __fmul_rn((float)(int)((uint32_t)pos[2] + zo - 10u), wgt);
-                s_terms[3][r - seg] = wgt;
+            if (kCompact) {
+                // every non-zero cell goes to the list at its rank in reference order ...
+#pragma unroll
+                for (int j = 0; j < kMsLoads; ++j) {
+                    if (v[j] != 0u) {
+                        const uint32_t c = (uint32_t)j * kMsWarps + warp;
+                        const uint32_t r = s_off[c] + (uint32_t)__popc(s_mask[c] & ((1u << lane) - 1u)) - seg;
+                        if (r < (uint32_t)kMsSegment) s_list[r] = make_uint2((uint32_t)j * kMsThreads + tid, v[j]);
+                    }
+                }
+                __syncthreads();
+                // ... and its four summands are computed by the thread of that rank
+                const uint32_t cnt = min((uint32_t)kMsSegment, nnz - seg);
+                for (uint32_t r = tid; r < cnt; r += kMsThreads) {
+                    const uint2 e = s_list[r];
+                    const uint32_t xo = e.x / 400u, yo = (e.x / 20u) % 20u, zo = e.x % 20u;
+                    // influence * factor with kernel[(x+10, y+10, z+10)], dense index z*400 + y*20 + x
+                    // (meanshift.rs:370-377, 78-88); then abs_pos * that
+                    const float wgt = __fmul_rn(__ldg(f.ms_kernel + zo * 400u + yo * 20u + xo), (float)e.y);
+                    s_terms[0][r] = __fmul_rn((float)(int)((uint32_t)pos[0] + xo - 10u), wgt);
+                    s_terms[1][r] = __fmul_rn((float)(int)((uint32_t)pos[1] + yo - 10u), wgt);
+                    s_terms[2][r] = __fmul_rn((float)(int)((uint32_t)pos[2] + zo - 10u), wgt);
+                    s_terms[3][r] = wgt;
+                }
+            } else {
+                // every non-zero cell stages its four summands at its rank in reference order
+                for (uint32_t c = warp; c < kMsChunks; c += kMsWarps) {
+                    if (s_off[c + 1] <= seg || s_off[c] >= seg + kMsSegment) continue;  // warp-uniform
+                    const uint32_t m = s_mask[c];
+                    if (!((m >> lane) & 1u)) continue;
+                    const uint32_t r = s_off[c] + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    if (r < seg || r >= seg + kMsSegment) continue;
+                    const uint32_t ord = c * 32u + lane;
+                    const uint32_t xo = ord / 400u, yo = (ord / 20u) % 20u, zo = ord % 20u;
+                    const float wgt = __fmul_rn(__ldg(f.ms_kernel + zo * 400u + yo * 20u + xo), (float)s_win[ord]);
+                    s_terms[0][r - seg] = __fmul_rn((float)(int)((uint32_t)pos[0] + xo - 10u), wgt);
+                    s_terms[1][r - seg] = __fmul_rn((float)(int)((uint32_t)pos[1] + yo - 10u), wgt);
+                    s_terms[2][r - seg] = __fmul_rn((float)(int)((uint32_t)pos[2] + zo - 10u), wgt);
+                    s_terms[3][r - seg] = wgt;
+                }
             }
             __syncthreads();
             if (warp == 0 && lane < 4) {  // sequential f32 accumulation in reference order (meanshift.rs:337-380)
@@ -2295,7 +2543,7 @@ int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames
 
 uint32_t traverse_smem_bytes(uint32_t tw, uint32_t th, uint32_t patches_per_tile) {
     const uint32_t tile_bytes = (tw * th * 4u + 15u) & ~15u;
-    return 128u + tile_bytes + 16u + ((patches_per_tile + 31u) & ~31u) * 4u + 64u;
+    return 128u + tile_bytes + 16u + 2u * ((patches_per_tile + 31u) & ~31u) * 4u + 64u;  // tile, barrier, live list, code sums
 }
 
 int traverse_kernel_attrs(int* regs, int* max_smem) {
@@ -2307,9 +2555,11 @@ int traverse_kernel_attrs(int* regs, int* max_smem) {
     return 0;
 }
 
+// returns true when the launched variant applies the patch gate in its tail (GateTail::gated set and the
+// default box-sum / texture walk selected)
 template <int kThreads>
-static void launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
-                              const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
+static bool launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
+                              const ForestDev& f, const GateTail& gt_in, uint32_t n_frames, cudaStream_t s) {
     static SmemConfig configured;
     if (configured.raise(tp.smem_bytes)) {
         cudaFuncSetAttribute(traverse_kernel<kThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
@@ -2323,42 +2573,47 @@ static void launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b,
     }
     static const bool two_walks = std::getenv("DH_TRAV_ILP") && std::atoi(std::getenv("DH_TRAV_ILP")) == 2;
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
+    GateTail gt = gt_in;
+    const bool default_walk = f.uni && g.rw && f.hot_tex && !f.pair_recs && !two_walks;
+    if (!default_walk) gt.cand = nullptr;  // only that walk carries the tail
     if (f.uni && g.rw && f.pair_recs)
         traverse_kernel<kThreads, 7><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
     else if (f.uni && g.rw && f.hot_tex && two_walks)
         traverse_kernel<kThreads, 6><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
     else if (f.uni && g.rw && f.hot_tex)
         traverse_kernel<kThreads, 4><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
     else if (f.uni && g.rw)
         traverse_kernel<kThreads, 5><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box, b.fs, g,
-                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
+                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
     else if (f.uni && f.hot_tex)
         traverse_kernel<kThreads, 2><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
     else if (f.uni)
         traverse_kernel<kThreads, 3><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat, b.fs, g,
-                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
+                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
     else if (f.hot_tex)
         traverse_kernel<kThreads, 1><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat,
-                                                                       b.fs, g, tp, 0u, 0u, nullptr, nullptr, nullptr);
+                                                                       b.fs, g, tp, 0u, 0u, nullptr, nullptr, nullptr, gt);
     else
         traverse_kernel<kThreads, 0><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat, b.fs, g,
-                                                                       tp, 0u, 0u, nullptr, nullptr, nullptr);
+                                                                       tp, 0u, 0u, nullptr, nullptr, nullptr, gt);
+    return gt.cand != nullptr;
 }
 
-void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
-                     const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
-    if (tp.threads >= 1024) launch_traverse_t<1024>(sat_map, b, g, tp, f, n_frames, s);
-    else if (tp.threads >= 768) launch_traverse_t<768>(sat_map, b, g, tp, f, n_frames, s);
-    else launch_traverse_t<512>(sat_map, b, g, tp, f, n_frames, s);
+bool launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
+                     const ForestDev& f, const GateTail& gt, uint32_t n_frames, cudaStream_t s) {
+    if (tp.threads >= 1024) return launch_traverse_t<1024>(sat_map, b, g, tp, f, gt, n_frames, s);
+    if (tp.threads >= 768) return launch_traverse_t<768>(sat_map, b, g, tp, f, gt, n_frames, s);
+    return launch_traverse_t<512>(sat_map, b, g, tp, f, gt, n_frames, s);
 }
 
-void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width, cudaStream_t s) {
+void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width,
+                       const double* prob_codes, cudaStream_t s) {
     if (n_nodes == 0) return;
-    plan_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(nodes, hot, uni, n_nodes, tile_width);
+    plan_nodes_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(nodes, hot, uni, n_nodes, tile_width, prob_codes);
 }
 
 void launch_plan_pairs(const PairTopo* topo, const UniNode* uni, PairRec* recs, size_t n_recs, cudaStream_t s) {
@@ -2372,17 +2627,37 @@ uint32_t vote_box_dim() { return (uint32_t)kBox; }
 
 // The back end after the traversal, in launch order.  The coarse grids, the accumulator cubes
 // and the queue header must be zero when these run.  Each returns the kernels it launched.
-int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
+int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, bool from_list,
+                       const GateTail* tail, const TilePlan& tp, int n_sms, cudaStream_t s) {
     if (!g.P) return 0;
     static SmemConfig configured;
     if (configured.raise((uint32_t)kGateSmemBytes)) {
-        cudaFuncSetAttribute(gate_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateSmemBytes);
-        cudaFuncSetAttribute(gate_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateSmemBytes);
+        cudaFuncSetAttribute(gate_coarse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateSmemBytes);
+        cudaFuncSetAttribute(gate_coarse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateSmemBytes);
+        cudaFuncSetAttribute(gate_coarse_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateSmemBytes);
     }
     static const bool fused = !(std::getenv("DH_GATE_FUSED") && std::atoi(std::getenv("DH_GATE_FUSED")) == 0);
-    dim3 gr((g.P + kGateThreads - 1) / kGateThreads, n_frames);
-    if (fused) gate_coarse_kernel<true><<<gr, kGateThreads, kGateSmemBytes, s>>>(b, g, f);
-    else gate_coarse_kernel<false><<<gr, kGateThreads, kGateSmemBytes, s>>>(b, g, f);
+    const uint32_t per_frame = (g.P + kGateThreads - 1) / kGateThreads;
+    if (from_list) {
+        // the patch gate writes the frames' gated-patch lists, the seed-grid CTAs take slices of them.  Few CTAs per
+        // frame when there are many frames (a slice is a full CTA of work), every possible slice its own
+        // CTA when there are few frames (a single frame must still spread over the GPU).
+        static const uint32_t want = std::getenv("DH_GATE_CTAS") ? (uint32_t)std::atoi(std::getenv("DH_GATE_CTAS")) : 0u;
+        const uint32_t fill = (6u * (uint32_t)n_sms + n_frames - 1u) / n_frames;
+        const uint32_t ctas = std::max<uint32_t>(1u, std::min<uint32_t>(per_frame, want ? want : std::max<uint32_t>(4u, fill)));
+        if (tail) {  // the traversal left candidates per tile
+            const uint32_t npt = tp.tpx * tp.tpy, n_tiles = tp.tiles_x * tp.tiles_y;
+            gate_compact_kernel<<<dim3((n_tiles + kPatchGateThreads / 32 - 1) / (kPatchGateThreads / 32), n_frames), kPatchGateThreads, 0, s>>>(
+                b, g, f, *tail, npt, n_tiles);
+        } else {     // the traversal variant that ran has no gate tail
+            patch_gate_kernel<<<dim3((g.P + kPatchGateThreads - 1) / kPatchGateThreads, n_frames), kPatchGateThreads, 0, s>>>(b, g, f);
+        }
+        gate_coarse_kernel<true, true><<<dim3(ctas, n_frames), kGateThreads, kGateSmemBytes, s>>>(b, g, f);
+        return 2;
+    }
+    dim3 gr(per_frame, n_frames);
+    if (fused) gate_coarse_kernel<true, false><<<gr, kGateThreads, kGateSmemBytes, s>>>(b, g, f);
+    else gate_coarse_kernel<false, false><<<gr, kGateThreads, kGateSmemBytes, s>>>(b, g, f);
     return 1;
 }
 
@@ -2401,8 +2676,13 @@ int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const Forest
 int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t iterations,
                      cudaStream_t s) {
     static SmemConfig configured;
-    if (configured.raise((uint32_t)kMsSmemBytes)) cudaFuncSetAttribute(meanshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes);
-    meanshift_kernel<<<2u * n_frames, kMsThreads, kMsSmemBytes, s>>>(b, g, f, iterations);
+    if (configured.raise((uint32_t)kMsSmemBytes)) {
+        cudaFuncSetAttribute(meanshift_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes);
+        cudaFuncSetAttribute(meanshift_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytesCompact);
+    }
+    static const bool compact = !(std::getenv("DH_MS_COMPACT") && std::atoi(std::getenv("DH_MS_COMPACT")) == 0);
+    if (compact) meanshift_kernel<true><<<2u * n_frames, kMsThreads, kMsSmemBytesCompact, s>>>(b, g, f, iterations);
+    else meanshift_kernel<false><<<2u * n_frames, kMsThreads, kMsSmemBytes, s>>>(b, g, f, iterations);
     return 1;
 }
 

@@ -105,14 +105,34 @@ struct FrameBuffers {
                             // pass finds the cubes empty without a memset of all of them)
 };
 
+// The traversal's patch-gate tail (default walk only; `cand` null: no tail).  Leaf children of the
+// uniform node table may carry a probability code (plan_nodes_kernel): leaf_mask recovers the leaf id
+// (all ones below bit 31 when the table is not packed).
+constexpr uint32_t kProbCodeShift = 23u;
+constexpr uint32_t kLeafIdMask = (1u << kProbCodeShift) - 1u;
+struct GateTail {
+    uint32_t* cand;           // [F][cand_pitch] per tile (tile * patches per tile): patch index | 0x80000000 if the code sum
+                              // could not decide; null: no tail
+    uint32_t* tile_cnt;       // [F][tiles] candidates of every tile (zeroed before the traversal)
+    uint32_t cand_pitch;      // tiles * patches per tile
+    uint32_t leaf_mask;       // kLeafIdMask when the uniform table is packed, else 0x7fffffff
+    uint32_t pass_min;        // sum of codes >= pass_min: the patch passes for certain
+    uint32_t fail_max;        // sum of codes + n_trees <= fail_max: it fails for certain
+};
+
 int launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s);
 int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, int n_sms, cudaStream_t s);
 bool box_image_supported(uint32_t w, uint32_t h, uint32_t sw, uint32_t sh, uint32_t rw, uint32_t rh);
-void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
-                     const ForestDev& f, uint32_t n_frames, cudaStream_t s);
-void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width, cudaStream_t s);
+bool launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
+                     const ForestDev& f, const GateTail& gt, uint32_t n_frames, cudaStream_t s);  // true: the gate tail ran
+void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width,
+                       const double* prob_codes, cudaStream_t s);
 void launch_plan_pairs(const PairTopo* topo, const UniNode* uni, PairRec* recs, size_t n_recs, cudaStream_t s);
-int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, cudaStream_t s);
+// from_list: the patch gate runs as its own kernel and writes the frames' gated-patch lists; the seed-grid CTAs take
+// slices of the lists (DH_GATE_SPLIT, default) instead of gating the patches of their own index range
+// tail: the traversal's tail left candidates (gate_compact_kernel makes the lists), else patch_gate_kernel runs first
+int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, bool from_list,
+                       const GateTail* tail, const TilePlan& tp, int n_sms, cudaStream_t s);
 int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
                           uint32_t iterations, cudaStream_t s);
 int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t iterations,

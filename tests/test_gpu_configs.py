@@ -59,6 +59,16 @@ VARIANTS = [
     {"DH_CUBE_CLEAR_FUSED": "0"},                   # one memset of all accumulator cubes per pass instead of the clear behind mean-shift
     {"DH_LANES": "1"},
     {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},
+    {"DH_NODE_ALIGN": "0"},                         # device node table in host order (no pad records in front of sibling pairs)
+    {"DH_NODE_ALIGN": "0", "DH_TRAV_PAIR": "1"},
+    {"DH_MS_COMPACT": "0"},                         # mean-shift: window staged in shared memory, summands per 32-cell chunk
+    {"DH_PROB_CODES": "0"},                         # no probability codes in the node table: the patch gate runs as its own kernel
+    {"DH_PROB_CODES": "0", "DH_GATE_CTAS": "2"},
+    {"DH_GATE_SPLIT": "0"},                         # patch gate inside the seed-grid kernel instead of the traversal's tail
+    {"DH_GATE_SPLIT": "0", "DH_GATE_FUSED": "0"},
+    {"DH_GATE_CTAS": "1"},                          # one seed-grid CTA per frame walks every slice of the gated-patch list
+    {"DH_GATE_CTAS": "2", "DH_TRAV_THREADS": "512"},
+    {"DH_BOX_IMAGE": "0", "DH_UNIFORM": "0", "DH_GATE_CTAS": "3"},
 ]
 
 

@@ -130,6 +130,37 @@ def test_exact_ties_in_the_node_test(ctx):
         _compare_frame(ctx, hp, of, d)
 
 
+@pytest.mark.parametrize("n_trees", [1, 3, 10])
+def test_patch_gate_at_the_threshold(ctx, n_trees):
+    """prob > 0.7 (prediction.rs:582-584) with leaf probabilities whose sums sit on, one ulp around and
+    within 1/256 of 0.7 * T: the traversal's gate tail decides from 8-bit probability codes and must send
+    every such patch through the exact f64 fold; probabilities of exactly 0.0 and 1.0 sit at the ends of
+    the code range."""
+    rng = np.random.default_rng(n_trees)
+    arr = synth.make_forest(seed=40 + n_trees, n_trees=n_trees, max_depth=6)
+    NL = len(arr["prob"])
+    base = np.full(NL, 0.7)
+    kind = rng.integers(0, 8, NL)
+    prob = np.where(kind == 0, np.nextafter(base, 1.0), base)
+    prob = np.where(kind == 1, np.nextafter(base, 0.0), prob)
+    prob = np.where(kind == 2, 0.7 + 1.0 / 300, prob)
+    prob = np.where(kind == 3, 0.7 - 1.0 / 300, prob)
+    prob = np.where(kind == 4, 1.0, prob)
+    prob = np.where(kind == 5, 0.0, prob)
+    prob = np.where(kind == 6, 0.4, prob)
+    nv = np.diff(arr["vote_off"])
+    prob = np.where((nv == 0) & (prob > 0), 0.0, prob)  # prob > 0 needs votes (prediction.rs:594)
+    arr["prob"] = prob.astype(np.float64)
+    js = synth.forest_to_json(arr, stepwidth=6)
+    hp = HoughPrediction.from_json(js)
+    of = oracle.OracleForest.from_json(js)
+    gates = 0
+    for d in synth.make_frames(2, seed=61):
+        _, tr = _compare_frame(ctx, hp, of, d)
+        gates += int(tr.gate.sum())
+    assert gates > 0
+
+
 def test_caller_seeds(ctx, small_case):
     arr, js, frames = small_case
     hp = HoughPrediction.from_json(js)
