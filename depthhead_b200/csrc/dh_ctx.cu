@@ -382,6 +382,8 @@ void Context::ensure_forest(const HostForest& hf) {
         for (size_t l = 0; l < NL && prob_codes_ok_; ++l)
             if (!(hf.leaf_prob[l] >= 0.0 && hf.leaf_prob[l] <= 1.0)) prob_codes_ok_ = false;
         if (!env_flag("DH_PROB_CODES", true)) prob_codes_ok_ = false;
+        // the walks store the packed words only from the uniform (box-sum) node table, one level per fetch
+        leaf_codes_ = prob_codes_ok_ && gate_split_ && df_uni_ && !df_pair_recs_;
         df_serial_ = hf.serial;
         df_sigma_version_ = 0;
         df_n_leaves_ = NL;
@@ -425,8 +427,6 @@ void Context::free_lane(Lane& L) {
     dev_free(L.p3);
     dev_free(L.gate);
     dev_free(L.gated);
-    dev_free(L.cand);
-    dev_free(L.tile_cnt);
     dev_free(L.cubes);
     dev_free(L.grids);
     dev_free(L.fs);
@@ -466,10 +466,6 @@ void Context::alloc_lane(Lane& L) {
     dev_alloc(L.p3, F * P * 3);
     dev_alloc(L.gate, F * P);
     dev_alloc(L.gated, F * P);
-    if (g.P) {
-        dev_alloc(L.cand, F * (size_t)tiles_.tiles_x * tiles_.tiles_y * tiles_.tpx * tiles_.tpy);
-        dev_alloc(L.tile_cnt, F * (size_t)tiles_.tiles_x * tiles_.tiles_y);
-    }
     dev_alloc(L.cubes, F * 2 * (size_t)vote_box_cells());
     DH_CUDA(cudaMemsetAsync(L.cubes, 0, sizeof(uint32_t) * F * 2 * (size_t)vote_box_cells(), stream_));
     L.cubes_clean = true;
@@ -617,6 +613,10 @@ void Context::ensure_scratch(const HostForest& hf, uint32_t w, uint32_t h, uint3
             while (smin / t > 0.7) smin = std::nextafter(smin, -HUGE_VAL);
             while (!(smin / t > 0.7)) smin = std::nextafter(smin, HUGE_VAL);
             g.gate_min_sum = smin;
+            // the f64 fold of T probabilities differs from their real sum by less than T^2 * 2^-52
+            const double slack = t * t * std::ldexp(1.0, -50);
+            g.gate_pass_codes = (uint32_t)std::min(4.0e9, std::ceil((smin + slack) * 256.0));
+            g.gate_fail_codes = (uint32_t)std::max(0.0, std::min(4.0e9, std::ceil((smin - slack) * 256.0) - 1.0));
         }
         if ((uint64_t)g.P * g.n_trees > 0x7fffffffull) throw ModelError(DH_E_SHAPE, "too many patch x tree pairs per frame");
         if (g.P) tiles_ = plan_tiles(g);
@@ -657,6 +657,7 @@ FrameBuffers Context::buffers(const Lane& L, const uint16_t* depth) const {
     b.results = L.results;
     b.ms_trace = L.ms_trace;
     b.ms_trace_cap = sk_.trace_iters;
+    b.leaf_mask = leaf_codes_ ? kLeafIdMask : 0x7fffffffu;
     b.debug = debug_ ? 1u : 0u;
     b.clear_cubes = (!debug_ && cube_clear_fused_) ? 1u : 0u;  // debug passes export the cubes after the call
     return b;
@@ -701,7 +702,7 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
         launches_ += 1;
     }
     if (g.P && hot_tw_ != tiles_.tw) {  // node table for this tile plan (once per forest x plan)
-        launch_plan_nodes(df_nodes_, df_hot_, df_uni_, df_n_nodes_, tiles_.tw, prob_codes_ok_ ? df_leaf_prob_ : nullptr, stream_);
+        launch_plan_nodes(df_nodes_, df_hot_, df_uni_, df_n_nodes_, tiles_.tw, leaf_codes_ ? df_leaf_prob_ : nullptr, stream_);
         if (df_pair_recs_) launch_plan_pairs(df_pair_topo_, df_uni_, df_pair_recs_, df_n_pairs_, stream_);
         DH_CUDA(cudaStreamSynchronize(stream_));
         hot_tw_ = tiles_.tw;
@@ -718,23 +719,7 @@ void Context::run_front(Lane& L, const FrameBuffers& b, uint32_t n, const FrameS
             DH_CUDA(cudaMemsetAsync(L.leaf, 0xFF, sizeof(int32_t) * (size_t)n * g.n_trees * g.P, st));
         else
             DH_CUDA(cudaMemset2DAsync(L.leaf, sizeof(int32_t) * (size_t)g.n_trees * g.P, 0xFF, sizeof(int32_t) * (size_t)g.P, n, st));
-        // the default walk also applies the patch gate (prediction.rs:582-584) to the patches it has just
-        // walked and writes the frame's gated-patch list: see GateTail
-        GateTail gt{};
-        gt.leaf_mask = prob_codes_ok_ ? kLeafIdMask : 0x7fffffffu;
-        if (gate_split_ && prob_codes_ok_ && g.n_trees <= 4096u) {
-            gt.cand = L.cand;
-            gt.tile_cnt = L.tile_cnt;
-            gt.cand_pitch = tiles_.tiles_x * tiles_.tiles_y * tiles_.tpx * tiles_.tpy;
-            // the f64 fold of T probabilities differs from their real sum by less than T^2 * 2^-52
-            const double T = (double)g.n_trees, slack = T * T * std::ldexp(1.0, -50);
-            gt.pass_min = (uint32_t)std::ceil((g.gate_min_sum + slack) * 256.0);
-            gt.fail_max = (uint32_t)std::max(0.0, std::ceil((g.gate_min_sum - slack) * 256.0) - 1.0);
-            DH_CUDA(cudaMemsetAsync(L.tile_cnt, 0, sizeof(uint32_t) * (size_t)n * tiles_.tiles_x * tiles_.tiles_y, st));
-            if (debug_) DH_CUDA(cudaMemsetAsync(L.gate, 0, (size_t)n * g.P, st));  // gate_compact_kernel marks the passing patches only
-        }
-        L.have_list = launch_traverse(L.sat_map, b, g, tiles_, fdev_, gt, n, st);
-        L.tail = gt;
+        launch_traverse(L.sat_map, b, g, tiles_, fdev_, n, st);
         launches_ += 1;
         stage_check("traverse");
     }
@@ -744,7 +729,7 @@ void Context::run_back(Lane& L, const FrameBuffers& b, uint32_t n, uint32_t iter
     const Geometry& g = geom_;
     cudaStream_t st = L.stream;
     mark(DH_STAGE_GATE);
-    launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, gate_split_, L.have_list ? &L.tail : nullptr, tiles_, n_sms_, st);
+    launches_ += (uint64_t)launch_gate_coarse(b, g, fdev_, n, gate_split_, n_sms_, st);
     stage_check("gate + coarse grids");
     mark(DH_STAGE_VOTE);
     // the accumulator cubes of this pass start empty: either the previous pass's mean-shift CTAs
@@ -754,7 +739,7 @@ void Context::run_back(Lane& L, const FrameBuffers& b, uint32_t n, uint32_t iter
     launches_ += (uint64_t)launch_seed_and_cubes(b, g, fdev_, n, iterations, st);
     stage_check("seeds + accumulator cubes");
     mark(DH_STAGE_MEANSHIFT);
-    launches_ += (uint64_t)launch_meanshift(b, g, fdev_, n, iterations, st);
+    launches_ += (uint64_t)launch_meanshift(b, g, fdev_, n, iterations, n_sms_, st);
     if (b.clear_cubes) L.cubes_clean = true;
     stage_check("mean-shift");
     mark(DH_STAGE_D2H);
@@ -1520,7 +1505,10 @@ void Context::debug_leaf(int32_t* leaf) {
     std::vector<int32_t> tmp(P * T);
     DH_CUDA(cudaMemcpy(tmp.data(), lanes_[0].leaf, P * T * sizeof(int32_t), cudaMemcpyDeviceToHost));
     for (size_t t = 0; t < T; ++t)  // device layout [T][P] -> exported [P][T]
-        for (size_t p = 0; p < P; ++p) leaf[p * T + t] = tmp[t * P + p];
+        for (size_t p = 0; p < P; ++p) {
+            const int32_t w = tmp[t * P + p];  // leaf word: id | probability code << 23 when codes ride along
+            leaf[p * T + t] = (w >= 0 && leaf_codes_) ? (int32_t)((uint32_t)w & kLeafIdMask) : w;
+        }
 }
 void Context::debug_patches(float* p3, uint8_t* gate) {
     require_debug();

@@ -37,10 +37,6 @@ struct Lane {
     uint32_t* cubes = nullptr;      // [F][2][kBox^3]
     CUtensorMap sat_map{};
     bool allocated = false;
-    uint32_t* cand = nullptr;       // [F][tiles * patches per tile] gate candidates of the traversal's tail (GateTail)
-    uint32_t* tile_cnt = nullptr;   // [F][tiles]
-    GateTail tail{};                // of the lane's last traversal
-    bool have_list = false;         // the last traversal of this lane wrote the frames' gated-patch lists (GateTail)
     bool cubes_clean = false;       // every cube is zero (meanshift_kernel cleared behind itself)
 };
 constexpr int kMaxLanes = 4;
@@ -255,6 +251,7 @@ private:
     uint64_t graph_launches_ = 0;
     bool use_graphs_ = true;
     bool prob_codes_ok_ = false;     // the uploaded forest's leaf probabilities can ride in the node table as 8-bit codes
+    bool leaf_codes_ = false;        // ... and do: leaf words carry them (FrameBuffers::leaf_mask, patch_gate_kernel)
     bool gate_split_ = true;         // DH_GATE_SPLIT=0: the patch gate inside the seed-grid kernel instead of its own kernel + list
     bool cube_clear_fused_ = true;   // DH_CUBE_CLEAR_FUSED=0: one memset of all cubes per pass instead
 

@@ -460,8 +460,9 @@ __global__ void __launch_bounds__(kBoxMaxWarps * 32) box_image_kernel(const uint
 // ================================================================ K2: forest traversal
 // Node table prepared for one tile plan: see HotNode (dh_types.hpp).
 // prob_codes != nullptr: a leaf child of a UniNode carries the leaf's probability code in bits 23..30
-// of the complemented word, ~(leaf | code << 23) with code = min(floor(prob * 256), 255), so that a walk
-// knows prob to within 1/256 without another fetch (kLeafIdMask recovers the id; GateTail).
+// of the complemented word, ~(leaf | code << 23) with code = min(floor(prob * 256), 255).  The walk
+// stores the word as its leaf id, so that the patch gate knows every prob to within 1/256 from the
+// leaf words alone (patch_gate_kernel); every reader of leaf ids applies FrameBuffers::leaf_mask.
 __global__ void __launch_bounds__(256) plan_nodes_kernel(const NodeRec* __restrict__ nodes, HotNode* __restrict__ hot,
                                                          UniNode* __restrict__ uni, size_t n, uint32_t tw,
                                                          const double* __restrict__ prob_codes) {
@@ -562,9 +563,6 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void atomicAdd_smem(uint32_t addr, uint32_t v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
 }
@@ -603,8 +601,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
                                                             const uint32_t* __restrict__ sat,
                                                             FrameState* __restrict__ fs, Geometry g, TilePlan tp,
                                                             uint32_t uni_rw, uint32_t uni_rh, const PairRec* __restrict__ pair_recs,
-                                                            const int32_t* __restrict__ pair_roots, const int32_t* __restrict__ pair_perm,
-                                                            const GateTail gt) {
+                                                            const int32_t* __restrict__ pair_roots, const int32_t* __restrict__ pair_perm) {
     extern __shared__ uint8_t smem_raw[];
     // 128-byte aligned tile (TMA destination), then the barrier, then the compacted patch list;
     // everything is addressed through 32-bit shared-window addresses
@@ -612,14 +609,13 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
     const uint32_t tile_bytes = tp.tw * tp.th * 4u;
     const uint32_t bar_a = tile_a + ((tile_bytes + 15u) & ~15u);
     const uint32_t live_a = bar_a + 16u;
-    __shared__ uint32_t s_nlive, s_empty, s_ncand;
+    __shared__ uint32_t s_nlive, s_empty;
 
     const uint32_t frame = blockIdx.y;
     const uint32_t tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
     const uint32_t px0 = tile_x * tp.tpx, py0 = tile_y * tp.tpy;  // first patch of the tile
     const uint32_t tid = threadIdx.x;
     const uint32_t npt = tp.tpx * tp.tpy;
-    const uint32_t sum_a = live_a + ((npt + 31u) & ~31u) * 4u;  // per live patch: sum of its leaves' probability codes (GateTail)
     const int T = (int)g.n_trees;
     int32_t* leaf_f = leaf + (size_t)frame * T * g.P;
 
@@ -631,7 +627,6 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1u) : "memory");
         fence_mbar_init();
         s_nlive = 0;
-        s_ncand = 0;
         if (tp.tma_first) {
             // the load is issued before the tile's background check and lands while warp 0 tests
             // the window (one global round trip less in front of every non-empty tile)
@@ -704,8 +699,6 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
     // patches in row order, 32 per warp, or (tp.blocked) in blocks of 8 x 4 patches, one per warp
     const uint32_t nbx = (tp.tpx + 7u) >> 3;
     const uint32_t n_lp = tp.blocked ? nbx * ((tp.tpy + 3u) >> 2) * 32u : ((npt + 31u) & ~31u);
-    if (kMode == 4 && gt.cand)
-        for (uint32_t i = tid; i < npt; i += kThreads) sts_u32(sum_a + 4u * i, 0u);
     for (uint32_t lp = tid; lp < n_lp; lp += kThreads) {
         bool ok = false;
         uint32_t packed = 0;
@@ -817,8 +810,8 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
                     ++visits;
                 }
             }
-            leaf_f[(size_t)tA * g.P + (py0 + (lpA >> 24)) * g.npx + (px0 + ((lpA >> 16) & 0xffu))] = (int32_t)((uint32_t)~nA & gt.leaf_mask);
-            if (hasB) leaf_f[(size_t)tB * g.P + (py0 + (lpB >> 24)) * g.npx + (px0 + ((lpB >> 16) & 0xffu))] = (int32_t)((uint32_t)~nB & gt.leaf_mask);
+            leaf_f[(size_t)tA * g.P + (py0 + (lpA >> 24)) * g.npx + (px0 + ((lpA >> 16) & 0xffu))] = ~nA;
+            if (hasB) leaf_f[(size_t)tB * g.P + (py0 + (lpB >> 24)) * g.npx + (px0 + ((lpB >> 16) & 0xffu))] = ~nB;
         }
     } else if (kMode == 4) {
         // the default walk (uniform rectangles, box-sum tile, nodes through the texture path), in two
@@ -849,9 +842,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
             any_tie |= tie;
             visits += tie ? 0u : nv;
             const uint32_t gp = (py0 + (lp >> 24)) * g.npx + (px0 + ((lp >> 16) & 0xffu));
-            const uint32_t lw = (uint32_t)~node;  // leaf | probability code << 23 (plan_nodes_kernel)
-            leaf_f[(size_t)t * g.P + gp] = tie ? kTieMark : (int32_t)(lw & gt.leaf_mask);
-            if (gt.cand && !tie) atomicAdd_smem(sum_a + 4u * (it - t * nlive), lw >> kProbCodeShift);
+            leaf_f[(size_t)t * g.P + gp] = tie ? kTieMark : ~node;  // leaf id | probability code << 23 (plan_nodes_kernel)
         }
         if (any_tie) {
             for (uint32_t it = tid; it < items; it += kThreads) {
@@ -871,9 +862,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
                     node = next;
                     ++visits;
                 }
-                const uint32_t lw = (uint32_t)~node;
-                *slot = (int32_t)(lw & gt.leaf_mask);
-                if (gt.cand) atomicAdd_smem(sum_a + 4u * (it - t * nlive), lw >> kProbCodeShift);
+                *slot = ~node;
             }
         }
     } else if (kMode == 7) {
@@ -919,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
                     node = next;
                     ++visits;
                 }
-                leaf_id = (int32_t)((uint32_t)~node & gt.leaf_mask);
+                leaf_id = ~node;
             }
             const uint32_t lp = lds_u32(live_a + 4u * (it - t * nlive));
             const uint32_t gp = (py0 + (lp >> 24)) * g.npx + (px0 + ((lp >> 16) & 0xffu));
@@ -978,40 +967,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
             ++visits;
         }
         const uint32_t gp = (py0 + ly) * g.npx + (px0 + lx);
-        leaf_f[(size_t)t * g.P + gp] = kMode >= 2 ? (int32_t)((uint32_t)~node & gt.leaf_mask) : ~node;
-    }
-
-    // ---- patch gate (prediction.rs:582-584) of the tile's live patches, decided from the sums of the
-    //      probability codes the walks brought along: prob_t lies in [code_t / 256, (code_t + 1) / 256],
-    //      so the f64 fold of the reference lies within [S, S + T] / 256 (up to its own rounding, which
-    //      gt.pass_min / gt.fail_max leave room for).  A patch that passes for certain, or whose sum
-    //      lies inside that band (flagged: a few percent), goes to the tile's candidate list; nothing
-    //      here waits for global memory.  gate_compact_kernel settles the flagged ones with the exact
-    //      fold and turns the candidates into the frame's gated-patch list.
-    if (kMode == 4 && gt.cand && nlive) {
-        __syncthreads();            // every walk of the tile has added its code
-        uint32_t* cand = gt.cand + (size_t)frame * gt.cand_pitch + (size_t)blockIdx.x * npt;
-        for (uint32_t i0 = tid & ~31u; i0 < nlive; i0 += kThreads) {  // warp-uniform trip count
-            const uint32_t i = i0 + (tid & 31u);
-            uint32_t word = 0;
-            bool keep = false;
-            if (i < nlive) {
-                const uint32_t lp = lds_u32(live_a + 4u * i);
-                const uint32_t S = lds_u32(sum_a + 4u * i);
-                const bool pass = S >= gt.pass_min;
-                keep = pass || S + (uint32_t)T > gt.fail_max;
-                word = ((py0 + (lp >> 24)) * g.npx + (px0 + ((lp >> 16) & 0xffu))) | (pass ? 0u : 0x80000000u);
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, keep);
-            if (!m) continue;
-            uint32_t base = 0;
-            if ((tid & 31u) == 0) {
-                base = atomicAdd(&s_ncand, (uint32_t)__popc(m));                                          // rank inside the tile
-                atomicAdd(gt.tile_cnt + (size_t)frame * gridDim.x + blockIdx.x, (uint32_t)__popc(m));  // nobody waits for this one
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) cand[base + __popc(m & ((1u << (tid & 31u)) - 1u))] = word;
-        }
+        leaf_f[(size_t)t * g.P + gp] = ~node;
     }
 
     // ---- per-frame counters (measured mean depth feeds the roofline arithmetic)
@@ -1112,19 +1068,49 @@ __device__ __forceinline__ void for_each_vote(uint32_t n, uint32_t v0, uint32_t 
 constexpr int kGateSmemBytes = kGateThreads * 16 + (kGateThreads / 32) * 32 * 32 + (kPosGridCells + kRotGridCells) * 4 + kTouchedCap * 2;
 
 // The patch gate on its own (phase A of gate_coarse_kernel), one thread per patch: the passing patches
-// are appended to the frame's gated-patch list, one reservation per warp.  gate_coarse_kernel<., true>
-// then reads slices of that list.  Runs when the traversal variant of the pass has no gate tail
-// (GateTail): it re-reads every leaf id and gathers every leaf's probability (0.19 ms per 1024
-// frames of configs[1], bound by the L1 miss path), which the tail avoids.
+// are appended to the frame's gated-patch list, one reservation per warp; gate_coarse_kernel<., true>
+// then reads slices of that list.  With probability codes in the leaf words (b.leaf_mask ==
+// kLeafIdMask) the gate is decided from the T leaf words of the patch alone, coalesced loads, no
+// gather: prob_t lies in [code_t / 256, (code_t + 1) / 256], so the f64 fold of the reference lies
+// within [S, S + T] / 256 (up to its own rounding, which g.gate_pass_codes / g.gate_fail_codes leave
+// room for); only a sum inside that band (a few percent of the patches) gathers the leaves'
+// probabilities and folds them in tree order.  Without codes every patch does (0.19 ms per 1024
+// frames of configs[1]: 34 M random 8-byte gathers, bound by the L1 miss path).
 constexpr int kPatchGateThreads = 256;
+constexpr int kPatchGatePer = 4;  // patches per thread (one: 0.15 ms per 1024 frames of configs[1], four: 0.10 ms).  The kernel
+                                  // sits at a third of the HBM rate; loading every leaf word of a patch up front,
+                                  // background or not, to save dependent round trips was slower (it reads 40 % more)
 __global__ void __launch_bounds__(kPatchGateThreads) patch_gate_kernel(FrameBuffers b, Geometry g, ForestDev f) {
     const uint32_t frame = blockIdx.y, lane = threadIdx.x & 31u;
-    const uint32_t p = blockIdx.x * kPatchGateThreads + threadIdx.x;
     const uint32_t T = g.n_trees;
     const int32_t* leaf_f = b.leaf + (size_t)frame * T * g.P;
-    bool gate = false;
-    if (p < g.P) {
-        if (leaf_f[p] >= 0) {
+    const bool codes = b.leaf_mask == kLeafIdMask;
+    uint32_t p[kPatchGatePer], S[kPatchGatePer];
+    bool valid[kPatchGatePer], gate[kPatchGatePer];
+#pragma unroll
+    for (int k = 0; k < kPatchGatePer; ++k) {
+        p[k] = (blockIdx.x * kPatchGatePer + k) * kPatchGateThreads + threadIdx.x;
+        const int32_t w0 = p[k] < g.P ? leaf_f[p[k]] : -1;
+        valid[k] = w0 >= 0;  // background patches carry -1 in the slice of tree 0
+        S[k] = (uint32_t)w0 >> kProbCodeShift;
+        gate[k] = false;
+    }
+    if (codes) {
+        for (uint32_t t = 1; t < T; ++t) {
+#pragma unroll
+            for (int k = 0; k < kPatchGatePer; ++k)
+                if (valid[k]) S[k] += (uint32_t)leaf_f[(size_t)t * g.P + p[k]] >> kProbCodeShift;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kPatchGatePer; ++k) {
+        if (!valid[k]) continue;
+        bool exact = !codes;
+        if (codes) {
+            gate[k] = S[k] >= g.gate_pass_codes;
+            exact = !gate[k] && S[k] + T > g.gate_fail_codes;
+        }
+        if (exact) {
             // prob = sum(leaf.prob) / len: f64 fold from 0.0 in tree order (prediction.rs:582);
             // four independent gathers in flight, the additions stay in tree order
             double s = 0.0;
@@ -1133,7 +1119,7 @@ __global__ void __launch_bounds__(kPatchGateThreads) patch_gate_kernel(FrameBuff
                 double pr[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (t0 + u < T) L[u] = leaf_f[(size_t)(t0 + u) * g.P + p];
+                    if (t0 + u < T) L[u] = (int32_t)((uint32_t)leaf_f[(size_t)(t0 + u) * g.P + p[k]] & b.leaf_mask);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (t0 + u < T) pr[u] = __ldg(f.leaf_prob + L[u]);
@@ -1141,78 +1127,47 @@ __global__ void __launch_bounds__(kPatchGateThreads) patch_gate_kernel(FrameBuff
                 for (int u = 0; u < 4; ++u)
                     if (t0 + u < T) s = __dadd_rn(s, pr[u]);
             }
-            gate = s >= g.gate_min_sum;  // sum / T > 0.7 (prediction.rs:584), see Geometry::gate_min_sum
+            gate[k] = s >= g.gate_min_sum;  // sum / T > 0.7 (prediction.rs:584), see Geometry::gate_min_sum
         }
-        if (b.gate) b.gate[(size_t)frame * g.P + p] = gate ? 1 : 0;
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, gate);
-    if (!m) return;
+    // the depth under the centre of every passing patch (prediction.rs:551), in flight with the list reservation
+    uint16_t z[kPatchGatePer];
+    uint32_t m[kPatchGatePer], total = 0;
+#pragma unroll
+    for (int k = 0; k < kPatchGatePer; ++k) {
+        z[k] = 0;
+        if (gate[k]) {
+            const uint32_t gx = p[k] % g.npx, gy = p[k] / g.npx;
+            z[k] = b.depth[((size_t)frame * g.h + g.left_h + gy * g.stride) * g.w + g.left_w + gx * g.stride];
+        }
+        if (b.gate && p[k] < g.P) b.gate[(size_t)frame * g.P + p[k]] = gate[k] ? 1 : 0;
+        m[k] = __ballot_sync(0xffffffffu, gate[k]);
+        total += (uint32_t)__popc(m[k]);
+    }
+    if (!total) return;
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&b.fs[frame].n_gate, (uint32_t)__popc(m));
+    if (lane == 0) base = atomicAdd(&b.fs[frame].n_gate, total);  // one reservation per warp
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (gate) {
-        const uint32_t gx = p % g.npx, gy = p / g.npx;
-        const uint32_t x = g.left_w + gx * g.stride, y = g.left_h + gy * g.stride;
-        const uint16_t z = b.depth[((size_t)frame * g.h + y) * g.w + x];  // prediction.rs:551
-        float p3[3];
-        img_to_space(g.Kinv, (float)x, (float)y, (float)z, p3);           // prediction.rs:554
-        b.gated[(size_t)frame * g.P + base + __popc(m & ((1u << lane) - 1u))] = make_float4(p3[0], p3[1], p3[2], __uint_as_float(p));
-        if (b.p3) {
-            float* o = b.p3 + ((size_t)frame * g.P + p) * 3;
-            o[0] = p3[0]; o[1] = p3[1]; o[2] = p3[2];
-        }
-    }
-}
-
-// Candidates of the traversal's gate tail (GateTail) -> the frame's gated-patch list.  One warp per
-// tile, a lane per candidate: a flagged candidate (its code sum could not decide) gets the exact fold
-// of patch_gate_kernel; a patch that passes is back-projected and appended, one reservation per warp.
-__global__ void __launch_bounds__(kPatchGateThreads) gate_compact_kernel(FrameBuffers b, Geometry g, ForestDev f, GateTail gt,
-                                                                         uint32_t npt, uint32_t n_tiles) {
-    const uint32_t frame = blockIdx.y, lane = threadIdx.x & 31u;
-    const uint32_t tile = blockIdx.x * (kPatchGateThreads / 32) + (threadIdx.x >> 5);  // a warp per tile
-    if (tile >= n_tiles) return;
-    const uint32_t T = g.n_trees;
-    const uint32_t n = gt.tile_cnt[(size_t)frame * n_tiles + tile];
-    const uint32_t* cand = gt.cand + (size_t)frame * gt.cand_pitch + (size_t)tile * npt;
-    for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
-        bool gate = false;
-        uint32_t p = 0;
-        if (i0 + lane < n) {
-            const uint32_t w = cand[i0 + lane];
-            p = w & 0x7fffffffu;
-            gate = true;
-            if (w >> 31) {
-                const int32_t* leaf_f = b.leaf + (size_t)frame * T * g.P;
-                double s = 0.0;  // prob = sum(leaf.prob) / len: f64 fold from 0.0 in tree order (prediction.rs:582)
-                for (uint32_t t = 0; t < T; ++t) s = __dadd_rn(s, __ldg(f.leaf_prob + leaf_f[(size_t)t * g.P + p]));
-                gate = s >= g.gate_min_sum;
-            }
-            if (b.gate && gate) b.gate[(size_t)frame * g.P + p] = 1;  // zeroed by the caller
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, gate);
-        if (!m) continue;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&b.fs[frame].n_gate, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (gate) {
-            const uint32_t gx = p % g.npx, gy = p / g.npx;
+#pragma unroll
+    for (int k = 0; k < kPatchGatePer; ++k) {
+        if (gate[k]) {
+            const uint32_t gx = p[k] % g.npx, gy = p[k] / g.npx;
             const uint32_t x = g.left_w + gx * g.stride, y = g.left_h + gy * g.stride;
-            const uint16_t z = b.depth[((size_t)frame * g.h + y) * g.w + x];  // prediction.rs:551
             float p3[3];
-            img_to_space(g.Kinv, (float)x, (float)y, (float)z, p3);           // prediction.rs:554
-            b.gated[(size_t)frame * g.P + base + __popc(m & ((1u << lane) - 1u))] = make_float4(p3[0], p3[1], p3[2], __uint_as_float(p));
+            img_to_space(g.Kinv, (float)x, (float)y, (float)z[k], p3);  // prediction.rs:554
+            b.gated[(size_t)frame * g.P + base + __popc(m[k] & ((1u << lane) - 1u))] = make_float4(p3[0], p3[1], p3[2], __uint_as_float(p[k]));
             if (b.p3) {
-                float* o = b.p3 + ((size_t)frame * g.P + p) * 3;
+                float* o = b.p3 + ((size_t)frame * g.P + p[k]) * 3;
                 o[0] = p3[0]; o[1] = p3[1]; o[2] = p3[2];
             }
         }
+        base += (uint32_t)__popc(m[k]);
     }
 }
 
 // kFused: one pass over the votes of every pair feeds both grids (a vote is an offset and a rotation;
 // the pair's tag says which of the two spread gates is open) instead of one pass per grid.
-// kFromList: the patch gate has already been applied (traversal tail or patch_gate_kernel): the CTA
+// kFromList: the patch gate has already been applied by patch_gate_kernel: the CTA
 // takes slices of kGateThreads entries of the frame's gated-patch list (blockIdx.x, + gridDim.x, ...)
 // instead of gating the kGateThreads patches of its own index range, so that every CTA that runs
 // has a full slice behind the fixed costs of its seed grids (clearing and flushing 8400 cells);
@@ -1232,7 +1187,7 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
     FrameState* fs = b.fs + frame;
     uint32_t slice0 = blockIdx.x * kGateThreads, n_list = 0;
     if (kFromList) {
-        n_list = fs->n_gate;  // complete: written by the traversal's tail or by patch_gate_kernel
+        n_list = fs->n_gate;  // complete: written by patch_gate_kernel
         if (slice0 >= n_list) return;
     }
     if (tid == 0) {
@@ -1259,7 +1214,7 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
                     double pr[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (t0 + u < T) L[u] = leaf_f[(size_t)(t0 + u) * g.P + p];
+                        if (t0 + u < T) L[u] = (int32_t)((uint32_t)leaf_f[(size_t)(t0 + u) * g.P + p] & b.leaf_mask);
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (t0 + u < T) pr[u] = __ldg(f.leaf_prob + L[u]);
@@ -1321,7 +1276,7 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
             if (i < npairs) {
                 const uint32_t t = i / ngate;
                 h = s_gated[i - t * ngate];
-                const int32_t L = leaf_f[(size_t)t * g.P + __float_as_uint(h.w)];
+                const int32_t L = (int32_t)((uint32_t)leaf_f[(size_t)t * g.P + __float_as_uint(h.w)] & b.leaf_mask);
                 const LeafInfo li = f.leaf_info[L];
                 if (li.flags & kLeafVotes) {  // prob > 0 (prediction.rs:590), weight != 0, a spread gate open
                     v0 = li.vote_start;
@@ -1531,7 +1486,7 @@ __device__ __forceinline__ bool misses_box(int lo, int hi, int org) {
 // pairs 32 at a time (one per lane) and spreads their votes over its lanes (flat_owner).
 // which_mask: bit0 centre cube, bit1 rotation cube.  All 32 lanes of a warp must call.
 __device__ __forceinline__ void accumulate_pairs(const float4* __restrict__ gated, uint32_t ngate, uint32_t T,
-                                                 const int32_t* __restrict__ leaf_f, uint32_t P, uint32_t first_warp,
+                                                 const int32_t* __restrict__ leaf_f, uint32_t leaf_mask, uint32_t P, uint32_t first_warp,
                                                  uint32_t n_warps, const ForestDev& f, uint32_t which_mask,
                                                  const int32_t* org_c, uint32_t* cube_c, const int32_t* org_r,
                                                  uint32_t* cube_r) {
@@ -1544,7 +1499,7 @@ __device__ __forceinline__ void accumulate_pairs(const float4* __restrict__ gate
         if (i < npairs) {
             const uint32_t t = i / ngate;
             h = __ldg(gated + (i - t * ngate));
-            const int32_t L = leaf_f[(size_t)t * P + __float_as_uint(h.w)];
+            const int32_t L = (int32_t)((uint32_t)leaf_f[(size_t)t * P + __float_as_uint(h.w)] & leaf_mask);
             const LeafInfo li = f.leaf_info[L];
             if (li.flags & kLeafVotes) {
                 // Skip the leaf when the bounding box of its votes misses the cube.  Conservative,
@@ -1620,7 +1575,7 @@ __global__ void __launch_bounds__(kBuildThreads) box_build_kernel(FrameBuffers b
     const int32_t org_c[3] = {fs->box_org[0][0], fs->box_org[0][1], fs->box_org[0][2]};
     const int32_t org_r[3] = {fs->box_org[1][0], fs->box_org[1][1], fs->box_org[1][2]};
     uint32_t* cube_c = b.cubes + (size_t)(2u * frame) * kBoxCells;
-    accumulate_pairs(b.gated + (size_t)frame * g.P, fs->n_gate, g.n_trees, b.leaf + (size_t)frame * g.n_trees * g.P, g.P,
+    accumulate_pairs(b.gated + (size_t)frame * g.P, fs->n_gate, g.n_trees, b.leaf + (size_t)frame * g.n_trees * g.P, b.leaf_mask, g.P,
                      blockIdx.x * (kBuildThreads / 32) + (threadIdx.x >> 5), gridDim.x * (kBuildThreads / 32), f, 3u, org_c,
                      cube_c, org_r, cube_c + kBoxCells);
 }
@@ -1660,7 +1615,7 @@ __device__ __forceinline__ void store_result(dh_result* r, uint32_t which, const
 
 // Clears one cube and re-accumulates the frame's votes around a new origin (whole CTA).
 __device__ __noinline__ void rebuild_cube(const float4* __restrict__ gated, uint32_t ngate, uint32_t T,
-                                          const int32_t* __restrict__ leaf_f, uint32_t P, const LeafInfo* leaf_info,
+                                          const int32_t* __restrict__ leaf_f, uint32_t leaf_mask, uint32_t P, const LeafInfo* leaf_info,
                                           const LeafBox* leaf_box, const float4* offsets, const uint32_t* rot_bins,
                                           uint32_t which, int32_t ox, int32_t oy, int32_t oz, uint32_t* box) {
     const int32_t org[3] = {ox, oy, oz};
@@ -1673,7 +1628,7 @@ __device__ __noinline__ void rebuild_cube(const float4* __restrict__ gated, uint
     for (int i = threadIdx.x; i < kBoxCells / 4; i += kMsThreads) __stcg(bz + i, make_uint4(0u, 0u, 0u, 0u));
     __threadfence();
     __syncthreads();
-    accumulate_pairs(gated, ngate, T, leaf_f, P, threadIdx.x >> 5, kMsThreads / 32, f, 1u << which, org, box, org, box);
+    accumulate_pairs(gated, ngate, T, leaf_f, leaf_mask, P, threadIdx.x >> 5, kMsThreads / 32, f, 1u << which, org, box, org, box);
     __threadfence();
     __syncthreads();
 }
@@ -1683,7 +1638,8 @@ __device__ __noinline__ void rebuild_cube(const float4* __restrict__ gated, uint
 // are then computed densely, one thread per non-zero cell (the kCompact = false form walks all 250
 // chunks of 32 cells with only the non-zero lanes working: 53 % of the kernel's instructions, measured).
 template <bool kCompact>
-__global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b, Geometry g, ForestDev f, uint32_t iterations) {
+__global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b, Geometry g, ForestDev f, uint32_t iterations,
+                                                                  uint32_t n_items) {
     extern __shared__ __align__(16) uint8_t ms_smem[];
     uint32_t* s_win = reinterpret_cast<uint32_t*>(ms_smem);  // [8000] window cells in reference order (!kCompact)
     uint2* s_list = reinterpret_cast<uint2*>(ms_smem);       // [kMsSegment] (ord, value) of the non-zero cells by rank (kCompact)
@@ -1695,19 +1651,8 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
     __shared__ int32_t s_hist[kMsHistory + 1][3];      // positions P_0 (seed), P_1, ... for cycle detection
     __shared__ int32_t s_pos[3], s_org[3];
     __shared__ uint32_t s_flags, s_done;
+    __shared__ uint32_t s_item;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t item = blockIdx.x, frame = item >> 1, which = item & 1u;
-    FrameState* fs = b.fs + frame;
-    uint32_t* box = b.cubes + (size_t)item * kBoxCells;
-    if (tid == 0) {
-        s_flags = 0;
-        s_done = 0;
-        const int32_t* seed = which == 0 ? fs->seed_mid : fs->seed_rot;
-        for (int k = 0; k < 3; ++k) {
-            s_pos[k] = s_hist[0][k] = seed[k];
-            s_org[k] = fs->box_org[which][k];
-        }
-    }
     // kCompact: cube offsets of this thread's window cells ord = j * kMsThreads + tid, two per word,
     // computed once and parked in shared memory (eight registers less across the rounds)
     if (kCompact) {
@@ -1721,6 +1666,22 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
                 pk |= (ord < (uint32_t)kKernelCells ? (xo * kBox + yo) * kBox + zo : kMsNoCell) << (16 * u);
             }
             s_offp[(j >> 1) * kMsThreads + tid] = pk;
+        }
+    }
+    // The CTAs of the launch (as many as fit the GPU at once) take accumulators from a counter: the first
+    // one by their index, the following ones as they become free (a launch of one CTA per accumulator ran
+    // 2.3 rounds of CTAs and paid for three).
+    for (uint32_t item = blockIdx.x; item < n_items;) {
+    const uint32_t frame = item >> 1, which = item & 1u;
+    FrameState* fs = b.fs + frame;
+    uint32_t* box = b.cubes + (size_t)item * kBoxCells;
+    if (tid == 0) {
+        s_flags = 0;
+        s_done = 0;
+        const int32_t* seed = which == 0 ? fs->seed_mid : fs->seed_rot;
+        for (int k = 0; k < 3; ++k) {
+            s_pos[k] = s_hist[0][k] = seed[k];
+            s_org[k] = fs->box_org[which][k];
         }
     }
     uint32_t rebuilds = 0;
@@ -1741,7 +1702,7 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
             for (int k = 0; k < 3; ++k) org[k] = (int32_t)((uint32_t)pos[k] - (uint32_t)(kBox / 2));
             if (tid == 0)
                 for (int k = 0; k < 3; ++k) s_org[k] = org[k];
-            rebuild_cube(b.gated + (size_t)frame * g.P, fs->n_gate, g.n_trees, b.leaf + (size_t)frame * g.n_trees * g.P, g.P,
+            rebuild_cube(b.gated + (size_t)frame * g.P, fs->n_gate, g.n_trees, b.leaf + (size_t)frame * g.n_trees * g.P, b.leaf_mask, g.P,
                          f.leaf_info, f.leaf_box, f.offsets, f.rot_bins, which, org[0], org[1], org[2], box);
         }
         const uint32_t base = ((uint32_t)((long long)pos[0] - 10 - org[0]) * kBox + (uint32_t)((long long)pos[1] - 10 - org[1])) * kBox +
@@ -1933,6 +1894,11 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
         for (int k = 0; k < 3; ++k) fs->box_org[which][k] = s_org[k];
         const int32_t fin[3] = {s_pos[0], s_pos[1], s_pos[2]};
         store_result(b.results + frame, which, fin);
+        s_item = gridDim.x + atomicAdd(&b.fs[0].work_next, 1u);
+    }
+    __syncthreads();  // the next accumulator; nobody still reads this one's shared state
+    item = s_item;
+    __syncthreads();
     }
 }
 
@@ -2056,7 +2022,7 @@ __global__ void __launch_bounds__(256) mask_kernel(FrameBuffers b, Geometry g, c
     const int T = (int)g.n_trees;
     if (b.leaf[p] < 0) return;
     double s = 0.0;
-    for (int t = 0; t < T; ++t) s = __dadd_rn(s, __ldg(leaf_prob + b.leaf[(size_t)t * g.P + p]));
+    for (int t = 0; t < T; ++t) s = __dadd_rn(s, __ldg(leaf_prob + ((uint32_t)b.leaf[(size_t)t * g.P + p] & b.leaf_mask)));
     const double prob = __ddiv_rn(s, (double)T);
     const double scaled = __dmul_rn(prob, 255.0);
     // `as u8`: saturating, NaN -> 0
@@ -2080,7 +2046,7 @@ __global__ void __launch_bounds__(256) hough_image_kernel(FrameBuffers b, Geomet
     if (idx >= g.P * T) return;
     const uint32_t p = idx % g.P, t = idx / g.P;
     if (b.leaf[p] < 0) return;  // background patch: decided on the slice of tree 0 (the only one prefilled with -1)
-    const int32_t L = b.leaf[(size_t)t * g.P + p];
+    const int32_t L = (int32_t)((uint32_t)b.leaf[(size_t)t * g.P + p] & b.leaf_mask);
     const double lp = f.leaf_prob[L];
     if (!(lp >= 0.95)) return;                                             // :805
     const uint32_t v0 = f.leaf_info[L].vote_start, n = f.leaf_info[L].n_votes;
@@ -2543,7 +2509,7 @@ int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames
 
 uint32_t traverse_smem_bytes(uint32_t tw, uint32_t th, uint32_t patches_per_tile) {
     const uint32_t tile_bytes = (tw * th * 4u + 15u) & ~15u;
-    return 128u + tile_bytes + 16u + 2u * ((patches_per_tile + 31u) & ~31u) * 4u + 64u;  // tile, barrier, live list, code sums
+    return 128u + tile_bytes + 16u + ((patches_per_tile + 31u) & ~31u) * 4u + 64u;
 }
 
 int traverse_kernel_attrs(int* regs, int* max_smem) {
@@ -2555,11 +2521,9 @@ int traverse_kernel_attrs(int* regs, int* max_smem) {
     return 0;
 }
 
-// returns true when the launched variant applies the patch gate in its tail (GateTail::gated set and the
-// default box-sum / texture walk selected)
 template <int kThreads>
-static bool launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
-                              const ForestDev& f, const GateTail& gt_in, uint32_t n_frames, cudaStream_t s) {
+static void launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
+                              const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
     static SmemConfig configured;
     if (configured.raise(tp.smem_bytes)) {
         cudaFuncSetAttribute(traverse_kernel<kThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_bytes);
@@ -2573,41 +2537,37 @@ static bool launch_traverse_t(const CUtensorMap& sat_map, const FrameBuffers& b,
     }
     static const bool two_walks = std::getenv("DH_TRAV_ILP") && std::atoi(std::getenv("DH_TRAV_ILP")) == 2;
     dim3 gr(tp.tiles_x * tp.tiles_y, n_frames);
-    GateTail gt = gt_in;
-    const bool default_walk = f.uni && g.rw && f.hot_tex && !f.pair_recs && !two_walks;
-    if (!default_walk) gt.cand = nullptr;  // only that walk carries the tail
     if (f.uni && g.rw && f.pair_recs)
         traverse_kernel<kThreads, 7><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.uni && g.rw && f.hot_tex && two_walks)
         traverse_kernel<kThreads, 6><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.uni && g.rw && f.hot_tex)
         traverse_kernel<kThreads, 4><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.uni && g.rw)
         traverse_kernel<kThreads, 5><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.box, b.fs, g,
-                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
+                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.uni && f.hot_tex)
         traverse_kernel<kThreads, 2><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat,
-                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
+                                                                       b.fs, g, tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.uni)
         traverse_kernel<kThreads, 3><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat, b.fs, g,
-                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm, gt);
+                                                                       tp, f.uni_rw, f.uni_rh, f.pair_recs, f.pair_roots, f.pair_leaf_perm);
     else if (f.hot_tex)
         traverse_kernel<kThreads, 1><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, f.hot_tex, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat,
-                                                                       b.fs, g, tp, 0u, 0u, nullptr, nullptr, nullptr, gt);
+                                                                       b.fs, g, tp, 0u, 0u, nullptr, nullptr, nullptr);
     else
         traverse_kernel<kThreads, 0><<<gr, kThreads, tp.smem_bytes, s>>>(sat_map, 0, f.hot, f.uni, f.nodes, f.roots, b.leaf, b.sat, b.fs, g,
-                                                                       tp, 0u, 0u, nullptr, nullptr, nullptr, gt);
-    return gt.cand != nullptr;
+                                                                       tp, 0u, 0u, nullptr, nullptr, nullptr);
 }
 
-bool launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
-                     const ForestDev& f, const GateTail& gt, uint32_t n_frames, cudaStream_t s) {
-    if (tp.threads >= 1024) return launch_traverse_t<1024>(sat_map, b, g, tp, f, gt, n_frames, s);
-    if (tp.threads >= 768) return launch_traverse_t<768>(sat_map, b, g, tp, f, gt, n_frames, s);
-    return launch_traverse_t<512>(sat_map, b, g, tp, f, gt, n_frames, s);
+void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
+                     const ForestDev& f, uint32_t n_frames, cudaStream_t s) {
+    if (tp.threads >= 1024) launch_traverse_t<1024>(sat_map, b, g, tp, f, n_frames, s);
+    else if (tp.threads >= 768) launch_traverse_t<768>(sat_map, b, g, tp, f, n_frames, s);
+    else launch_traverse_t<512>(sat_map, b, g, tp, f, n_frames, s);
 }
 
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width,
@@ -2627,8 +2587,8 @@ uint32_t vote_box_dim() { return (uint32_t)kBox; }
 
 // The back end after the traversal, in launch order.  The coarse grids, the accumulator cubes
 // and the queue header must be zero when these run.  Each returns the kernels it launched.
-int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, bool from_list,
-                       const GateTail* tail, const TilePlan& tp, int n_sms, cudaStream_t s) {
+int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, bool from_list, int n_sms,
+                       cudaStream_t s) {
     if (!g.P) return 0;
     static SmemConfig configured;
     if (configured.raise((uint32_t)kGateSmemBytes)) {
@@ -2645,13 +2605,8 @@ int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev
         static const uint32_t want = std::getenv("DH_GATE_CTAS") ? (uint32_t)std::atoi(std::getenv("DH_GATE_CTAS")) : 0u;
         const uint32_t fill = (6u * (uint32_t)n_sms + n_frames - 1u) / n_frames;
         const uint32_t ctas = std::max<uint32_t>(1u, std::min<uint32_t>(per_frame, want ? want : std::max<uint32_t>(4u, fill)));
-        if (tail) {  // the traversal left candidates per tile
-            const uint32_t npt = tp.tpx * tp.tpy, n_tiles = tp.tiles_x * tp.tiles_y;
-            gate_compact_kernel<<<dim3((n_tiles + kPatchGateThreads / 32 - 1) / (kPatchGateThreads / 32), n_frames), kPatchGateThreads, 0, s>>>(
-                b, g, f, *tail, npt, n_tiles);
-        } else {     // the traversal variant that ran has no gate tail
-            patch_gate_kernel<<<dim3((g.P + kPatchGateThreads - 1) / kPatchGateThreads, n_frames), kPatchGateThreads, 0, s>>>(b, g, f);
-        }
+        patch_gate_kernel<<<dim3((g.P + kPatchGateThreads * kPatchGatePer - 1) / (kPatchGateThreads * kPatchGatePer), n_frames),
+                            kPatchGateThreads, 0, s>>>(b, g, f);
         gate_coarse_kernel<true, true><<<dim3(ctas, n_frames), kGateThreads, kGateSmemBytes, s>>>(b, g, f);
         return 2;
     }
@@ -2674,15 +2629,19 @@ int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const Forest
 }
 
 int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t iterations,
-                     cudaStream_t s) {
+                     int n_sms, cudaStream_t s) {
     static SmemConfig configured;
     if (configured.raise((uint32_t)kMsSmemBytes)) {
         cudaFuncSetAttribute(meanshift_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes);
         cudaFuncSetAttribute(meanshift_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytesCompact);
     }
     static const bool compact = !(std::getenv("DH_MS_COMPACT") && std::atoi(std::getenv("DH_MS_COMPACT")) == 0);
-    if (compact) meanshift_kernel<true><<<2u * n_frames, kMsThreads, kMsSmemBytesCompact, s>>>(b, g, f, iterations);
-    else meanshift_kernel<false><<<2u * n_frames, kMsThreads, kMsSmemBytes, s>>>(b, g, f, iterations);
+    // persistent CTAs: three per SM (registers), DH_MS_PERSIST=0: one CTA per accumulator
+    static const bool persist = !(std::getenv("DH_MS_PERSIST") && std::atoi(std::getenv("DH_MS_PERSIST")) == 0);
+    const uint32_t n_items = 2u * n_frames;
+    const uint32_t grid = persist ? std::min<uint32_t>(n_items, 3u * (uint32_t)std::max(n_sms, 1)) : n_items;
+    if (compact) meanshift_kernel<true><<<grid, kMsThreads, kMsSmemBytesCompact, s>>>(b, g, f, iterations, n_items);
+    else meanshift_kernel<false><<<grid, kMsThreads, kMsSmemBytes, s>>>(b, g, f, iterations, n_items);
     return 1;
 }
 

@@ -30,6 +30,8 @@ struct alignas(16) FrameState {
     uint32_t has_guess;       // bit0 midp_guess, bit1 rot_guess supplied by the caller
     float midp_guess[3];
     double rot_guess[3];
+    uint32_t work_next;       // frame 0's: accumulators handed out to the persistent mean-shift CTAs beyond the first round
+    uint32_t _pad[3];
 };
 
 struct Geometry {
@@ -47,6 +49,8 @@ struct Geometry {
     uint32_t box_w, box_h;    // w - rw + 1, h - rh + 1
     uint32_t box_pitch;       // elements per row of B (multiple of 4)
     float K[9], Kinv[9];
+    uint32_t gate_pass_codes; // patch gate from 8-bit probability codes (patch_gate_kernel): a code sum >= this passes for certain,
+    uint32_t gate_fail_codes; // a code sum + n_trees <= this fails for certain, anything between takes the exact fold
     double gate_min_sum;      // smallest f64 s with fl(s / n_trees) > 0.7: the patch gate of prediction.rs:582-584
                               // without the division (IEEE division by a positive constant is monotone in s)
 };
@@ -100,43 +104,33 @@ struct FrameBuffers {
     dh_result* results;     // [F]
     int32_t* ms_trace;      // [F][2][iters][3] or nullptr
     uint32_t ms_trace_cap;  // iterations per trace
+    uint32_t leaf_mask;     // leaf id = leaf word & leaf_mask: kLeafIdMask when the words carry probability codes, else 0x7fffffff
     uint32_t debug;         // 1: compute the seed grids even when the caller supplied seeds
     uint32_t clear_cubes;   // 1: meanshift_kernel zeroes its accumulator cube when it is done with it (the next
                             // pass finds the cubes empty without a memset of all of them)
 };
 
-// The traversal's patch-gate tail (default walk only; `cand` null: no tail).  Leaf children of the
-// uniform node table may carry a probability code (plan_nodes_kernel): leaf_mask recovers the leaf id
-// (all ones below bit 31 when the table is not packed).
+// Leaf words: the walk stores ~child of the node it left; with probability codes in the uniform node
+// table (plan_nodes_kernel) that is leaf id | code << 23, and FrameBuffers::leaf_mask recovers the id.
 constexpr uint32_t kProbCodeShift = 23u;
 constexpr uint32_t kLeafIdMask = (1u << kProbCodeShift) - 1u;
-struct GateTail {
-    uint32_t* cand;           // [F][cand_pitch] per tile (tile * patches per tile): patch index | 0x80000000 if the code sum
-                              // could not decide; null: no tail
-    uint32_t* tile_cnt;       // [F][tiles] candidates of every tile (zeroed before the traversal)
-    uint32_t cand_pitch;      // tiles * patches per tile
-    uint32_t leaf_mask;       // kLeafIdMask when the uniform table is packed, else 0x7fffffff
-    uint32_t pass_min;        // sum of codes >= pass_min: the patch passes for certain
-    uint32_t fail_max;        // sum of codes + n_trees <= fail_max: it fails for certain
-};
 
 int launch_sat(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, cudaStream_t s);
 int launch_box_image(const FrameBuffers& b, const Geometry& g, uint32_t n_frames, int n_sms, cudaStream_t s);
 bool box_image_supported(uint32_t w, uint32_t h, uint32_t sw, uint32_t sh, uint32_t rw, uint32_t rh);
-bool launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
-                     const ForestDev& f, const GateTail& gt, uint32_t n_frames, cudaStream_t s);  // true: the gate tail ran
+void launch_traverse(const CUtensorMap& sat_map, const FrameBuffers& b, const Geometry& g, const TilePlan& tp,
+                     const ForestDev& f, uint32_t n_frames, cudaStream_t s);
 void launch_plan_nodes(const NodeRec* nodes, HotNode* hot, UniNode* uni, size_t n_nodes, uint32_t tile_width,
                        const double* prob_codes, cudaStream_t s);
 void launch_plan_pairs(const PairTopo* topo, const UniNode* uni, PairRec* recs, size_t n_recs, cudaStream_t s);
 // from_list: the patch gate runs as its own kernel and writes the frames' gated-patch lists; the seed-grid CTAs take
 // slices of the lists (DH_GATE_SPLIT, default) instead of gating the patches of their own index range
-// tail: the traversal's tail left candidates (gate_compact_kernel makes the lists), else patch_gate_kernel runs first
-int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, bool from_list,
-                       const GateTail* tail, const TilePlan& tp, int n_sms, cudaStream_t s);
+int launch_gate_coarse(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, bool from_list, int n_sms,
+                       cudaStream_t s);
 int launch_seed_and_cubes(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames,
                           uint32_t iterations, cudaStream_t s);
 int launch_meanshift(const FrameBuffers& b, const Geometry& g, const ForestDev& f, uint32_t n_frames, uint32_t iterations,
-                     cudaStream_t s);
+                     int n_sms, cudaStream_t s);
 uint32_t sat_band_rows();
 uint32_t vote_box_cells();
 uint32_t vote_box_dim();

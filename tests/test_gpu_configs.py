@@ -61,6 +61,8 @@ VARIANTS = [
     {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},
     {"DH_NODE_ALIGN": "0"},                         # device node table in host order (no pad records in front of sibling pairs)
     {"DH_NODE_ALIGN": "0", "DH_TRAV_PAIR": "1"},
+    {"DH_MS_PERSIST": "0"},                         # mean-shift: one CTA per accumulator instead of persistent CTAs
+    {"DH_MS_PERSIST": "0", "DH_MS_COMPACT": "0"},
     {"DH_MS_COMPACT": "0"},                         # mean-shift: window staged in shared memory, summands per 32-cell chunk
     {"DH_PROB_CODES": "0"},                         # no probability codes in the node table: the patch gate runs as its own kernel
     {"DH_PROB_CODES": "0", "DH_GATE_CTAS": "2"},
