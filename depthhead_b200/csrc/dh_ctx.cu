@@ -496,7 +496,8 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
     const uint32_t want_threads = env_u32("DH_TRAV_THREADS", 1024);
     const uint32_t trav_threads = want_threads >= 1024 ? 1024u : (want_threads >= 768 ? 768u : 512u);
     const uint32_t big = trav_threads >= 768 ? 1u : 0u;  // two CTAs per SM; 512 threads: three
-    const uint32_t limits[3] = {big ? 113000u : 75000u, 113000u, smem_optin_ > 2048u ? smem_optin_ - 1024u : smem_optin_};
+    const uint32_t two = env_u32("DH_TRAV_SMEM", 113000u);  // bytes per CTA that still let two CTAs share an SM
+    const uint32_t limits[3] = {big ? two : 75000u, 113000u, smem_optin_ > 2048u ? smem_optin_ - 1024u : smem_optin_};
     for (uint32_t limit : limits) {
         TilePlan best{};
         double best_cost = 1e300;
@@ -521,6 +522,7 @@ TilePlan Context::plan_tiles(const Geometry& g) const {
             }
         if (best.tpx) {
             best.tma_first = env_flag("DH_TRAV_TMA_FIRST", true) ? 1u : 0u;  // measured: 1.110 -> 1.052 ms per 1024 frames
+            best.ldg_levels = env_u32("DH_TRAV_LDG_LEVELS", 7);  // measured: 1.071 -> 1.048 ms (3: 1.057, 5: 1.051, 7-11: 1.048, 13: 1.057)
             if (env_flag("DH_TRAV_BLOCK", true)) {  // measured with the early load: 1.052 -> 1.037 ms
                 // a warp walks a block of 8 x 4 neighbouring patches: its lanes stay on the same nodes for
                 // longer.  On one node lane (c, r) reads word stride * (c + r * tw) + const: with

@@ -828,7 +828,21 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 768 ? 2 : 3) traverse_ke
             int32_t node = __ldg(roots + t);
             uint32_t nv = 0;
             bool tie = false;
-            while (node >= 0) {
+            // the first levels below the root, where the lanes of a warp still sit on a handful of nodes, through
+            // the LSU path (a warp-wide load of one address is one wavefront; a texture fetch costs eight or more
+            // whatever the addresses): DH_TRAV_LDG_LEVELS
+            for (uint32_t lv = 0; lv < tp.ldg_levels && node >= 0; ++lv) {
+                const uint4 U = __ldg(reinterpret_cast<const uint4*>(uni) + node);
+                const uint32_t s1 = lds_u32(o + ((U.x & 0xffffu) << 2)), s2 = lds_u32(o + ((U.x >> 16) << 2));
+                const int32_t d2 = (int32_t)(s1 - s2) << 1, E = (int32_t)U.w;
+                if (d2 == E) {
+                    tie = true;
+                    break;
+                }
+                node = d2 > E ? (int)U.z : (int)U.y;
+                ++nv;
+            }
+            while (node >= 0 && !tie) {
                 const uint4 U = tex1Dfetch<uint4>(hot_tex, node);
                 const uint32_t s1 = lds_u32(o + ((U.x & 0xffffu) << 2)), s2 = lds_u32(o + ((U.x >> 16) << 2));
                 const int32_t d2 = (int32_t)(s1 - s2) << 1, E = (int32_t)U.w;
@@ -1500,33 +1514,35 @@ __device__ __forceinline__ void accumulate_pairs(const float4* __restrict__ gate
             const uint32_t t = i / ngate;
             h = __ldg(gated + (i - t * ngate));
             const int32_t L = (int32_t)((uint32_t)leaf_f[(size_t)t * P + __float_as_uint(h.w)] & leaf_mask);
-            const LeafInfo li = f.leaf_info[L];
-            if (li.flags & kLeafVotes) {
+            // the leaf's record: vote range, weight, spread gates and vote bounding boxes in one sector
+            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L));
+            const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L) + 1);
+            const uint32_t flags = r0.y >> 24;
+            if (flags & kLeafVotes) {
                 // Skip the leaf when the bounding box of its votes misses the cube.  Conservative,
                 // hence exact: p3 - o and the truncation are monotone, so every vote cell lies in
-                // [trunc(p3 - omax), trunc(p3 - omin)] per axis; rotation bins lie in [rmin, rmax].
-                const uint4 bb0 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L));
-                const uint4 bb1 = __ldg(reinterpret_cast<const uint4*>(f.leaf_box + L) + 1);
-                bool do_c = (which_mask & 1u) && (li.flags & kLeafOffOk), do_r = (which_mask & 2u) && (li.flags & kLeafRotOk);
+                // [trunc(p3 - omax), trunc(p3 - omin)] per axis (the record's bounds are rounded
+                // outwards); rotation bins lie in [rmin, rmax].
+                bool do_c = (which_mask & 1u) && (flags & kLeafOffOk), do_r = (which_mask & 2u) && (flags & kLeafRotOk);
                 if (do_c) {
-                    const float omin[3] = {__uint_as_float(bb0.x), __uint_as_float(bb0.y), __uint_as_float(bb0.z)};
-                    const float omax[3] = {__uint_as_float(bb0.w), __uint_as_float(bb1.x), __uint_as_float(bb1.y)};
+                    const float omin[3] = {__uint_as_float(r1.x & 0xffff0000u), __uint_as_float(r1.y << 16), __uint_as_float(r1.y & 0xffff0000u)};
+                    const float omax[3] = {__uint_as_float(r1.z << 16), __uint_as_float(r1.z & 0xffff0000u), __uint_as_float(r1.w << 16)};
                     const float pc[3] = {h.x, h.y, h.z};
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
                         if (misses_box(__float2int_rz(__fsub_rn(pc[k], omax[k])), __float2int_rz(__fsub_rn(pc[k], omin[k])), org_c[k])) do_c = false;
                 }
                 if (do_r) {
+                    const int rmin[3] = {(int)(r0.w & 0xffu), (int)((r0.w >> 8) & 0xffu), (int)((r0.w >> 16) & 0xffu)};
+                    const int rmax[3] = {(int)(r0.w >> 24), (int)(r1.x & 0xffu), (int)((r1.x >> 8) & 0xffu)};
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int rmin = (int)((bb1.z >> (8 * k)) & 0xffu), rmax = (int)((bb1.w >> (8 * k)) & 0xffu);
-                        if (misses_box(rmin, rmax, org_r[k])) do_r = false;
-                    }
+                    for (int k = 0; k < 3; ++k)
+                        if (misses_box(rmin[k], rmax[k], org_r[k])) do_r = false;
                 }
-                v0 = li.vote_start;
-                wgt = li.valtoadd;
-                if (do_c) n_c = li.n_votes;
-                if (do_r) n_r = li.n_votes;
+                v0 = r0.x;
+                wgt = r0.z;
+                if (do_c) n_c = r0.y & 0xffffffu;
+                if (do_r) n_r = r0.y & 0xffffffu;
             }
         }
         if (which_mask & 1u) {
@@ -1902,6 +1918,16 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
     }
 }
 
+// float -> bfloat16 bit pattern, rounded towards -inf / +inf (exact for values a bfloat16 holds; inf stays inf)
+__device__ __forceinline__ uint16_t bf16_down(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return (uint16_t)(((b >> 31) && (b & 0xffffu) && (b & 0x7f800000u) != 0x7f800000u ? b + 0x10000u : b) >> 16);
+}
+__device__ __forceinline__ uint16_t bf16_up(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return (uint16_t)((!(b >> 31) && (b & 0xffffu) && (b & 0x7f800000u) != 0x7f800000u ? b + 0x10000u : b) >> 16);
+}
+
 // ================================================================ K5: per-leaf static gates
 // estimate_mean_cov (meancov_estimation.rs:359-378) in reference order, one thread per leaf.
 // Only the diagonal of the covariance is needed for the trace (entries are independent).
@@ -1974,11 +2000,8 @@ __global__ void __launch_bounds__(128) leaf_gate_kernel(const double* __restrict
     // bounding boxes of the leaf's votes (box_build skips leaves that cannot reach a cube) and
     // the coarse rotation cell of every vote: rough = r * 20 / 120 per axis, dense index
     // z*400 + y*20 + x (prediction.rs:630-636)
-    LeafBox bx;
-    for (int k = 0; k < 4; ++k) {
-        if (k < 3) bx.omin[k] = bx.omax[k] = 0.0f;
-        bx.rmin[k] = bx.rmax[k] = 0;
-    }
+    float omin[3] = {0.0f, 0.0f, 0.0f}, omax[3] = {0.0f, 0.0f, 0.0f};
+    uint8_t rmin[3] = {0, 0, 0}, rmax[3] = {0, 0, 0};
     uint32_t n_cells = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t bins = rot_bins[v0 + i];
@@ -1986,14 +2009,14 @@ __global__ void __launch_bounds__(128) leaf_gate_kernel(const double* __restrict
         for (int k = 0; k < 3; ++k) {
             const float o = offsets[(size_t)(v0 + i) * 3 + k];
             const uint8_t r = (uint8_t)((bins >> (8 * k)) & 0xffu);
-            if (i == 0 || o < bx.omin[k]) bx.omin[k] = o;
-            if (i == 0 || o > bx.omax[k]) bx.omax[k] = o;
-            if (!isfinite(o)) {
-                bx.omin[k] = -INFINITY;
-                bx.omax[k] = INFINITY;
+            if (i == 0 || o < omin[k]) omin[k] = o;
+            if (i == 0 || o > omax[k]) omax[k] = o;
+            if (!isfinite(o) || !isfinite(omin[k])) {  // stays open once a non-finite offset was seen
+                omin[k] = -INFINITY;
+                omax[k] = INFINITY;
             }
-            if (i == 0 || r < bx.rmin[k]) bx.rmin[k] = r;
-            if (i == 0 || r > bx.rmax[k]) bx.rmax[k] = r;
+            if (i == 0 || r < rmin[k]) rmin[k] = r;
+            if (i == 0 || r > rmax[k]) rmax[k] = r;
             q[k] = (uint32_t)r * kGuessGridParts / kRotGridParts;
         }
         // compact list of the leaf's cells: (cell | votes in it << 13) in the first n_cells slots of its
@@ -2006,6 +2029,15 @@ __global__ void __launch_bounds__(128) leaf_gate_kernel(const double* __restrict
         if (j < n_cells) rot_cells[v0 + j] += 1u << kRotCellBits;
         else rot_cells[v0 + n_cells++] = cell | (1u << kRotCellBits);
     }
+    LeafBox bx;
+    bx.vote_start = v0;
+    bx.n_votes_flags = n | ((li.flags & 7u) << 24);
+    bx.valtoadd = li.valtoadd;
+    bx.rmin[0] = rmin[0]; bx.rmin[1] = rmin[1]; bx.rmin[2] = rmin[2];
+    bx.rmax0 = rmax[0]; bx.rmax1 = rmax[1]; bx.rmax2 = rmax[2];
+    bx.omin0 = bf16_down(omin[0]); bx.omin1 = bf16_down(omin[1]); bx.omin2 = bf16_down(omin[2]);
+    bx.omax[0] = bf16_up(omax[0]); bx.omax[1] = bf16_up(omax[1]); bx.omax[2] = bf16_up(omax[2]);
+    bx.spare = 0;
     box_out[l] = bx;
     out[l].flags = li.flags | (n_cells << kLeafRotCellsShift);
 }

@@ -65,6 +65,7 @@ struct TilePlan {
     uint32_t blocked;         // 1: the patches of a tile are enumerated in blocks of 8 x 4 (a warp = a compact block)
                               // instead of row by row (experimental, DH_TRAV_BLOCK=1)
     uint32_t tma_first;       // 1: the tile's TMA load is issued before its background check (DH_TRAV_TMA_FIRST)
+    uint32_t ldg_levels;      // levels below the root whose nodes the default walk fetches through the LSU path (DH_TRAV_LDG_LEVELS)
 };
 
 struct ForestDev {

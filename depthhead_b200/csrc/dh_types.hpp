@@ -94,11 +94,23 @@ struct PairTopo {
     uint32_t first, tail;
 };
 
-// Bounding boxes of a leaf's votes: offsets (mm) per axis and rotation bins per axis.  A
-// non-finite offset opens its axis to (-inf, +inf), so such a leaf is never skipped.
+// Everything the accumulator-cube kernel needs to know about a leaf before it touches its votes, in ONE
+// 32-byte sector (the kernel gathers one record per gated patch x tree pair, 13.7 M per 1024 frames of
+// configs[1], and the L1 miss path delivers about half a sector per cycle per SM: with LeafInfo and a
+// separate 32-byte box it fetched three sectors per pair): the vote range, the weight, the spread
+// gates, and the bounding boxes of the votes — rotation bins per axis exactly, offsets (mm) per axis
+// as bfloat16 rounded outwards (min towards -inf, max towards +inf), which keeps the skip test
+// conservative.  A non-finite offset opens its axis to (-inf, +inf), so such a leaf is never skipped.
 struct alignas(32) LeafBox {
-    float omin[3], omax[3];
-    uint8_t rmin[4], rmax[4];  // [3] unused
+    uint32_t vote_start;
+    uint32_t n_votes_flags;   // n_votes (< 2^20) | LeafInfo flag bits 0..2 << 24
+    uint32_t valtoadd;
+    uint8_t rmin[3], rmax0;   // rotation bins in [0, 120)
+    uint8_t rmax1, rmax2;
+    uint16_t omin0;           // bfloat16 bit patterns
+    uint16_t omin1, omin2;
+    uint16_t omax[3];
+    uint16_t spare;
 };
 static_assert(sizeof(LeafBox) == 32, "LeafBox must be one 32-byte sector");
 constexpr uint32_t kLeafRotOk = 1u, kLeafOffOk = 2u, kLeafVotes = 4u;

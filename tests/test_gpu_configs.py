@@ -59,6 +59,9 @@ VARIANTS = [
     {"DH_CUBE_CLEAR_FUSED": "0"},                   # one memset of all accumulator cubes per pass instead of the clear behind mean-shift
     {"DH_LANES": "1"},
     {"DH_LANES": "4", "DH_CHUNK_FRAMES": "2"},
+    {"DH_TRAV_LDG_LEVELS": "0"},                    # every node of the default walk through the texture path
+    {"DH_TRAV_LDG_LEVELS": "3", "DH_TRAV_SMEM": "98000"},
+    {"DH_TRAV_LDG_LEVELS": "40"},                   # ... through the LSU path
     {"DH_NODE_ALIGN": "0"},                         # device node table in host order (no pad records in front of sibling pairs)
     {"DH_NODE_ALIGN": "0", "DH_TRAV_PAIR": "1"},
     {"DH_MS_PERSIST": "0"},                         # mean-shift: one CTA per accumulator instead of persistent CTAs
