@@ -274,7 +274,9 @@ def run_reference(args):
 
 
 def traverse_roofline(counters, trav_ms, launches, clocks, n_sms, build_id):
-    """roofline of traverse_kernel against the measured L1 data-stage peak"""
+    """roofline of traverse_kernel against the measured peaks of the SM's L1 data stage: the walk uses
+    two pipes of it (LSU: shared-memory taps and the node records of the first levels; TEX: the node
+    records of the deeper levels), so its roof is the pipe that runs closest to ITS measured peak"""
     peaks = load_json("measured_l1_peaks.json")
     prof = load_json("traverse_profile.json")
     visits = counters["node_visits"]
@@ -282,33 +284,45 @@ def traverse_roofline(counters, trav_ms, launches, clocks, n_sms, build_id):
     out = {"kernel": "traverse_kernel", "bound": "l1", "unit": "GB/s", "achieved": None, "peak": None, "frac": None, "traffic": None,
            "launches": launches, "avg_launch_ms": trav_ms / launches if launches else None,
            "node_visits_per_launch": visits / launches if launches else None, "build_id": build_id}
+    if trav_ms > 0:
+        out["node_visits_per_cycle_per_sm"] = visits / (trav_ms / 1000.0) / sm_hz / n_sms
     if peaks:
-        per_cycle = float(peaks["concurrent_wavefronts_per_cycle_per_sm"])
-        out["peak"] = per_cycle * WAVEFRONT_BYTES * n_sms * sm_hz / 1e9
-        out["peak_source"] = ("measured: %.3f L1 data-stage wavefronts per cycle per SM with the LSU (shared-memory) and TEX pipes loaded "
-                              "together (profiles/measured_l1_peaks.json, tools/peak_l1_gather.cu; alone: LSU %.3f, TEX %.3f) x 128 B x %d SMs "
-                              "x the SM clock of this run" % (per_cycle, float(peaks["lsu_wavefronts_per_cycle_per_sm"]),
-                                                             float(peaks["tex_wavefronts_per_cycle_per_sm"]), n_sms))
         out["measured_peaks"] = {k: peaks[k] for k in peaks if k.endswith("_per_sm")}
-    if prof and trav_ms > 0:
+    if peaks and prof and trav_ms > 0:
         match = prof.get("build_id") == build_id
-        wf = float(prof["lsu_wavefronts_per_visit"]) + float(prof["tex_wavefronts_per_visit"])
-        out["achieved"] = wf * visits * WAVEFRONT_BYTES / (trav_ms / 1000.0) / 1e9
-        out["wavefronts_per_node_visit"] = {"lsu": prof["lsu_wavefronts_per_visit"], "tex": prof["tex_wavefronts_per_visit"],
-                                            "source": prof.get("source"), "profile_build_id": prof.get("build_id"),
-                                            "profile_matches_this_build": match}
+        to_gbs = visits * WAVEFRONT_BYTES / (trav_ms / 1000.0) / 1e9          # wavefronts per visit -> GB/s of wavefronts
+        peak_gbs = lambda per_cycle: per_cycle * WAVEFRONT_BYTES * n_sms * sm_hz / 1e9  # noqa: E731
+        pipes = {}
+        for pipe in ("lsu", "tex"):
+            wf = float(prof["%s_wavefronts_per_visit" % pipe])
+            pk = float(peaks["%s_wavefronts_per_cycle_per_sm" % pipe])
+            pipes[pipe] = {"achieved": wf * to_gbs, "peak": peak_gbs(pk), "frac": wf * to_gbs / peak_gbs(pk),
+                           "wavefronts_per_node_visit": wf, "peak_wavefronts_per_cycle_per_sm": pk}
+        top = max(pipes, key=lambda k: pipes[k]["frac"])
+        out.update(achieved=pipes[top]["achieved"], peak=pipes[top]["peak"], frac=pipes[top]["frac"], pipe=top)
+        both = float(peaks["concurrent_wavefronts_per_cycle_per_sm"])
+        wf_both = pipes["lsu"]["wavefronts_per_node_visit"] + pipes["tex"]["wavefronts_per_node_visit"]
+        out["pipes"] = pipes
+        out["both_pipes"] = {"achieved": wf_both * to_gbs, "peak": peak_gbs(both), "frac": wf_both * to_gbs / peak_gbs(both),
+                             "peak_wavefronts_per_cycle_per_sm": both}
+        out["peak_source"] = ("measured with tools/peak_l1_gather.cu on this pool's B200s (profiles/measured_l1_peaks.json): divergent loads "
+                              "through one pipe of the L1 data stage alone reach %.3f (LSU) and %.3f (TEX) wavefronts per cycle per SM, both "
+                              "pipes loaded together %.3f; x 128 B x %d SMs x the SM clock of this run.  `frac` is the %s pipe, the one "
+                              "closer to its own peak; `both_pipes` is the sum against the concurrent peak"
+                              % (float(peaks["lsu_wavefronts_per_cycle_per_sm"]), float(peaks["tex_wavefronts_per_cycle_per_sm"]), both, n_sms,
+                                 top.upper()))
+        out["wavefront_source"] = {"source": prof.get("source"), "profile_build_id": prof.get("build_id"), "profile_matches_this_build": match}
         if match:
             out["traffic"] = float(prof["dram_bytes_per_launch"]) * (visits / launches) / float(prof["node_visits_per_launch"])
             out["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu capture of this build, scaled by node visits"
         else:
             out["traffic_note"] = "dropped: profiles/traverse_profile.json was captured on build %s, this library is build %s" % (prof.get("build_id"), build_id)
-        if out["peak"]:
-            out["frac"] = out["achieved"] / out["peak"]
         out["other_ceilings"] = {"l2_to_l1_sectors_per_cycle_per_sm": {"kernel": prof.get("l2_sectors_per_cycle_per_sm"),
-                                                                       "measured_random_gather_ceiling": (peaks or {}).get("l2_random_sectors_per_cycle_per_sm")}}
-    out["note"] = ("achieved = (LSU + TEX data-stage wavefronts per node visit, ncu capture of the named build) x node visits of this run x 128 B / "
-                   "CUDA-event time of the kernel; the taps are served from the TMA-staged shared-memory tile and the node records from L1/L2, "
-                   "so HBM carries almost none of it (roofline_hbm)")
+                                                                       "measured_random_gather_ceiling": peaks.get("l2_random_sectors_per_cycle_per_sm")}}
+    out["note"] = ("achieved = data-stage wavefronts per node visit of the named pipe (ncu capture of the named build) x node visits of this run "
+                   "x 128 B / CUDA-event time of the kernel; the taps are served from the TMA-staged shared-memory tile and the node records "
+                   "from L1/L2, so HBM carries almost none of it (roofline_hbm).  The walk is a dependent chain (fetch node -> two taps -> "
+                   "compare -> next node): it is bound by the latency of that chain under L1 misses, with both pipes below their peaks")
     return out
 
 

@@ -252,6 +252,7 @@ private:
     bool use_graphs_ = true;
     bool prob_codes_ok_ = false;     // the uploaded forest's leaf probabilities can ride in the node table as 8-bit codes
     bool leaf_codes_ = false;        // ... and do: leaf words carry them (FrameBuffers::leaf_mask, patch_gate_kernel)
+    uint32_t gate_split_min_ = 64;   // frames per pass from which the patch gate runs as its own kernel (DH_GATE_SPLIT_MIN)
     bool gate_split_ = true;         // DH_GATE_SPLIT=0: the patch gate inside the seed-grid kernel instead of its own kernel + list
     bool cube_clear_fused_ = true;   // DH_CUBE_CLEAR_FUSED=0: one memset of all cubes per pass instead
 

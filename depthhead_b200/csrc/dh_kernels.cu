@@ -7,8 +7,11 @@
 //                                summed-area table for forests with mixed rectangle sizes
 //   K2  traverse_kernel          TMA-staged tile of B (or of the SAT) in shared memory; one thread per
 //                                patch x tree walks root->leaf (houghforest.rs:185-193, types.rs:317-339)
-//   K3  gate_coarse_kernel       ordered f64 prob sum, 0.7 gate, back-projection, gated-patch list and the two
-//                                coarse seed grids (prediction.rs:551-554,582-595,630-636,661-675)
+//   K3a patch_gate_kernel        0.7 gate of every patch from the 8-bit probability codes its leaf words carry
+//                                (ordered f64 prob sum only where the codes cannot decide), back-projection,
+//                                gated-patch list (prediction.rs:551-554,582-584)
+//   K3b gate_coarse_kernel       the two coarse seed grids from slices of the gated-patch list
+//                                (prediction.rs:590-595,630-636,661-675); <., false>: gate and grids in one kernel
 //   K4a seed_kernel              arg-max seeds (prediction.rs:694-752, 437-460)
 //   K4b box_build_kernel         dense local cubes of the SparseArray3D<u32> accumulators
 //                                (meanshift.rs:14-68, prediction.rs:635,667)

@@ -8,6 +8,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# The library keeps the patch gate inside the seed-grid kernel for passes of fewer than 64 frames (they are
+# bound by the chain of launches) and runs it as its own kernel over probability codes from there on.  The
+# tests work on a handful of frames: they take the large-batch path unless a test says otherwise
+# (test_kernel_variants restores the library's threshold, test_large_batch_crosses_both_gate_paths uses both).
+os.environ.setdefault("DH_GATE_SPLIT_MIN", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

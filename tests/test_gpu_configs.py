@@ -67,6 +67,7 @@ VARIANTS = [
     {"DH_MS_PERSIST": "0"},                         # mean-shift: one CTA per accumulator instead of persistent CTAs
     {"DH_MS_PERSIST": "0", "DH_MS_COMPACT": "0"},
     {"DH_MS_COMPACT": "0"},                         # mean-shift: window staged in shared memory, summands per 32-cell chunk
+    {"DH_GATE_SPLIT_MIN": "64"},                    # the library's default: small passes gate inside the seed-grid kernel
     {"DH_PROB_CODES": "0"},                         # no probability codes in the node table: the patch gate runs as its own kernel
     {"DH_PROB_CODES": "0", "DH_GATE_CTAS": "2"},
     {"DH_GATE_SPLIT": "0"},                         # patch gate inside the seed-grid kernel instead of the traversal's tail
@@ -94,6 +95,29 @@ def test_kernel_variants(monkeypatch, env):
             for i, d in enumerate(frames):
                 tr = of.predict(d, synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
                 assert np.array_equal(out["mid_point"][i], tr.mid_point) and np.array_equal(out["rotation"][i], tr.rotation)
+    finally:
+        c.close()
+
+
+def test_large_batch_crosses_both_gate_paths(monkeypatch):
+    """library defaults: a batch of 80 frames gates its patches in patch_gate_kernel (probability codes in
+    the leaf words, seed grids from slices of the gated-patch lists), single frames gate inside the
+    seed-grid kernel; both must give the oracle's poses"""
+    monkeypatch.delenv("DH_GATE_SPLIT_MIN", raising=False)
+    c = Context(0)
+    try:
+        arr = synth.make_forest(seed=9, n_trees=5, max_depth=8)
+        js = synth.forest_to_json(arr, stepwidth=8)
+        hp = HoughPrediction.from_json(js)
+        of = oracle.OracleForest.from_json(js)
+        frames = synth.make_frames(80, seed=71)
+        out = hp.predict_batch(frames, K, ctx=c)
+        for i in (0, 1, 17, 40, 79):
+            tr = of.predict(frames[i], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
+            assert np.array_equal(out["mid_point"][i], tr.mid_point) and np.array_equal(out["rotation"][i], tr.rotation), i
+            res = hp.predict_parameter_parallel(frames[i], K, ctx=c)
+            assert np.array_equal(res.mid_point, tr.mid_point) and np.array_equal(res.rotation, tr.rotation), i
+        assert len({tuple(m) for m in out["mid_point"].tolist()}) > 10
     finally:
         c.close()
 

@@ -16,11 +16,11 @@ tail -c 400 gpurun_out/bench_$tag.json
 SMALL="--no-cpu-baseline --no-strong --no-extra-forests"
 DH_LANES=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
     python bench.py --steps 2 --warmup 3 $SMALL > gpurun_out/ncu_launches_$tag.log 2>&1
-K='regex:box_image|traverse_kernel|gate_coarse|box_build|meanshift_kernel|seed_kernel'
+K='regex:box_image|traverse_kernel|patch_gate|gate_coarse|box_build|meanshift_kernel|seed_kernel'
 python bench.py --frames 512 --chunk 512 --steps 2 --warmup 3 $SMALL > gpurun_out/bench_prof_$tag.json 2> gpurun_out/bench_prof_$tag.err &&
-ncu --set full --import-source on --clock-control none -k "$K" -s 6 -c 6 \
+ncu --set full --import-source on --clock-control none -k "$K" -s 7 -c 7 \
     -o gpurun_out/prof_step_$tag -f python bench.py --frames 512 --chunk 512 --steps 1 --warmup 3 $SMALL > gpurun_out/ncu_full_$tag.log 2>&1
 M=l1tex__data_pipe_lsu_wavefronts.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_pipe_tex_wavefronts.sum,l1tex__m_xbar2l1tex_read_sectors.sum,l1tex__t_sectors.sum,l1tex__t_sectors_lookup_hit.sum,l1tex__t_set_accesses.sum,sm__cycles_elapsed.max,smsp__inst_executed.sum,gpu__time_duration.sum
-ncu --metrics $M --clock-control none -k "$K" -s 6 -c 6 --csv --log-file gpurun_out/prof_wf_$tag.csv \
+ncu --metrics $M --clock-control none -k "$K" -s 7 -c 7 --csv --log-file gpurun_out/prof_wf_$tag.csv \
     python bench.py --frames 512 --chunk 512 --steps 1 --warmup 3 $SMALL > gpurun_out/ncu_wf_$tag.log 2>&1
 ls -la gpurun_out/*$tag*
