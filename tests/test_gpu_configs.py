@@ -112,12 +112,13 @@ def test_large_batch_crosses_both_gate_paths(monkeypatch):
         of = oracle.OracleForest.from_json(js)
         frames = synth.make_frames(80, seed=71)
         out = hp.predict_batch(frames, K, ctx=c)
+        assert c.counters()["gate_patches"] > 80 * 100  # the gate passes a few hundred patches per frame
         for i in (0, 1, 17, 40, 79):
             tr = of.predict(frames[i], synth.KINECT_K, mode=oracle.MODE_SAT, keep=False)
             assert np.array_equal(out["mid_point"][i], tr.mid_point) and np.array_equal(out["rotation"][i], tr.rotation), i
             res = hp.predict_parameter_parallel(frames[i], K, ctx=c)
             assert np.array_equal(res.mid_point, tr.mid_point) and np.array_equal(res.rotation, tr.rotation), i
-        assert len({tuple(m) for m in out["mid_point"].tolist()}) > 10
+        assert len({tuple(r) for r in out["rotation"].tolist()}) > 3
     finally:
         c.close()
 
