@@ -1375,8 +1375,8 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
 // ================================================================ K4a: seeds
 // One CTA per frame: arg-max of the two coarse grids -> mean-shift seeds (prediction.rs:694-752,
 // 437-460) and the origin of the frame's two accumulator cubes.
-constexpr int kBox = 40;                      // cells per axis of the dense accumulator cube
-constexpr int kBoxCells = kBox * kBox * kBox; // 64 000 cells = 250 KB
+constexpr int kBox = 32;                      // cells per axis of the dense accumulator cube: the 20-cell window plus 6 cells of margin
+constexpr int kBoxCells = kBox * kBox * kBox; // 32 768 cells = 128 KB (40^3: 414 k frames/s, 32^3: 434 k, 28^3: 439 k, 24^3: 398 k with 1269 rebuilds per 1024 frames)
 constexpr int kSeedThreads = 256;
 constexpr int kMsHistory = 64;
 
@@ -1475,7 +1475,8 @@ __global__ void __launch_bounds__(kSeedThreads) seed_kernel(FrameBuffers b, Geom
         for (int k = 0; k < 3; ++k) {
             fs->seed_mid[k] = sm[k];
             fs->seed_rot[k] = sr[k];
-            // cube centred on the seed: 10 cells of margin around the 20^3 window = every position one mean-shift step away
+            // cube centred on the seed: kBox/2 - 10 cells of margin around the seed's 20^3 window; a window that leaves it
+            // makes the mean-shift CTA rebuild the cube around its position
             fs->box_org[0][k] = (int32_t)((uint32_t)sm[k] - (uint32_t)(kBox / 2));
             fs->box_org[1][k] = (int32_t)((uint32_t)sr[k] - (uint32_t)(kBox / 2));
         }
@@ -1605,8 +1606,9 @@ __global__ void __launch_bounds__(kBuildThreads) box_build_kernel(FrameBuffers b
 // cells in reference order (ballots + one cross-warp prefix) (x outermost, z innermost, offsets -10..+9: meanshift.rs:340-346),
 // stage the summands in shared memory at that rank and four lanes fold them into the f32
 // accumulators one after the other in exactly that order.  A round moves the position by at most
-// 10 cells and the cube leaves 10 cells of margin around the seed's window; if the window would
-// leave the cube, the cube is rebuilt around the current position from the frame's gated patches
+// 10 cells and the cube leaves 6 cells of margin around the seed's window (most runs move a cell or
+// two per round; a larger cube costs more in clears and cache misses than rebuilds do); if the window
+// would leave the cube, the cube is rebuilt around the current position from the frame's gated patches
 // (counted in FrameState::rebuilds), so the results stay exactly those of the unbounded map.
 constexpr int kMsThreads = 512;
 constexpr int kMsWarps = kMsThreads / 32;
@@ -1901,7 +1903,7 @@ __global__ void __launch_bounds__(kMsThreads, 3) meanshift_kernel(FrameBuffers b
     }
     __syncthreads();
     if (b.clear_cubes) {
-        // leave the cube empty for the next pass over this scratch: 250 KB of stores that overlap the
+        // leave the cube empty for the next pass over this scratch: 128 KB of stores that overlap the
         // other CTAs' rounds instead of one memset of every cube in front of the vote stage
         uint4* bz = reinterpret_cast<uint4*>(box);
         for (int i = tid; i < kBoxCells / 4; i += kMsThreads) __stcg(bz + i, make_uint4(0u, 0u, 0u, 0u));

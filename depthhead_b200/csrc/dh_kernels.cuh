@@ -25,7 +25,7 @@ struct alignas(16) FrameState {
     uint32_t ms_iters[2];     // mean-shift rounds actually executed (centre, rotation)
     uint32_t ms_flags[2];     // bit0 zero-sum break
     uint32_t rebuilds[2];     // times the accumulator cube had to be rebuilt around a new position
-    int32_t box_org[2][3];    // origin of the accumulator cube (seed - 24, or the last rebuild)
+    int32_t box_org[2][3];    // origin of the accumulator cube (seed - 16, or the last rebuild)
     uint32_t box_valid[2];
     uint32_t has_guess;       // bit0 midp_guess, bit1 rot_guess supplied by the caller
     float midp_guess[3];

@@ -59,7 +59,7 @@ def _compare_frame(ctx, hp, of, depth, midp_guess=None, rot_guess=None, check_pa
         if of.meanshift_iterations == 0:
             assert dim == 0
             continue
-        assert dim >= 20 + 2 * 10
+        assert dim >= 20 + 2 * 6  # the 20-cell window of the seed and a margin
         ek, ev = _filter_acc(ok, ov, org, dim)
         assert np.array_equal(gk, ek), "accumulator %d keys differ (%d vs %d cells)" % (which, len(gk), len(ek))
         assert np.array_equal(gv, ev), "accumulator %d sums differ" % which
