@@ -1377,7 +1377,7 @@ __global__ void __launch_bounds__(kGateThreads, 3) gate_coarse_kernel(FrameBuffe
 // 437-460) and the origin of the frame's two accumulator cubes.
 constexpr int kBox = 32;                      // cells per axis of the dense accumulator cube: the 20-cell window plus 6 cells of margin
 constexpr int kBoxCells = kBox * kBox * kBox; // 32 768 cells = 128 KB (40^3: 414 k frames/s, 32^3: 434 k, 28^3: 439 k, 24^3: 398 k with 1269 rebuilds per 1024 frames)
-constexpr int kSeedThreads = 256;
+constexpr int kSeedThreads = 512;
 constexpr int kMsHistory = 64;
 
 struct Best {
