@@ -1071,8 +1071,14 @@ void Context::run_batch(const HostForest& hf, const uint16_t* depth, const uint8
 // every chunk as Biwi run-length files (biwi.rs:81-103: the format biwi_decode_kernel expands)
 // straight into pinned memory; only those bytes cross PCIe and the frames are rebuilt on the GPU,
 // bit for bit.  Chunks whose sampled density says the rewrite would not pay are copied raw.
+// A context with only a few worker threads copies raw (unless DH_HOST_ENCODE=1 insists): that is a rank of
+// a multi-GPU box, where the contexts together are bound by the host's memory system, not by one PCIe link,
+// and a rewritten frame costs that system 870 KB of traffic against 614 KB for a raw copy (8 ranks with 3
+// workers each on a 32-core box: 264 k frames/s rewriting, 303 k copying raw; one rank with 15 workers:
+// 135 k against 86 k).
 bool Context::want_encode(uint32_t n, uint32_t w, uint32_t h) const {
     if (host_encode_ == 0) return false;
+    if (host_encode_ < 0 && (encode_threads_req_ ? encode_threads_req_ : default_encode_threads()) < 6u) return false;
     const size_t px = (size_t)w * h;
     return px >= 16384 && px <= 0x3fffffffull && (size_t)n * px >= (size_t)8 * 640 * 480;
 }
